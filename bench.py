@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the differentiable ray-march hot path (BASELINE.json metric: Gsamples/s forward and forward+backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of views: brick the volume, forward march, backward march
+(TF + volume gradients), un-brick the gradient (and, for N > 1, all-reduce [volume grad | TF grad]).  A "sample" is one
+ACTIVE ray-march step; the count is the sum of the forward kernel's per-ray K.
+
+Prints ONE JSON line on rank 0.  `value` = device-resident throughput through the C ABI; `e2e` = the same metric through
+the public `Raycaster` autograd API with inputs coming from pinned host memory every step.
+`--impl reference` times the CPU oracle (oracle/cpu_ref.c, kind "port": the real reference needs Taichi, which is not
+installable here) on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: volume N^3, dtype, image (w,h), views per GPU, mode
+    "c1": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="nondiff", sr=16.0, M=1, jitter=False,
+               desc="C1 forward-only nondiff render, 256^3 fp32, 512x512, 1 view, sr 16"),
+    "c2": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="tf", sr=1.0, M=2048, jitter=True,
+               desc="C2 TF optimisation step: fwd+bwd w.r.t. TF only + momentum update, 256^3 fp32, 512x512, 1 view"),
+    "c3": dict(n=256, dtype="f32", res=(1024, 1024), views=16, mode="full", sr=1.0, M=2048, jitter=True,
+               desc="C3 volume-gradient backprop: fwd+bwd (TF+volume grad), 256^3 fp32, 1024x1024, 16 views per GPU"),
+    "c4": dict(n=512, dtype="f32", res=(1024, 1024), views=8, mode="full", sr=1.0, M=4096, jitter=True,
+               desc="C4 multi-view batch: fwd+bwd, 512^3 fp32, 1024x1024, 8 views per GPU (64 over 8 GPUs)"),
+    "c5": dict(n=1024, dtype="f16", res=(2048, 2048), views=32, mode="full", sr=1.0, M=8192, jitter=True,
+               desc="C5 large volume: fwd+bwd, 1024^3 fp16-stored, 2048x2048, jittered, 32 views per GPU (256 over 8 GPUs)"),
+}
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    p.add_argument("--views", type=int, default=None, help="views per GPU (default: the config's)")
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline / --impl reference)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample(cfg, budget_s=20.0):
+    """Times the CPU restatement on a bounded sample of the workload: view 0 with 1/4 of its rays (w/2 x h/2).
+    Returns dict(value Gsamples/s, seconds, samples, cores, sample description)."""
+    import numpy as np
+    import torch
+    from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
+    from oracle import cpu_oracle as co
+    co.build()
+    n = min(cfg["n"], 256)                      # the CPU leg keeps the volume at <= 256^3 (memory/time); per-sample work is size-independent
+    w, h = max(cfg["res"][0] // 2, 32), max(cfg["res"][1] // 2, 32)
+    vol = make_volume(n).numpy()
+    if cfg["dtype"] == "f16":
+        vol = vol.astype(np.float16).astype(np.float32)
+    tf = make_tf("tf1", 128).numpy()
+    cam = make_cameras(max(cfg["views"], 1))[0].numpy()
+    jit = make_jitter(1, h, w)[0].numpy() if cfg["jitter"] else None
+    nondiff = cfg["mode"] == "nondiff"
+    kw = dict(sampling_rate=cfg["sr"], max_samples=max(cfg["M"], 1), jitter=jit, fast=True)
+    cores = co.num_threads(fast=True)
+    t0 = time.perf_counter()
+    img, K, _ = co.forward(vol, tf, cam, (w, h), nondiff=nondiff, return_counts=True, **kw)
+    t_f = time.perf_counter() - t0
+    samples = int(K.sum())
+    t_b = 0.0
+    if not nondiff:
+        go = (2.0 * (img - 0.5) / img.size).astype(np.float32)
+        t0 = time.perf_counter()
+        co.backward(vol, tf, cam, go, (w, h), want_vol=cfg["mode"] == "full", want_tf=True, **kw)
+        t_b = time.perf_counter() - t0
+    return dict(value=samples / (t_f + t_b) / 1e9, fwd_value=samples / t_f / 1e9, seconds=t_f + t_b, samples=samples, cores=cores,
+                sample=f"view 0 of the workload on a {n}^3 volume at {w}x{h} rays (1/4 of the view's rays), "
+                       f"{'forward' if nondiff else 'forward+backward'}, {samples} active samples, {t_f + t_b:.1f} s")
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_sample(cfg)
+        if i >= args.warmup:
+            vals.append(last)
+    secs = sum(v["seconds"] for v in vals)
+    samples = sum(v["samples"] for v in vals)
+    value = samples / secs / 1e9
+    line = {
+        "impl": "reference", "metric": "Gsamples/s fwd+bwd (TF+volume grad)" if cfg["mode"] != "nondiff" else "Gsamples/s fwd",
+        "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "note": "CPU restatement of the reference (oracle/cpu_ref.c); Taichi ti.cpu is not installable here"},
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from differender_b200 import Raycaster, VolumeRaycaster
+    from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, (w, h), R, M, sr = cfg["n"], cfg["res"], 128, cfg["M"], cfg["sr"]
+    views = args.views or cfg["views"]
+    mode = cfg["mode"]
+    vdtype = torch.float16 if cfg["dtype"] == "f16" else torch.float32
+    vol = make_volume(n, device=dev, dtype=vdtype)                                   # (1, D, H, W), replicated on every rank
+    tf = make_tf("tf1", R, device=dev)                                               # (4, R)
+    all_cams = make_cameras(views * world, device=dev)
+    cams = all_cams[rank * views:(rank + 1) * views].contiguous()                   # this rank's shard of the view batch
+    jit = make_jitter(views, h, w, seed=4321 + rank, device=dev) if cfg["jitter"] else None
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    target = torch.rand((views, 4, h, w), generator=g, device=dev)
+
+    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R)
+    vol_lin = vol.reshape(1, n, n, n)
+    tf_r4 = tf.t().contiguous()[None]
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    need_vol, need_tf = mode == "full", mode in ("full", "tf")
+    momentum = torch.zeros_like(tf)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phase_ms = {"brick": 0.0, "fwd": 0.0, "bwd": 0.0, "post": 0.0}
+    samples_per_step = [0]
+    launches = [0]
+
+    def step(timed):
+        e = [ev() for _ in range(5)] if timed else None
+        flush.zero_()                                                                # L2 flush between steps
+        if timed: e[0].record()
+        bricked = vr.brick(vol_lin)
+        if timed: e[1].record()
+        out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")
+        if timed: e[2].record()
+        n_k = 2                                                                      # brick_kernel + fwd_kernel
+        if mode != "nondiff":
+            go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
+            gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf)
+            if timed: e[3].record()
+            n_k += 1 + (1 if need_tf else 0) + (1 if need_vol else 0)                 # bwd_kernel (+ tf_reduce_kernel) (+ unbrick_kernel)
+            if world > 1:
+                flat = torch.cat([t.reshape(-1) for t in (gvol, gtf) if t is not None])
+                dist.all_reduce(flat)
+            if mode == "tf":                                                         # C2: momentum update (reference example :375-381)
+                gt = gtf[0].t().clamp(-0.1, 0.1)
+                momentum.mul_(0.9).add_(gt, alpha=0.1)
+        elif timed:
+            e[3].record()
+        if timed:
+            e[4].record()
+        return e, K, n_k
+
+    for _ in range(max(args.warmup, 3)):
+        _, K, n_k = step(False)
+    samples_per_step[0] = int(K.sum().item())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    t0, t1 = ev(), ev()
+    t0.record()
+    evs = []
+    for _ in range(args.steps):
+        e, K, n_k = step(True)
+        evs.append(e)
+        launches[0] += n_k
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    total_ms = t0.elapsed_time(t1)
+    for e in evs:
+        for name, a, b in (("brick", 0, 1), ("fwd", 1, 2), ("bwd", 2, 3), ("post", 3, 4)):
+            phase_ms[name] += e[a].elapsed_time(e[b])
+    tot = torch.tensor([total_ms, float(samples_per_step[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, all_samples = float(mx[0]), float(sm[1])
+    else:
+        all_samples = float(tot[1])
+    value = all_samples * args.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- end-to-end through the public autograd API, inputs from pinned host memory every step ---------------------
+    e2e = None
+    if not args.no_e2e:
+        rc = Raycaster((n, n, n), (w, h), R, sampling_rate=sr, jitter=cfg["jitter"], max_samples=M)
+        pin = lambda t: t.detach().cpu().pin_memory()
+        h_vol, h_tf, h_cams, h_target = pin(vol), pin(tf), pin(cams), pin(target)
+        h_jit = pin(jit) if jit is not None else None
+        h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        h_gtf = torch.empty((4, R), dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in (h_vol, h_tf, h_cams, h_target) + ((h_jit,) if h_jit is not None else ()))
+        d2h = 4 + (h_gtf.numel() * 4 if need_tf else 0)
+
+        def e2e_step():
+            flush.zero_()
+            v = h_vol.to(dev, non_blocking=True)
+            t = h_tf.to(dev, non_blocking=True)
+            c = h_cams.to(dev, non_blocking=True)
+            tg = h_target.to(dev, non_blocking=True)
+            j = h_jit.to(dev, non_blocking=True) if h_jit is not None else None
+            if mode == "nondiff":
+                img = rc.raycast_nondiff(v, t, c, sampling_rate=sr)
+                loss = ((img - tg) ** 2).mean()
+            else:
+                v.requires_grad_(need_vol); t.requires_grad_(need_tf)
+                img = rc(v, t, c, j)
+                loss = ((img - tg) ** 2).mean()
+                loss.backward()
+                if world > 1:
+                    flat = torch.cat([x.grad.reshape(-1).float() for x in (v, t) if x.grad is not None])
+                    dist.all_reduce(flat)
+                if need_tf:
+                    h_gtf.copy_(t.grad, non_blocking=True)
+            h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.synchronize()                                                  # the user reads the loss every step
+            return float(h_loss[0])
+
+        for _ in range(2):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(args.steps):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": all_samples * args.steps / (float(ms[0]) * 1e-3) / 1e9, "unit": "Gsamples/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ms[0]) / args.steps,
+               "api": "differender_b200.Raycaster.forward + loss.backward()" if mode != "nondiff" else "Raycaster.raycast_nondiff"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        vox_b = 2 if cfg["dtype"] == "f16" else 4
+        s = samples_per_step[0]
+        fwd_ms, bwd_ms = phase_ms["fwd"] / args.steps, phase_ms["bwd"] / args.steps
+        # algorithmic bytes per sample (SURVEY 8(d) / BASELINE.md 5): forward 8 corner voxels; backward 8 corner reads +
+        # 8 fp32 atomic read-modify-writes (TF-only backward = forward figure)
+        fwd_bytes = 8 * vox_b
+        bwd_bytes = 8 * vox_b + (64 if need_vol else 0)
+        dominant = "bwd_kernel" if (mode != "nondiff" and bwd_ms >= fwd_ms) else "fwd_kernel"
+        dom_bytes, dom_ms = (bwd_bytes, bwd_ms) if dominant == "bwd_kernel" else (fwd_bytes, fwd_ms)
+        achieved = dom_bytes * s / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        line = {
+            "metric": "Gsamples/s fwd+bwd (TF+volume grad)" if mode == "full" else ("Gsamples/s fwd+bwd (TF grad)" if mode == "tf" else "Gsamples/s fwd"),
+            "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "volume": f"{n}^3 {cfg['dtype']}", "image": f"{w}x{h}", "views_per_gpu": views,
+                       "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
+                       "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
+                       "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
+                       "active_samples_per_step_per_gpu": s},
+            "fwd": {"value": s / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "unit": "Gsamples/s", "ms": fwd_ms},
+            "bwd": {"value": s / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "unit": "Gsamples/s", "ms": bwd_ms},
+            "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "algorithmic_bytes_per_sample": dom_bytes,
+                         "note": "L2-level algorithmic bytes (SURVEY 8(d)); the march is L1/LSU- and issue-bound, HBM traffic is far below"},
+            "clocks": clocks, "gpu_launches": launches[0],
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            cb = cpu_sample(cfg)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,416 @@
+// diffrender.cu -- sm_100a kernels and the C ABI (include/diffrender.h) of the differentiable ray-march.
+//
+// Kernels (DESIGN.md has the roofline of each):
+//   brick_kernel     linear [Y][Z][X] volume -> 8x8x8 bricks                 (set_volume, reference :118-119)
+//   fwd_kernel       ray set-up + march + compositing + final image          (:221-372)
+//   bwd_kernel       tape-free reverse march, TF + volume gradient scatter   (raycast.grad, :460-461)
+//   tf_reduce_kernel sums the privatised TF-gradient copies                  (tf_tex.grad.to_torch, :464,475)
+//   unbrick_kernel   bricked fp32 gradient -> linear, nan_to_num             (volume.grad.to_torch, :463,474)
+//
+// Thread mapping: one ray per thread; a warp is an 8x4 pixel tile, a CTA (4 warps) a 16x8 tile, so the 32 rays of
+// a warp traverse neighbouring voxels and their corner fetches fall into a few 128-byte lines of the same bricks.
+// No tensor cores: nothing here is a dense contraction (north_star).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "diffrender.h"
+#include "dr_desc.h"
+#include "dr_math.cuh"
+
+using namespace dr;
+
+namespace {
+
+constexpr int kTileW = 16, kTileH = 8, kThreads = 128;
+constexpr int kTfSlots = 1024;          // privatised TF-gradient copies (power of two)
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return DR_ECUDA;
+}
+
+__host__ __device__ inline Layout make_layout(const DrDesc& d)
+{
+    Layout L;
+    L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
+    L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bricking / un-bricking  (HBM-bound: 2 * sizeof(voxel) bytes per voxel)
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT>
+__global__ void __launch_bounds__(256) brick_kernel(DrDesc d, const VT* __restrict__ lin, VT* __restrict__ br, size_t elems)
+{
+    // one thread per bricked element: writes are fully coalesced, reads are 8-voxel (32/16-byte) row segments
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= elems) return;
+    const int b = blockIdx.y;
+    const int inb = (int)(e & 511);
+    size_t brick = e >> 9;
+    const int bx = (int)(brick % d.nbx); brick /= d.nbx;
+    const int by = (int)(brick % d.nby);
+    const int bz = (int)(brick / d.nby);
+    const int x = bx * 8 + (inb & 7), y = by * 8 + ((inb >> 3) & 7), z = bz * 8 + (inb >> 6);
+    VT v = VT(0.0f);
+    if (x < d.X && y < d.Y && z < d.Z)
+        v = lin[(size_t)b * d.X * d.Y * d.Z + ((size_t)y * d.Z + z) * d.X + x];
+    br[(size_t)b * elems + e] = v;
+}
+
+__global__ void __launch_bounds__(256) unbrick_kernel(DrDesc d, const float* __restrict__ br, float* __restrict__ lin,
+                                                       size_t elems, int accumulate)
+{
+    const size_t n = (size_t)d.X * d.Y * d.Z;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int b = blockIdx.y;
+    const int x = (int)(e % d.X);
+    const size_t r = e / d.X;
+    const int z = (int)(r % d.Z), y = (int)(r / d.Z);
+    const Layout L = make_layout(d);
+    float v = br[(size_t)b * elems + offx(x) + offy(y, L.sY) + offz(z, L.sZ)];
+    // torch.nan_to_num (:463, :474)
+    if (v != v) v = 0.0f;
+    else if (v > 3.4028234663852886e38f) v = 3.4028234663852886e38f;
+    else if (v < -3.4028234663852886e38f) v = -3.4028234663852886e38f;
+    float* o = lin + (size_t)b * n + e;
+    *o = accumulate ? (*o + v) : v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shared prologue: stage the view's transfer function in shared memory as R float4 (RGBA) entries
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tf(const DrDesc& d, const float* __restrict__ tf, int tb, F4* s_tf)
+{
+    const float* src = tf + (size_t)tb * d.R * 4;
+    if (d.flags & DR_F_TF_4R) {
+        for (int e = threadIdx.x; e < d.R * 4; e += blockDim.x) {
+            const int c = e / d.R, r = e - c * d.R;            // coalesced read of [4][R]
+            reinterpret_cast<float*>(s_tf)[r * 4 + c] = __ldg(src + e);
+        }
+    } else {
+        for (int e = threadIdx.x; e < d.R; e += blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + e);
+            s_tf[e] = F4 { v.x, v.y, v.z, v.w };
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
+{
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    i = blockIdx.x * kTileW + (w & 1) * 8 + (l & 7);
+    j = blockIdx.y * kTileH + (w >> 1) * 4 + (l >> 3);
+    return i < d.W && j < d.H;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT, bool NONDIFF, bool GENERIC>
+__global__ void __launch_bounds__(kThreads)
+fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
+           const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
+           float* __restrict__ outT, size_t vol_elems)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    F4* s_tf = reinterpret_cast<F4*>(s_raw);
+    const int b = blockIdx.z;
+    stage_tf(d, tf, d.Btf == 1 ? 0 : b, s_tf);
+    int i, j;
+    if (!pixel_of_thread(d, i, j)) return;
+    const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;      // image orientation
+    const F3 cam = { __ldg(camp + 3 * b), __ldg(camp + 3 * b + 1), __ldg(camp + 3 * b + 2) };
+    const float jit = (d.flags & DR_F_HAS_JITTER) ? __ldg(jitter + pix) : 0.0f;
+    Ray r;
+    setup_ray(d, cam, i, j, jit, r);
+    const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
+    const Layout L = make_layout(d);
+    F4 A; int K; float Tp;
+    march_forward<VT, NONDIFF, GENERIC>(d, vol, L, s_tf, cam, r, A, K, Tp);
+    if (d.flags & DR_F_OUT_IMAGE) {
+        const size_t plane = (size_t)d.W * d.H;
+        float* o = out + (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
+        o[0] = A.x; o[plane] = A.y; o[2 * plane] = A.z; o[3 * plane] = A.w;
+    } else {
+        reinterpret_cast<float4*>(out)[((size_t)b * d.W + i) * d.H + j] = make_float4(A.x, A.y, A.z, A.w);
+    }
+    if (outK) outK[pix] = K;
+    if (outT) outT[pix] = Tp;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+struct RedVolSink {
+    float* g;
+    __device__ __forceinline__ void add(int off, float v) { atomicAdd(g + off, v); }      // RED.E.ADD.F32 (no return)
+};
+// TF gradient: two 16-byte vector reductions per sample into one of kTfSlots privatised copies of the table.
+// (Shared-memory fp32 atomicAdd is a CAS spin loop on sm_100a -- ATOMS.CAST.SPIN -- so privatisation lives in L2.)
+struct RedTfSink {
+    float4* g;      // [R] of this CTA's slot
+    __device__ __forceinline__ void add(int lo, int hi, float f, F4 dc)
+    {
+        const float w0 = 1.0f - f;
+        atomicAdd(g + lo, make_float4(dc.x * w0, dc.y * w0, dc.z * w0, dc.w * w0));         // RED.E.ADD.F32x4
+        atomicAdd(g + hi, make_float4(dc.x * f, dc.y * f, dc.z * f, dc.w * f));
+    }
+};
+
+template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF>
+__global__ void __launch_bounds__(kThreads)
+bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
+           const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
+           const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float* __restrict__ gvol,
+           float4* __restrict__ tf_slots, size_t vol_elems)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    F4* s_tf = reinterpret_cast<F4*>(s_raw);
+    const int b = blockIdx.z;
+    const int tb = d.Btf == 1 ? 0 : b;
+    stage_tf(d, tf, tb, s_tf);
+    int i, j;
+    if (!pixel_of_thread(d, i, j)) return;
+    const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;
+    const int K = __ldg(Kp + pix);
+    if (K <= 0) return;
+    const F3 cam = { __ldg(camp + 3 * b), __ldg(camp + 3 * b + 1), __ldg(camp + 3 * b + 2) };
+    const float jit = (d.flags & DR_F_HAS_JITTER) ? __ldg(jitter + pix) : 0.0f;
+    Ray r;
+    setup_ray(d, cam, i, j, jit, r);
+    F4 A, g;
+    if (d.flags & DR_F_OUT_IMAGE) {
+        const size_t plane = (size_t)d.W * d.H;
+        const size_t o = (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
+        A = F4 { __ldg(outp + o), __ldg(outp + o + plane), __ldg(outp + o + 2 * plane), __ldg(outp + o + 3 * plane) };
+        g = F4 { __ldg(gout + o), __ldg(gout + o + plane), __ldg(gout + o + 2 * plane), __ldg(gout + o + 3 * plane) };
+    } else {
+        const size_t o = ((size_t)b * d.W + i) * d.H + j;
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(outp) + o);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gout) + o);
+        A = F4 { a4.x, a4.y, a4.z, a4.w };
+        g = F4 { g4.x, g4.y, g4.z, g4.w };
+    }
+    const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
+    const VolView<VT> vol { volp + voff };
+    const Layout L = make_layout(d);
+    RedVolSink vs { WANT_VOL ? gvol + voff : nullptr };
+    const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
+    RedTfSink ts { WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr };
+    march_backward<VT, GENERIC, WANT_VOL, WANT_TF>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
+}
+
+// sums the kTfSlots privatised copies; one thread per (tf, bin, channel); adds into grad_tf in the caller's layout
+__global__ void __launch_bounds__(256) tf_reduce_kernel(DrDesc d, const float* __restrict__ slots, float* __restrict__ grad_tf)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // r*4 + c
+    const int tb = blockIdx.y;
+    if (e >= d.R * 4) return;
+    const float* p = slots + (size_t)tb * kTfSlots * d.R * 4 + e;
+    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+    for (int s = 0; s < kTfSlots; s += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __ldg(p + (size_t)(s + u) * d.R * 4);
+    }
+    float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    if (v != v) v = 0.0f;                                      // torch.nan_to_num (:464, :475)
+    const int r = e >> 2, c = e & 3;
+    float* o = grad_tf + (size_t)tb * d.R * 4 + ((d.flags & DR_F_TF_4R) ? (c * d.R + r) : e);
+    *o += v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+int check_desc(const DrDesc* d)
+{
+    if (!d) return fail(DR_EINVAL, "null descriptor");
+    if (d->X < 2 || d->Y < 2 || d->Z < 2 || d->W < 1 || d->H < 1 || d->R < 2 || d->M < 1 || d->BS < 1)
+        return fail(DR_EINVAL, "descriptor not initialised (use dr_desc_init)");
+    if (d->nbx != (d->X + 7) / 8 || d->nby != (d->Y + 7) / 8 || d->nbz != (d->Z + 7) / 8)
+        return fail(DR_EINVAL, "descriptor brick counts inconsistent (use dr_desc_init)");
+    if (d->vox_dtype != DR_VOX_F32 && d->vox_dtype != DR_VOX_F16) return fail(DR_EDTYPE, "unsupported voxel dtype");
+    if (d->BS > 65535) return fail(DR_EINVAL, "more than 65535 views in one call");
+    return DR_OK;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+template <typename K> int set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) {
+        if (bytes > 200 * 1024) return fail(DR_EINVAL, "tf resolution too large for shared memory staging");
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute");
+    }
+    return DR_OK;
+}
+
+template <typename VT, bool NONDIFF, bool GENERIC>
+int launch_fwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, float* out,
+               int32_t* K, float* T, cudaStream_t st)
+{
+    const size_t smem = (size_t)d->R * sizeof(F4);
+    auto kern = fwd_kernel<VT, NONDIFF, GENERIC>;
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
+    kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, out, K, T, dr_bricked_elems(d));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
+}
+
+template <typename VT, bool GENERIC, bool WV, bool WT>
+int launch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+               const float* gout, const float* out, const int32_t* K, const float* T, float* gvol, float4* slots,
+               cudaStream_t st)
+{
+    const size_t smem = (size_t)d->R * sizeof(F4);
+    auto kern = bwd_kernel<VT, GENERIC, WV, WT>;
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
+    kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, gout, out, K, T, gvol, slots,
+                                       dr_bricked_elems(d));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
+}
+
+template <typename VT, bool GENERIC>
+int dispatch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+                 const float* gout, const float* out, const int32_t* K, const float* T, float* gvol, float4* slots,
+                 cudaStream_t st)
+{
+    const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
+    if (wv && wt) return launch_bwd<VT, GENERIC, true, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st);
+    if (wv) return launch_bwd<VT, GENERIC, true, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st);
+    return launch_bwd<VT, GENERIC, false, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dr_version(void) { return DR_VERSION; }
+
+const char* dr_last_error(void) { return g_err; }
+
+int dr_desc_init(DrDesc* d, int32_t X, int32_t Y, int32_t Z, int32_t W, int32_t H, int32_t R, int32_t M, int32_t BS,
+                 int32_t Bvol, int32_t Btf, int32_t vox_dtype, uint32_t flags, double sampling_rate, double fov_deg,
+                 double near_plane)
+{
+    const char* msg = desc_init(d, X, Y, Z, W, H, R, M, BS, Bvol, Btf, vox_dtype, flags, sampling_rate, fov_deg, near_plane);
+    if (msg) return fail(strstr(msg, "dtype") ? DR_EDTYPE : DR_EINVAL, msg);
+    return DR_OK;
+}
+
+size_t dr_bricked_elems(const DrDesc* d) { return d ? (size_t)d->nbx * d->nby * d->nbz * 512 : 0; }
+
+size_t dr_workspace_bytes(const DrDesc* d)
+{
+    if (!d || !(d->flags & DR_F_NEEDS_TF_GRAD)) return 0;
+    return (size_t)d->Btf * kTfSlots * d->R * sizeof(float4);
+}
+
+int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!vol_linear || !vol_bricked) return fail(DR_EINVAL, "dr_brick_volume: null pointer");
+    const size_t elems = dr_bricked_elems(d);
+    dim3 grid((unsigned)((elems + 255) / 256), d->Bvol);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->vox_dtype == DR_VOX_F32)
+        brick_kernel<float><<<grid, 256, 0, st>>>(*d, static_cast<const float*>(vol_linear), static_cast<float*>(vol_bricked), elems);
+    else
+        brick_kernel<__half><<<grid, 256, 0, st>>>(*d, static_cast<const __half*>(vol_linear), static_cast<__half*>(vol_bricked), elems);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "brick_kernel launch");
+}
+
+int dr_forward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+               float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!vol_bricked || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
+    if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_forward: DR_F_HAS_JITTER set but jitter is null");
+    if (!aligned(tf, 16) || !aligned(out_rgba, 16)) return fail(DR_EALIGN, "dr_forward: tf and out_rgba must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool nd = d->flags & DR_F_NONDIFF, gen = d->tap_generic;
+#define DR_FWD(VT)                                                                                                  \
+    (nd ? (gen ? launch_fwd<VT, true, true>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)        \
+               : launch_fwd<VT, true, false>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st))      \
+        : (gen ? launch_fwd<VT, false, true>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)       \
+               : launch_fwd<VT, false, false>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)))
+    return d->vox_dtype == DR_VOX_F32 ? DR_FWD(float) : DR_FWD(__half);
+#undef DR_FWD
+}
+
+int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+                const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
+                float* grad_vol_bricked, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (d->flags & DR_F_NONDIFF) return fail(DR_EINVAL, "dr_backward: the non-differentiable march has no backward");
+    const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
+    if (!wv && !wt) return DR_OK;
+    if (!vol_bricked || !tf || !cam || !grad_out || !out_rgba || !K || !Tprev) return fail(DR_EINVAL, "dr_backward: null pointer");
+    if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_backward: DR_F_HAS_JITTER set but jitter is null");
+    if (wv && !grad_vol_bricked) return fail(DR_EINVAL, "dr_backward: grad_vol_bricked is null");
+    if (wt && !grad_tf) return fail(DR_EINVAL, "dr_backward: grad_tf is null");
+    if (!aligned(tf, 16) || !aligned(out_rgba, 16) || !aligned(grad_out, 16))
+        return fail(DR_EALIGN, "dr_backward: tf, out_rgba and grad_out must be 16-byte aligned");
+    const size_t need = dr_workspace_bytes(d);
+    if (wt) {
+        if (!workspace || workspace_bytes < need) return fail(DR_EWORKSPACE, "dr_backward: workspace too small (dr_workspace_bytes)");
+        if (!aligned(workspace, 16)) return fail(DR_EALIGN, "dr_backward: workspace must be 16-byte aligned");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (wt) {
+        cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
+    }
+    float4* slots = static_cast<float4*>(workspace);
+    int rc;
+    if (d->vox_dtype == DR_VOX_F32)
+        rc = d->tap_generic ? dispatch_bwd<float, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st)
+                            : dispatch_bwd<float, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st);
+    else
+        rc = d->tap_generic ? dispatch_bwd<__half, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st)
+                            : dispatch_bwd<__half, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st);
+    if (rc) return rc;
+    if (wt) {
+        dim3 grid((d->R * 4 + 255) / 256, d->Btf);
+        tf_reduce_kernel<<<grid, 256, 0, st>>>(*d, static_cast<const float*>(workspace), grad_tf);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(e, "tf_reduce_kernel launch");
+    }
+    return DR_OK;
+}
+
+int dr_unbrick_grad(const DrDesc* d, const float* grad_vol_bricked, float* grad_linear, int accumulate, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!grad_vol_bricked || !grad_linear) return fail(DR_EINVAL, "dr_unbrick_grad: null pointer");
+    const size_t n = (size_t)d->X * d->Y * d->Z;
+    dim3 grid((unsigned)((n + 255) / 256), d->Bvol);
+    unbrick_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_bricked, grad_linear, dr_bricked_elems(d), accumulate);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "unbrick_kernel launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,609 @@
+// dr_math.cuh -- per-ray arithmetic of the differentiable ray-march, shared by the forward and backward kernels.
+//
+// Follows the reference's differender/volume_raycaster.py (cited per function as :line).  Written from the
+// behavioural spec, not translated from the Taichi source.
+//
+// Rounding contract (DESIGN.md "Numerics"): the alpha path (ray set-up -> sample position -> trilinear taps
+// -> TF alpha -> opacity -> accumulated alpha) uses explicitly rounded operations (DR_MUL/DR_ADD/DR_FMA ...,
+// never contracted by the compiler), so the discrete decisions (sample count n, early termination K) and the
+// ill-conditioned central-difference normal are reproducible.  Shading and all adjoint arithmetic use plain
+// operators (the compiler may fuse them).
+//
+// The functions are __host__ __device__ so that tests/hostsim can compile this very file with g++ and compare
+// it to the oracle without a GPU.  That harness is test-only; the product never runs this code on the CPU.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "diffrender.h"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
+
+#if defined(__CUDACC__)
+#define DR_HD __host__ __device__ __forceinline__
+#else
+#define DR_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define DR_MUL(a, b) __fmul_rn((a), (b))
+#define DR_ADD(a, b) __fadd_rn((a), (b))
+#define DR_SUB(a, b) __fsub_rn((a), (b))
+#define DR_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define DR_DIV(a, b) __fdiv_rn((a), (b))
+#define DR_SQRT(a) __fsqrt_rn((a))
+#define DR_RSQRT(a) rsqrtf((a))
+#define DR_SAT(a) __saturatef((a))
+#else
+// host build (tests/hostsim): compiled with -ffp-contract=off, so each operator is one IEEE operation
+#define DR_MUL(a, b) ((a) * (b))
+#define DR_ADD(a, b) ((a) + (b))
+#define DR_SUB(a, b) ((a) - (b))
+#define DR_FMA(a, b, c) fmaf((a), (b), (c))
+#define DR_DIV(a, b) ((a) / (b))
+#define DR_SQRT(a) sqrtf((a))
+#define DR_RSQRT(a) (1.0f / sqrtf((a)))
+#define DR_SAT(a) fminf(1.0f, fmaxf(0.0f, (a)))
+#endif
+
+namespace dr {
+
+DR_HD int imin(int a, int b) { return a < b ? a : b; }
+
+struct F3 { float x, y, z; };
+struct F4 { float x, y, z, w; };
+
+// ---------------------------------------------------------------------------------------------------------
+// exact helpers
+// ---------------------------------------------------------------------------------------------------------
+// taichi_glsl.mix(x, y, a) = x*(1-a) + y*a, rounded as fma(x, 1-a, y*a)  (omt = 1-a precomputed)
+DR_HD float mix_e(float a, float b, float omt, float t) { return DR_FMA(a, omt, DR_MUL(b, t)); }
+DR_HD float dot_e(F3 a, F3 b) { return DR_ADD(DR_ADD(DR_MUL(a.x, b.x), DR_MUL(a.y, b.y)), DR_MUL(a.z, b.z)); }
+DR_HD F3 cross_e(F3 a, F3 b)
+{
+    F3 r;
+    r.x = DR_SUB(DR_MUL(a.y, b.z), DR_MUL(a.z, b.y));
+    r.y = DR_SUB(DR_MUL(a.z, b.x), DR_MUL(a.x, b.z));
+    r.z = DR_SUB(DR_MUL(a.x, b.y), DR_MUL(a.y, b.x));
+    return r;
+}
+// Taichi Vector.normalized(): v * (1 / sqrt(v.v))
+DR_HD F3 normalized_e(F3 a)
+{
+    float inv = DR_DIV(1.0f, DR_SQRT(dot_e(a, a)));
+    F3 r = { DR_MUL(a.x, inv), DR_MUL(a.y, inv), DR_MUL(a.z, inv) };
+    return r;
+}
+
+// floor of a value in [0, 2^22): returns floor as float, writes the integer.            low_high_frac :7-21
+DR_HD float floor_pos(float p, int& lo)
+{
+#if defined(__CUDA_ARCH__)
+    // p + 2^23 rounded toward -inf is exactly 2^23 + floor(p); all on the FMA/ALU pipes (no F2I/I2F)
+    float r = __fadd_rd(p, 8388608.0f);
+    lo = __float_as_int(r) - 0x4B000000;
+    return __fsub_rn(r, 8388608.0f);
+#else
+    float l = floorf(p);
+    lo = (int)l;
+    return l;
+#endif
+}
+
+struct Loc { int lo; float f; };
+
+// address part of sample_volume_trilinear for one axis                                   :163-172
+DR_HD Loc locate(float pos, float scale)
+{
+    float p = DR_MUL(DR_SAT(DR_FMA(0.5f, pos, 0.5f)), scale);
+    Loc r;
+    float l = floor_pos(p, r.lo);
+    r.f = DR_SUB(p, l);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bricked volume addressing: 8x8x8 bricks, x fastest inside a brick, bricks in x,y,z raster order.
+// The element offset is separable: off(x,y,z) = offx(x) + offy(y) + offz(z).
+// ---------------------------------------------------------------------------------------------------------
+struct Layout {
+    int sY, sZ;           // element strides between bricks along y and z: nbx*512, nbx*nby*512
+    int mx, my, mz;       // dim - 1 (index clamps)
+};
+DR_HD int offx(int x) { return ((x >> 3) << 9) | (x & 7); }
+DR_HD int offy(int y, int sY) { return (y >> 3) * sY + ((y & 7) << 3); }
+DR_HD int offz(int z, int sZ) { return (z >> 3) * sZ + ((z & 7) << 6); }
+
+DR_HD float load_vox(const float* p, int off)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p + off);
+#else
+    return p[off];
+#endif
+}
+#if defined(__CUDACC__)
+DR_HD float load_vox(const __half* p, int off)
+{
+#if defined(__CUDA_ARCH__)
+    return __half2float(__ldg(p + off));
+#else
+    return __half2float(p[off]);
+#endif
+}
+#endif
+template <typename VT> struct VolView {
+    const VT* p;
+    DR_HD float ld(int off) const { return load_vox(p, off); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// ray set-up: compute_entry_exit :221-259, get_ray_direction :127-151, get_entry_exit_points :28-53
+// ---------------------------------------------------------------------------------------------------------
+struct Ray {
+    F3 dir;
+    float t0;       // entry + 0.5*len/n                                                     :273-275
+    float texit;    // exit
+    float inv_nm1;  // unused when n <= 1
+    int n;          // sample_step_nums
+};
+
+DR_HD void setup_ray(const DrDesc& d, F3 cam, int i, int j, float jit, Ray& r)
+{
+    float cn = DR_DIV(1.0f, DR_SQRT(dot_e(cam, cam)));
+    F3 view = { DR_MUL(-cam.x, cn), DR_MUL(-cam.y, cn), DR_MUL(-cam.z, cn) };          // :233
+    float x = DR_DIV(DR_ADD((float)i, 0.5f), (float)d.W);                               // :239
+    float y = DR_DIV(DR_ADD((float)j, 0.5f), (float)d.H);                               // :240
+    float u = DR_SUB(x, 0.5f), v = DR_SUB(y, 0.5f);                                     // :140-141
+    F3 up0 = { 0.0f, 1.0f, 0.0f };
+    F3 right = normalized_e(cross_e(view, up0));                                        // :144
+    F3 up = normalized_e(cross_e(right, view));                                         // :145
+    float a = DR_MUL(u, d.near_w), b = DR_MUL(v, d.near_h);
+    F3 nm = { DR_ADD(cam.x, DR_MUL(d.near_, view.x)), DR_ADD(cam.y, DR_MUL(d.near_, view.y)),
+              DR_ADD(cam.z, DR_MUL(d.near_, view.z)) };                                 // :148
+    F3 np = { DR_ADD(DR_ADD(nm.x, DR_MUL(a, right.x)), DR_MUL(b, up.x)),
+              DR_ADD(DR_ADD(nm.y, DR_MUL(a, right.y)), DR_MUL(b, up.y)),
+              DR_ADD(DR_ADD(nm.z, DR_MUL(a, right.z)), DR_MUL(b, up.z)) };              // :149
+    F3 dd = { DR_SUB(np.x, cam.x), DR_SUB(np.y, cam.y), DR_SUB(np.z, cam.z) };
+    r.dir = normalized_e(dd);                                                           // :151
+    // slab test against [-1,1]^3                                                          :41-52
+    float ix = DR_DIV(1.0f, r.dir.x), iy = DR_DIV(1.0f, r.dir.y), iz = DR_DIV(1.0f, r.dir.z);
+    float t1 = DR_MUL(DR_SUB(-1.0f, cam.x), ix), t2 = DR_MUL(DR_SUB(1.0f, cam.x), ix);
+    float t3 = DR_MUL(DR_SUB(-1.0f, cam.y), iy), t4 = DR_MUL(DR_SUB(1.0f, cam.y), iy);
+    float t5 = DR_MUL(DR_SUB(-1.0f, cam.z), iz), t6 = DR_MUL(DR_SUB(1.0f, cam.z), iz);
+    float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    bool hit = !(tmax < 0.0f || tmin > tmax);
+    float len = DR_SUB(tmax, tmin);                                                     // :250
+    float nf = floorf(DR_MUL(DR_MUL(d.sr, len), d.vol_diag)) + 1.0f;                    // :251-253
+    int n = hit ? (int)nf : 0;
+    float entry = tmin;
+    if ((d.flags & DR_F_HAS_JITTER) && n > 0) entry = DR_ADD(tmin, DR_DIV(DR_MUL(jit, len), nf));   // :254-255
+    float len2 = DR_SUB(tmax, entry);                                                   // :272 (jittered entry)
+    r.n = n;
+    r.texit = tmax;
+    r.t0 = (n > 0) ? DR_ADD(entry, DR_DIV(DR_MUL(0.5f, len2), (float)n)) : entry;       // :273-275
+    r.inv_nm1 = 0.0f;
+}
+
+// sample position :277-280 (H3: n == 1 -> t = t0)
+DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
+{
+    float t = r.t0;
+    if (r.n > 1) {
+        float q = DR_DIV((float)s, (float)(r.n - 1));
+        t = mix_e(r.t0, r.texit, DR_SUB(1.0f, q), q);
+    }
+    F3 p = { DR_FMA(t, r.dir.x, cam.x), DR_FMA(t, r.dir.y, cam.y), DR_FMA(t, r.dir.z, cam.z) };
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One sample: centre tap + the six normal taps of get_volume_normal (:191-203) with corner reuse.
+// A tap whose cell equals the centre cell is the same trilinear polynomial at a shifted fraction, so only the
+// mixes downstream of the shifted axis are redone (x: 7, y: 3, z: 1) on register-held values.  A tap that
+// crosses a cell face (|dlo| == 1) fetches the 4 corners of the one new voxel plane.  Both give exactly the
+// value a full 8-load trilinear evaluation would give (same operations, same order).
+// ---------------------------------------------------------------------------------------------------------
+struct Taps {
+    Loc cx, cy, cz;               // centre cell
+    Loc xp, xm, yp, ym, zp, zm;   // tap cells (only the shifted axis differs from the centre)
+    float I;                      // centre intensity
+    F3 g;                         // (f(x+d)-f(x-d), ...), un-normalised                     :197-202
+};
+
+template <typename VT>
+DR_HD float trilinear_full(const VolView<VT>& vol, const Layout& L, Loc ax, Loc ay, Loc az)
+{
+    int x0 = offx(ax.lo), x1 = offx(imin(ax.lo + 1, L.mx));
+    int y0 = offy(ay.lo, L.sY), y1 = offy(imin(ay.lo + 1, L.my), L.sY);
+    int z0 = offz(az.lo, L.sZ), z1 = offz(imin(az.lo + 1, L.mz), L.sZ);
+    float ox = DR_SUB(1.0f, ax.f), oy = DR_SUB(1.0f, ay.f), oz = DR_SUB(1.0f, az.f);
+    float a = mix_e(vol.ld(x0 + y0 + z0), vol.ld(x1 + y0 + z0), ox, ax.f);
+    float b = mix_e(vol.ld(x0 + y1 + z0), vol.ld(x1 + y1 + z0), ox, ax.f);
+    float lo = mix_e(a, b, oy, ay.f);
+    a = mix_e(vol.ld(x0 + y0 + z1), vol.ld(x1 + y0 + z1), ox, ax.f);
+    b = mix_e(vol.ld(x0 + y1 + z1), vol.ld(x1 + y1 + z1), ox, ax.f);
+    float hi = mix_e(a, b, oy, ay.f);
+    return mix_e(lo, hi, oz, az.f);
+}
+
+template <typename VT, bool GENERIC>
+DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Taps& t)
+{
+    t.cx = locate(pos.x, d.scale[0]);
+    t.cy = locate(pos.y, d.scale[1]);
+    t.cz = locate(pos.z, d.scale[2]);
+    const float dl = d.delta;
+    t.xp = locate(DR_ADD(pos.x, dl), d.scale[0]);
+    t.xm = locate(DR_SUB(pos.x, dl), d.scale[0]);
+    t.yp = locate(DR_ADD(pos.y, dl), d.scale[1]);
+    t.ym = locate(DR_SUB(pos.y, dl), d.scale[1]);
+    t.zp = locate(DR_ADD(pos.z, dl), d.scale[2]);
+    t.zm = locate(DR_SUB(pos.z, dl), d.scale[2]);
+    if (GENERIC) {
+        t.I = trilinear_full(vol, L, t.cx, t.cy, t.cz);
+        t.g.x = DR_SUB(trilinear_full(vol, L, t.xp, t.cy, t.cz), trilinear_full(vol, L, t.xm, t.cy, t.cz));
+        t.g.y = DR_SUB(trilinear_full(vol, L, t.cx, t.yp, t.cz), trilinear_full(vol, L, t.cx, t.ym, t.cz));
+        t.g.z = DR_SUB(trilinear_full(vol, L, t.cx, t.cy, t.zp), trilinear_full(vol, L, t.cx, t.cy, t.zm));
+        return;
+    }
+    const int x0 = offx(t.cx.lo), x1 = offx(imin(t.cx.lo + 1, L.mx));
+    const int y0 = offy(t.cy.lo, L.sY), y1 = offy(imin(t.cy.lo + 1, L.my), L.sY);
+    const int z0 = offz(t.cz.lo, L.sZ), z1 = offz(imin(t.cz.lo + 1, L.mz), L.sZ);
+    const float v000 = vol.ld(x0 + y0 + z0), v100 = vol.ld(x1 + y0 + z0);
+    const float v010 = vol.ld(x0 + y1 + z0), v110 = vol.ld(x1 + y1 + z0);
+    const float v001 = vol.ld(x0 + y0 + z1), v101 = vol.ld(x1 + y0 + z1);
+    const float v011 = vol.ld(x0 + y1 + z1), v111 = vol.ld(x1 + y1 + z1);
+    const float fx = t.cx.f, fy = t.cy.f, fz = t.cz.f;
+    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
+    // centre: x mixes, y mixes, z mix                                                       :173-189
+    const float xm00 = mix_e(v000, v100, ox, fx), xm10 = mix_e(v010, v110, ox, fx);
+    const float xm01 = mix_e(v001, v101, ox, fx), xm11 = mix_e(v011, v111, ox, fx);
+    const float ym0 = mix_e(xm00, xm10, oy, fy), ym1 = mix_e(xm01, xm11, oy, fy);
+    t.I = mix_e(ym0, ym1, oz, fz);
+
+    // ---- z taps: only the last mix changes
+    float zv[2];
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const Loc q = sgn ? t.zm : t.zp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float val;
+        if (q.lo == t.cz.lo) {
+            val = mix_e(ym0, ym1, o, f);
+        } else {
+            // new plane: above the centre's high plane (+) or below its low plane (-)
+            const int zn = offz(sgn ? q.lo : imin(q.lo + 1, L.mz), L.sZ);
+            const float a = mix_e(vol.ld(x0 + y0 + zn), vol.ld(x1 + y0 + zn), ox, fx);
+            const float b = mix_e(vol.ld(x0 + y1 + zn), vol.ld(x1 + y1 + zn), ox, fx);
+            const float yn = mix_e(a, b, oy, fy);
+            val = sgn ? mix_e(yn, ym0, o, f) : mix_e(ym1, yn, o, f);
+        }
+        zv[sgn] = val;
+    }
+    t.g.z = DR_SUB(zv[0], zv[1]);
+
+    // ---- y taps: y mixes and the z mix change
+    float yv[2];
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const Loc q = sgn ? t.ym : t.yp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float a, b;
+        if (q.lo == t.cy.lo) {
+            a = mix_e(xm00, xm10, o, f);
+            b = mix_e(xm01, xm11, o, f);
+        } else {
+            const int yn = offy(sgn ? q.lo : imin(q.lo + 1, L.my), L.sY);
+            const float n0 = mix_e(vol.ld(x0 + yn + z0), vol.ld(x1 + yn + z0), ox, fx);
+            const float n1 = mix_e(vol.ld(x0 + yn + z1), vol.ld(x1 + yn + z1), ox, fx);
+            a = sgn ? mix_e(n0, xm00, o, f) : mix_e(xm10, n0, o, f);
+            b = sgn ? mix_e(n1, xm01, o, f) : mix_e(xm11, n1, o, f);
+        }
+        yv[sgn] = mix_e(a, b, oz, fz);
+    }
+    t.g.y = DR_SUB(yv[0], yv[1]);
+
+    // ---- x taps: everything downstream of the corners changes
+    float xv[2];
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const Loc q = sgn ? t.xm : t.xp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float a00, a10, a01, a11;
+        if (q.lo == t.cx.lo) {
+            a00 = mix_e(v000, v100, o, f); a10 = mix_e(v010, v110, o, f);
+            a01 = mix_e(v001, v101, o, f); a11 = mix_e(v011, v111, o, f);
+        } else {
+            const int xn = offx(sgn ? q.lo : imin(q.lo + 1, L.mx));
+            const float n00 = vol.ld(xn + y0 + z0), n10 = vol.ld(xn + y1 + z0);
+            const float n01 = vol.ld(xn + y0 + z1), n11 = vol.ld(xn + y1 + z1);
+            if (sgn) {
+                a00 = mix_e(n00, v000, o, f); a10 = mix_e(n10, v010, o, f);
+                a01 = mix_e(n01, v001, o, f); a11 = mix_e(n11, v011, o, f);
+            } else {
+                a00 = mix_e(v100, n00, o, f); a10 = mix_e(v110, n10, o, f);
+                a01 = mix_e(v101, n01, o, f); a11 = mix_e(v111, n11, o, f);
+            }
+        }
+        const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);
+        xv[sgn] = mix_e(lo, hi, oz, fz);
+    }
+    t.g.x = DR_SUB(xv[0], xv[1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// transfer function lookup :205-219 (tf table: R float4 entries, in shared memory on the device)
+// ---------------------------------------------------------------------------------------------------------
+struct TfHit { int lo, hi; float f, x; F4 c; F4 d; };   // c = colour, d = tf[hi] - tf[lo] (for dI)
+
+DR_HD void apply_tf(const DrDesc& d, const F4* tf, float intensity, TfHit& h, bool want_diff)
+{
+    float x = fmaxf(DR_MUL(intensity, d.tf_len), 0.0f);
+    h.x = x;
+    int lo;
+    float l = floor_pos(x, lo);
+    h.f = DR_SUB(x, l);
+    lo = imin(lo, d.R - 1);                      // H9
+    h.lo = lo;
+    h.hi = imin(lo + 1, d.R - 1);
+    const F4 a = tf[h.lo], b = tf[h.hi];
+    const float o = DR_SUB(1.0f, h.f);
+    h.c.x = mix_e(a.x, b.x, o, h.f); h.c.y = mix_e(a.y, b.y, o, h.f);
+    h.c.z = mix_e(a.z, b.z, o, h.f); h.c.w = mix_e(a.w, b.w, o, h.f);
+    if (want_diff) { h.d.x = b.x - a.x; h.d.y = b.y - a.y; h.d.z = b.z - a.z; h.d.w = b.w - a.w; }
+}
+
+// opacity = 1 - pow(1 - alpha, 1/sr)                                                       :284-285
+DR_HD float opacity(const DrDesc& d, float alpha)
+{
+    float base = DR_SUB(1.0f, alpha);
+    if (d.inv_sr == 1.0f) return DR_SUB(1.0f, base);
+    return DR_SUB(1.0f, powf(base, d.inv_sr));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Phong factor :287-298.  Not on the exact path (only rgb depends on it).
+// ---------------------------------------------------------------------------------------------------------
+struct Shade {
+    F3 N, l;
+    float inv_g;       // 1/|g| (0 when flat)
+    float nl, rv, rdv, pw31, kraw, k;
+};
+
+DR_HD void shade(const DrDesc& d, F3 cam, F3 dir, F3 pos, F3 g, bool clamp_k, Shade& s)
+{
+    float g2 = g.x * g.x + g.y * g.y + g.z * g.z;
+    bool flat = !(g2 > 0.0f);                     // H4: 0/0 normal -> ambient only
+    float ig = flat ? 0.0f : DR_RSQRT(g2);
+    s.inv_g = ig;
+    s.N.x = g.x * ig; s.N.y = g.y * ig; s.N.z = g.z * ig;
+    float lx = pos.x - cam.x, ly = pos.y - (cam.y + 1.0f), lz = pos.z - cam.z;    // light at cam + (0,1,0) :281
+    float il = DR_RSQRT(lx * lx + ly * ly + lz * lz);
+    s.l.x = lx * il; s.l.y = ly * il; s.l.z = lz * il;
+    s.nl = s.N.x * s.l.x + s.N.y * s.l.y + s.N.z * s.l.z;
+    float ndl = fmaxf(s.nl, 0.0f);                                                 // :291
+    float t2 = 2.0f * s.nl;
+    float rx = s.l.x - t2 * s.N.x, ry = s.l.y - t2 * s.N.y, rz = s.l.z - t2 * s.N.z;   // reflect :293
+    s.rv = flat ? 0.0f : -(rx * dir.x + ry * dir.y + rz * dir.z);                 // NaN normal -> max(NaN,0) = 0
+    s.rdv = fmaxf(s.rv, 0.0f);                                                     // :295
+    float p2 = s.rdv * s.rdv, p4 = p2 * p2, p8 = p4 * p4, p16 = p8 * p8;
+    float p32 = p16 * p16;                                                         // shininess 32 :296
+    s.pw31 = p16 * p8 * p4 * p2 * s.rdv;
+    s.kraw = d.diffuse * ndl + d.specular * p32 + d.ambient;
+    s.k = clamp_k ? fminf(1.0f, s.kraw) : s.kraw;                                  // :298 vs :345
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adjoint of one sample (Taichi reverse-mode of :281-302).
+//   in : T = transmittance before the sample, g = dL/dA_s (rgb constant along the ray, w evolves)
+//   out: dc (adjoint of the TF sample), dI (centre intensity), dgr (un-normalised gradient g)
+// returns C.g so that the caller can update g.w
+// ---------------------------------------------------------------------------------------------------------
+struct SampleAdj { F4 dc; float dI; F3 dg; bool has_dg; };
+
+DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, const Shade& s, float T, F4 g,
+                           bool want_vol, SampleAdj& a)
+{
+    const float ko = s.k * o;
+    const float Cg = ko * (h.c.x * g.x + h.c.y * g.y + h.c.z * g.z) + o * g.w;     // C . g
+    const float cd = T * (h.c.x * g.x + h.c.y * g.y + h.c.z * g.z);                // c.rgb . dC.rgb
+    const float d_o = s.k * cd + T * g.w;
+    const float dk = o * cd;
+    float dpow = 1.0f;
+    if (d.inv_sr != 1.0f) dpow = d.inv_sr * powf(fmaxf(1.0f - h.c.w, 1e-12f), d.inv_sr - 1.0f);   // H8
+    const float kT = ko * T;
+    a.dc.x = kT * g.x; a.dc.y = kT * g.y; a.dc.z = kT * g.z; a.dc.w = d_o * dpow;
+    a.has_dg = false;
+    if (want_vol) {
+        const float df = a.dc.x * h.d.x + a.dc.y * h.d.y + a.dc.z * h.d.z + a.dc.w * h.d.w;
+        a.dI = (h.x > 0.0f) ? df * d.tf_len : 0.0f;
+        a.dg.x = a.dg.y = a.dg.z = 0.0f;
+        if (s.inv_g > 0.0f && !(1.0f < s.kraw)) {
+            const float d_ndl = (s.nl > 0.0f) ? d.diffuse * dk : 0.0f;
+            const float d_rdv = (s.rv > 0.0f) ? d.specular * 32.0f * s.pw31 * dk : 0.0f;
+            const float drx = -dir.x * d_rdv, dry = -dir.y * d_rdv, drz = -dir.z * d_rdv;
+            const float drN = drx * s.N.x + dry * s.N.y + drz * s.N.z;
+            const float cN = d_ndl - 2.0f * drN, c2 = 2.0f * s.nl;
+            const float dNx = cN * s.l.x - c2 * drx, dNy = cN * s.l.y - c2 * dry, dNz = cN * s.l.z - c2 * drz;
+            const float NdN = s.N.x * dNx + s.N.y * dNy + s.N.z * dNz;
+            a.dg.x = (dNx - s.N.x * NdN) * s.inv_g;
+            a.dg.y = (dNy - s.N.y * NdN) * s.inv_g;
+            a.dg.z = (dNz - s.N.z * NdN) * s.inv_g;
+            a.has_dg = true;
+        }
+    }
+    return Cg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Volume-gradient scatter.  The 7 taps' 56 trilinear weights are merged into at most 32 distinct voxels:
+// the 8 corners of the centre cell plus, per axis, the 4 corners of the plane before / after it when a tap
+// crossed that face.  Per axis the two taps are folded into 4 slot coefficients e[0..3] for the voxel indices
+// lo-1, lo, lo+1, lo+2.  `Sink::add(offset, value)` is an atomic add into the bricked gradient volume.
+// ---------------------------------------------------------------------------------------------------------
+DR_HD void axis_slots(Loc c, Loc tp, Loc tm, float dg, float& e0, float& e1, float& e2, float& e3)
+{
+    const float wp0 = dg * (1.0f - tp.f), wp1 = dg * tp.f;
+    const float wm0 = dg * (1.0f - tm.f), wm1 = dg * tm.f;
+    const bool cp = tp.lo != c.lo, cm = tm.lo != c.lo;
+    e0 = cm ? -wm0 : 0.0f;
+    e1 = (cp ? 0.0f : wp0) - (cm ? wm1 : wm0);
+    e2 = (cp ? wp0 : wp1) - (cm ? 0.0f : wm1);
+    e3 = cp ? wp1 : 0.0f;
+}
+
+template <typename Sink>
+DR_HD void scatter_tap_full(Sink& sink, const Layout& L, Loc ax, Loc ay, Loc az, float adj)
+{
+    int x0 = offx(ax.lo), x1 = offx(imin(ax.lo + 1, L.mx));
+    int y0 = offy(ay.lo, L.sY), y1 = offy(imin(ay.lo + 1, L.my), L.sY);
+    int z0 = offz(az.lo, L.sZ), z1 = offz(imin(az.lo + 1, L.mz), L.sZ);
+    float wx0 = 1.0f - ax.f, wx1 = ax.f, wy0 = 1.0f - ay.f, wy1 = ay.f;
+    float z0w = adj * (1.0f - az.f), z1w = adj * az.f;
+    sink.add(x0 + y0 + z0, z0w * wy0 * wx0); sink.add(x1 + y0 + z0, z0w * wy0 * wx1);
+    sink.add(x0 + y1 + z0, z0w * wy1 * wx0); sink.add(x1 + y1 + z0, z0w * wy1 * wx1);
+    sink.add(x0 + y0 + z1, z1w * wy0 * wx0); sink.add(x1 + y0 + z1, z1w * wy0 * wx1);
+    sink.add(x0 + y1 + z1, z1w * wy1 * wx0); sink.add(x1 + y1 + z1, z1w * wy1 * wx1);
+}
+
+template <typename Sink, bool GENERIC>
+DR_HD void scatter_volume_grad(Sink& sink, const Layout& L, const Taps& t, const SampleAdj& a)
+{
+    if (GENERIC) {
+        scatter_tap_full(sink, L, t.cx, t.cy, t.cz, a.dI);
+        if (a.has_dg) {
+            scatter_tap_full(sink, L, t.xp, t.cy, t.cz, a.dg.x); scatter_tap_full(sink, L, t.xm, t.cy, t.cz, -a.dg.x);
+            scatter_tap_full(sink, L, t.cx, t.yp, t.cz, a.dg.y); scatter_tap_full(sink, L, t.cx, t.ym, t.cz, -a.dg.y);
+            scatter_tap_full(sink, L, t.cx, t.cy, t.zp, a.dg.z); scatter_tap_full(sink, L, t.cx, t.cy, t.zm, -a.dg.z);
+        }
+        return;
+    }
+    float ex0, ex1, ex2, ex3, ey0, ey1, ey2, ey3, ez0, ez1, ez2, ez3;
+    axis_slots(t.cx, t.xp, t.xm, a.dg.x, ex0, ex1, ex2, ex3);
+    axis_slots(t.cy, t.yp, t.ym, a.dg.y, ey0, ey1, ey2, ey3);
+    axis_slots(t.cz, t.zp, t.zm, a.dg.z, ez0, ez1, ez2, ez3);
+    const float wx0 = 1.0f - t.cx.f, wx1 = t.cx.f, wy0 = 1.0f - t.cy.f, wy1 = t.cy.f;
+    const float wz0 = 1.0f - t.cz.f, wz1 = t.cz.f;
+    const float X0 = a.dI * wx0 + ex1, X1 = a.dI * wx1 + ex2;
+    const float yz00 = wy0 * wz0, yz10 = wy1 * wz0, yz01 = wy0 * wz1, yz11 = wy1 * wz1;
+    const float xz00 = wx0 * wz0, xz10 = wx1 * wz0, xz01 = wx0 * wz1, xz11 = wx1 * wz1;
+    const float xy00 = wx0 * wy0, xy10 = wx1 * wy0, xy01 = wx0 * wy1, xy11 = wx1 * wy1;
+    const int x0 = offx(t.cx.lo), x1 = offx(imin(t.cx.lo + 1, L.mx));
+    const int y0 = offy(t.cy.lo, L.sY), y1 = offy(imin(t.cy.lo + 1, L.my), L.sY);
+    const int z0 = offz(t.cz.lo, L.sZ), z1 = offz(imin(t.cz.lo + 1, L.mz), L.sZ);
+    // centre cell: G[a][b][c] = wyz[b][c]*X_a + wxz[a][c]*ey[1+b] + wxy[a][b]*ez[1+c]
+    sink.add(x0 + y0 + z0, yz00 * X0 + xz00 * ey1 + xy00 * ez1);
+    sink.add(x1 + y0 + z0, yz00 * X1 + xz10 * ey1 + xy10 * ez1);
+    sink.add(x0 + y1 + z0, yz10 * X0 + xz00 * ey2 + xy01 * ez1);
+    sink.add(x1 + y1 + z0, yz10 * X1 + xz10 * ey2 + xy11 * ez1);
+    sink.add(x0 + y0 + z1, yz01 * X0 + xz01 * ey1 + xy00 * ez2);
+    sink.add(x1 + y0 + z1, yz01 * X1 + xz11 * ey1 + xy10 * ez2);
+    sink.add(x0 + y1 + z1, yz11 * X0 + xz01 * ey2 + xy01 * ez2);
+    sink.add(x1 + y1 + z1, yz11 * X1 + xz11 * ey2 + xy11 * ez2);
+    if (!a.has_dg) return;
+    // outer planes, only where a tap crossed a face
+    if (t.xm.lo != t.cx.lo) {
+        const int xn = offx(t.xm.lo);
+        sink.add(xn + y0 + z0, ex0 * yz00); sink.add(xn + y1 + z0, ex0 * yz10);
+        sink.add(xn + y0 + z1, ex0 * yz01); sink.add(xn + y1 + z1, ex0 * yz11);
+    }
+    if (t.xp.lo != t.cx.lo) {
+        const int xn = offx(imin(t.xp.lo + 1, L.mx));
+        sink.add(xn + y0 + z0, ex3 * yz00); sink.add(xn + y1 + z0, ex3 * yz10);
+        sink.add(xn + y0 + z1, ex3 * yz01); sink.add(xn + y1 + z1, ex3 * yz11);
+    }
+    if (t.ym.lo != t.cy.lo) {
+        const int yn = offy(t.ym.lo, L.sY);
+        sink.add(x0 + yn + z0, ey0 * xz00); sink.add(x1 + yn + z0, ey0 * xz10);
+        sink.add(x0 + yn + z1, ey0 * xz01); sink.add(x1 + yn + z1, ey0 * xz11);
+    }
+    if (t.yp.lo != t.cy.lo) {
+        const int yn = offy(imin(t.yp.lo + 1, L.my), L.sY);
+        sink.add(x0 + yn + z0, ey3 * xz00); sink.add(x1 + yn + z0, ey3 * xz10);
+        sink.add(x0 + yn + z1, ey3 * xz01); sink.add(x1 + yn + z1, ey3 * xz11);
+    }
+    if (t.zm.lo != t.cz.lo) {
+        const int zn = offz(t.zm.lo, L.sZ);
+        sink.add(x0 + y0 + zn, ez0 * xy00); sink.add(x1 + y0 + zn, ez0 * xy10);
+        sink.add(x0 + y1 + zn, ez0 * xy01); sink.add(x1 + y1 + zn, ez0 * xy11);
+    }
+    if (t.zp.lo != t.cz.lo) {
+        const int zn = offz(imin(t.zp.lo + 1, L.mz), L.sZ);
+        sink.add(x0 + y0 + zn, ez3 * xy00); sink.add(x1 + y0 + zn, ez3 * xy10);
+        sink.add(x0 + y1 + zn, ez3 * xy01); sink.add(x1 + y1 + zn, ez3 * xy11);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-ray forward march: raycast :261-306 / raycast_nondiff :308-351 + get_final_image(_nondiff) :353-372.
+// State per ray is O(1): A (accumulated premultiplied RGBA), K (active samples), Tprev (transmittance before
+// the last active sample).  Nothing per sample is stored (the reference stores 16*M bytes per ray, :82,102-103).
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT, bool NONDIFF, bool GENERIC>
+DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
+                         const Ray& r, F4& A, int& K, float& Tprev)
+{
+    A.x = A.y = A.z = A.w = 0.0f;                       // H1: tape[-1] = 0
+    K = 0;
+    Tprev = 1.0f;
+    const int nn = NONDIFF ? r.n : imin(r.n, d.M);      // :267-269 (s < max_samples only in the diff kernel)
+    for (int s = 0; s < nn; ++s) {
+        if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
+        const F3 pos = sample_pos(r, cam, s);
+        Taps t;
+        eval_taps<VT, GENERIC>(d, vol, L, pos, t);
+        TfHit h;
+        apply_tf(d, tf, t.I, h, false);
+        if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334
+        const float o = opacity(d, h.c.w);
+        Shade sh;
+        shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);
+        const float T = DR_SUB(1.0f, A.w);
+        const float ko = sh.k * o;
+        Tprev = T;
+        A.x = DR_FMA(T, ko * h.c.x, A.x);
+        A.y = DR_FMA(T, ko * h.c.y, A.y);
+        A.z = DR_FMA(T, ko * h.c.z, A.z);
+        A.w = DR_FMA(T, o, A.w);                        // :300-302
+        ++K;                                            // :303
+    }
+    if (NONDIFF) { A.x = fminf(1.0f, A.x); A.y = fminf(1.0f, A.y); A.z = fminf(1.0f, A.z); A.w = fminf(1.0f, A.w); }   // :358
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-ray backward: get_final_image.grad + raycast.grad (:460-461, :470-471) without a tape.
+// The ray is re-marched from its last active sample K-1 down to 0.  The transmittance before sample s is
+// reconstructed as T_{s-1} = T_s / (1 - o_s); the last active sample uses the saved Tprev (so an opaque last
+// sample never divides by ~0), and 1 - o_s > 1 - ert for every earlier sample because sample s+1 was active.
+// dL/dA_s.rgb is constant along the ray (= grad_out.rgb); only dL/dA_s.w evolves: g.w -= C_s . g.
+// TfSink::add(lo, hi, f, dc) accumulates the TF gradient; VolSink::add(off, v) the volume gradient.
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF, typename VolSink, typename TfSink>
+DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
+                          const Ray& r, F4 Afinal, int K, float Tprev, F4 g, VolSink& vsink, TfSink& tsink)
+{
+    float Tafter = 1.0f - Afinal.w;                     // transmittance after sample K-1
+    for (int s = K - 1; s >= 0; --s) {
+        const F3 pos = sample_pos(r, cam, s);
+        Taps t;
+        eval_taps<VT, GENERIC>(d, vol, L, pos, t);
+        TfHit h;
+        apply_tf(d, tf, t.I, h, WANT_VOL);
+        const float o = opacity(d, h.c.w);
+        Shade sh;
+        shade(d, cam, r.dir, pos, t.g, true, sh);
+        const float T = (s == K - 1) ? Tprev : Tafter / (1.0f - o);
+        Tafter = T;
+        SampleAdj a;
+        const float Cg = sample_adjoint(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
+        g.w -= Cg;
+        if (WANT_TF) tsink.add(h.lo, h.hi, h.f, a.dc);
+        if (WANT_VOL) scatter_volume_grad<VolSink, GENERIC>(vsink, L, t, a);
+    }
+}
+
+}  // namespace dr

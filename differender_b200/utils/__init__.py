@@ -1,0 +1,2 @@
+from .tf_presets import get_tf, tex_from_pts  # noqa: F401
+from .cameras import in_circles, get_rand_pos  # noqa: F401

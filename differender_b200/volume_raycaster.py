@@ -1,0 +1,266 @@
+"""PyTorch-facing raycaster API, mirroring the reference's differender/volume_raycaster.py.
+
+Same names, arguments and return shapes as the reference (`Raycaster` :478-574, `RaycastFunction` :392-476,
+`VolumeRaycaster` :56-116), but the Taichi kernels are replaced by the sm_100a library behind include/diffrender.h.
+There is no Taichi, no Triton, no CPU fallback: non-CUDA tensors raise.
+
+Differences from the reference, all additive or fixes listed in SURVEY.md 7.3:
+  * `forward(..., jitter_tensor=None)`: jitter is a supplied uniform [0,1) tensor ([BS,]H,W) in output-image orientation
+    (drawn with torch.rand when `jitter=True` and none is given) and the SAME tensor is used by the backward (H7).
+  * un-batched volume / TF with batched cameras are shared, not cloned BS times (:566-567), and their gradient is
+    accumulated once on the device instead of materialising BS per-view gradients.
+  * fp16 volumes stay fp16 in HBM (no `.float()` up-cast, :119); arithmetic is fp32.
+  * the forward keeps no state in the object (:429-430): everything the backward needs is in `ctx` (H10).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (F_HAS_JITTER, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, VOX_F16, VOX_F32)
+
+__all__ = ["VolumeRaycaster", "RaycastFunction", "Raycaster"]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class VolumeRaycaster:
+    """Replaces the reference's Taichi-side object (:56-116): resolutions and camera constants only.
+
+    It owns no device memory and no global runtime (the reference calls ti.init, :486, and allocates a
+    16*W*H*max_samples-byte render tape plus its gradient, :82,102-103).
+    """
+
+    def __init__(self, volume_resolution, render_resolution, max_samples=512, tf_resolution=128, fov=30.0,
+                 nearfar=(0.1, 100.0)):
+        self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
+        self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
+        self.max_samples = int(max_samples)
+        self.tf_resolution = int(tf_resolution)
+        self.fov_deg = float(fov)
+        self.near, self.far = float(nearfar[0]), float(nearfar[1])
+        self.ambient, self.diffuse, self.specular, self.shininess = 0.4, 0.8, 0.3, 32.0    # :91-94
+        self.last_K = None           # per-ray active sample counts of the most recent forward ([BS,H,W] int32)
+
+    # -- thin wrappers over the C ABI (one distinct volume is bricked once, not once per view) ---------------
+    def desc(self, BS, Bvol, Btf, vox_dtype, flags, sampling_rate):
+        X, Y, Z = self.volume_resolution
+        w, h = self.resolution
+        return _lib.make_desc(X, Y, Z, w, h, self.tf_resolution, self.max_samples, BS, Bvol, Btf, vox_dtype, flags,
+                              sampling_rate, self.fov_deg, self.near)
+
+    def brick(self, vol_lin):
+        """[Bvol, Y, Z, X] contiguous fp32/fp16 CUDA tensor -> bricked tensor [Bvol, elems] of the same dtype."""
+        X, Y, Z = self.volume_resolution
+        if tuple(vol_lin.shape[1:]) != (Y, Z, X):
+            raise ValueError(f"volume has spatial shape {tuple(vol_lin.shape[1:])}, raycaster was built for (D,H,W)={(Y, Z, X)}")
+        vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
+        d = self.desc(1, 1, 1, vox, 0, 1.0)
+        d.Bvol = vol_lin.shape[0]
+        lib = _lib.load()
+        out = torch.empty((vol_lin.shape[0], lib.dr_bricked_elems(ctypes.byref(d))), dtype=vol_lin.dtype, device=vol_lin.device)
+        _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
+        return out
+
+    def march(self, bricked, tf_r4, cam, sampling_rate, jitter=None, nondiff=False, image_layout=True, want_aux=True):
+        """Forward of cam.shape[0] views.  Returns (out, K, Tprev)."""
+        BS = cam.shape[0]
+        w, h = self.resolution
+        vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
+        flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0)
+        d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
+        dev = bricked.device
+        out = torch.empty((BS, 4, h, w) if image_layout else (BS, w, h, 4), dtype=torch.float32, device=dev)
+        K = torch.empty((BS, h, w), dtype=torch.int32, device=dev) if want_aux else None
+        Tp = torch.empty((BS, h, w), dtype=torch.float32, device=dev) if (want_aux and not nondiff) else None
+        _lib.check(_lib.load().dr_forward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                          _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp), _stream()), "dr_forward")
+        return out, K, Tp
+
+    def march_backward(self, bricked, tf_r4, cam, sampling_rate, jitter, grad_out, out, K, Tprev, need_vol, need_tf,
+                       image_layout=True, grad_bricked=None):
+        """Backward of cam.shape[0] views.  Returns (grad_vol_linear [Bvol,Y,Z,X] fp32 or None, grad_tf [Btf,R,4] or None).
+        If `grad_bricked` is given the volume gradient is accumulated there and NOT un-bricked (returns it instead)."""
+        BS = cam.shape[0]
+        X, Y, Z = self.volume_resolution
+        vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
+        flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
+                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0)
+        d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
+        dev = bricked.device
+        lib = _lib.load()
+        keep_bricked = grad_bricked is not None
+        if need_vol and grad_bricked is None:
+            grad_bricked = torch.zeros(bricked.shape, dtype=torch.float32, device=dev)
+        gtf = torch.zeros(tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
+        ws_bytes = lib.dr_workspace_bytes(ctypes.byref(d))
+        ws = torch.empty((max(ws_bytes, 16) + 3) // 4, dtype=torch.float32, device=dev)
+        _lib.check(lib.dr_backward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                   _lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
+                                   _lib.ptr(grad_bricked) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
+                                   _stream()), "dr_backward")
+        if not need_vol:
+            return None, gtf
+        if keep_bricked:
+            return grad_bricked, gtf
+        return self.unbrick(grad_bricked), gtf
+
+    def unbrick(self, grad_bricked):
+        X, Y, Z = self.volume_resolution
+        d = self.desc(1, 1, 1, VOX_F32, 0, 1.0)
+        d.Bvol = grad_bricked.shape[0]
+        gl = torch.empty((grad_bricked.shape[0], Y, Z, X), dtype=torch.float32, device=grad_bricked.device)
+        _lib.check(_lib.load().dr_unbrick_grad(ctypes.byref(d), _lib.ptr(grad_bricked), _lib.ptr(gl), 0, _stream()), "dr_unbrick_grad")
+        return gl
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("differender_b200: the ray-march runs on CUDA (sm_100a) only; got a CPU tensor. "
+                               "There is no CPU fallback.")
+
+
+class RaycastFunction(torch.autograd.Function):
+    """Drop-in for the reference's autograd Function (:392-476); same positional arguments, two optional extras."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, vr, volume, tf, look_from, sampling_rate, batched, jitter=True, jitter_tensor=None, image_layout=False):
+        """volume ([BS,] X, Y, Z) in the reference's Taichi order (a permuted view of the torch tensor is fine, no copy is
+        made when the underlying memory is the contiguous torch (D,H,W) tensor); tf ([BS,] R, 4); look_from ([BS,] 3).
+        Returns ([BS,] W, H, 4) like the reference, or ([BS,] 4, H, W) already flipped when image_layout=True."""
+        _require_cuda(volume, tf, look_from, jitter_tensor)
+        is_batched, bs = batched
+        BS = int(bs) if is_batched else 1
+        w, h = vr.resolution
+        with torch.cuda.device(volume.device):
+            vol_b = volume.ndim == 4
+            v = volume if vol_b else volume[None]
+            if vol_b and v.shape[0] > 1 and v.stride(0) == 0:
+                v = v[:1]                                          # an .expand()ed shared volume: do not clone it (:566)
+            if v.dtype not in (torch.float16, torch.float32):
+                v = v.float()                                      # set_volume's .float() (:119); fp16 is kept
+            vol_lin = v.permute(0, 2, 3, 1).contiguous()           # [Bvol, Y, Z, X] == torch (D, H, W); no-op for our views
+            if vol_lin.shape[0] not in (1, BS):
+                raise ValueError(f"volume batch {vol_lin.shape[0]} does not match batch size {BS}")
+            t = tf if tf.ndim == 3 else tf[None]
+            if t.shape[0] > 1 and t.stride(0) == 0:
+                t = t[:1]
+            tf_r4 = t.float().contiguous()                         # [Btf, R, 4]
+            if tf_r4.shape[-1] != 4 or tf_r4.shape[-2] != vr.tf_resolution:
+                raise ValueError(f"tf has shape {tuple(tf.shape)}, expected ([BS,] {vr.tf_resolution}, 4)")
+            if tf_r4.shape[0] not in (1, BS):
+                raise ValueError(f"tf batch {tf_r4.shape[0]} does not match batch size {BS}")
+            cam = look_from.float().reshape(-1, 3)
+            if cam.shape[0] == 1 and BS > 1:
+                cam = cam.expand(BS, 3)
+            cam = cam.contiguous()
+            if cam.shape[0] != BS:
+                raise ValueError(f"look_from batch {cam.shape[0]} does not match batch size {BS}")
+            jit = None
+            if jitter:
+                if jitter_tensor is None:
+                    jit = torch.rand((BS, h, w), dtype=torch.float32, device=volume.device)     # replaces ti.random (:255)
+                else:
+                    jit = jitter_tensor.float().reshape(-1, h, w)
+                    if jit.shape[0] == 1 and BS > 1:
+                        jit = jit.expand(BS, h, w)
+                    jit = jit.contiguous()
+                    if jit.shape[0] != BS:
+                        raise ValueError(f"jitter_tensor batch {jit.shape[0]} does not match batch size {BS}")
+            bricked = vr.brick(vol_lin)
+            out, K, Tp = vr.march(bricked, tf_r4, cam, sampling_rate, jit, nondiff=False, image_layout=image_layout)
+        vr.last_K = K
+        ctx.vr, ctx.sampling_rate, ctx.image_layout = vr, sampling_rate, image_layout
+        ctx.is_batched, ctx.vol_batched, ctx.tf_batched = is_batched, vol_b, tf.ndim == 3
+        ctx.vol_shape, ctx.tf_shape = tuple(volume.shape), tuple(tf.shape)
+        ctx.bricked, ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = bricked, tf_r4, cam, jit, out, K, Tp
+        return out if is_batched else out[0]
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        need_vol, need_tf = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_vol or need_tf):
+            return (None,) * 9
+        vr = ctx.vr
+        with torch.cuda.device(grad_output.device):
+            go = grad_output if ctx.is_batched else grad_output[None]
+            go = go.float().contiguous()
+            gvol, gtf = vr.march_backward(ctx.bricked, ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, go, ctx.out, ctx.K,
+                                          ctx.Tp, need_vol, need_tf, image_layout=ctx.image_layout)
+        gv = gt = None
+        if need_vol:
+            gv = gvol.permute(0, 3, 1, 2)                          # [Bvol, X, Y, Z] view (Taichi order, :447)
+            if not ctx.vol_batched:
+                gv = gv[0]
+            elif gv.shape[0] != ctx.vol_shape[0]:
+                gv = gv.expand(ctx.vol_shape)                      # caller passed an expanded shared volume
+        if need_tf:
+            gt = gtf if ctx.tf_batched else gtf[0]
+            if ctx.tf_batched and gt.shape[0] != ctx.tf_shape[0]:
+                gt = gt.expand(ctx.tf_shape)
+        return None, gv, gt, None, None, None, None, None, None
+
+
+class Raycaster(torch.nn.Module):
+    """Same constructor and methods as the reference's `Raycaster` (:478-574)."""
+
+    def __init__(self, volume_shape, output_shape, tf_shape, sampling_rate=1.0, jitter=True, max_samples=512, fov=30.0,
+                 near=0.1, far=100.0, ti_kwargs={}):
+        super().__init__()
+        self.volume_shape = (volume_shape[2], volume_shape[0], volume_shape[1])       # torch (D,H,W) -> Taichi (W,D,H) :481
+        self.output_shape = output_shape
+        self.tf_shape = tf_shape
+        self.sampling_rate = sampling_rate
+        self.jitter = jitter
+        self.ti_kwargs = dict(ti_kwargs)      # accepted for signature compatibility; there is no Taichi runtime to configure
+        _lib.load()                           # fail loudly at construction if the CUDA library is missing
+        self.vr = VolumeRaycaster(self.volume_shape, output_shape, max_samples=max_samples, tf_resolution=tf_shape,
+                                  fov=fov, nearfar=(near, far))
+
+    def raycast_nondiff(self, volume, tf, look_from, sampling_rate=None):
+        """Non-differentiable render (:490-523): alpha-skip, no shading clamp, output clamped to 1, jitter off,
+        default sampling rate 4x."""
+        with torch.no_grad(), torch.autocast("cuda", enabled=False):
+            _require_cuda(volume, tf, look_from)
+            batched, bs, vol_in, tf_in, lf_in = self._determine_batch(volume, tf, look_from)
+            sr = sampling_rate if sampling_rate is not None else 4.0 * self.sampling_rate
+            BS = bs if batched else 1
+            with torch.cuda.device(volume.device):
+                v = vol_in if vol_in.ndim == 4 else vol_in[None]
+                if v.dtype not in (torch.float16, torch.float32):
+                    v = v.float()
+                vol_lin = v.permute(0, 2, 3, 1).contiguous()
+                t = (tf_in if tf_in.ndim == 3 else tf_in[None]).float().contiguous()
+                cam = lf_in.float().reshape(-1, 3)
+                if cam.shape[0] == 1 and BS > 1:
+                    cam = cam.expand(BS, 3)
+                cam = cam.contiguous()
+                out, K, _ = self.vr.march(self.vr.brick(vol_lin), t, cam, sr, None, nondiff=True, image_layout=True)
+            self.vr.last_K = K
+            return out if batched else out[0]
+
+    def forward(self, volume, tf, look_from, jitter_tensor=None):
+        """volume ([BS,] 1, D, H, W), tf ([BS,] 4, R), look_from ([BS,] 3)  ->  ([BS,] 4, H, W)   (:525-548).
+        The volume lives in [-1,1]^3 centred at the origin; the camera looks at the origin."""
+        batched, bs, vol_in, tf_in, lf_in = self._determine_batch(volume, tf, look_from)
+        return RaycastFunction.apply(self.vr, vol_in, tf_in, lf_in, self.sampling_rate, (batched, bs), self.jitter,
+                                     jitter_tensor, True)
+
+    def _determine_batch(self, volume, tf, look_from):
+        """Same rule as the reference (:551-571): anything batched => batch size from the first batched input.
+        Returns Taichi-order VIEWS; un-batched inputs are shared, not expanded and cloned (:566-568)."""
+        b_vol, b_tf, b_lf = volume.ndim == 5, tf.ndim == 3, look_from.ndim == 2
+        if b_vol or b_tf or b_lf:
+            bs = [volume, tf, look_from][[b_vol, b_tf, b_lf].index(True)].size(0)
+            vol_out = volume.squeeze(1).permute(0, 3, 1, 2) if b_vol else volume.squeeze(0).permute(2, 0, 1)
+            tf_out = tf.permute(0, 2, 1) if b_tf else tf.permute(1, 0)
+            return True, bs, vol_out, tf_out, look_from
+        return False, 0, volume.squeeze(0).permute(2, 0, 1), tf.permute(1, 0), look_from
+
+    def extra_repr(self):
+        return f'Volume ({self.volume_shape}), Output Render ({self.output_shape}), TF ({self.tf_shape}), Max Samples = {self.vr.max_samples}'

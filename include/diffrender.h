@@ -1,0 +1,143 @@
+/*
+ * diffrender.h -- C ABI of libdiffrender.so, the sm_100a implementation of Differender's differentiable
+ * ray-march hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI: its "operator API" is the torch.autograd.Function
+ * `RaycastFunction` (reference differender/volume_raycaster.py:392-476), which drives the Taichi object
+ * `VolumeRaycaster` (:56-389).  Each entry point below names the reference calls it replaces.  The Python host
+ * (differender_b200/volume_raycaster.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller (PyTorch);
+ *     the library never allocates, frees or retains memory and has no global mutable state
+ *     (contrast: Taichi's process-global runtime :486 and forward state held in the object :429-430).
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); no internal syncs.
+ *   - return 0 on success, a negative DR_E* code otherwise; dr_last_error() gives a thread-local message.
+ *   - volume axes use the reference's Taichi order (:481): X = torch W (unit stride), Y = torch D
+ *     (slowest), Z = torch H.  A "linear" volume is the contiguous torch tensor [B][Y][Z][X].
+ *   - images: DR_F_OUT_IMAGE set  -> [BS][4][H][W], row H-1-j holds raw row j (the flip/permute of :538-548
+ *     fused into the kernel); clear -> the reference's raw `output_rgba.to_torch()` order [BS][W][H][4].
+ *     grad_out uses the same layout as out_rgba.
+ *   - jitter, out_K, out_Tprev: [BS][H][W] in image orientation: pixel (i,j) -> [H-1-j][i].
+ */
+#ifndef DIFFRENDER_H_
+#define DIFFRENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_VERSION 100
+
+/* error codes */
+#define DR_OK 0
+#define DR_EINVAL (-1)    /* bad shape / flag / null pointer            */
+#define DR_EDTYPE (-2)    /* unsupported voxel dtype                    */
+#define DR_EALIGN (-3)    /* pointer not aligned as required            */
+#define DR_ECUDA (-4)     /* a CUDA call / launch failed                */
+#define DR_EWORKSPACE (-5) /* workspace too small                        */
+
+/* voxel storage types */
+#define DR_VOX_F32 0
+#define DR_VOX_F16 1
+
+/* DrDesc.flags */
+#define DR_F_NONDIFF 1u        /* raycast_nondiff + get_final_image_nondiff (:308-361) instead of raycast (:261-306) */
+#define DR_F_NEEDS_VOL_GRAD 2u /* ctx.needs_input_grad[volume]                                       */
+#define DR_F_NEEDS_TF_GRAD 4u  /* ctx.needs_input_grad[tf]                                           */
+#define DR_F_HAS_JITTER 8u     /* `jitter` flag of compute_entry_exit (:222, 254); jitter pointer must be non-null */
+#define DR_F_OUT_IMAGE 16u     /* out_rgba / grad_out are [BS][4][H][W] flipped (else raw [BS][W][H][4])   */
+#define DR_F_TF_4R 32u         /* tf / grad_tf are [Btf][4][R] (torch layout; else the reference's [Btf][R][4], :567,571) */
+#define DR_F_GENERIC_TAPS 64u  /* force the 7x8-load tap path (always used when a normal tap can skip a whole cell) */
+
+/* Plain-data description of one call.  Fill it with dr_desc_init(); do not hand-edit derived fields. */
+typedef struct DrDesc {
+    int32_t X, Y, Z;        /* volume resolution, Taichi order                (:58-60, :481)         */
+    int32_t W, H;           /* render resolution (w, h)                        (:74)                  */
+    int32_t R;              /* transfer-function resolution                    (:113)                 */
+    int32_t M;              /* max_samples                                     (:90)                  */
+    int32_t BS;             /* number of views (camera positions) in this call                        */
+    int32_t Bvol, Btf;      /* 1 (shared by all views, no clones - contrast :566-567) or BS           */
+    int32_t vox_dtype;      /* DR_VOX_*                                                               */
+    uint32_t flags;         /* DR_F_*                                                                 */
+    /* derived (folded on the host in double, rounded to fp32 like Python scalars captured by the Taichi kernels) */
+    float sr, inv_sr;       /* sampling_rate, 1/sampling_rate                  (:222, :285)           */
+    float near_, near_w, near_h; /* :146-148                                                          */
+    float scale[3];         /* (X,Y,Z) - 1 - 1e-4                              (:165)                 */
+    float vol_diag;         /* ||(X,Y,Z) - 1||                                 (:248-249)             */
+    float tf_len;           /* R - 1                                           (:215)                 */
+    float ambient, diffuse, specular; /* 0.4, 0.8, 0.3                         (:91-93); shininess is fixed at 32 (:94) */
+    float ert;              /* early-ray-termination threshold 0.99            (:267, :318)           */
+    float delta;            /* normal tap offset 1e-3                          (:193)                 */
+    float alpha_skip;       /* nondiff alpha skip 1e-3                         (:334)                 */
+    int32_t nbx, nby, nbz;  /* bricks (8x8x8 voxels) per axis                                         */
+    int32_t tap_generic;    /* 1 if delta spans >= 1 voxel on some axis (dims > ~2000): generic taps  */
+} DrDesc;
+
+/* Library version (DR_VERSION of the build). */
+int dr_version(void);
+
+/* Thread-local message of the last failure on this thread ("" if none). */
+const char* dr_last_error(void);
+
+/*
+ * Fills *d.  Replaces VolumeRaycaster.__init__ (:58-116): resolution bookkeeping, constants, layout choice.
+ * fov_deg/near as in Raycaster.__init__ (:479); sampling_rate as in RaycastFunction.forward (:395).
+ */
+int dr_desc_init(DrDesc* d, int32_t X, int32_t Y, int32_t Z, int32_t W, int32_t H, int32_t R, int32_t M,
+                 int32_t BS, int32_t Bvol, int32_t Btf, int32_t vox_dtype, uint32_t flags,
+                 double sampling_rate, double fov_deg, double near_plane);
+
+/* Elements (not bytes) of ONE bricked volume / bricked gradient volume: nbx*nby*nbz*512. */
+size_t dr_bricked_elems(const DrDesc* d);
+
+/*
+ * Re-lays Bvol linear volumes [Bvol][Y][Z][X] (fp32 or fp16 per vox_dtype) into 8x8x8 bricks
+ * [Bvol][nbz][nby][nbx][8][8][8], x fastest, same dtype.  Replaces set_volume / field.from_torch (:118-119),
+ * which copied into Taichi's 4x4x4-bricked SNode (:97-101).  Needed once per DISTINCT volume, not per view.
+ */
+int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, void* stream);
+
+/*
+ * Forward march of BS views.  Replaces, per view: set_cam_pos/set_tf_tex (:121-125), clear_framebuffer
+ * (:374-382), compute_entry_exit (:221-259), raycast (:261-306) or raycast_nondiff (:308-351), and
+ * get_final_image (:363-372) or get_final_image_nondiff (:353-361), i.e. the body of
+ * RaycastFunction.forward (:418-438) and Raycaster.raycast_nondiff (:502-523).
+ *   vol_bricked [Bvol] bricked volumes     tf [Btf][R][4] or [Btf][4][R]     cam [BS][3]
+ *   jitter [BS][H][W] uniform [0,1) or NULL (replaces ti.random, :255)
+ *   out_rgba  see layout note            out_K [BS][H][W] active samples per ray (valid_sample_step_count-1,
+ *   :303,367) or NULL      out_Tprev [BS][H][W] transmittance before the last active sample, or NULL
+ *   (out_K and out_Tprev are what the backward needs instead of the O(W*H*M) render_tape, :82,102-103).
+ */
+int dr_forward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+               float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream);
+
+/* Bytes of scratch dr_backward needs for this descriptor (privatised TF-gradient copies). */
+size_t dr_workspace_bytes(const DrDesc* d);
+
+/*
+ * Backward of BS views.  Replaces, per view: clear_grad (:384-389), output_rgba.grad.from_torch (:459,469),
+ * get_final_image.grad() (:460,470) and raycast.grad() (:461,471), i.e. RaycastFunction.backward (:440-476).
+ * Each ray is re-marched in reverse from (out_rgba, K, Tprev); no per-sample tape exists.
+ *   grad_vol_bricked [Bvol] bricked fp32, ACCUMULATED into (caller zeroes); may be NULL without NEEDS_VOL_GRAD
+ *   grad_tf [Btf] in the tf layout, fp32, ACCUMULATED into (caller zeroes); may be NULL without NEEDS_TF_GRAD
+ *   workspace: dr_workspace_bytes(d) bytes, 16-byte aligned, contents undefined on entry and exit.
+ */
+int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+                const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
+                float* grad_vol_bricked, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Bricked fp32 gradient -> linear [Bvol][Y][Z][X] fp32 with nan_to_num applied (NaN -> 0, +-inf -> +-FLT_MAX),
+ * as volume.grad.to_torch + torch.nan_to_num (:463, :474).  accumulate != 0 adds into grad_linear.
+ */
+int dr_unbrick_grad(const DrDesc* d, const float* grad_vol_bricked, float* grad_linear, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFRENDER_H_ */

@@ -1,0 +1,122 @@
+// tests/hostsim/hostsim.cpp -- TEST-ONLY host build of the kernels' per-ray arithmetic.
+//
+// Compiles differender_b200/csrc/dr_math.cuh (the very file the CUDA kernels are built from) with g++ so that
+// the "not gpu" test suite can compare the device math against the oracle without a GPU: corner-reuse taps vs
+// full taps, tape-free reverse march vs the oracle's taped adjoint, merged 32-voxel scatter vs 56-weight scatter.
+// It is NOT a CPU fallback: nothing under differender_b200/ builds, loads or calls it.
+#include <stdlib.h>
+#include <string.h>
+
+#include "dr_desc.h"
+#include "dr_math.cuh"
+
+using namespace dr;
+
+namespace {
+struct HostVolSink {
+    float* g;
+    void add(int off, float v) { g[off] += v; }
+};
+struct HostTfSink {
+    float* g;   // [R][4]
+    void add(int lo, int hi, float f, F4 dc)
+    {
+        const float w0 = 1.0f - f, w1 = f;
+        g[4 * lo + 0] += dc.x * w0; g[4 * lo + 1] += dc.y * w0; g[4 * lo + 2] += dc.z * w0; g[4 * lo + 3] += dc.w * w0;
+        g[4 * hi + 0] += dc.x * w1; g[4 * hi + 1] += dc.y * w1; g[4 * hi + 2] += dc.z * w1; g[4 * hi + 3] += dc.w * w1;
+    }
+};
+Layout make_layout(const DrDesc& d)
+{
+    Layout L;
+    L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
+    L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
+    return L;
+}
+}  // namespace
+
+extern "C" {
+
+int sim_desc_init(DrDesc* d, int X, int Y, int Z, int W, int H, int R, int M, unsigned flags, double sr, double fov,
+                  double near_plane)
+{
+    return desc_init(d, X, Y, Z, W, H, R, M, 1, 1, 1, DR_VOX_F32, flags, sr, fov, near_plane) ? -1 : 0;
+}
+
+size_t sim_bricked_elems(const DrDesc* d) { return (size_t)d->nbx * d->nby * d->nbz * 512; }
+
+// linear [Y][Z][X] -> bricked
+void sim_brick(const DrDesc* d, const float* lin, float* bricked)
+{
+    Layout L = make_layout(*d);
+    memset(bricked, 0, sizeof(float) * sim_bricked_elems(d));
+    for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
+        bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)] = lin[((size_t)y * d->Z + z) * d->X + x];
+}
+void sim_unbrick(const DrDesc* d, const float* bricked, float* lin)
+{
+    Layout L = make_layout(*d);
+    for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
+        lin[((size_t)y * d->Z + z) * d->X + x] = bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)];
+}
+
+// one view; tf is [R][4]; jitter/out_K/out_Tprev are [H][W] image orientation; out is [4][H][W]
+void sim_forward(const DrDesc* d, const float* vol_bricked, const float* tf, const float* cam3, const float* jitter,
+                 float* out, int* out_K, float* out_Tprev, int* out_n)
+{
+    Layout L = make_layout(*d);
+    VolView<float> vol { vol_bricked };
+    const F4* tf4 = (const F4*)tf;
+    F3 cam = { cam3[0], cam3[1], cam3[2] };
+    const size_t plane = (size_t)d->W * d->H;
+    for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {
+        const size_t pix = (size_t)(d->H - 1 - j) * d->W + i;
+        Ray r;
+        setup_ray(*d, cam, i, j, jitter ? jitter[pix] : 0.0f, r);
+        F4 A; int K; float Tp;
+        const bool nd = d->flags & DR_F_NONDIFF;
+        if (d->tap_generic) {
+            if (nd) march_forward<float, true, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            else march_forward<float, false, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
+        } else {
+            if (nd) march_forward<float, true, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            else march_forward<float, false, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+        }
+        out[pix] = A.x; out[plane + pix] = A.y; out[2 * plane + pix] = A.z; out[3 * plane + pix] = A.w;
+        if (out_K) out_K[pix] = K;
+        if (out_Tprev) out_Tprev[pix] = Tp;
+        if (out_n) out_n[pix] = r.n;
+    }
+}
+
+void sim_backward(const DrDesc* d, const float* vol_bricked, const float* tf, const float* cam3, const float* jitter,
+                  const float* grad_out, const float* out, const int* Kin, const float* Tprev,
+                  float* gvol_bricked, float* gtf)
+{
+    Layout L = make_layout(*d);
+    VolView<float> vol { vol_bricked };
+    const F4* tf4 = (const F4*)tf;
+    F3 cam = { cam3[0], cam3[1], cam3[2] };
+    const size_t plane = (size_t)d->W * d->H;
+    HostVolSink vs { gvol_bricked };
+    HostTfSink ts { gtf };
+    const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
+    for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {
+        const size_t pix = (size_t)(d->H - 1 - j) * d->W + i;
+        Ray r;
+        setup_ray(*d, cam, i, j, jitter ? jitter[pix] : 0.0f, r);
+        F4 A = { out[pix], out[plane + pix], out[2 * plane + pix], out[3 * plane + pix] };
+        F4 g = { grad_out[pix], grad_out[plane + pix], grad_out[2 * plane + pix], grad_out[3 * plane + pix] };
+        const int K = Kin[pix];
+        const float Tp = Tprev[pix];
+#define CALL(GEN, WV, WT) march_backward<float, GEN, WV, WT>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts)
+        if (d->tap_generic) {
+            if (wv && wt) CALL(true, true, true); else if (wv) CALL(true, true, false); else if (wt) CALL(true, false, true);
+        } else {
+            if (wv && wt) CALL(false, true, true); else if (wv) CALL(false, true, false); else if (wt) CALL(false, false, true);
+        }
+#undef CALL
+    }
+}
+
+}  // extern "C"
