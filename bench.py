@@ -5,7 +5,7 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one batch of views: brick the volume, forward march, backward march
-(TF + volume gradients), un-brick the gradient (and, for N > 1, all-reduce [volume grad | TF grad]).  A "sample" is one
+(TF + volume gradients), gather the cell-major gradient (and, for N > 1, all-reduce [volume grad | TF grad]).  A "sample" is one
 ACTIVE ray-march step; the count is the sum of the forward kernel's per-ray K.
 
 Prints ONE JSON line on rank 0.  `value` = device-resident throughput through the C ABI; `e2e` = the same metric through
@@ -51,6 +51,9 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-reg-accum", action="store_true", help="tuning: backward without register accumulation (DR_F_NO_REG_ACCUM)")
+    p.add_argument("--cuda-profiler-range", action="store_true",
+                   help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     return p.parse_args()
 
 
@@ -212,9 +215,10 @@ def run_ours(args, cfg):
         n_k = 2                                                                      # brick_kernel + fwd_kernel
         if mode != "nondiff":
             go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
-            gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf)
+            gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf,
+                                          extra_flags=128 if args.no_reg_accum else 0)
             if timed: e[3].record()
-            n_k += 1 + (1 if need_tf else 0) + (1 if need_vol else 0)                 # bwd_kernel (+ tf_reduce_kernel) (+ unbrick_kernel)
+            n_k += 1 + (1 if need_tf else 0) + (1 if need_vol else 0)                 # bwd_kernel (+ tf_reduce_kernel) (+ gather_grad_kernel)
             if world > 1:
                 flat = torch.cat([t.reshape(-1) for t in (gvol, gtf) if t is not None])
                 dist.all_reduce(flat)
@@ -238,6 +242,8 @@ def run_ours(args, cfg):
     time.sleep(0.25)
     torch.cuda.synchronize()
     t_wall0 = time.time()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.start()
     t0, t1 = ev(), ev()
     t0.record()
     evs = []
@@ -247,6 +253,8 @@ def run_ours(args, cfg):
         launches[0] += n_k
     t1.record()
     torch.cuda.synchronize()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()

@@ -9,10 +9,10 @@ LIB_PATH = os.path.join(_PKG, "libdiffrender.so")
 # include/diffrender.h
 DR_VERSION = 100
 VOX_F32, VOX_F16 = 0, 1
-F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS = 1, 2, 4, 8, 16, 32, 64
+F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM = 1, 2, 4, 8, 16, 32, 64, 128
 
 EXPORTS = ("dr_version", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_forward",
-           "dr_workspace_bytes", "dr_backward", "dr_unbrick_grad")
+           "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad")
 
 
 class DrDesc(ctypes.Structure):
@@ -49,7 +49,8 @@ def load():
     lib.dr_brick_volume.argtypes = [dp, vp, vp, vp]; lib.dr_brick_volume.restype = ctypes.c_int
     lib.dr_forward.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp]; lib.dr_forward.restype = ctypes.c_int
     lib.dr_backward.argtypes = [dp] + [vp] * 11 + [ctypes.c_size_t, vp]; lib.dr_backward.restype = ctypes.c_int
-    lib.dr_unbrick_grad.argtypes = [dp, vp, vp, ctypes.c_int, vp]; lib.dr_unbrick_grad.restype = ctypes.c_int
+    lib.dr_grad_cells_elems.argtypes = [dp]; lib.dr_grad_cells_elems.restype = ctypes.c_size_t
+    lib.dr_gather_grad.argtypes = [dp, vp, vp, ctypes.c_int, vp]; lib.dr_gather_grad.restype = ctypes.c_int
     if lib.dr_version() != DR_VERSION:
         raise RuntimeError(f"differender_b200: libdiffrender.so version {lib.dr_version()} != binding {DR_VERSION}; rebuild")
     _lib = lib

@@ -5,7 +5,7 @@
 //   fwd_kernel       ray set-up + march + compositing + final image          (:221-372)
 //   bwd_kernel       tape-free reverse march, TF + volume gradient scatter   (raycast.grad, :460-461)
 //   tf_reduce_kernel sums the privatised TF-gradient copies                  (tf_tex.grad.to_torch, :464,475)
-//   unbrick_kernel   bricked fp32 gradient -> linear, nan_to_num             (volume.grad.to_torch, :463,474)
+//   gather_grad_kernel cell-major fp32 gradient -> linear, nan_to_num        (volume.grad.to_torch, :463,474)
 //
 // Thread mapping: one ray per thread; a warp is an 8x4 pixel tile, a CTA (4 warps) a 16x8 tile, so the 32 rays of
 // a warp traverse neighbouring voxels and their corner fetches fall into a few 128-byte lines of the same bricks.
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(256) brick_kernel(DrDesc d, const VT* __restri
     br[(size_t)b * elems + e] = v;
 }
 
-__global__ void __launch_bounds__(256) unbrick_kernel(DrDesc d, const float* __restrict__ br, float* __restrict__ lin,
-                                                       size_t elems, int accumulate)
+// cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 (HBM-bound: reads 32 B per voxel once, L2 serves the 8x reuse)
+__global__ void __launch_bounds__(256) gather_grad_kernel(DrDesc d, const float* __restrict__ gcell, float* __restrict__ lin, int accumulate)
 {
     const size_t n = (size_t)d.X * d.Y * d.Z;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(256) unbrick_kernel(DrDesc d, const float* __r
     const int x = (int)(e % d.X);
     const size_t r = e / d.X;
     const int z = (int)(r % d.Z), y = (int)(r / d.Z);
-    const Layout L = make_layout(d);
-    float v = br[(size_t)b * elems + offx(x) + offy(y, L.sY) + offz(z, L.sZ)];
+    float v = gather_voxel(d, gcell + (size_t)b * n * 8, x, y, z);
     // torch.nan_to_num (:463, :474)
     if (v != v) v = 0.0f;
     else if (v > 3.4028234663852886e38f) v = 3.4028234663852886e38f;
@@ -155,27 +154,64 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
 // ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
-struct RedVolSink {
-    float* g;
-    __device__ __forceinline__ void add(int off, float v) { atomicAdd(g + off, v); }      // RED.E.ADD.F32 (no return)
+// Volume gradient: one cell = one 32-byte sector = two RED.E.ADD.F32x4.  With ACCUM the centre cell's 8-vector stays in
+// registers while consecutive samples of the ray fall into the same cell (about 3 samples per cell at sampling rate 1).
+template <bool ACCUM> struct CellVolSink {
+    float4* g;
+    int cur;
+    float acc[8];
+    __device__ __forceinline__ void red(int cell, const float* v)
+    {
+        float4* p = g + (size_t)cell * 2;
+        atomicAdd(p, make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(p + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    __device__ __forceinline__ void centre(int cell, const float* v)
+    {
+        if (!ACCUM) { red(cell, v); return; }
+        if (cell == cur) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += v[q];
+        } else {
+            if (cur >= 0) red(cur, acc);
+            cur = cell;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = v[q];
+        }
+    }
+    __device__ __forceinline__ void direct(int cell, const float* v) { red(cell, v); }
+    __device__ __forceinline__ void flush() { if (ACCUM && cur >= 0) red(cur, acc); }
 };
-// TF gradient: two 16-byte vector reductions per sample into one of kTfSlots privatised copies of the table.
-// (Shared-memory fp32 atomicAdd is a CAS spin loop on sm_100a -- ATOMS.CAST.SPIN -- so privatisation lives in L2.)
-struct RedTfSink {
+// TF gradient: two 16-byte vector reductions (bins lo, hi) into one of kTfSlots privatised copies of the table, summed by
+// tf_reduce_kernel.  Shared-memory fp32 atomicAdd is a CAS spin loop on sm_100a (ATOMS.CAST.SPIN) and measured 4x slower
+// than RED.F32x4 into L2 (profiles/r01_atomic_microbench.txt), so the privatised copies live in L2, not in shared memory.
+// With ACCUM the two bins stay in registers while consecutive samples of the ray hit the same bin.
+template <bool ACCUM> struct RedTfSink {
     float4* g;      // [R] of this CTA's slot
+    int cur, cur_hi;
+    float4 a0, a1;
     __device__ __forceinline__ void add(int lo, int hi, float f, F4 dc)
     {
         const float w0 = 1.0f - f;
-        atomicAdd(g + lo, make_float4(dc.x * w0, dc.y * w0, dc.z * w0, dc.w * w0));         // RED.E.ADD.F32x4
-        atomicAdd(g + hi, make_float4(dc.x * f, dc.y * f, dc.z * f, dc.w * f));
+        const float4 v0 = make_float4(dc.x * w0, dc.y * w0, dc.z * w0, dc.w * w0);
+        const float4 v1 = make_float4(dc.x * f, dc.y * f, dc.z * f, dc.w * f);
+        if (!ACCUM) { atomicAdd(g + lo, v0); atomicAdd(g + hi, v1); return; }
+        if (lo == cur) {
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        } else {
+            if (cur >= 0) { atomicAdd(g + cur, a0); atomicAdd(g + cur_hi, a1); }
+            cur = lo; cur_hi = hi; a0 = v0; a1 = v1;
+        }
     }
+    __device__ __forceinline__ void flush() { if (ACCUM && cur >= 0) { atomicAdd(g + cur, a0); atomicAdd(g + cur_hi, a1); } }
 };
 
-template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF>
+template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool ACCUM>
 __global__ void __launch_bounds__(kThreads)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
-           const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float* __restrict__ gvol,
+           const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
            float4* __restrict__ tf_slots, size_t vol_elems)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -208,9 +244,13 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
     const VolView<VT> vol { volp + voff };
     const Layout L = make_layout(d);
-    RedVolSink vs { WANT_VOL ? gvol + voff : nullptr };
+    CellVolSink<ACCUM> vs;
+    vs.g = WANT_VOL ? gcell + (d.Bvol == 1 ? 0 : (size_t)b * d.X * d.Y * d.Z * 2) : nullptr;
+    vs.cur = -1;
     const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
-    RedTfSink ts { WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr };
+    RedTfSink<ACCUM> ts;
+    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
+    ts.cur = -1;
     march_backward<VT, GENERIC, WANT_VOL, WANT_TF>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
 }
 
@@ -273,13 +313,13 @@ int launch_fwd(const DrDesc* d, const void* vol, const float* tf, const float* c
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
 
-template <typename VT, bool GENERIC, bool WV, bool WT>
+template <typename VT, bool GENERIC, bool WV, bool WT, bool ACC>
 int launch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
-               const float* gout, const float* out, const int32_t* K, const float* T, float* gvol, float4* slots,
+               const float* gout, const float* out, const int32_t* K, const float* T, float4* gvol, float4* slots,
                cudaStream_t st)
 {
     const size_t smem = (size_t)d->R * sizeof(F4);
-    auto kern = bwd_kernel<VT, GENERIC, WV, WT>;
+    auto kern = bwd_kernel<VT, GENERIC, WV, WT, ACC>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, gout, out, K, T, gvol, slots,
@@ -290,13 +330,18 @@ int launch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* c
 
 template <typename VT, bool GENERIC>
 int dispatch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
-                 const float* gout, const float* out, const int32_t* K, const float* T, float* gvol, float4* slots,
+                 const float* gout, const float* out, const int32_t* K, const float* T, float4* gvol, float4* slots,
                  cudaStream_t st)
 {
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
-    if (wv && wt) return launch_bwd<VT, GENERIC, true, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st);
-    if (wv) return launch_bwd<VT, GENERIC, true, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st);
-    return launch_bwd<VT, GENERIC, false, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st);
+    const bool acc = !(d->flags & DR_F_NO_REG_ACCUM);
+#define DR_BWD(WV, WT)                                                                                              \
+    (acc ? launch_bwd<VT, GENERIC, WV, WT, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st)        \
+         : launch_bwd<VT, GENERIC, WV, WT, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st))
+    if (wv && wt) return DR_BWD(true, true);
+    if (wv) return DR_BWD(true, false);
+    return DR_BWD(false, true);
+#undef DR_BWD
 }
 
 }  // namespace
@@ -362,7 +407,7 @@ int dr_forward(const DrDesc* d, const void* vol_bricked, const float* tf, const 
 
 int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
                 const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
-                float* grad_vol_bricked, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
+                float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (int rc = check_desc(d)) return rc;
     if (d->flags & DR_F_NONDIFF) return fail(DR_EINVAL, "dr_backward: the non-differentiable march has no backward");
@@ -370,7 +415,8 @@ int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const
     if (!wv && !wt) return DR_OK;
     if (!vol_bricked || !tf || !cam || !grad_out || !out_rgba || !K || !Tprev) return fail(DR_EINVAL, "dr_backward: null pointer");
     if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_backward: DR_F_HAS_JITTER set but jitter is null");
-    if (wv && !grad_vol_bricked) return fail(DR_EINVAL, "dr_backward: grad_vol_bricked is null");
+    if (wv && !grad_vol_cells) return fail(DR_EINVAL, "dr_backward: grad_vol_cells is null");
+    if (wv && !aligned(grad_vol_cells, 32)) return fail(DR_EALIGN, "dr_backward: grad_vol_cells must be 32-byte aligned");
     if (wt && !grad_tf) return fail(DR_EINVAL, "dr_backward: grad_tf is null");
     if (!aligned(tf, 16) || !aligned(out_rgba, 16) || !aligned(grad_out, 16))
         return fail(DR_EALIGN, "dr_backward: tf, out_rgba and grad_out must be 16-byte aligned");
@@ -385,13 +431,14 @@ int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const
         if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
     }
     float4* slots = static_cast<float4*>(workspace);
+    float4* gcells = reinterpret_cast<float4*>(grad_vol_cells);
     int rc;
     if (d->vox_dtype == DR_VOX_F32)
-        rc = d->tap_generic ? dispatch_bwd<float, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st)
-                            : dispatch_bwd<float, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st);
+        rc = d->tap_generic ? dispatch_bwd<float, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st)
+                            : dispatch_bwd<float, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st);
     else
-        rc = d->tap_generic ? dispatch_bwd<__half, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st)
-                            : dispatch_bwd<__half, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_bricked, slots, st);
+        rc = d->tap_generic ? dispatch_bwd<__half, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st)
+                            : dispatch_bwd<__half, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st);
     if (rc) return rc;
     if (wt) {
         dim3 grid((d->R * 4 + 255) / 256, d->Btf);
@@ -402,15 +449,17 @@ int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const
     return DR_OK;
 }
 
-int dr_unbrick_grad(const DrDesc* d, const float* grad_vol_bricked, float* grad_linear, int accumulate, void* stream)
+size_t dr_grad_cells_elems(const DrDesc* d) { return d ? (size_t)d->X * d->Y * d->Z * 8 : 0; }
+
+int dr_gather_grad(const DrDesc* d, const float* grad_vol_cells, float* grad_linear, int accumulate, void* stream)
 {
     if (int rc = check_desc(d)) return rc;
-    if (!grad_vol_bricked || !grad_linear) return fail(DR_EINVAL, "dr_unbrick_grad: null pointer");
+    if (!grad_vol_cells || !grad_linear) return fail(DR_EINVAL, "dr_gather_grad: null pointer");
     const size_t n = (size_t)d->X * d->Y * d->Z;
     dim3 grid((unsigned)((n + 255) / 256), d->Bvol);
-    unbrick_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_bricked, grad_linear, dr_bricked_elems(d), accumulate);
+    gather_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_cells, grad_linear, accumulate);
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? DR_OK : fail_cuda(e, "unbrick_kernel launch");
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "gather_grad_kernel launch");
 }
 
 }  // extern "C"

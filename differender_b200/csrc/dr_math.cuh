@@ -440,102 +440,93 @@ DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, con
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Volume-gradient scatter.  The 7 taps' 56 trilinear weights are merged into at most 32 distinct voxels:
-// the 8 corners of the centre cell plus, per axis, the 4 corners of the plane before / after it when a tap
-// crossed that face.  Per axis the two taps are folded into 4 slot coefficients e[0..3] for the voxel indices
-// lo-1, lo, lo+1, lo+2.  `Sink::add(offset, value)` is an atomic add into the bricked gradient volume.
+// Volume-gradient scatter into a CELL-MAJOR buffer: gcell[cell][8], cell = (cy*Z + cz)*X + cx (the torch linear
+// index of the cell's low corner), slot = a + 2b + 4c for corner (cx+a, cy+b, cz+c).  One cell is one 32-byte
+// sector, so a tap's 8 trilinear weights go out as two 16-byte vector reductions (RED.E.ADD.F32x4) instead of 8
+// scalar ones -- measured 3.5x faster on B200 (profiles/r01_atomic_microbench.txt).  A gather pass
+// (gather_grad_kernel) sums the 8 slots that alias each voxel.
+//   * taps that stay in the centre cell are merged with the centre tap into one 8-vector (Sink::centre);
+//   * a tap that crossed a face goes to its own (neighbour) cell (Sink::direct);
+//   * Sink::centre may keep the 8-vector in registers while consecutive samples stay in the same cell.
 // ---------------------------------------------------------------------------------------------------------
-DR_HD void axis_slots(Loc c, Loc tp, Loc tm, float dg, float& e0, float& e1, float& e2, float& e3)
-{
-    const float wp0 = dg * (1.0f - tp.f), wp1 = dg * tp.f;
-    const float wm0 = dg * (1.0f - tm.f), wm1 = dg * tm.f;
-    const bool cp = tp.lo != c.lo, cm = tm.lo != c.lo;
-    e0 = cm ? -wm0 : 0.0f;
-    e1 = (cp ? 0.0f : wp0) - (cm ? wm1 : wm0);
-    e2 = (cp ? wp0 : wp1) - (cm ? 0.0f : wm1);
-    e3 = cp ? wp1 : 0.0f;
-}
+DR_HD int cell_index(const DrDesc& d, int cx, int cy, int cz) { return (cy * d.Z + cz) * d.X + cx; }
 
-template <typename Sink>
-DR_HD void scatter_tap_full(Sink& sink, const Layout& L, Loc ax, Loc ay, Loc az, float adj)
+DR_HD void tap_weights(float adj, Loc ax, Loc ay, Loc az, float v[8])
 {
-    int x0 = offx(ax.lo), x1 = offx(imin(ax.lo + 1, L.mx));
-    int y0 = offy(ay.lo, L.sY), y1 = offy(imin(ay.lo + 1, L.my), L.sY);
-    int z0 = offz(az.lo, L.sZ), z1 = offz(imin(az.lo + 1, L.mz), L.sZ);
-    float wx0 = 1.0f - ax.f, wx1 = ax.f, wy0 = 1.0f - ay.f, wy1 = ay.f;
-    float z0w = adj * (1.0f - az.f), z1w = adj * az.f;
-    sink.add(x0 + y0 + z0, z0w * wy0 * wx0); sink.add(x1 + y0 + z0, z0w * wy0 * wx1);
-    sink.add(x0 + y1 + z0, z0w * wy1 * wx0); sink.add(x1 + y1 + z0, z0w * wy1 * wx1);
-    sink.add(x0 + y0 + z1, z1w * wy0 * wx0); sink.add(x1 + y0 + z1, z1w * wy0 * wx1);
-    sink.add(x0 + y1 + z1, z1w * wy1 * wx0); sink.add(x1 + y1 + z1, z1w * wy1 * wx1);
+    const float z0 = adj * (1.0f - az.f), z1 = adj * az.f;
+    const float wx0 = 1.0f - ax.f, wx1 = ax.f, wy0 = 1.0f - ay.f, wy1 = ay.f;
+    const float a00 = z0 * wy0, a10 = z0 * wy1, a01 = z1 * wy0, a11 = z1 * wy1;
+    v[0] = a00 * wx0; v[1] = a00 * wx1; v[2] = a10 * wx0; v[3] = a10 * wx1;
+    v[4] = a01 * wx0; v[5] = a01 * wx1; v[6] = a11 * wx0; v[7] = a11 * wx1;
 }
 
 template <typename Sink, bool GENERIC>
-DR_HD void scatter_volume_grad(Sink& sink, const Layout& L, const Taps& t, const SampleAdj& a)
+DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const SampleAdj& a)
 {
+    float v[8];
+    const int cc = cell_index(d, t.cx.lo, t.cy.lo, t.cz.lo);
     if (GENERIC) {
-        scatter_tap_full(sink, L, t.cx, t.cy, t.cz, a.dI);
+        tap_weights(a.dI, t.cx, t.cy, t.cz, v); sink.centre(cc, v);
         if (a.has_dg) {
-            scatter_tap_full(sink, L, t.xp, t.cy, t.cz, a.dg.x); scatter_tap_full(sink, L, t.xm, t.cy, t.cz, -a.dg.x);
-            scatter_tap_full(sink, L, t.cx, t.yp, t.cz, a.dg.y); scatter_tap_full(sink, L, t.cx, t.ym, t.cz, -a.dg.y);
-            scatter_tap_full(sink, L, t.cx, t.cy, t.zp, a.dg.z); scatter_tap_full(sink, L, t.cx, t.cy, t.zm, -a.dg.z);
+            tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cell_index(d, t.xp.lo, t.cy.lo, t.cz.lo), v);
+            tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cell_index(d, t.xm.lo, t.cy.lo, t.cz.lo), v);
+            tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.yp.lo, t.cz.lo), v);
+            tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.ym.lo, t.cz.lo), v);
+            tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zp.lo), v);
+            tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zm.lo), v);
         }
         return;
     }
-    float ex0, ex1, ex2, ex3, ey0, ey1, ey2, ey3, ez0, ez1, ez2, ez3;
-    axis_slots(t.cx, t.xp, t.xm, a.dg.x, ex0, ex1, ex2, ex3);
-    axis_slots(t.cy, t.yp, t.ym, a.dg.y, ey0, ey1, ey2, ey3);
-    axis_slots(t.cz, t.zp, t.zm, a.dg.z, ez0, ez1, ez2, ez3);
     const float wx0 = 1.0f - t.cx.f, wx1 = t.cx.f, wy0 = 1.0f - t.cy.f, wy1 = t.cy.f;
     const float wz0 = 1.0f - t.cz.f, wz1 = t.cz.f;
-    const float X0 = a.dI * wx0 + ex1, X1 = a.dI * wx1 + ex2;
+    // per axis: coefficients of the two voxel planes of the centre cell contributed by the taps that did NOT cross
+    const bool xpc = t.xp.lo != t.cx.lo, xmc = t.xm.lo != t.cx.lo;
+    const bool ypc = t.yp.lo != t.cy.lo, ymc = t.ym.lo != t.cy.lo;
+    const bool zpc = t.zp.lo != t.cz.lo, zmc = t.zm.lo != t.cz.lo;
+    const float ex0 = a.dg.x * ((xpc ? 0.0f : 1.0f - t.xp.f) - (xmc ? 0.0f : 1.0f - t.xm.f));
+    const float ex1 = a.dg.x * ((xpc ? 0.0f : t.xp.f) - (xmc ? 0.0f : t.xm.f));
+    const float ey0 = a.dg.y * ((ypc ? 0.0f : 1.0f - t.yp.f) - (ymc ? 0.0f : 1.0f - t.ym.f));
+    const float ey1 = a.dg.y * ((ypc ? 0.0f : t.yp.f) - (ymc ? 0.0f : t.ym.f));
+    const float ez0 = a.dg.z * ((zpc ? 0.0f : 1.0f - t.zp.f) - (zmc ? 0.0f : 1.0f - t.zm.f));
+    const float ez1 = a.dg.z * ((zpc ? 0.0f : t.zp.f) - (zmc ? 0.0f : t.zm.f));
+    const float X0 = a.dI * wx0 + ex0, X1 = a.dI * wx1 + ex1;
     const float yz00 = wy0 * wz0, yz10 = wy1 * wz0, yz01 = wy0 * wz1, yz11 = wy1 * wz1;
     const float xz00 = wx0 * wz0, xz10 = wx1 * wz0, xz01 = wx0 * wz1, xz11 = wx1 * wz1;
     const float xy00 = wx0 * wy0, xy10 = wx1 * wy0, xy01 = wx0 * wy1, xy11 = wx1 * wy1;
-    const int x0 = offx(t.cx.lo), x1 = offx(imin(t.cx.lo + 1, L.mx));
-    const int y0 = offy(t.cy.lo, L.sY), y1 = offy(imin(t.cy.lo + 1, L.my), L.sY);
-    const int z0 = offz(t.cz.lo, L.sZ), z1 = offz(imin(t.cz.lo + 1, L.mz), L.sZ);
-    // centre cell: G[a][b][c] = wyz[b][c]*X_a + wxz[a][c]*ey[1+b] + wxy[a][b]*ez[1+c]
-    sink.add(x0 + y0 + z0, yz00 * X0 + xz00 * ey1 + xy00 * ez1);
-    sink.add(x1 + y0 + z0, yz00 * X1 + xz10 * ey1 + xy10 * ez1);
-    sink.add(x0 + y1 + z0, yz10 * X0 + xz00 * ey2 + xy01 * ez1);
-    sink.add(x1 + y1 + z0, yz10 * X1 + xz10 * ey2 + xy11 * ez1);
-    sink.add(x0 + y0 + z1, yz01 * X0 + xz01 * ey1 + xy00 * ez2);
-    sink.add(x1 + y0 + z1, yz01 * X1 + xz11 * ey1 + xy10 * ez2);
-    sink.add(x0 + y1 + z1, yz11 * X0 + xz01 * ey2 + xy01 * ez2);
-    sink.add(x1 + y1 + z1, yz11 * X1 + xz11 * ey2 + xy11 * ez2);
+    // G[a][b][c] = wyz[b][c]*X_a + wxz[a][c]*ey_b + wxy[a][b]*ez_c
+    v[0] = yz00 * X0 + xz00 * ey0 + xy00 * ez0;
+    v[1] = yz00 * X1 + xz10 * ey0 + xy10 * ez0;
+    v[2] = yz10 * X0 + xz00 * ey1 + xy01 * ez0;
+    v[3] = yz10 * X1 + xz10 * ey1 + xy11 * ez0;
+    v[4] = yz01 * X0 + xz01 * ey0 + xy00 * ez1;
+    v[5] = yz01 * X1 + xz11 * ey0 + xy10 * ez1;
+    v[6] = yz11 * X0 + xz01 * ey1 + xy01 * ez1;
+    v[7] = yz11 * X1 + xz11 * ey1 + xy11 * ez1;
+    sink.centre(cc, v);
     if (!a.has_dg) return;
-    // outer planes, only where a tap crossed a face
-    if (t.xm.lo != t.cx.lo) {
-        const int xn = offx(t.xm.lo);
-        sink.add(xn + y0 + z0, ex0 * yz00); sink.add(xn + y1 + z0, ex0 * yz10);
-        sink.add(xn + y0 + z1, ex0 * yz01); sink.add(xn + y1 + z1, ex0 * yz11);
-    }
-    if (t.xp.lo != t.cx.lo) {
-        const int xn = offx(imin(t.xp.lo + 1, L.mx));
-        sink.add(xn + y0 + z0, ex3 * yz00); sink.add(xn + y1 + z0, ex3 * yz10);
-        sink.add(xn + y0 + z1, ex3 * yz01); sink.add(xn + y1 + z1, ex3 * yz11);
-    }
-    if (t.ym.lo != t.cy.lo) {
-        const int yn = offy(t.ym.lo, L.sY);
-        sink.add(x0 + yn + z0, ey0 * xz00); sink.add(x1 + yn + z0, ey0 * xz10);
-        sink.add(x0 + yn + z1, ey0 * xz01); sink.add(x1 + yn + z1, ey0 * xz11);
-    }
-    if (t.yp.lo != t.cy.lo) {
-        const int yn = offy(imin(t.yp.lo + 1, L.my), L.sY);
-        sink.add(x0 + yn + z0, ey3 * xz00); sink.add(x1 + yn + z0, ey3 * xz10);
-        sink.add(x0 + yn + z1, ey3 * xz01); sink.add(x1 + yn + z1, ey3 * xz11);
-    }
-    if (t.zm.lo != t.cz.lo) {
-        const int zn = offz(t.zm.lo, L.sZ);
-        sink.add(x0 + y0 + zn, ez0 * xy00); sink.add(x1 + y0 + zn, ez0 * xy10);
-        sink.add(x0 + y1 + zn, ez0 * xy01); sink.add(x1 + y1 + zn, ez0 * xy11);
-    }
-    if (t.zp.lo != t.cz.lo) {
-        const int zn = offz(imin(t.zp.lo + 1, L.mz), L.sZ);
-        sink.add(x0 + y0 + zn, ez3 * xy00); sink.add(x1 + y0 + zn, ez3 * xy10);
-        sink.add(x0 + y1 + zn, ez3 * xy01); sink.add(x1 + y1 + zn, ez3 * xy11);
-    }
+    if (xpc) { tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cell_index(d, t.xp.lo, t.cy.lo, t.cz.lo), v); }
+    if (xmc) { tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cell_index(d, t.xm.lo, t.cy.lo, t.cz.lo), v); }
+    if (ypc) { tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.yp.lo, t.cz.lo), v); }
+    if (ymc) { tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.ym.lo, t.cz.lo), v); }
+    if (zpc) { tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zp.lo), v); }
+    if (zmc) { tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zm.lo), v); }
+}
+
+// Gather pass: the gradient of voxel (x,y,z) is the sum of every (cell, slot) that aliases it, i.e. all (c, a) per axis
+// with min(c + a, dim-1) == v: (v,0), (v-1,1) and, on the last plane only, the clamped (dim-1,1)  (:170-172).
+DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int z)
+{
+    int cx[3], ax[3], cy[3], ay[3], cz[3], az[3];
+    int nx = 0, ny = 0, nz = 0;
+    cx[nx] = x; ax[nx++] = 0; if (x > 0) { cx[nx] = x - 1; ax[nx++] = 1; } if (x == d.X - 1) { cx[nx] = x; ax[nx++] = 1; }
+    cy[ny] = y; ay[ny++] = 0; if (y > 0) { cy[ny] = y - 1; ay[ny++] = 1; } if (y == d.Y - 1) { cy[ny] = y; ay[ny++] = 1; }
+    cz[nz] = z; az[nz++] = 0; if (z > 0) { cz[nz] = z - 1; az[nz++] = 1; } if (z == d.Z - 1) { cz[nz] = z; az[nz++] = 1; }
+    float s = 0.0f;
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i)
+                s += gcell[(size_t)cell_index(d, cx[i], cy[j], cz[k]) * 8 + (ax[i] + 2 * ay[j] + 4 * az[k])];
+    return s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -580,7 +571,8 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
 // reconstructed as T_{s-1} = T_s / (1 - o_s); the last active sample uses the saved Tprev (so an opaque last
 // sample never divides by ~0), and 1 - o_s > 1 - ert for every earlier sample because sample s+1 was active.
 // dL/dA_s.rgb is constant along the ray (= grad_out.rgb); only dL/dA_s.w evolves: g.w -= C_s . g.
-// TfSink::add(lo, hi, f, dc) accumulates the TF gradient; VolSink::add(off, v) the volume gradient.
+// TfSink::add(lo, hi, f, dc) accumulates the TF gradient; VolSink::centre/direct(cell, v[8]) the volume gradient;
+// both may hold a partial sum in registers and are flushed at the end of the ray.
 // ---------------------------------------------------------------------------------------------------------
 template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF, typename VolSink, typename TfSink>
 DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
@@ -602,8 +594,10 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         const float Cg = sample_adjoint(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
         g.w -= Cg;
         if (WANT_TF) tsink.add(h.lo, h.hi, h.f, a.dc);
-        if (WANT_VOL) scatter_volume_grad<VolSink, GENERIC>(vsink, L, t, a);
+        if (WANT_VOL) scatter_volume_grad<VolSink, GENERIC>(d, vsink, t, a);
     }
+    if (WANT_TF) tsink.flush();
+    if (WANT_VOL) vsink.flush();
 }
 
 }  // namespace dr

@@ -80,39 +80,41 @@ class VolumeRaycaster:
         return out, K, Tp
 
     def march_backward(self, bricked, tf_r4, cam, sampling_rate, jitter, grad_out, out, K, Tprev, need_vol, need_tf,
-                       image_layout=True, grad_bricked=None):
+                       image_layout=True, grad_cells=None, extra_flags=0):
         """Backward of cam.shape[0] views.  Returns (grad_vol_linear [Bvol,Y,Z,X] fp32 or None, grad_tf [Btf,R,4] or None).
-        If `grad_bricked` is given the volume gradient is accumulated there and NOT un-bricked (returns it instead)."""
+        The volume gradient is scattered into a cell-major buffer [Bvol, X*Y*Z*8] (zeroed here) and gathered once.
+        If `grad_cells` is given it is accumulated into and NOT gathered (it is returned instead), so that several calls
+        (e.g. chunks of a large view batch) share one buffer and one gather."""
         BS = cam.shape[0]
-        X, Y, Z = self.volume_resolution
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
-                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0)
+                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
         dev = bricked.device
         lib = _lib.load()
-        keep_bricked = grad_bricked is not None
-        if need_vol and grad_bricked is None:
-            grad_bricked = torch.zeros(bricked.shape, dtype=torch.float32, device=dev)
+        keep_cells = grad_cells is not None
+        if need_vol and grad_cells is None:
+            grad_cells = torch.zeros((bricked.shape[0], lib.dr_grad_cells_elems(ctypes.byref(d))), dtype=torch.float32, device=dev)
         gtf = torch.zeros(tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
         ws_bytes = lib.dr_workspace_bytes(ctypes.byref(d))
         ws = torch.empty((max(ws_bytes, 16) + 3) // 4, dtype=torch.float32, device=dev)
         _lib.check(lib.dr_backward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
                                    _lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
-                                   _lib.ptr(grad_bricked) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
+                                   _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
                                    _stream()), "dr_backward")
         if not need_vol:
             return None, gtf
-        if keep_bricked:
-            return grad_bricked, gtf
-        return self.unbrick(grad_bricked), gtf
+        if keep_cells:
+            return grad_cells, gtf
+        return self.gather(grad_cells), gtf
 
-    def unbrick(self, grad_bricked):
+    def gather(self, grad_cells):
+        """Cell-major gradient [Bvol, X*Y*Z*8] -> linear [Bvol, Y, Z, X] fp32 with nan_to_num."""
         X, Y, Z = self.volume_resolution
         d = self.desc(1, 1, 1, VOX_F32, 0, 1.0)
-        d.Bvol = grad_bricked.shape[0]
-        gl = torch.empty((grad_bricked.shape[0], Y, Z, X), dtype=torch.float32, device=grad_bricked.device)
-        _lib.check(_lib.load().dr_unbrick_grad(ctypes.byref(d), _lib.ptr(grad_bricked), _lib.ptr(gl), 0, _stream()), "dr_unbrick_grad")
+        d.Bvol = grad_cells.shape[0]
+        gl = torch.empty((grad_cells.shape[0], Y, Z, X), dtype=torch.float32, device=grad_cells.device)
+        _lib.check(_lib.load().dr_gather_grad(ctypes.byref(d), _lib.ptr(grad_cells), _lib.ptr(gl), 0, _stream()), "dr_gather_grad")
         return gl
 
 

@@ -53,6 +53,7 @@ extern "C" {
 #define DR_F_OUT_IMAGE 16u     /* out_rgba / grad_out are [BS][4][H][W] flipped (else raw [BS][W][H][4])   */
 #define DR_F_TF_4R 32u         /* tf / grad_tf are [Btf][4][R] (torch layout; else the reference's [Btf][R][4], :567,571) */
 #define DR_F_GENERIC_TAPS 64u  /* force the 7x8-load tap path (always used when a normal tap can skip a whole cell) */
+#define DR_F_NO_REG_ACCUM 128u  /* tuning/debug: backward issues its reductions per sample instead of keeping the current cell / TF bin in registers */
 
 /* Plain-data description of one call.  Fill it with dr_desc_init(); do not hand-edit derived fields. */
 typedef struct DrDesc {
@@ -92,7 +93,7 @@ int dr_desc_init(DrDesc* d, int32_t X, int32_t Y, int32_t Z, int32_t W, int32_t 
                  int32_t BS, int32_t Bvol, int32_t Btf, int32_t vox_dtype, uint32_t flags,
                  double sampling_rate, double fov_deg, double near_plane);
 
-/* Elements (not bytes) of ONE bricked volume / bricked gradient volume: nbx*nby*nbz*512. */
+/* Elements (not bytes) of ONE bricked volume: nbx*nby*nbz*512. */
 size_t dr_bricked_elems(const DrDesc* d);
 
 /*
@@ -119,23 +120,29 @@ int dr_forward(const DrDesc* d, const void* vol_bricked, const float* tf, const 
 /* Bytes of scratch dr_backward needs for this descriptor (privatised TF-gradient copies). */
 size_t dr_workspace_bytes(const DrDesc* d);
 
+/* Floats (not bytes) of ONE cell-major volume-gradient buffer: X*Y*Z*8 (one 32-byte cell per voxel position). */
+size_t dr_grad_cells_elems(const DrDesc* d);
+
 /*
  * Backward of BS views.  Replaces, per view: clear_grad (:384-389), output_rgba.grad.from_torch (:459,469),
  * get_final_image.grad() (:460,470) and raycast.grad() (:461,471), i.e. RaycastFunction.backward (:440-476).
  * Each ray is re-marched in reverse from (out_rgba, K, Tprev); no per-sample tape exists.
- *   grad_vol_bricked [Bvol] bricked fp32, ACCUMULATED into (caller zeroes); may be NULL without NEEDS_VOL_GRAD
+ *   grad_vol_cells [Bvol][Y*Z*X][8] fp32 cell-major gradient (slot a+2b+4c of cell (x,y,z) belongs to voxel
+ *     (x+a, y+b, z+c)), ACCUMULATED into (caller zeroes), 32-byte aligned; may be NULL without NEEDS_VOL_GRAD.
+ *     It is shared by all views of the call, so one shared volume gets ONE summed gradient (contrast :447, :463).
  *   grad_tf [Btf] in the tf layout, fp32, ACCUMULATED into (caller zeroes); may be NULL without NEEDS_TF_GRAD
  *   workspace: dr_workspace_bytes(d) bytes, 16-byte aligned, contents undefined on entry and exit.
  */
 int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
                 const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
-                float* grad_vol_bricked, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
+                float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * Bricked fp32 gradient -> linear [Bvol][Y][Z][X] fp32 with nan_to_num applied (NaN -> 0, +-inf -> +-FLT_MAX),
- * as volume.grad.to_torch + torch.nan_to_num (:463, :474).  accumulate != 0 adds into grad_linear.
+ * Cell-major fp32 gradient -> linear [Bvol][Y][Z][X] fp32 (sums the up-to-8 cell slots that alias each voxel) with
+ * nan_to_num applied (NaN -> 0, +-inf -> +-FLT_MAX), as volume.grad.to_torch + torch.nan_to_num (:463, :474).
+ * accumulate != 0 adds into grad_linear.
  */
-int dr_unbrick_grad(const DrDesc* d, const float* grad_vol_bricked, float* grad_linear, int accumulate, void* stream);
+int dr_gather_grad(const DrDesc* d, const float* grad_vol_cells, float* grad_linear, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

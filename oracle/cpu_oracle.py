@@ -65,10 +65,10 @@ def _f32(a):
 
 
 def _real(a, fp64):
-    """Inputs are always fp32 values; the fp64 library takes them widened to double."""
+    """fp32 library: inputs rounded to fp32.  fp64 library: inputs widened to (or kept as) double."""
     if a is None:
         return None
-    return np.ascontiguousarray(_f32(a).astype(np.float64)) if fp64 else _f32(a)
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)) if fp64 else _f32(a)
 
 
 def _ptr(a, ty=None):
@@ -99,7 +99,7 @@ def _image_to_raw(img):
 def _jitter_raw(jitter):
     if jitter is None:
         return None
-    return np.ascontiguousarray(_image_to_raw(_f32(jitter)[None])[..., 0])
+    return np.ascontiguousarray(_image_to_raw(np.asarray(jitter)[None])[..., 0])
 
 
 def forward(volume, tf, look_from, output_shape, sampling_rate=1.0, max_samples=512, fov=30.0, near=0.1,
@@ -133,7 +133,7 @@ def backward(volume, tf, look_from, grad_image, output_shape, sampling_rate=1.0,
     cam = _real(look_from, fp64).reshape(3)
     d = _desc(vol, tfa, output_shape, sampling_rate, max_samples, fov, near, False, jitter is not None)
     jr = _real(_jitter_raw(jitter), fp64)
-    go = _real(_image_to_raw(_f32(grad_image)), fp64)
+    go = _real(_image_to_raw(np.asarray(grad_image)), fp64)
     gvol = np.zeros(vol.shape, np.float64)
     gtf = np.zeros(tf_r4.shape, np.float64)
     flags = (1 if want_vol else 0) | (2 if want_tf else 0)

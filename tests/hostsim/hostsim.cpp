@@ -13,9 +13,11 @@
 using namespace dr;
 
 namespace {
-struct HostVolSink {
+struct HostVolSink {          // cell-major [cell][8]; same interface as the device CellVolSink, no register accumulation
     float* g;
-    void add(int off, float v) { g[off] += v; }
+    void centre(int cell, const float* v) { for (int q = 0; q < 8; ++q) g[(size_t)cell * 8 + q] += v[q]; }
+    void direct(int cell, const float* v) { centre(cell, v); }
+    void flush() {}
 };
 struct HostTfSink {
     float* g;   // [R][4]
@@ -25,6 +27,7 @@ struct HostTfSink {
         g[4 * lo + 0] += dc.x * w0; g[4 * lo + 1] += dc.y * w0; g[4 * lo + 2] += dc.z * w0; g[4 * lo + 3] += dc.w * w0;
         g[4 * hi + 0] += dc.x * w1; g[4 * hi + 1] += dc.y * w1; g[4 * hi + 2] += dc.z * w1; g[4 * hi + 3] += dc.w * w1;
     }
+    void flush() {}
 };
 Layout make_layout(const DrDesc& d)
 {
@@ -53,11 +56,11 @@ void sim_brick(const DrDesc* d, const float* lin, float* bricked)
     for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
         bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)] = lin[((size_t)y * d->Z + z) * d->X + x];
 }
-void sim_unbrick(const DrDesc* d, const float* bricked, float* lin)
+// cell-major gradient [Y*Z*X][8] -> linear [Y][Z][X]
+void sim_gather(const DrDesc* d, const float* gcell, float* lin)
 {
-    Layout L = make_layout(*d);
     for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
-        lin[((size_t)y * d->Z + z) * d->X + x] = bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)];
+        lin[((size_t)y * d->Z + z) * d->X + x] = gather_voxel(*d, gcell, x, y, z);
 }
 
 // one view; tf is [R][4]; jitter/out_K/out_Tprev are [H][W] image orientation; out is [4][H][W]
@@ -91,14 +94,14 @@ void sim_forward(const DrDesc* d, const float* vol_bricked, const float* tf, con
 
 void sim_backward(const DrDesc* d, const float* vol_bricked, const float* tf, const float* cam3, const float* jitter,
                   const float* grad_out, const float* out, const int* Kin, const float* Tprev,
-                  float* gvol_bricked, float* gtf)
+                  float* gvol_cells, float* gtf)
 {
     Layout L = make_layout(*d);
     VolView<float> vol { vol_bricked };
     const F4* tf4 = (const F4*)tf;
     F3 cam = { cam3[0], cam3[1], cam3[2] };
     const size_t plane = (size_t)d->W * d->H;
-    HostVolSink vs { gvol_bricked };
+    HostVolSink vs { gvol_cells };
     HostTfSink ts { gtf };
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
     for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {

@@ -89,12 +89,12 @@ def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_s
     ne = L.sim_bricked_elems(ctypes.byref(d))
     br = np.zeros(ne, np.float32)
     L.sim_brick(ctypes.byref(d), _p(vol), _p(br))
-    gbr = np.zeros(ne, np.float32); gtf = np.zeros_like(tf_r4)
+    gbr = np.zeros(vol.size * 8, np.float32); gtf = np.zeros_like(tf_r4)
     cam = np.ascontiguousarray(cam, np.float32)
     jit = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
     go = np.ascontiguousarray(grad_image, np.float32)
     L.sim_backward(ctypes.byref(d), _p(br), _p(tf_r4), _p(cam), _p(jit), _p(go), _p(out), _p(K, ctypes.c_int32),
                    _p(Tp), _p(gbr), _p(gtf))
     gv = np.zeros_like(vol)
-    L.sim_unbrick(ctypes.byref(d), _p(gbr), _p(gv))
+    L.sim_gather(ctypes.byref(d), _p(gbr), _p(gv))
     return gv, np.ascontiguousarray(gtf.T)
