@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--layout", default="linear", choices=["linear", "brick8"], help="volume layout read by the march kernels")
     p.add_argument("--no-reg-accum", action="store_true", help="tuning: backward without register accumulation (DR_F_NO_REG_ACCUM)")
     p.add_argument("--cuda-profiler-range", action="store_true",
                    help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
@@ -103,15 +104,15 @@ class ClockSampler:
 # CPU oracle leg (cpu_baseline / --impl reference)
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_sample(cfg, budget_s=20.0):
-    """Times the CPU restatement on a bounded sample of the workload: view 0 with 1/4 of its rays (w/2 x h/2).
-    Returns dict(value Gsamples/s, seconds, samples, cores, sample description)."""
+    """Times the CPU restatement on a bounded sample of the workload: view 0 of the batch at the workload's ray count
+    (volume capped at 256^3).  Returns dict(value Gsamples/s, seconds, samples, cores, sample description)."""
     import numpy as np
     import torch
     from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
     from oracle import cpu_oracle as co
     co.build()
     n = min(cfg["n"], 256)                      # the CPU leg keeps the volume at <= 256^3 (memory/time); per-sample work is size-independent
-    w, h = max(cfg["res"][0] // 2, 32), max(cfg["res"][1] // 2, 32)
+    w, h = min(cfg["res"][0], 1024), min(cfg["res"][1], 1024)
     vol = make_volume(n).numpy()
     if cfg["dtype"] == "f16":
         vol = vol.astype(np.float16).astype(np.float32)
@@ -120,6 +121,7 @@ def cpu_sample(cfg, budget_s=20.0):
     jit = make_jitter(1, h, w)[0].numpy() if cfg["jitter"] else None
     nondiff = cfg["mode"] == "nondiff"
     kw = dict(sampling_rate=cfg["sr"], max_samples=max(cfg["M"], 1), jitter=jit, fast=True)
+    co.set_num_threads(os.cpu_count() or 1, fast=True)      # torchrun exports OMP_NUM_THREADS=1; use every host core
     cores = co.num_threads(fast=True)
     t0 = time.perf_counter()
     img, K, _ = co.forward(vol, tf, cam, (w, h), nondiff=nondiff, return_counts=True, **kw)
@@ -132,7 +134,7 @@ def cpu_sample(cfg, budget_s=20.0):
         co.backward(vol, tf, cam, go, (w, h), want_vol=cfg["mode"] == "full", want_tf=True, **kw)
         t_b = time.perf_counter() - t0
     return dict(value=samples / (t_f + t_b) / 1e9, fwd_value=samples / t_f / 1e9, seconds=t_f + t_b, samples=samples, cores=cores,
-                sample=f"view 0 of the workload on a {n}^3 volume at {w}x{h} rays (1/4 of the view's rays), "
+                sample=f"view 0 of the workload's {max(cfg['views'], 1)} views on a {n}^3 volume at {w}x{h} rays, "
                        f"{'forward' if nondiff else 'forward+backward'}, {samples} active samples, {t_f + t_b:.1f} s")
 
 
@@ -193,7 +195,7 @@ def run_ours(args, cfg):
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     target = torch.rand((views, 4, h, w), generator=g, device=dev)
 
-    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R)
+    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=args.layout)
     vol_lin = vol.reshape(1, n, n, n)
     tf_r4 = tf.t().contiguous()[None]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
@@ -212,7 +214,7 @@ def run_ours(args, cfg):
         if timed: e[1].record()
         out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")
         if timed: e[2].record()
-        n_k = 2                                                                      # brick_kernel + fwd_kernel
+        n_k = 2 if args.layout == "brick8" else 1                                    # (brick_kernel +) fwd_kernel
         if mode != "nondiff":
             go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
             gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf,
@@ -275,7 +277,7 @@ def run_ours(args, cfg):
     # ---- end-to-end through the public autograd API, inputs from pinned host memory every step ---------------------
     e2e = None
     if not args.no_e2e:
-        rc = Raycaster((n, n, n), (w, h), R, sampling_rate=sr, jitter=cfg["jitter"], max_samples=M)
+        rc = Raycaster((n, n, n), (w, h), R, sampling_rate=sr, jitter=cfg["jitter"], max_samples=M, layout=args.layout)
         pin = lambda t: t.detach().cpu().pin_memory()
         h_vol, h_tf, h_cams, h_target = pin(vol), pin(tf), pin(cams), pin(target)
         h_jit = pin(jit) if jit is not None else None
@@ -349,7 +351,7 @@ def run_ours(args, cfg):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "volume": f"{n}^3 {cfg['dtype']}", "image": f"{w}x{h}", "views_per_gpu": views,
-                       "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
+                       "volume_layout": args.layout, "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
                        "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
                        "active_samples_per_step_per_gpu": s},
@@ -364,7 +366,7 @@ def run_ours(args, cfg):
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             cb = cpu_sample(cfg)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
         print(json.dumps(line), flush=True)

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_PKG, "libdiffrender.so")
 # include/diffrender.h
 DR_VERSION = 100
 VOX_F32, VOX_F16 = 0, 1
-F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM = 1, 2, 4, 8, 16, 32, 64, 128
+F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM, F_LAYOUT_BRICK8 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 EXPORTS = ("dr_version", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_forward",
            "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad")

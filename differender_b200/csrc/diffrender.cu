@@ -119,7 +119,7 @@ __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, bool NONDIFF, bool GENERIC>
+template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 __global__ void __launch_bounds__(kThreads)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
@@ -139,7 +139,7 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
     const Layout L = make_layout(d);
     F4 A; int K; float Tp;
-    march_forward<VT, NONDIFF, GENERIC>(d, vol, L, s_tf, cam, r, A, K, Tp);
+    march_forward<VT, LAYOUT, NONDIFF, GENERIC>(d, vol, L, s_tf, cam, r, A, K, Tp);
     if (d.flags & DR_F_OUT_IMAGE) {
         const size_t plane = (size_t)d.W * d.H;
         float* o = out + (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
@@ -207,7 +207,7 @@ template <bool ACCUM> struct RedTfSink {
     __device__ __forceinline__ void flush() { if (ACCUM && cur >= 0) { atomicAdd(g + cur, a0); atomicAdd(g + cur_hi, a1); } }
 };
 
-template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool ACCUM>
+template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool ACCUM>
 __global__ void __launch_bounds__(kThreads)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
@@ -251,7 +251,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     RedTfSink<ACCUM> ts;
     ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
     ts.cur = -1;
-    march_backward<VT, GENERIC, WANT_VOL, WANT_TF>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
+    march_backward<VT, LAYOUT, GENERIC, WANT_VOL, WANT_TF>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
 }
 
 // sums the kTfSlots privatised copies; one thread per (tf, bin, channel); adds into grad_tf in the caller's layout
@@ -285,6 +285,8 @@ int check_desc(const DrDesc* d)
         return fail(DR_EINVAL, "descriptor brick counts inconsistent (use dr_desc_init)");
     if (d->vox_dtype != DR_VOX_F32 && d->vox_dtype != DR_VOX_F16) return fail(DR_EDTYPE, "unsupported voxel dtype");
     if (d->BS > 65535) return fail(DR_EINVAL, "more than 65535 views in one call");
+    if (d->tap_generic && (d->flags & DR_F_LAYOUT_BRICK8))
+        return fail(DR_EINVAL, "the generic tap path (volumes > ~2000 voxels per axis) needs the linear layout");
     return DR_OK;
 }
 
@@ -300,35 +302,40 @@ template <typename K> int set_smem(K kernel, size_t bytes)
     return DR_OK;
 }
 
-template <typename VT, bool NONDIFF, bool GENERIC>
+size_t vol_stride(const DrDesc* d)
+{
+    return (d->flags & DR_F_LAYOUT_BRICK8) ? dr_bricked_elems(d) : (size_t)d->X * d->Y * d->Z;
+}
+
+template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 int launch_fwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, float* out,
                int32_t* K, float* T, cudaStream_t st)
 {
     const size_t smem = (size_t)d->R * sizeof(F4);
-    auto kern = fwd_kernel<VT, NONDIFF, GENERIC>;
+    auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, GENERIC>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
-    kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, out, K, T, dr_bricked_elems(d));
+    kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, out, K, T, vol_stride(d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
 
-template <typename VT, bool GENERIC, bool WV, bool WT, bool ACC>
+template <typename VT, int LAYOUT, bool GENERIC, bool WV, bool WT, bool ACC>
 int launch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                const float* gout, const float* out, const int32_t* K, const float* T, float4* gvol, float4* slots,
                cudaStream_t st)
 {
     const size_t smem = (size_t)d->R * sizeof(F4);
-    auto kern = bwd_kernel<VT, GENERIC, WV, WT, ACC>;
+    auto kern = bwd_kernel<VT, LAYOUT, GENERIC, WV, WT, ACC>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, gout, out, K, T, gvol, slots,
-                                       dr_bricked_elems(d));
+                                       vol_stride(d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
 }
 
-template <typename VT, bool GENERIC>
+template <typename VT, int LAYOUT, bool GENERIC>
 int dispatch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                  const float* gout, const float* out, const int32_t* K, const float* T, float4* gvol, float4* slots,
                  cudaStream_t st)
@@ -336,8 +343,8 @@ int dispatch_bwd(const DrDesc* d, const void* vol, const float* tf, const float*
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
     const bool acc = !(d->flags & DR_F_NO_REG_ACCUM);
 #define DR_BWD(WV, WT)                                                                                              \
-    (acc ? launch_bwd<VT, GENERIC, WV, WT, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st)        \
-         : launch_bwd<VT, GENERIC, WV, WT, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st))
+    (acc ? launch_bwd<VT, LAYOUT, GENERIC, WV, WT, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st) \
+         : launch_bwd<VT, LAYOUT, GENERIC, WV, WT, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st))
     if (wv && wt) return DR_BWD(true, true);
     if (wv) return DR_BWD(true, false);
     return DR_BWD(false, true);
@@ -387,25 +394,26 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "brick_kernel launch");
 }
 
-int dr_forward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+int dr_forward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream)
 {
     if (int rc = check_desc(d)) return rc;
-    if (!vol_bricked || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
+    if (!vol || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
     if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_forward: DR_F_HAS_JITTER set but jitter is null");
     if (!aligned(tf, 16) || !aligned(out_rgba, 16)) return fail(DR_EALIGN, "dr_forward: tf and out_rgba must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool nd = d->flags & DR_F_NONDIFF, gen = d->tap_generic;
+    const bool nd = d->flags & DR_F_NONDIFF, gen = d->tap_generic, brick = d->flags & DR_F_LAYOUT_BRICK8;
+#define DR_FWD1(VT, LAY, ND, GEN) launch_fwd<VT, LAY, ND, GEN>(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)
 #define DR_FWD(VT)                                                                                                  \
-    (nd ? (gen ? launch_fwd<VT, true, true>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)        \
-               : launch_fwd<VT, true, false>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st))      \
-        : (gen ? launch_fwd<VT, false, true>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)       \
-               : launch_fwd<VT, false, false>(d, vol_bricked, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)))
+    (brick ? (nd ? DR_FWD1(VT, LAYOUT_BRICK8, true, false) : DR_FWD1(VT, LAYOUT_BRICK8, false, false))              \
+           : (nd ? (gen ? DR_FWD1(VT, LAYOUT_LINEAR, true, true) : DR_FWD1(VT, LAYOUT_LINEAR, true, false))         \
+                 : (gen ? DR_FWD1(VT, LAYOUT_LINEAR, false, true) : DR_FWD1(VT, LAYOUT_LINEAR, false, false))))
     return d->vox_dtype == DR_VOX_F32 ? DR_FWD(float) : DR_FWD(__half);
+#undef DR_FWD1
 #undef DR_FWD
 }
 
-int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+int dr_backward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                 const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
                 float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
 {
@@ -413,7 +421,7 @@ int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const
     if (d->flags & DR_F_NONDIFF) return fail(DR_EINVAL, "dr_backward: the non-differentiable march has no backward");
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
     if (!wv && !wt) return DR_OK;
-    if (!vol_bricked || !tf || !cam || !grad_out || !out_rgba || !K || !Tprev) return fail(DR_EINVAL, "dr_backward: null pointer");
+    if (!vol || !tf || !cam || !grad_out || !out_rgba || !K || !Tprev) return fail(DR_EINVAL, "dr_backward: null pointer");
     if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_backward: DR_F_HAS_JITTER set but jitter is null");
     if (wv && !grad_vol_cells) return fail(DR_EINVAL, "dr_backward: grad_vol_cells is null");
     if (wv && !aligned(grad_vol_cells, 32)) return fail(DR_EALIGN, "dr_backward: grad_vol_cells must be 32-byte aligned");
@@ -433,12 +441,12 @@ int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const
     float4* slots = static_cast<float4*>(workspace);
     float4* gcells = reinterpret_cast<float4*>(grad_vol_cells);
     int rc;
-    if (d->vox_dtype == DR_VOX_F32)
-        rc = d->tap_generic ? dispatch_bwd<float, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st)
-                            : dispatch_bwd<float, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st);
-    else
-        rc = d->tap_generic ? dispatch_bwd<__half, true>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st)
-                            : dispatch_bwd<__half, false>(d, vol_bricked, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st);
+    const bool brick = d->flags & DR_F_LAYOUT_BRICK8;
+#define DR_BWDL(VT, LAY, GEN) dispatch_bwd<VT, LAY, GEN>(d, vol, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st)
+#define DR_BWDV(VT) (brick ? DR_BWDL(VT, LAYOUT_BRICK8, false) : (d->tap_generic ? DR_BWDL(VT, LAYOUT_LINEAR, true) : DR_BWDL(VT, LAYOUT_LINEAR, false)))
+    rc = d->vox_dtype == DR_VOX_F32 ? DR_BWDV(float) : DR_BWDV(__half);
+#undef DR_BWDV
+#undef DR_BWDL
     if (rc) return rc;
     if (wt) {
         dim3 grid((d->R * 4 + 255) / 256, d->Btf);

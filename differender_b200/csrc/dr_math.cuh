@@ -138,6 +138,10 @@ template <typename VT> struct VolView {
     const VT* p;
     DR_HD float ld(int off) const { return load_vox(p, off); }
 };
+// Volume storage layouts.  LAYOUT_LINEAR reads the caller's contiguous torch tensor [y][z][x] in place (zero copy):
+// x-neighbours are immediate offsets of a row pointer, y/z-neighbours one stride add.  LAYOUT_BRICK8 reads the 8x8x8
+// bricked copy made by brick_kernel (separable offsets offx/offy/offz).
+enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1 };
 
 // ---------------------------------------------------------------------------------------------------------
 // ray set-up: compute_entry_exit :221-259, get_ray_direction :127-151, get_entry_exit_points :28-53
@@ -146,7 +150,7 @@ struct Ray {
     F3 dir;
     float t0;       // entry + 0.5*len/n                                                     :273-275
     float texit;    // exit
-    float inv_nm1;  // unused when n <= 1
+    float inv_nm1;  // fl(1/(n-1)); 0 when n <= 1
     int n;          // sample_step_nums
 };
 
@@ -185,15 +189,16 @@ DR_HD void setup_ray(const DrDesc& d, F3 cam, int i, int j, float jit, Ray& r)
     r.n = n;
     r.texit = tmax;
     r.t0 = (n > 0) ? DR_ADD(entry, DR_DIV(DR_MUL(0.5f, len2), (float)n)) : entry;       // :273-275
-    r.inv_nm1 = 0.0f;
+    r.inv_nm1 = (n > 1) ? DR_DIV(1.0f, (float)(n - 1)) : 0.0f;
 }
 
-// sample position :277-280 (H3: n == 1 -> t = t0)
+// sample position :277-280.  float(s)/float(n-1) is evaluated as s * fl(1/(n-1)) (reciprocal-multiply, what a
+// fast-math compiler emits for the reference's division; the oracle defines it the same way).  H3: n == 1 -> t = t0.
 DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
 {
     float t = r.t0;
     if (r.n > 1) {
-        float q = DR_DIV((float)s, (float)(r.n - 1));
+        float q = DR_MUL((float)s, r.inv_nm1);
         t = mix_e(r.t0, r.texit, DR_SUB(1.0f, q), q);
     }
     F3 p = { DR_FMA(t, r.dir.x, cam.x), DR_FMA(t, r.dir.y, cam.y), DR_FMA(t, r.dir.z, cam.z) };
@@ -210,6 +215,7 @@ DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
 struct Taps {
     Loc cx, cy, cz;               // centre cell
     Loc xp, xm, yp, ym, zp, zm;   // tap cells (only the shifted axis differs from the centre)
+    int cidx;                     // torch-linear index (cy*Z + cz)*X + cx of the centre cell's low corner
     float I;                      // centre intensity
     F3 g;                         // (f(x+d)-f(x-d), ...), un-normalised                     :197-202
 };
@@ -230,8 +236,7 @@ DR_HD float trilinear_full(const VolView<VT>& vol, const Layout& L, Loc ax, Loc 
     return mix_e(lo, hi, oz, az.f);
 }
 
-template <typename VT, bool GENERIC>
-DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Taps& t)
+DR_HD void locate_taps(const DrDesc& d, F3 pos, Taps& t)
 {
     t.cx = locate(pos.x, d.scale[0]);
     t.cy = locate(pos.y, d.scale[1]);
@@ -243,6 +248,118 @@ DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F
     t.ym = locate(DR_SUB(pos.y, dl), d.scale[1]);
     t.zp = locate(DR_ADD(pos.z, dl), d.scale[2]);
     t.zm = locate(DR_SUB(pos.z, dl), d.scale[2]);
+    t.cidx = (t.cy.lo * d.Z + t.cz.lo) * d.X + t.cx.lo;
+}
+
+// full 8-load trilinear tap on the linear layout (generic path: clamps hi = min(lo+1, dim-1), :170-172)
+template <typename VT>
+DR_HD float trilinear_full_linear(const DrDesc& d, const VT* p, Loc ax, Loc ay, Loc az)
+{
+    const int x0 = ax.lo, x1 = imin(ax.lo + 1, d.X - 1);
+    const int r00 = (ay.lo * d.Z + az.lo) * d.X, r10 = (imin(ay.lo + 1, d.Y - 1) * d.Z + az.lo) * d.X;
+    const int r01 = (ay.lo * d.Z + imin(az.lo + 1, d.Z - 1)) * d.X, r11 = (imin(ay.lo + 1, d.Y - 1) * d.Z + imin(az.lo + 1, d.Z - 1)) * d.X;
+    const float ox = DR_SUB(1.0f, ax.f), oy = DR_SUB(1.0f, ay.f), oz = DR_SUB(1.0f, az.f);
+    float a = mix_e(load_vox(p, r00 + x0), load_vox(p, r00 + x1), ox, ax.f);
+    float b = mix_e(load_vox(p, r10 + x0), load_vox(p, r10 + x1), ox, ax.f);
+    const float lo = mix_e(a, b, oy, ay.f);
+    a = mix_e(load_vox(p, r01 + x0), load_vox(p, r01 + x1), ox, ax.f);
+    b = mix_e(load_vox(p, r11 + x0), load_vox(p, r11 + x1), ox, ax.f);
+    const float hi = mix_e(a, b, oy, ay.f);
+    return mix_e(lo, hi, oz, az.f);
+}
+
+// Linear-layout version of eval_taps (same arithmetic, same order; only the addressing differs).  In the corner-reuse
+// path lo <= dim-2 on every axis (scale < dim-1 for dims <= 2000), so hi = lo+1 and the crossed planes lo-1 / lo+2 are
+// in range without clamps: every corner is `row pointer + immediate`.
+template <typename VT, bool GENERIC>
+DR_HD void eval_taps_linear(const DrDesc& d, const VT* vp, F3 pos, Taps& t)
+{
+    locate_taps(d, pos, t);
+    if (GENERIC) {
+        t.I = trilinear_full_linear(d, vp, t.cx, t.cy, t.cz);
+        t.g.x = DR_SUB(trilinear_full_linear(d, vp, t.xp, t.cy, t.cz), trilinear_full_linear(d, vp, t.xm, t.cy, t.cz));
+        t.g.y = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.yp, t.cz), trilinear_full_linear(d, vp, t.cx, t.ym, t.cz));
+        t.g.z = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.cy, t.zp), trilinear_full_linear(d, vp, t.cx, t.cy, t.zm));
+        return;
+    }
+    const int sz = d.X, sy = d.X * d.Z;
+    const VT* r00 = vp + t.cidx;          // row (y0, z0), starting at x0
+    const VT* r10 = r00 + sy;             // (y1, z0)
+    const VT* r01 = r00 + sz;             // (y0, z1)
+    const VT* r11 = r10 + sz;             // (y1, z1)
+    const float v000 = load_vox(r00, 0), v100 = load_vox(r00, 1);
+    const float v010 = load_vox(r10, 0), v110 = load_vox(r10, 1);
+    const float v001 = load_vox(r01, 0), v101 = load_vox(r01, 1);
+    const float v011 = load_vox(r11, 0), v111 = load_vox(r11, 1);
+    const float fx = t.cx.f, fy = t.cy.f, fz = t.cz.f;
+    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
+    const float xm00 = mix_e(v000, v100, ox, fx), xm10 = mix_e(v010, v110, ox, fx);
+    const float xm01 = mix_e(v001, v101, ox, fx), xm11 = mix_e(v011, v111, ox, fx);
+    const float ym0 = mix_e(xm00, xm10, oy, fy), ym1 = mix_e(xm01, xm11, oy, fy);
+    t.I = mix_e(ym0, ym1, oz, fz);
+    float zv[2], yv[2], xv[2];
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {        // z taps: + then -
+        const Loc q = sgn ? t.zm : t.zp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float val;
+        if (q.lo == t.cz.lo) {
+            val = mix_e(ym0, ym1, o, f);
+        } else {
+            const VT* n0 = sgn ? r00 - sz : r01 + sz;      // (y0, z0-1) or (y0, z0+2)
+            const VT* n1 = sgn ? r10 - sz : r11 + sz;      // (y1, ..)
+            const float a = mix_e(load_vox(n0, 0), load_vox(n0, 1), ox, fx);
+            const float b = mix_e(load_vox(n1, 0), load_vox(n1, 1), ox, fx);
+            const float yn = mix_e(a, b, oy, fy);
+            val = sgn ? mix_e(yn, ym0, o, f) : mix_e(ym1, yn, o, f);
+        }
+        zv[sgn] = val;
+    }
+    t.g.z = DR_SUB(zv[0], zv[1]);
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {        // y taps
+        const Loc q = sgn ? t.ym : t.yp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float a, b;
+        if (q.lo == t.cy.lo) {
+            a = mix_e(xm00, xm10, o, f);
+            b = mix_e(xm01, xm11, o, f);
+        } else {
+            const VT* n0 = sgn ? r00 - sy : r10 + sy;      // (y0-1, z0) or (y0+2, z0)
+            const VT* n1 = sgn ? r01 - sy : r11 + sy;      // (.., z1)
+            const float m0 = mix_e(load_vox(n0, 0), load_vox(n0, 1), ox, fx);
+            const float m1 = mix_e(load_vox(n1, 0), load_vox(n1, 1), ox, fx);
+            a = sgn ? mix_e(m0, xm00, o, f) : mix_e(xm10, m0, o, f);
+            b = sgn ? mix_e(m1, xm01, o, f) : mix_e(xm11, m1, o, f);
+        }
+        yv[sgn] = mix_e(a, b, oz, fz);
+    }
+    t.g.y = DR_SUB(yv[0], yv[1]);
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {        // x taps
+        const Loc q = sgn ? t.xm : t.xp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float a00, a10, a01, a11;
+        if (q.lo == t.cx.lo) {
+            a00 = mix_e(v000, v100, o, f); a10 = mix_e(v010, v110, o, f);
+            a01 = mix_e(v001, v101, o, f); a11 = mix_e(v011, v111, o, f);
+        } else if (sgn) {
+            a00 = mix_e(load_vox(r00, -1), v000, o, f); a10 = mix_e(load_vox(r10, -1), v010, o, f);
+            a01 = mix_e(load_vox(r01, -1), v001, o, f); a11 = mix_e(load_vox(r11, -1), v011, o, f);
+        } else {
+            a00 = mix_e(v100, load_vox(r00, 2), o, f); a10 = mix_e(v110, load_vox(r10, 2), o, f);
+            a01 = mix_e(v101, load_vox(r01, 2), o, f); a11 = mix_e(v111, load_vox(r11, 2), o, f);
+        }
+        const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);
+        xv[sgn] = mix_e(lo, hi, oz, fz);
+    }
+    t.g.x = DR_SUB(xv[0], xv[1]);
+}
+
+template <typename VT, bool GENERIC>
+DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Taps& t)
+{
+    locate_taps(d, pos, t);
     if (GENERIC) {
         t.I = trilinear_full(vol, L, t.cx, t.cy, t.cz);
         t.g.x = DR_SUB(trilinear_full(vol, L, t.xp, t.cy, t.cz), trilinear_full(vol, L, t.xm, t.cy, t.cz));
@@ -464,7 +581,7 @@ template <typename Sink, bool GENERIC>
 DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const SampleAdj& a)
 {
     float v[8];
-    const int cc = cell_index(d, t.cx.lo, t.cy.lo, t.cz.lo);
+    const int cc = t.cidx;
     if (GENERIC) {
         tap_weights(a.dI, t.cx, t.cy, t.cz, v); sink.centre(cc, v);
         if (a.has_dg) {
@@ -504,12 +621,14 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
     v[7] = yz11 * X1 + xz11 * ey1 + xy11 * ez1;
     sink.centre(cc, v);
     if (!a.has_dg) return;
-    if (xpc) { tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cell_index(d, t.xp.lo, t.cy.lo, t.cz.lo), v); }
-    if (xmc) { tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cell_index(d, t.xm.lo, t.cy.lo, t.cz.lo), v); }
-    if (ypc) { tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.yp.lo, t.cz.lo), v); }
-    if (ymc) { tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.ym.lo, t.cz.lo), v); }
-    if (zpc) { tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zp.lo), v); }
-    if (zmc) { tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zm.lo), v); }
+    // a crossed tap lives in the face-neighbour cell: +-1 (x), +-X (z), +-X*Z (y) in the torch-linear cell order
+    const int sz = d.X, sy = d.X * d.Z;
+    if (xpc) { tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cc + 1, v); }
+    if (xmc) { tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cc - 1, v); }
+    if (ypc) { tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cc + sy, v); }
+    if (ymc) { tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cc - sy, v); }
+    if (zpc) { tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cc + sz, v); }
+    if (zmc) { tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cc - sz, v); }
 }
 
 // Gather pass: the gradient of voxel (x,y,z) is the sum of every (cell, slot) that aliases it, i.e. all (c, a) per axis
@@ -534,7 +653,14 @@ DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int 
 // State per ray is O(1): A (accumulated premultiplied RGBA), K (active samples), Tprev (transmittance before
 // the last active sample).  Nothing per sample is stored (the reference stores 16*M bytes per ray, :82,102-103).
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, bool NONDIFF, bool GENERIC>
+template <typename VT, int LAYOUT, bool GENERIC>
+DR_HD void eval_sample(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Taps& t)
+{
+    if (LAYOUT == LAYOUT_LINEAR) eval_taps_linear<VT, GENERIC>(d, vol.p, pos, t);
+    else eval_taps<VT, GENERIC>(d, vol, L, pos, t);
+}
+
+template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
                          const Ray& r, F4& A, int& K, float& Tprev)
 {
@@ -546,7 +672,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
         const F3 pos = sample_pos(r, cam, s);
         Taps t;
-        eval_taps<VT, GENERIC>(d, vol, L, pos, t);
+        eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
         TfHit h;
         apply_tf(d, tf, t.I, h, false);
         if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334
@@ -574,7 +700,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
 // TfSink::add(lo, hi, f, dc) accumulates the TF gradient; VolSink::centre/direct(cell, v[8]) the volume gradient;
 // both may hold a partial sum in registers and are flushed at the end of the ray.
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, bool GENERIC, bool WANT_VOL, bool WANT_TF, typename VolSink, typename TfSink>
+template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, typename VolSink, typename TfSink>
 DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
                           const Ray& r, F4 Afinal, int K, float Tprev, F4 g, VolSink& vsink, TfSink& tsink)
 {
@@ -582,7 +708,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
     for (int s = K - 1; s >= 0; --s) {
         const F3 pos = sample_pos(r, cam, s);
         Taps t;
-        eval_taps<VT, GENERIC>(d, vol, L, pos, t);
+        eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
         TfHit h;
         apply_tf(d, tf, t.I, h, WANT_VOL);
         const float o = opacity(d, h.c.w);

@@ -17,7 +17,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (F_HAS_JITTER, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, VOX_F16, VOX_F32)
+from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, VOX_F16, VOX_F32)
 
 __all__ = ["VolumeRaycaster", "RaycastFunction", "Raycaster"]
 
@@ -34,7 +34,10 @@ class VolumeRaycaster:
     """
 
     def __init__(self, volume_resolution, render_resolution, max_samples=512, tf_resolution=128, fov=30.0,
-                 nearfar=(0.1, 100.0)):
+                 nearfar=(0.1, 100.0), layout="linear"):
+        if layout not in ("linear", "brick8"):
+            raise ValueError("layout must be 'linear' (read the torch tensor in place) or 'brick8' (8x8x8-bricked copy)")
+        self.layout = layout
         self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
         self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
         self.max_samples = int(max_samples)
@@ -51,11 +54,19 @@ class VolumeRaycaster:
         return _lib.make_desc(X, Y, Z, w, h, self.tf_resolution, self.max_samples, BS, Bvol, Btf, vox_dtype, flags,
                               sampling_rate, self.fov_deg, self.near)
 
+    def _lflag(self):
+        return F_LAYOUT_BRICK8 if self.layout == "brick8" else 0
+
     def brick(self, vol_lin):
-        """[Bvol, Y, Z, X] contiguous fp32/fp16 CUDA tensor -> bricked tensor [Bvol, elems] of the same dtype."""
+        """[Bvol, Y, Z, X] contiguous fp32/fp16 CUDA tensor -> what the march kernels read: the tensor itself for the
+        default 'linear' layout (zero copy), or a bricked copy [Bvol, elems] of the same dtype for 'brick8'."""
         X, Y, Z = self.volume_resolution
         if tuple(vol_lin.shape[1:]) != (Y, Z, X):
             raise ValueError(f"volume has spatial shape {tuple(vol_lin.shape[1:])}, raycaster was built for (D,H,W)={(Y, Z, X)}")
+        if not vol_lin.is_contiguous():
+            raise ValueError("volume must be contiguous")
+        if self.layout == "linear":
+            return vol_lin
         vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
         d = self.desc(1, 1, 1, vox, 0, 1.0)
         d.Bvol = vol_lin.shape[0]
@@ -69,7 +80,8 @@ class VolumeRaycaster:
         BS = cam.shape[0]
         w, h = self.resolution
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
-        flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0)
+        flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
+                self._lflag()
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
         dev = bricked.device
         out = torch.empty((BS, 4, h, w) if image_layout else (BS, w, h, 4), dtype=torch.float32, device=dev)
@@ -88,7 +100,7 @@ class VolumeRaycaster:
         BS = cam.shape[0]
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
-                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags
+                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags | self._lflag()
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
         dev = bricked.device
         lib = _lib.load()
@@ -179,7 +191,13 @@ class RaycastFunction(torch.autograd.Function):
         ctx.vr, ctx.sampling_rate, ctx.image_layout = vr, sampling_rate, image_layout
         ctx.is_batched, ctx.vol_batched, ctx.tf_batched = is_batched, vol_b, tf.ndim == 3
         ctx.vol_shape, ctx.tf_shape = tuple(volume.shape), tuple(tf.shape)
-        ctx.bricked, ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = bricked, tf_r4, cam, jit, out, K, Tp
+        ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = tf_r4, cam, jit, out, K, Tp
+        if bricked.data_ptr() == volume.data_ptr():
+            ctx.save_for_backward(volume)          # zero-copy layout: let autograd detect in-place edits before backward
+            ctx.bricked = None
+        else:
+            ctx.save_for_backward()
+            ctx.bricked = bricked                  # our own copy (bricked layout, or a cast/contiguous copy)
         return out if is_batched else out[0]
 
     @staticmethod
@@ -192,7 +210,14 @@ class RaycastFunction(torch.autograd.Function):
         with torch.cuda.device(grad_output.device):
             go = grad_output if ctx.is_batched else grad_output[None]
             go = go.float().contiguous()
-            gvol, gtf = vr.march_backward(ctx.bricked, ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, go, ctx.out, ctx.K,
+            bricked = ctx.bricked
+            if bricked is None:
+                (volume,) = ctx.saved_tensors
+                v = volume if ctx.vol_batched else volume[None]
+                if ctx.vol_batched and v.shape[0] > 1 and v.stride(0) == 0:
+                    v = v[:1]
+                bricked = v.permute(0, 2, 3, 1).contiguous()           # the same zero-copy view the forward read
+            gvol, gtf = vr.march_backward(bricked, ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, go, ctx.out, ctx.K,
                                           ctx.Tp, need_vol, need_tf, image_layout=ctx.image_layout)
         gv = gt = None
         if need_vol:
@@ -212,7 +237,7 @@ class Raycaster(torch.nn.Module):
     """Same constructor and methods as the reference's `Raycaster` (:478-574)."""
 
     def __init__(self, volume_shape, output_shape, tf_shape, sampling_rate=1.0, jitter=True, max_samples=512, fov=30.0,
-                 near=0.1, far=100.0, ti_kwargs={}):
+                 near=0.1, far=100.0, ti_kwargs={}, layout="linear"):
         super().__init__()
         self.volume_shape = (volume_shape[2], volume_shape[0], volume_shape[1])       # torch (D,H,W) -> Taichi (W,D,H) :481
         self.output_shape = output_shape
@@ -222,7 +247,7 @@ class Raycaster(torch.nn.Module):
         self.ti_kwargs = dict(ti_kwargs)      # accepted for signature compatibility; there is no Taichi runtime to configure
         _lib.load()                           # fail loudly at construction if the CUDA library is missing
         self.vr = VolumeRaycaster(self.volume_shape, output_shape, max_samples=max_samples, tf_resolution=tf_shape,
-                                  fov=fov, nearfar=(near, far))
+                                  fov=fov, nearfar=(near, far), layout=layout)
 
     def raycast_nondiff(self, volume, tf, look_from, sampling_rate=None):
         """Non-differentiable render (:490-523): alpha-skip, no shading clamp, output clamped to 1, jitter off,

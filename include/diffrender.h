@@ -53,6 +53,7 @@ extern "C" {
 #define DR_F_OUT_IMAGE 16u     /* out_rgba / grad_out are [BS][4][H][W] flipped (else raw [BS][W][H][4])   */
 #define DR_F_TF_4R 32u         /* tf / grad_tf are [Btf][4][R] (torch layout; else the reference's [Btf][R][4], :567,571) */
 #define DR_F_GENERIC_TAPS 64u  /* force the 7x8-load tap path (always used when a normal tap can skip a whole cell) */
+#define DR_F_LAYOUT_BRICK8 256u /* `vol` is the 8x8x8-bricked copy made by dr_brick_volume; clear: `vol` is the caller's linear [Bvol][Y][Z][X] tensor, read in place */
 #define DR_F_NO_REG_ACCUM 128u  /* tuning/debug: backward issues its reductions per sample instead of keeping the current cell / TF bin in registers */
 
 /* Plain-data description of one call.  Fill it with dr_desc_init(); do not hand-edit derived fields. */
@@ -99,7 +100,8 @@ size_t dr_bricked_elems(const DrDesc* d);
 /*
  * Re-lays Bvol linear volumes [Bvol][Y][Z][X] (fp32 or fp16 per vox_dtype) into 8x8x8 bricks
  * [Bvol][nbz][nby][nbx][8][8][8], x fastest, same dtype.  Replaces set_volume / field.from_torch (:118-119),
- * which copied into Taichi's 4x4x4-bricked SNode (:97-101).  Needed once per DISTINCT volume, not per view.
+ * which copied into Taichi's 4x4x4-bricked SNode (:97-101).  Needed once per DISTINCT volume, not per view, and only
+ * for calls that set DR_F_LAYOUT_BRICK8 (the default layout reads the linear tensor in place).
  */
 int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, void* stream);
 
@@ -108,13 +110,14 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
  * (:374-382), compute_entry_exit (:221-259), raycast (:261-306) or raycast_nondiff (:308-351), and
  * get_final_image (:363-372) or get_final_image_nondiff (:353-361), i.e. the body of
  * RaycastFunction.forward (:418-438) and Raycaster.raycast_nondiff (:502-523).
- *   vol_bricked [Bvol] bricked volumes     tf [Btf][R][4] or [Btf][4][R]     cam [BS][3]
+ *   vol [Bvol] volumes: linear [Y][Z][X] (default, zero copy) or bricked (DR_F_LAYOUT_BRICK8), fp32/fp16
+ *   tf [Btf][R][4] or [Btf][4][R]     cam [BS][3]
  *   jitter [BS][H][W] uniform [0,1) or NULL (replaces ti.random, :255)
  *   out_rgba  see layout note            out_K [BS][H][W] active samples per ray (valid_sample_step_count-1,
  *   :303,367) or NULL      out_Tprev [BS][H][W] transmittance before the last active sample, or NULL
  *   (out_K and out_Tprev are what the backward needs instead of the O(W*H*M) render_tape, :82,102-103).
  */
-int dr_forward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+int dr_forward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream);
 
 /* Bytes of scratch dr_backward needs for this descriptor (privatised TF-gradient copies). */
@@ -133,7 +136,7 @@ size_t dr_grad_cells_elems(const DrDesc* d);
  *   grad_tf [Btf] in the tf layout, fp32, ACCUMULATED into (caller zeroes); may be NULL without NEEDS_TF_GRAD
  *   workspace: dr_workspace_bytes(d) bytes, 16-byte aligned, contents undefined on entry and exit.
  */
-int dr_backward(const DrDesc* d, const void* vol_bricked, const float* tf, const float* cam, const float* jitter,
+int dr_backward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                 const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
                 float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -24,6 +24,7 @@
  * the ill-conditioned part:
  *     mix(a,b,t)      := fma(a, 1-t, b*t)         pos := fma(t, dir, cam)
  *     0.5*p + 0.5     := fma(0.5, p, 0.5)         A_s := fma(1 - A_{s-1}.w, C, A_{s-1})
+ *     float(s)/float(n-1) := s * fl(1/(n-1))      (reciprocal-multiply, what fast-math emits for a division)
  * Everything else is one IEEE-rounded operation per source operator, in source order
  * (-ffp-contract=off).  With -DORACLE_FP64 the same code runs in double (used to pin the adjoint
  * against torch.autograd in float64).
@@ -279,7 +280,7 @@ static inline v3 sample_pos(const Ray *r, int s)
     real ray_len = r->exit_ - r->entry;                              /* :272 */
     real t0 = r->entry + RC(0.5) * ray_len / (real)r->n;               /* :273-275 */
     real t;
-    if (r->n > 1) t = mixf(t0, r->exit_, (real)s / (real)(r->n - 1));   /* :277-280 */
+    if (r->n > 1) t = mixf(t0, r->exit_, (real)s * (RC(1.0) / (real)(r->n - 1)));   /* :277-280, see header */
     else t = t0;
     v3 p = { R_FMA(t, r->dir.x, r->cam.x), R_FMA(t, r->dir.y, r->cam.y), R_FMA(t, r->dir.z, r->cam.z) };
     return p;

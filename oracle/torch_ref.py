@@ -175,7 +175,7 @@ def render(volume, tf, look_from, output_shape, sampling_rate=1.0, max_samples=5
         if not bool(active.any()):
             break
         idx = active.nonzero(as_tuple=True)
-        ratio = torch.where(n[idx] > 1, float(s) / (nf[idx] - 1.0).clamp(min=1.0), torch.zeros_like(nf[idx]))  # H3
+        ratio = torch.where(n[idx] > 1, float(s) * (1.0 / (nf[idx] - 1.0).clamp(min=1.0)), torch.zeros_like(nf[idx]))  # H3; s * fl(1/(n-1))
         t = _mix(t0[idx], exit_[idx], ratio)                       # :277-280
         pos = cam + t.unsqueeze(-1) * vd[idx]
         C, alpha = _shade(c, volflat, tf_r4, cam, vd[idx], pos, nondiff)

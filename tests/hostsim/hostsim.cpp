@@ -63,12 +63,12 @@ void sim_gather(const DrDesc* d, const float* gcell, float* lin)
         lin[((size_t)y * d->Z + z) * d->X + x] = gather_voxel(*d, gcell, x, y, z);
 }
 
-// one view; tf is [R][4]; jitter/out_K/out_Tprev are [H][W] image orientation; out is [4][H][W]
-void sim_forward(const DrDesc* d, const float* vol_bricked, const float* tf, const float* cam3, const float* jitter,
+// one view; vol_data is linear [Y][Z][X] or bricked (DR_F_LAYOUT_BRICK8); tf is [R][4]; jitter/out_K/out_Tprev are [H][W] image orientation; out is [4][H][W]
+void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
                  float* out, int* out_K, float* out_Tprev, int* out_n)
 {
     Layout L = make_layout(*d);
-    VolView<float> vol { vol_bricked };
+    VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
     const F4* tf4 = (const F4*)tf;
     F3 cam = { cam3[0], cam3[1], cam3[2] };
     const size_t plane = (size_t)d->W * d->H;
@@ -78,12 +78,15 @@ void sim_forward(const DrDesc* d, const float* vol_bricked, const float* tf, con
         setup_ray(*d, cam, i, j, jitter ? jitter[pix] : 0.0f, r);
         F4 A; int K; float Tp;
         const bool nd = d->flags & DR_F_NONDIFF;
-        if (d->tap_generic) {
-            if (nd) march_forward<float, true, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
-            else march_forward<float, false, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
+        if (d->flags & DR_F_LAYOUT_BRICK8) {
+            if (nd) march_forward<float, LAYOUT_BRICK8, true, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            else march_forward<float, LAYOUT_BRICK8, false, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+        } else if (d->tap_generic) {
+            if (nd) march_forward<float, LAYOUT_LINEAR, true, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            else march_forward<float, LAYOUT_LINEAR, false, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
         } else {
-            if (nd) march_forward<float, true, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
-            else march_forward<float, false, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            if (nd) march_forward<float, LAYOUT_LINEAR, true, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            else march_forward<float, LAYOUT_LINEAR, false, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
         }
         out[pix] = A.x; out[plane + pix] = A.y; out[2 * plane + pix] = A.z; out[3 * plane + pix] = A.w;
         if (out_K) out_K[pix] = K;
@@ -92,12 +95,12 @@ void sim_forward(const DrDesc* d, const float* vol_bricked, const float* tf, con
     }
 }
 
-void sim_backward(const DrDesc* d, const float* vol_bricked, const float* tf, const float* cam3, const float* jitter,
+void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
                   const float* grad_out, const float* out, const int* Kin, const float* Tprev,
                   float* gvol_cells, float* gtf)
 {
     Layout L = make_layout(*d);
-    VolView<float> vol { vol_bricked };
+    VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
     const F4* tf4 = (const F4*)tf;
     F3 cam = { cam3[0], cam3[1], cam3[2] };
     const size_t plane = (size_t)d->W * d->H;
@@ -112,12 +115,12 @@ void sim_backward(const DrDesc* d, const float* vol_bricked, const float* tf, co
         F4 g = { grad_out[pix], grad_out[plane + pix], grad_out[2 * plane + pix], grad_out[3 * plane + pix] };
         const int K = Kin[pix];
         const float Tp = Tprev[pix];
-#define CALL(GEN, WV, WT) march_backward<float, GEN, WV, WT>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts)
-        if (d->tap_generic) {
-            if (wv && wt) CALL(true, true, true); else if (wv) CALL(true, true, false); else if (wt) CALL(true, false, true);
-        } else {
-            if (wv && wt) CALL(false, true, true); else if (wv) CALL(false, true, false); else if (wt) CALL(false, false, true);
-        }
+#define CALL(LAY, GEN, WV, WT) march_backward<float, LAY, GEN, WV, WT>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts)
+#define CALL3(LAY, GEN) do { if (wv && wt) CALL(LAY, GEN, true, true); else if (wv) CALL(LAY, GEN, true, false); else if (wt) CALL(LAY, GEN, false, true); } while (0)
+        if (d->flags & DR_F_LAYOUT_BRICK8) CALL3(LAYOUT_BRICK8, false);
+        else if (d->tap_generic) CALL3(LAYOUT_LINEAR, true);
+        else CALL3(LAYOUT_LINEAR, false);
+#undef CALL3
 #undef CALL
     }
 }

@@ -32,7 +32,7 @@ def _props(vr, bricked, tf_r4, cams, jit, M):
     assert out[:, 3].max().item() <= 1.0 + 1e-5
     term = out[:, 3] >= 0.99
     assert term.any() and (Tp[term] > 0.01 - 1e-6).all()                         # a terminated ray was still active before its last sample
-    assert (out[:, :, K == 0] == 0).all()                                        # rays without an active sample are empty
+    assert (out.permute(1, 0, 2, 3)[:, K == 0] == 0).all()                                       # rays without an active sample are empty
     one, K1, _ = vr.march(bricked, tf_r4, cams[:1].contiguous(), 1.0, jit[:1].contiguous())
     assert torch.equal(one[0], out[0]) and torch.equal(K1[0], K[0])              # batching does not change a view
     return out, K, Tp

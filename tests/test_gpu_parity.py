@@ -9,14 +9,15 @@ from helpers import GRAD_TOL, RGBA_TOL, case_inputs, oracle_backward_views, orac
 pytestmark = pytest.mark.gpu
 
 
-def _vr(vol, out_shape, R, M):
+def _vr(vol, out_shape, R, M, layout="linear"):
     from differender_b200 import VolumeRaycaster
     D, H, W = vol.shape[-3:]
-    return VolumeRaycaster((W, D, H), out_shape, max_samples=M, tf_resolution=R)
+    return VolumeRaycaster((W, D, H), out_shape, max_samples=M, tf_resolution=R, layout=layout)
 
 
-def _cuda_forward(vol, tf, cams, out_shape, jit, M=2048, sr=1.0, nondiff=False, dtype=torch.float32, image_layout=True):
-    vr = _vr(vol, out_shape, tf.shape[-1], M)
+def _cuda_forward(vol, tf, cams, out_shape, jit, M=2048, sr=1.0, nondiff=False, dtype=torch.float32, image_layout=True,
+                  layout="linear"):
+    vr = _vr(vol, out_shape, tf.shape[-1], M, layout)
     dev = "cuda:0"
     bricked = vr.brick(vol.to(dev, dtype).reshape(1, *vol.shape[-3:]).contiguous())
     tf_r4 = tf.to(dev).t().contiguous()[None]
@@ -85,7 +86,7 @@ def test_fp16_volume_matches_oracle_on_rounded_values():
     vol16 = vol.half()
     ref, Kr, _ = oracle_forward_views(vol16.float(), tf, cams, (64, 48), jit, max_samples=2048)
     vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol16, tf, cams, (64, 48), jit, dtype=torch.float16)
-    assert bricked.dtype == torch.float16
+    assert bricked.dtype == torch.float16 and bricked.data_ptr() != 0
     same = K.cpu().numpy() == Kr
     assert (~same).mean() <= 1e-4
     assert np.moveaxis(np.abs(out.cpu().numpy() - ref), 1, 0)[:, same].max() <= RGBA_TOL
@@ -118,6 +119,21 @@ def test_generic_tap_path_equals_corner_reuse_path():
     vr.desc = orig
     gv, gt = vr.march_backward(*a)
     assert rel_l2(gv2.cpu().numpy(), gv.cpu().numpy()) <= 1e-4 and rel_l2(gt2.cpu().numpy(), gt.cpu().numpy()) <= 1e-4
+
+
+def test_bricked_layout_is_bit_identical_to_linear_layout():
+    vol, tf, cams, jit = case_inputs((37, 29, 45), (56, 40), 64, seed=13, views=2)
+    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (56, 40), jit)
+    vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (56, 40), jit, layout="brick8")
+    assert vlin.shape == (1, 37, 29, 45) and bricked.shape == (1, 5 * 4 * 6 * 512)       # zero-copy view vs bricked copy
+    assert torch.equal(out, out_b) and torch.equal(K, K_b) and torch.equal(Tp, Tp_b)     # same arithmetic, same order
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).cuda()
+    c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
+    gv, gt = vr.march_backward(vlin, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
+    gv_b, gt_b = vb.march_backward(bricked, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
+    assert rel_l2(gv_b.cpu().numpy(), gv.cpu().numpy()) <= 1e-5 and rel_l2(gt_b.cpu().numpy(), gt.cpu().numpy()) <= 1e-5
+    ref, Kr, _ = oracle_forward_views(vol, tf, cams, (56, 40), jit, max_samples=2048)
+    assert np.array_equal(K_b.cpu().numpy(), Kr) and np.abs(out_b.cpu().numpy() - ref).max() <= RGBA_TOL
 
 
 def test_raw_layout_equals_image_layout():

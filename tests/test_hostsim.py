@@ -14,18 +14,18 @@ from oracle import cpu_oracle as co
     ((37, 29, 45), (33, 29), 128, 1.0, False),
     ((24, 24, 24), (32, 32), 32, 0.7, True),
 ])
-@pytest.mark.parametrize("generic", [False, True])
-def test_device_math_matches_oracle(shape, out_shape, R, sr, jitter, generic):
+@pytest.mark.parametrize("generic,brick", [(False, False), (True, False), (False, True)])
+def test_device_math_matches_oracle(shape, out_shape, R, sr, jitter, generic, brick):
     vol, tf, cams, jit = case_inputs(shape, out_shape, R, seed=R, jitter=jitter)
     J = None if jit is None else jit[0].numpy()
     img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, jitter=J, return_counts=True)
-    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, jitter=J, generic=generic)
+    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, jitter=J, generic=generic, brick=brick)
     assert np.array_equal(n, n2) and np.array_equal(K, K2)
     assert np.array_equal(img[3], out[3])                      # alpha path: bit-identical by construction
     assert np.abs(img - out).max() <= 1e-6
     go = np.random.default_rng(5).normal(size=img.shape).astype(np.float32)
     gv, gt = co.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, jitter=J)
-    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, jitter=J, generic=generic)
+    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, jitter=J, generic=generic, brick=brick)
     assert rel_l2(gv2, gv) <= 1e-4 and rel_l2(gt2, gt) <= 1e-4
 
 
