@@ -51,7 +51,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--layout", default="linear", choices=["linear", "brick8"], help="volume layout read by the march kernels")
+    p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8"], help="volume layout read by the march kernels")
     p.add_argument("--no-reg-accum", action="store_true", help="tuning: backward without register accumulation (DR_F_NO_REG_ACCUM)")
     p.add_argument("--cuda-profiler-range", action="store_true",
                    help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
@@ -214,7 +214,7 @@ def run_ours(args, cfg):
         if timed: e[1].record()
         out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")
         if timed: e[2].record()
-        n_k = 2 if args.layout == "brick8" else 1                                    # (brick_kernel +) fwd_kernel
+        n_k = 2 if bricked.ndim == 2 else 1                                          # (brick_kernel +) fwd_kernel
         if mode != "nondiff":
             go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
             gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf,
@@ -351,7 +351,7 @@ def run_ours(args, cfg):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "volume": f"{n}^3 {cfg['dtype']}", "image": f"{w}x{h}", "views_per_gpu": views,
-                       "volume_layout": args.layout, "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
+                       "volume_layout": vr.resolve_layout(vol_lin), "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
                        "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
                        "active_samples_per_step_per_gpu": s},

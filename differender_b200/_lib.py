@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdiffrender.so")
+# DIFFRENDER_LIB selects another build of the same library (tuning experiments); default: the in-tree build
+LIB_PATH = os.environ.get("DIFFRENDER_LIB") or os.path.join(_PKG, "libdiffrender.so")
 
 # include/diffrender.h
 DR_VERSION = 100

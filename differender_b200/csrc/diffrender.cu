@@ -24,6 +24,14 @@ using namespace dr;
 namespace {
 
 constexpr int kTileW = 16, kTileH = 8, kThreads = 128;
+// minimum resident CTAs per SM the compiler must allow (caps registers); tuned on B200, see DESIGN.md
+// (B200, C3: forward 6 CTAs/SM = 80 regs, no spills: +2 %; backward 5 CTAs/SM = 96 regs spills and loses 5 %, so 4.)
+#ifndef DR_FWD_MIN_BLOCKS
+#define DR_FWD_MIN_BLOCKS 6
+#endif
+#ifndef DR_BWD_MIN_BLOCKS
+#define DR_BWD_MIN_BLOCKS 4
+#endif
 constexpr int kTfSlots = 1024;          // privatised TF-gradient copies (power of two)
 
 thread_local char g_err[256] = "";
@@ -120,7 +128,7 @@ __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
            float* __restrict__ outT, size_t vol_elems)
@@ -208,7 +216,7 @@ template <bool ACCUM> struct RedTfSink {
 };
 
 template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool ACCUM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, DR_BWD_MIN_BLOCKS)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,

@@ -112,10 +112,20 @@ struct Layout {
     int sY, sZ;           // element strides between bricks along y and z: nbx*512, nbx*nby*512
     int mx, my, mz;       // dim - 1 (index clamps)
 };
-DR_HD int offx(int x) { return ((x >> 3) << 9) | (x & 7); }
-DR_HD int offy(int y, int sY) { return (y >> 3) * sY + ((y & 7) << 3); }
-DR_HD int offz(int z, int sZ) { return (z >> 3) * sZ + ((z & 7) << 6); }
+// Offsets are UNSIGNED so that `pointer + offset` is one IMAD.WIDE.U32 (a signed int needs LEA + LEA.HI.X.SX32).
+typedef unsigned int uoff;
+DR_HD uoff offx(int x) { return (uoff)(((x >> 3) << 9) | (x & 7)); }
+DR_HD uoff offy(int y, int sY) { return (uoff)((y >> 3) * sY + ((y & 7) << 3)); }
+DR_HD uoff offz(int z, int sZ) { return (uoff)((z >> 3) * sZ + ((z & 7) << 6)); }
 
+DR_HD float load_vox(const float* p, uoff off)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p + off);
+#else
+    return p[off];
+#endif
+}
 DR_HD float load_vox(const float* p, int off)
 {
 #if defined(__CUDA_ARCH__)
@@ -125,6 +135,14 @@ DR_HD float load_vox(const float* p, int off)
 #endif
 }
 #if defined(__CUDACC__)
+DR_HD float load_vox(const __half* p, uoff off)
+{
+#if defined(__CUDA_ARCH__)
+    return __half2float(__ldg(p + off));
+#else
+    return __half2float(p[off]);
+#endif
+}
 DR_HD float load_vox(const __half* p, int off)
 {
 #if defined(__CUDA_ARCH__)
@@ -136,7 +154,7 @@ DR_HD float load_vox(const __half* p, int off)
 #endif
 template <typename VT> struct VolView {
     const VT* p;
-    DR_HD float ld(int off) const { return load_vox(p, off); }
+    DR_HD float ld(uoff off) const { return load_vox(p, off); }
 };
 // Volume storage layouts.  LAYOUT_LINEAR reads the caller's contiguous torch tensor [y][z][x] in place (zero copy):
 // x-neighbours are immediate offsets of a row pointer, y/z-neighbours one stride add.  LAYOUT_BRICK8 reads the 8x8x8
@@ -223,9 +241,9 @@ struct Taps {
 template <typename VT>
 DR_HD float trilinear_full(const VolView<VT>& vol, const Layout& L, Loc ax, Loc ay, Loc az)
 {
-    int x0 = offx(ax.lo), x1 = offx(imin(ax.lo + 1, L.mx));
-    int y0 = offy(ay.lo, L.sY), y1 = offy(imin(ay.lo + 1, L.my), L.sY);
-    int z0 = offz(az.lo, L.sZ), z1 = offz(imin(az.lo + 1, L.mz), L.sZ);
+    uoff x0 = offx(ax.lo), x1 = offx(imin(ax.lo + 1, L.mx));
+    uoff y0 = offy(ay.lo, L.sY), y1 = offy(imin(ay.lo + 1, L.my), L.sY);
+    uoff z0 = offz(az.lo, L.sZ), z1 = offz(imin(az.lo + 1, L.mz), L.sZ);
     float ox = DR_SUB(1.0f, ax.f), oy = DR_SUB(1.0f, ay.f), oz = DR_SUB(1.0f, az.f);
     float a = mix_e(vol.ld(x0 + y0 + z0), vol.ld(x1 + y0 + z0), ox, ax.f);
     float b = mix_e(vol.ld(x0 + y1 + z0), vol.ld(x1 + y1 + z0), ox, ax.f);
@@ -282,11 +300,11 @@ DR_HD void eval_taps_linear(const DrDesc& d, const VT* vp, F3 pos, Taps& t)
         t.g.z = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.cy, t.zp), trilinear_full_linear(d, vp, t.cx, t.cy, t.zm));
         return;
     }
-    const int sz = d.X, sy = d.X * d.Z;
-    const VT* r00 = vp + t.cidx;          // row (y0, z0), starting at x0
-    const VT* r10 = r00 + sy;             // (y1, z0)
-    const VT* r01 = r00 + sz;             // (y0, z1)
-    const VT* r11 = r10 + sz;             // (y1, z1)
+    const uoff sz = (uoff)d.X, sy = (uoff)(d.X * d.Z), i00 = (uoff)t.cidx;
+    const VT* r00 = vp + i00;                  // row (y0, z0), starting at x0       (one IMAD.WIDE.U32 each)
+    const VT* r10 = vp + (i00 + sy);           // (y1, z0)
+    const VT* r01 = vp + (i00 + sz);           // (y0, z1)
+    const VT* r11 = vp + (i00 + sy + sz);      // (y1, z1)
     const float v000 = load_vox(r00, 0), v100 = load_vox(r00, 1);
     const float v010 = load_vox(r10, 0), v110 = load_vox(r10, 1);
     const float v001 = load_vox(r01, 0), v101 = load_vox(r01, 1);
@@ -306,8 +324,9 @@ DR_HD void eval_taps_linear(const DrDesc& d, const VT* vp, F3 pos, Taps& t)
         if (q.lo == t.cz.lo) {
             val = mix_e(ym0, ym1, o, f);
         } else {
-            const VT* n0 = sgn ? r00 - sz : r01 + sz;      // (y0, z0-1) or (y0, z0+2)
-            const VT* n1 = sgn ? r10 - sz : r11 + sz;      // (y1, ..)
+            const uoff zo = sgn ? i00 - sz : i00 + 2u * sz;  // plane z0-1 or z0+2
+            const VT* n0 = vp + zo;                        // (y0, .)
+            const VT* n1 = vp + (zo + sy);                 // (y1, .)
             const float a = mix_e(load_vox(n0, 0), load_vox(n0, 1), ox, fx);
             const float b = mix_e(load_vox(n1, 0), load_vox(n1, 1), ox, fx);
             const float yn = mix_e(a, b, oy, fy);
@@ -325,8 +344,9 @@ DR_HD void eval_taps_linear(const DrDesc& d, const VT* vp, F3 pos, Taps& t)
             a = mix_e(xm00, xm10, o, f);
             b = mix_e(xm01, xm11, o, f);
         } else {
-            const VT* n0 = sgn ? r00 - sy : r10 + sy;      // (y0-1, z0) or (y0+2, z0)
-            const VT* n1 = sgn ? r01 - sy : r11 + sy;      // (.., z1)
+            const uoff yo = sgn ? i00 - sy : i00 + 2u * sy;  // plane y0-1 or y0+2
+            const VT* n0 = vp + yo;                        // (., z0)
+            const VT* n1 = vp + (yo + sz);                 // (., z1)
             const float m0 = mix_e(load_vox(n0, 0), load_vox(n0, 1), ox, fx);
             const float m1 = mix_e(load_vox(n1, 0), load_vox(n1, 1), ox, fx);
             a = sgn ? mix_e(m0, xm00, o, f) : mix_e(xm10, m0, o, f);
@@ -367,9 +387,9 @@ DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F
         t.g.z = DR_SUB(trilinear_full(vol, L, t.cx, t.cy, t.zp), trilinear_full(vol, L, t.cx, t.cy, t.zm));
         return;
     }
-    const int x0 = offx(t.cx.lo), x1 = offx(imin(t.cx.lo + 1, L.mx));
-    const int y0 = offy(t.cy.lo, L.sY), y1 = offy(imin(t.cy.lo + 1, L.my), L.sY);
-    const int z0 = offz(t.cz.lo, L.sZ), z1 = offz(imin(t.cz.lo + 1, L.mz), L.sZ);
+    const uoff x0 = offx(t.cx.lo), x1 = offx(imin(t.cx.lo + 1, L.mx));
+    const uoff y0 = offy(t.cy.lo, L.sY), y1 = offy(imin(t.cy.lo + 1, L.my), L.sY);
+    const uoff z0 = offz(t.cz.lo, L.sZ), z1 = offz(imin(t.cz.lo + 1, L.mz), L.sZ);
     const float v000 = vol.ld(x0 + y0 + z0), v100 = vol.ld(x1 + y0 + z0);
     const float v010 = vol.ld(x0 + y1 + z0), v110 = vol.ld(x1 + y1 + z0);
     const float v001 = vol.ld(x0 + y0 + z1), v101 = vol.ld(x1 + y0 + z1);
@@ -393,7 +413,7 @@ DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F
             val = mix_e(ym0, ym1, o, f);
         } else {
             // new plane: above the centre's high plane (+) or below its low plane (-)
-            const int zn = offz(sgn ? q.lo : imin(q.lo + 1, L.mz), L.sZ);
+            const uoff zn = offz(sgn ? q.lo : imin(q.lo + 1, L.mz), L.sZ);
             const float a = mix_e(vol.ld(x0 + y0 + zn), vol.ld(x1 + y0 + zn), ox, fx);
             const float b = mix_e(vol.ld(x0 + y1 + zn), vol.ld(x1 + y1 + zn), ox, fx);
             const float yn = mix_e(a, b, oy, fy);
@@ -414,7 +434,7 @@ DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F
             a = mix_e(xm00, xm10, o, f);
             b = mix_e(xm01, xm11, o, f);
         } else {
-            const int yn = offy(sgn ? q.lo : imin(q.lo + 1, L.my), L.sY);
+            const uoff yn = offy(sgn ? q.lo : imin(q.lo + 1, L.my), L.sY);
             const float n0 = mix_e(vol.ld(x0 + yn + z0), vol.ld(x1 + yn + z0), ox, fx);
             const float n1 = mix_e(vol.ld(x0 + yn + z1), vol.ld(x1 + yn + z1), ox, fx);
             a = sgn ? mix_e(n0, xm00, o, f) : mix_e(xm10, n0, o, f);
@@ -435,7 +455,7 @@ DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F
             a00 = mix_e(v000, v100, o, f); a10 = mix_e(v010, v110, o, f);
             a01 = mix_e(v001, v101, o, f); a11 = mix_e(v011, v111, o, f);
         } else {
-            const int xn = offx(sgn ? q.lo : imin(q.lo + 1, L.mx));
+            const uoff xn = offx(sgn ? q.lo : imin(q.lo + 1, L.mx));
             const float n00 = vol.ld(xn + y0 + z0), n10 = vol.ld(xn + y1 + z0);
             const float n01 = vol.ld(xn + y0 + z1), n11 = vol.ld(xn + y1 + z1);
             if (sgn) {
@@ -660,6 +680,16 @@ DR_HD void eval_sample(const DrDesc& d, const VolView<VT>& vol, const Layout& L,
     else eval_taps<VT, GENERIC>(d, vol, L, pos, t);
 }
 
+// centre tap only (same operations as the centre of eval_taps*): lets the non-differentiable march test the TF alpha
+// before paying for the six normal taps (:330-335)
+template <typename VT, int LAYOUT>
+DR_HD float eval_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos)
+{
+    const Loc cx = locate(pos.x, d.scale[0]), cy = locate(pos.y, d.scale[1]), cz = locate(pos.z, d.scale[2]);
+    if (LAYOUT == LAYOUT_LINEAR) return trilinear_full_linear(d, vol.p, cx, cy, cz);
+    return trilinear_full(vol, L, cx, cy, cz);
+}
+
 template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
                          const Ray& r, F4& A, int& K, float& Tprev)
@@ -672,10 +702,15 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
         const F3 pos = sample_pos(r, cam, s);
         Taps t;
-        eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
         TfHit h;
-        apply_tf(d, tf, t.I, h, false);
-        if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334
+        if (NONDIFF) {
+            apply_tf(d, tf, eval_centre<VT, LAYOUT>(d, vol, L, pos), h, false);
+            if (!(h.c.w > d.alpha_skip)) continue;             // :334: skipped samples never evaluate the normal
+            eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
+        } else {
+            eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
+            apply_tf(d, tf, t.I, h, false);
+        }
         const float o = opacity(d, h.c.w);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);

@@ -34,9 +34,9 @@ class VolumeRaycaster:
     """
 
     def __init__(self, volume_resolution, render_resolution, max_samples=512, tf_resolution=128, fov=30.0,
-                 nearfar=(0.1, 100.0), layout="linear"):
-        if layout not in ("linear", "brick8"):
-            raise ValueError("layout must be 'linear' (read the torch tensor in place) or 'brick8' (8x8x8-bricked copy)")
+                 nearfar=(0.1, 100.0), layout="auto"):
+        if layout not in ("auto", "linear", "brick8"):
+            raise ValueError("layout must be 'auto', 'linear' (read the torch tensor in place) or 'brick8' (8x8x8-bricked copy)")
         self.layout = layout
         self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
         self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
@@ -54,8 +54,22 @@ class VolumeRaycaster:
         return _lib.make_desc(X, Y, Z, w, h, self.tf_resolution, self.max_samples, BS, Bvol, Btf, vox_dtype, flags,
                               sampling_rate, self.fov_deg, self.near)
 
-    def _lflag(self):
-        return F_LAYOUT_BRICK8 if self.layout == "brick8" else 0
+    # Measured on B200: the linear layout wins while the volume is small relative to the rays' footprint
+    # (C3 256^3: forward 77 vs 54 Gsamples/s) and ties at 512^3; the bricked copy wins once the volume is far larger than
+    # L2 and a warp's corner fetches spread over many 128-byte rows (C5 1024^3 fp16: forward 48 vs 29 Gsamples/s).
+    AUTO_BRICK_BYTES = 1 << 30
+
+    def resolve_layout(self, vol_lin):
+        if self.layout != "auto":
+            return self.layout
+        X, Y, Z = self.volume_resolution
+        if max(X, Y, Z) > 2000:
+            return "linear"                      # the generic tap path exists for the linear layout only
+        return "brick8" if X * Y * Z * vol_lin.element_size() > self.AUTO_BRICK_BYTES else "linear"
+
+    def _lflag(self, vol):
+        """Layout flag for a tensor returned by brick(): a 2-D tensor is a bricked copy, a 4-D one the linear volume."""
+        return F_LAYOUT_BRICK8 if vol.ndim == 2 else 0
 
     def brick(self, vol_lin):
         """[Bvol, Y, Z, X] contiguous fp32/fp16 CUDA tensor -> what the march kernels read: the tensor itself for the
@@ -65,7 +79,7 @@ class VolumeRaycaster:
             raise ValueError(f"volume has spatial shape {tuple(vol_lin.shape[1:])}, raycaster was built for (D,H,W)={(Y, Z, X)}")
         if not vol_lin.is_contiguous():
             raise ValueError("volume must be contiguous")
-        if self.layout == "linear":
+        if self.resolve_layout(vol_lin) == "linear":
             return vol_lin
         vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
         d = self.desc(1, 1, 1, vox, 0, 1.0)
@@ -81,7 +95,7 @@ class VolumeRaycaster:
         w, h = self.resolution
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
-                self._lflag()
+                self._lflag(bricked)
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
         dev = bricked.device
         out = torch.empty((BS, 4, h, w) if image_layout else (BS, w, h, 4), dtype=torch.float32, device=dev)
@@ -100,7 +114,7 @@ class VolumeRaycaster:
         BS = cam.shape[0]
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
-                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags | self._lflag()
+                (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags | self._lflag(bricked)
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
         dev = bricked.device
         lib = _lib.load()
@@ -237,7 +251,7 @@ class Raycaster(torch.nn.Module):
     """Same constructor and methods as the reference's `Raycaster` (:478-574)."""
 
     def __init__(self, volume_shape, output_shape, tf_shape, sampling_rate=1.0, jitter=True, max_samples=512, fov=30.0,
-                 near=0.1, far=100.0, ti_kwargs={}, layout="linear"):
+                 near=0.1, far=100.0, ti_kwargs={}, layout="auto"):
         super().__init__()
         self.volume_shape = (volume_shape[2], volume_shape[0], volume_shape[1])       # torch (D,H,W) -> Taichi (W,D,H) :481
         self.output_shape = output_shape
