@@ -249,6 +249,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
         A = F4 { a4.x, a4.y, a4.z, a4.w };
         g = F4 { g4.x, g4.y, g4.z, g4.w };
     }
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;       // this ray's gradient is exactly zero
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
     const VolView<VT> vol { volp + voff };
     const Layout L = make_layout(d);

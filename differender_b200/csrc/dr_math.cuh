@@ -559,7 +559,8 @@ DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, con
         const float df = a.dc.x * h.d.x + a.dc.y * h.d.y + a.dc.z * h.d.z + a.dc.w * h.d.w;
         a.dI = (h.x > 0.0f) ? df * d.tf_len : 0.0f;
         a.dg.x = a.dg.y = a.dg.z = 0.0f;
-        if (s.inv_g > 0.0f && !(1.0f < s.kraw)) {
+        // dk == 0 (exactly transparent sample, or zero incoming gradient) makes every normal-path term exactly zero
+        if (dk != 0.0f && s.inv_g > 0.0f && !(1.0f < s.kraw)) {
             const float d_ndl = (s.nl > 0.0f) ? d.diffuse * dk : 0.0f;
             const float d_rdv = (s.rv > 0.0f) ? d.specular * 32.0f * s.pw31 * dk : 0.0f;
             const float drx = -dir.x * d_rdv, dry = -dir.y * d_rdv, drz = -dir.z * d_rdv;
@@ -641,14 +642,45 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
     v[7] = yz11 * X1 + xz11 * ey1 + xy11 * ez1;
     sink.centre(cc, v);
     if (!a.has_dg) return;
-    // a crossed tap lives in the face-neighbour cell: +-1 (x), +-X (z), +-X*Z (y) in the torch-linear cell order
+    // a crossed tap lives in the face-neighbour cell: +-1 (x), +-X (z), +-X*Z (y) in the torch-linear cell order.  Its 8
+    // weights reuse the centre's pair products: only the weight pair of the shifted axis differs.
     const int sz = d.X, sy = d.X * d.Z;
-    if (xpc) { tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cc + 1, v); }
-    if (xmc) { tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cc - 1, v); }
-    if (ypc) { tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cc + sy, v); }
-    if (ymc) { tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cc - sy, v); }
-    if (zpc) { tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cc + sz, v); }
-    if (zmc) { tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cc - sz, v); }
+    if (xpc | xmc) {
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            if (sgn ? xmc : xpc) {
+                const Loc q = sgn ? t.xm : t.xp;
+                const float dg = sgn ? -a.dg.x : a.dg.x, q0 = dg * (1.0f - q.f), q1 = dg * q.f;
+                v[0] = q0 * yz00; v[1] = q1 * yz00; v[2] = q0 * yz10; v[3] = q1 * yz10;
+                v[4] = q0 * yz01; v[5] = q1 * yz01; v[6] = q0 * yz11; v[7] = q1 * yz11;
+                sink.direct(sgn ? cc - 1 : cc + 1, v);
+            }
+        }
+    }
+    if (ypc | ymc) {
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            if (sgn ? ymc : ypc) {
+                const Loc q = sgn ? t.ym : t.yp;
+                const float dg = sgn ? -a.dg.y : a.dg.y, q0 = dg * (1.0f - q.f), q1 = dg * q.f;
+                v[0] = q0 * xz00; v[1] = q0 * xz10; v[2] = q1 * xz00; v[3] = q1 * xz10;
+                v[4] = q0 * xz01; v[5] = q0 * xz11; v[6] = q1 * xz01; v[7] = q1 * xz11;
+                sink.direct(sgn ? cc - sy : cc + sy, v);
+            }
+        }
+    }
+    if (zpc | zmc) {
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            if (sgn ? zmc : zpc) {
+                const Loc q = sgn ? t.zm : t.zp;
+                const float dg = sgn ? -a.dg.z : a.dg.z, q0 = dg * (1.0f - q.f), q1 = dg * q.f;
+                v[0] = q0 * xy00; v[1] = q0 * xy10; v[2] = q0 * xy01; v[3] = q0 * xy11;
+                v[4] = q1 * xy00; v[5] = q1 * xy10; v[6] = q1 * xy01; v[7] = q1 * xy11;
+                sink.direct(sgn ? cc - sz : cc + sz, v);
+            }
+        }
+    }
 }
 
 // Gather pass: the gradient of voxel (x,y,z) is the sum of every (cell, slot) that aliases it, i.e. all (c, a) per axis
@@ -703,18 +735,21 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         const F3 pos = sample_pos(r, cam, s);
         Taps t;
         TfHit h;
-        if (NONDIFF) {
-            apply_tf(d, tf, eval_centre<VT, LAYOUT>(d, vol, L, pos), h, false);
-            if (!(h.c.w > d.alpha_skip)) continue;             // :334: skipped samples never evaluate the normal
-            eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
-        } else {
-            eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
-            apply_tf(d, tf, t.I, h, false);
-        }
+        apply_tf(d, tf, eval_centre<VT, LAYOUT>(d, vol, L, pos), h, false);
+        if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334: skipped samples never evaluate the normal
         const float o = opacity(d, h.c.w);
+        const float T = DR_SUB(1.0f, A.w);
+        if (o == 0.0f) {
+            // Exactly transparent sample (TF alpha 0, the empty space between a transfer function's bumps):
+            // C = (k*c*0, 0), so A_s = fma(T, 0, A_{s-1}) = A_{s-1} bit for bit whatever the Phong factor k is.  The
+            // sample still counts as active (:303) but its six normal taps and shading are never evaluated.
+            Tprev = T;
+            ++K;
+            continue;
+        }
+        eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);   // centre again (L1-resident) + the six normal taps
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);
-        const float T = DR_SUB(1.0f, A.w);
         const float ko = sh.k * o;
         Tprev = T;
         A.x = DR_FMA(T, ko * h.c.x, A.x);
@@ -755,7 +790,8 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         const float Cg = sample_adjoint(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
         g.w -= Cg;
         if (WANT_TF) tsink.add(h.lo, h.hi, h.f, a.dc);
-        if (WANT_VOL) scatter_volume_grad<VolSink, GENERIC>(d, vsink, t, a);
+        if (WANT_VOL && (a.has_dg || a.dI != 0.0f))          // exactly-zero contributions (transparent samples) are not scattered
+            scatter_volume_grad<VolSink, GENERIC>(d, vsink, t, a);
     }
     if (WANT_TF) tsink.flush();
     if (WANT_VOL) vsink.flush();
