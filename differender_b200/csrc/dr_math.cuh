@@ -156,10 +156,6 @@ template <typename VT> struct VolView {
     const VT* p;
     DR_HD float ld(uoff off) const { return load_vox(p, off); }
 };
-// Volume storage layouts.  LAYOUT_LINEAR reads the caller's contiguous torch tensor [y][z][x] in place (zero copy):
-// x-neighbours are immediate offsets of a row pointer, y/z-neighbours one stride add.  LAYOUT_BRICK8 reads the 8x8x8
-// bricked copy made by brick_kernel (separable offsets offx/offy/offz).
-enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1 };
 
 // ---------------------------------------------------------------------------------------------------------
 // ray set-up: compute_entry_exit :221-259, get_ray_direction :127-151, get_entry_exit_points :28-53
@@ -229,36 +225,87 @@ DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
 // mixes downstream of the shifted axis are redone (x: 7, y: 3, z: 1) on register-held values.  A tap that
 // crosses a cell face (|dlo| == 1) fetches the 4 corners of the one new voxel plane.  Both give exactly the
 // value a full 8-load trilinear evaluation would give (same operations, same order).
+// The evaluation is split in two phases so that the forward can stop after the centre tap when the sample turns
+// out to be exactly transparent: eval_centre (8 corner loads, 7 mixes) and eval_normals (the six taps).
 // ---------------------------------------------------------------------------------------------------------
+struct Centre {
+    Loc cx, cy, cz;               // centre cell
+    int cidx;                     // torch-linear index (cy*Z + cz)*X + cx of the centre cell's low corner
+    float v000, v100, v010, v110, v001, v101, v011, v111;   // its 8 corners
+    float xm00, xm10, xm01, xm11; // x mixes at (y0,z0) (y1,z0) (y0,z1) (y1,z1)
+    float ym0, ym1;               // y mixes at z0, z1
+    float I;                      // centre intensity
+};
 struct Taps {
     Loc cx, cy, cz;               // centre cell
     Loc xp, xm, yp, ym, zp, zm;   // tap cells (only the shifted axis differs from the centre)
-    int cidx;                     // torch-linear index (cy*Z + cz)*X + cx of the centre cell's low corner
-    float I;                      // centre intensity
+    int cidx;
+    float I;
     F3 g;                         // (f(x+d)-f(x-d), ...), un-normalised                     :197-202
 };
 
-template <typename VT>
-DR_HD float trilinear_full(const VolView<VT>& vol, const Layout& L, Loc ax, Loc ay, Loc az)
+// Volume storage layouts, as addressing policies.  row(yi, zi) names the voxel row (y0+yi, z0+zi) and ld(row, xi) reads
+// voxel x0+xi of it, with xi, yi, zi in {-1, 0, 1, 2} relative to the centre cell's low corner (only plus-shaped
+// combinations occur: at most one coordinate outside {0, 1}).
+//   LAYOUT_LINEAR reads the caller's contiguous torch tensor [y][z][x] in place (zero copy): a row is a pointer
+//   (one IMAD.WIDE.U32), x-neighbours are immediate offsets.  No clamps: in the corner-reuse path lo <= dim-2 on every
+//   axis (scale < dim-1 for dims <= 2000) and a crossed plane lo-1 / lo+2 is in range by construction.
+//   LAYOUT_BRICK8 reads the 8x8x8-bricked copy made by brick_kernel (separable offsets offx/offy/offz).
+enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1 };
+
+template <typename VT> struct LinearAddr {
+    typedef const VT* Row;
+    const VT* vp; uoff sy, sz, i00;
+    DR_HD void init(const DrDesc& d, const VT* p, const Layout&, const Centre& c)
+    {
+        vp = p; sz = (uoff)d.X; sy = (uoff)(d.X * d.Z); i00 = (uoff)c.cidx;
+    }
+    DR_HD Row row(int yi, int zi) const { return vp + (i00 + (uoff)yi * sy + (uoff)zi * sz); }   // wraps correctly for -1
+    DR_HD float ld(Row r, int xi) const { return load_vox(r, xi); }
+};
+template <typename VT> struct BrickAddr {
+    typedef uoff Row;
+    const VT* vp; Layout L; int lx, ly, lz;
+    DR_HD void init(const DrDesc&, const VT* p, const Layout& L_, const Centre& c)
+    {
+        vp = p; L = L_; lx = c.cx.lo; ly = c.cy.lo; lz = c.cz.lo;
+    }
+    DR_HD Row row(int yi, int zi) const { return offy(imin(ly + yi, L.my), L.sY) + offz(imin(lz + zi, L.mz), L.sZ); }
+    DR_HD float ld(Row r, int xi) const { return load_vox(vp, r + offx(imin(lx + xi, L.mx))); }
+};
+template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };
+template <typename VT> struct AddrOf<VT, LAYOUT_BRICK8> { typedef BrickAddr<VT> type; };
+
+DR_HD void locate_centre(const DrDesc& d, F3 pos, Centre& c)
 {
-    uoff x0 = offx(ax.lo), x1 = offx(imin(ax.lo + 1, L.mx));
-    uoff y0 = offy(ay.lo, L.sY), y1 = offy(imin(ay.lo + 1, L.my), L.sY);
-    uoff z0 = offz(az.lo, L.sZ), z1 = offz(imin(az.lo + 1, L.mz), L.sZ);
-    float ox = DR_SUB(1.0f, ax.f), oy = DR_SUB(1.0f, ay.f), oz = DR_SUB(1.0f, az.f);
-    float a = mix_e(vol.ld(x0 + y0 + z0), vol.ld(x1 + y0 + z0), ox, ax.f);
-    float b = mix_e(vol.ld(x0 + y1 + z0), vol.ld(x1 + y1 + z0), ox, ax.f);
-    float lo = mix_e(a, b, oy, ay.f);
-    a = mix_e(vol.ld(x0 + y0 + z1), vol.ld(x1 + y0 + z1), ox, ax.f);
-    b = mix_e(vol.ld(x0 + y1 + z1), vol.ld(x1 + y1 + z1), ox, ax.f);
-    float hi = mix_e(a, b, oy, ay.f);
-    return mix_e(lo, hi, oz, az.f);
+    c.cx = locate(pos.x, d.scale[0]);
+    c.cy = locate(pos.y, d.scale[1]);
+    c.cz = locate(pos.z, d.scale[2]);
+    c.cidx = (c.cy.lo * d.Z + c.cz.lo) * d.X + c.cx.lo;
 }
 
-DR_HD void locate_taps(const DrDesc& d, F3 pos, Taps& t)
+// centre tap                                                                                :173-189
+template <typename A>
+DR_HD void eval_centre(const A& ad, Centre& c)
 {
-    t.cx = locate(pos.x, d.scale[0]);
-    t.cy = locate(pos.y, d.scale[1]);
-    t.cz = locate(pos.z, d.scale[2]);
+    const typename A::Row r00 = ad.row(0, 0), r10 = ad.row(1, 0), r01 = ad.row(0, 1), r11 = ad.row(1, 1);
+    c.v000 = ad.ld(r00, 0); c.v100 = ad.ld(r00, 1);
+    c.v010 = ad.ld(r10, 0); c.v110 = ad.ld(r10, 1);
+    c.v001 = ad.ld(r01, 0); c.v101 = ad.ld(r01, 1);
+    c.v011 = ad.ld(r11, 0); c.v111 = ad.ld(r11, 1);
+    const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
+    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
+    c.xm00 = mix_e(c.v000, c.v100, ox, fx); c.xm10 = mix_e(c.v010, c.v110, ox, fx);
+    c.xm01 = mix_e(c.v001, c.v101, ox, fx); c.xm11 = mix_e(c.v011, c.v111, ox, fx);
+    c.ym0 = mix_e(c.xm00, c.xm10, oy, fy); c.ym1 = mix_e(c.xm01, c.xm11, oy, fy);
+    c.I = mix_e(c.ym0, c.ym1, oz, fz);
+}
+
+// the six normal taps on top of an evaluated centre
+template <typename A>
+DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, Taps& t)
+{
+    t.cx = c.cx; t.cy = c.cy; t.cz = c.cz; t.cidx = c.cidx; t.I = c.I;
     const float dl = d.delta;
     t.xp = locate(DR_ADD(pos.x, dl), d.scale[0]);
     t.xm = locate(DR_SUB(pos.x, dl), d.scale[0]);
@@ -266,10 +313,76 @@ DR_HD void locate_taps(const DrDesc& d, F3 pos, Taps& t)
     t.ym = locate(DR_SUB(pos.y, dl), d.scale[1]);
     t.zp = locate(DR_ADD(pos.z, dl), d.scale[2]);
     t.zm = locate(DR_SUB(pos.z, dl), d.scale[2]);
-    t.cidx = (t.cy.lo * d.Z + t.cz.lo) * d.X + t.cx.lo;
+    const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
+    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
+    float zv[2], yv[2], xv[2];
+    // ---- z taps (+ then -): only the last mix changes
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const Loc q = sgn ? t.zm : t.zp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float val;
+        if (q.lo == c.cz.lo) {
+            val = mix_e(c.ym0, c.ym1, o, f);
+        } else {
+            // new plane: above the centre's high plane (+) or below its low plane (-)
+            const typename A::Row n0 = ad.row(0, sgn ? -1 : 2), n1 = ad.row(1, sgn ? -1 : 2);
+            const float a = mix_e(ad.ld(n0, 0), ad.ld(n0, 1), ox, fx);
+            const float b = mix_e(ad.ld(n1, 0), ad.ld(n1, 1), ox, fx);
+            const float yn = mix_e(a, b, oy, fy);
+            val = sgn ? mix_e(yn, c.ym0, o, f) : mix_e(c.ym1, yn, o, f);
+        }
+        zv[sgn] = val;
+    }
+    t.g.z = DR_SUB(zv[0], zv[1]);
+    // ---- y taps: y mixes and the z mix change
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const Loc q = sgn ? t.ym : t.yp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float a, b;
+        if (q.lo == c.cy.lo) {
+            a = mix_e(c.xm00, c.xm10, o, f);
+            b = mix_e(c.xm01, c.xm11, o, f);
+        } else {
+            const typename A::Row n0 = ad.row(sgn ? -1 : 2, 0), n1 = ad.row(sgn ? -1 : 2, 1);
+            const float m0 = mix_e(ad.ld(n0, 0), ad.ld(n0, 1), ox, fx);
+            const float m1 = mix_e(ad.ld(n1, 0), ad.ld(n1, 1), ox, fx);
+            a = sgn ? mix_e(m0, c.xm00, o, f) : mix_e(c.xm10, m0, o, f);
+            b = sgn ? mix_e(m1, c.xm01, o, f) : mix_e(c.xm11, m1, o, f);
+        }
+        yv[sgn] = mix_e(a, b, oz, fz);
+    }
+    t.g.y = DR_SUB(yv[0], yv[1]);
+    // ---- x taps: everything downstream of the corners changes
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const Loc q = sgn ? t.xm : t.xp;
+        const float f = q.f, o = DR_SUB(1.0f, f);
+        float a00, a10, a01, a11;
+        if (q.lo == c.cx.lo) {
+            a00 = mix_e(c.v000, c.v100, o, f); a10 = mix_e(c.v010, c.v110, o, f);
+            a01 = mix_e(c.v001, c.v101, o, f); a11 = mix_e(c.v011, c.v111, o, f);
+        } else {
+            const typename A::Row r00 = ad.row(0, 0), r10 = ad.row(1, 0), r01 = ad.row(0, 1), r11 = ad.row(1, 1);
+            const int xi = sgn ? -1 : 2;
+            const float n00 = ad.ld(r00, xi), n10 = ad.ld(r10, xi), n01 = ad.ld(r01, xi), n11 = ad.ld(r11, xi);
+            if (sgn) {
+                a00 = mix_e(n00, c.v000, o, f); a10 = mix_e(n10, c.v010, o, f);
+                a01 = mix_e(n01, c.v001, o, f); a11 = mix_e(n11, c.v011, o, f);
+            } else {
+                a00 = mix_e(c.v100, n00, o, f); a10 = mix_e(c.v110, n10, o, f);
+                a01 = mix_e(c.v101, n01, o, f); a11 = mix_e(c.v111, n11, o, f);
+            }
+        }
+        const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);
+        xv[sgn] = mix_e(lo, hi, oz, fz);
+    }
+    t.g.x = DR_SUB(xv[0], xv[1]);
 }
 
-// full 8-load trilinear tap on the linear layout (generic path: clamps hi = min(lo+1, dim-1), :170-172)
+// Generic path (a normal tap can skip a whole cell: dims > ~2000; linear layout only): every tap is a full 8-load
+// trilinear evaluation with the reference's clamps hi = min(lo+1, dim-1)                    :170-172
 template <typename VT>
 DR_HD float trilinear_full_linear(const DrDesc& d, const VT* p, Loc ax, Loc ay, Loc az)
 {
@@ -285,191 +398,36 @@ DR_HD float trilinear_full_linear(const DrDesc& d, const VT* p, Loc ax, Loc ay, 
     const float hi = mix_e(a, b, oy, ay.f);
     return mix_e(lo, hi, oz, az.f);
 }
-
-// Linear-layout version of eval_taps (same arithmetic, same order; only the addressing differs).  In the corner-reuse
-// path lo <= dim-2 on every axis (scale < dim-1 for dims <= 2000), so hi = lo+1 and the crossed planes lo-1 / lo+2 are
-// in range without clamps: every corner is `row pointer + immediate`.
-template <typename VT, bool GENERIC>
-DR_HD void eval_taps_linear(const DrDesc& d, const VT* vp, F3 pos, Taps& t)
+template <typename VT>
+DR_HD void eval_normals_generic(const DrDesc& d, const VT* vp, F3 pos, const Centre& c, Taps& t)
 {
-    locate_taps(d, pos, t);
-    if (GENERIC) {
-        t.I = trilinear_full_linear(d, vp, t.cx, t.cy, t.cz);
-        t.g.x = DR_SUB(trilinear_full_linear(d, vp, t.xp, t.cy, t.cz), trilinear_full_linear(d, vp, t.xm, t.cy, t.cz));
-        t.g.y = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.yp, t.cz), trilinear_full_linear(d, vp, t.cx, t.ym, t.cz));
-        t.g.z = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.cy, t.zp), trilinear_full_linear(d, vp, t.cx, t.cy, t.zm));
-        return;
-    }
-    const uoff sz = (uoff)d.X, sy = (uoff)(d.X * d.Z), i00 = (uoff)t.cidx;
-    const VT* r00 = vp + i00;                  // row (y0, z0), starting at x0       (one IMAD.WIDE.U32 each)
-    const VT* r10 = vp + (i00 + sy);           // (y1, z0)
-    const VT* r01 = vp + (i00 + sz);           // (y0, z1)
-    const VT* r11 = vp + (i00 + sy + sz);      // (y1, z1)
-    const float v000 = load_vox(r00, 0), v100 = load_vox(r00, 1);
-    const float v010 = load_vox(r10, 0), v110 = load_vox(r10, 1);
-    const float v001 = load_vox(r01, 0), v101 = load_vox(r01, 1);
-    const float v011 = load_vox(r11, 0), v111 = load_vox(r11, 1);
-    const float fx = t.cx.f, fy = t.cy.f, fz = t.cz.f;
-    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
-    const float xm00 = mix_e(v000, v100, ox, fx), xm10 = mix_e(v010, v110, ox, fx);
-    const float xm01 = mix_e(v001, v101, ox, fx), xm11 = mix_e(v011, v111, ox, fx);
-    const float ym0 = mix_e(xm00, xm10, oy, fy), ym1 = mix_e(xm01, xm11, oy, fy);
-    t.I = mix_e(ym0, ym1, oz, fz);
-    float zv[2], yv[2], xv[2];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {        // z taps: + then -
-        const Loc q = sgn ? t.zm : t.zp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float val;
-        if (q.lo == t.cz.lo) {
-            val = mix_e(ym0, ym1, o, f);
-        } else {
-            const uoff zo = sgn ? i00 - sz : i00 + 2u * sz;  // plane z0-1 or z0+2
-            const VT* n0 = vp + zo;                        // (y0, .)
-            const VT* n1 = vp + (zo + sy);                 // (y1, .)
-            const float a = mix_e(load_vox(n0, 0), load_vox(n0, 1), ox, fx);
-            const float b = mix_e(load_vox(n1, 0), load_vox(n1, 1), ox, fx);
-            const float yn = mix_e(a, b, oy, fy);
-            val = sgn ? mix_e(yn, ym0, o, f) : mix_e(ym1, yn, o, f);
-        }
-        zv[sgn] = val;
-    }
-    t.g.z = DR_SUB(zv[0], zv[1]);
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {        // y taps
-        const Loc q = sgn ? t.ym : t.yp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float a, b;
-        if (q.lo == t.cy.lo) {
-            a = mix_e(xm00, xm10, o, f);
-            b = mix_e(xm01, xm11, o, f);
-        } else {
-            const uoff yo = sgn ? i00 - sy : i00 + 2u * sy;  // plane y0-1 or y0+2
-            const VT* n0 = vp + yo;                        // (., z0)
-            const VT* n1 = vp + (yo + sz);                 // (., z1)
-            const float m0 = mix_e(load_vox(n0, 0), load_vox(n0, 1), ox, fx);
-            const float m1 = mix_e(load_vox(n1, 0), load_vox(n1, 1), ox, fx);
-            a = sgn ? mix_e(m0, xm00, o, f) : mix_e(xm10, m0, o, f);
-            b = sgn ? mix_e(m1, xm01, o, f) : mix_e(xm11, m1, o, f);
-        }
-        yv[sgn] = mix_e(a, b, oz, fz);
-    }
-    t.g.y = DR_SUB(yv[0], yv[1]);
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {        // x taps
-        const Loc q = sgn ? t.xm : t.xp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float a00, a10, a01, a11;
-        if (q.lo == t.cx.lo) {
-            a00 = mix_e(v000, v100, o, f); a10 = mix_e(v010, v110, o, f);
-            a01 = mix_e(v001, v101, o, f); a11 = mix_e(v011, v111, o, f);
-        } else if (sgn) {
-            a00 = mix_e(load_vox(r00, -1), v000, o, f); a10 = mix_e(load_vox(r10, -1), v010, o, f);
-            a01 = mix_e(load_vox(r01, -1), v001, o, f); a11 = mix_e(load_vox(r11, -1), v011, o, f);
-        } else {
-            a00 = mix_e(v100, load_vox(r00, 2), o, f); a10 = mix_e(v110, load_vox(r10, 2), o, f);
-            a01 = mix_e(v101, load_vox(r01, 2), o, f); a11 = mix_e(v111, load_vox(r11, 2), o, f);
-        }
-        const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);
-        xv[sgn] = mix_e(lo, hi, oz, fz);
-    }
-    t.g.x = DR_SUB(xv[0], xv[1]);
+    t.cx = c.cx; t.cy = c.cy; t.cz = c.cz; t.cidx = c.cidx; t.I = c.I;
+    const float dl = d.delta;
+    t.xp = locate(DR_ADD(pos.x, dl), d.scale[0]); t.xm = locate(DR_SUB(pos.x, dl), d.scale[0]);
+    t.yp = locate(DR_ADD(pos.y, dl), d.scale[1]); t.ym = locate(DR_SUB(pos.y, dl), d.scale[1]);
+    t.zp = locate(DR_ADD(pos.z, dl), d.scale[2]); t.zm = locate(DR_SUB(pos.z, dl), d.scale[2]);
+    t.g.x = DR_SUB(trilinear_full_linear(d, vp, t.xp, t.cy, t.cz), trilinear_full_linear(d, vp, t.xm, t.cy, t.cz));
+    t.g.y = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.yp, t.cz), trilinear_full_linear(d, vp, t.cx, t.ym, t.cz));
+    t.g.z = DR_SUB(trilinear_full_linear(d, vp, t.cx, t.cy, t.zp), trilinear_full_linear(d, vp, t.cx, t.cy, t.zm));
 }
 
-template <typename VT, bool GENERIC>
-DR_HD void eval_taps(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Taps& t)
+// phase 1 / phase 2 dispatch on layout and tap path
+template <typename VT, int LAYOUT, bool GENERIC>
+DR_HD void sample_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Centre& c)
 {
-    locate_taps(d, pos, t);
-    if (GENERIC) {
-        t.I = trilinear_full(vol, L, t.cx, t.cy, t.cz);
-        t.g.x = DR_SUB(trilinear_full(vol, L, t.xp, t.cy, t.cz), trilinear_full(vol, L, t.xm, t.cy, t.cz));
-        t.g.y = DR_SUB(trilinear_full(vol, L, t.cx, t.yp, t.cz), trilinear_full(vol, L, t.cx, t.ym, t.cz));
-        t.g.z = DR_SUB(trilinear_full(vol, L, t.cx, t.cy, t.zp), trilinear_full(vol, L, t.cx, t.cy, t.zm));
-        return;
-    }
-    const uoff x0 = offx(t.cx.lo), x1 = offx(imin(t.cx.lo + 1, L.mx));
-    const uoff y0 = offy(t.cy.lo, L.sY), y1 = offy(imin(t.cy.lo + 1, L.my), L.sY);
-    const uoff z0 = offz(t.cz.lo, L.sZ), z1 = offz(imin(t.cz.lo + 1, L.mz), L.sZ);
-    const float v000 = vol.ld(x0 + y0 + z0), v100 = vol.ld(x1 + y0 + z0);
-    const float v010 = vol.ld(x0 + y1 + z0), v110 = vol.ld(x1 + y1 + z0);
-    const float v001 = vol.ld(x0 + y0 + z1), v101 = vol.ld(x1 + y0 + z1);
-    const float v011 = vol.ld(x0 + y1 + z1), v111 = vol.ld(x1 + y1 + z1);
-    const float fx = t.cx.f, fy = t.cy.f, fz = t.cz.f;
-    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
-    // centre: x mixes, y mixes, z mix                                                       :173-189
-    const float xm00 = mix_e(v000, v100, ox, fx), xm10 = mix_e(v010, v110, ox, fx);
-    const float xm01 = mix_e(v001, v101, ox, fx), xm11 = mix_e(v011, v111, ox, fx);
-    const float ym0 = mix_e(xm00, xm10, oy, fy), ym1 = mix_e(xm01, xm11, oy, fy);
-    t.I = mix_e(ym0, ym1, oz, fz);
-
-    // ---- z taps: only the last mix changes
-    float zv[2];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        const Loc q = sgn ? t.zm : t.zp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float val;
-        if (q.lo == t.cz.lo) {
-            val = mix_e(ym0, ym1, o, f);
-        } else {
-            // new plane: above the centre's high plane (+) or below its low plane (-)
-            const uoff zn = offz(sgn ? q.lo : imin(q.lo + 1, L.mz), L.sZ);
-            const float a = mix_e(vol.ld(x0 + y0 + zn), vol.ld(x1 + y0 + zn), ox, fx);
-            const float b = mix_e(vol.ld(x0 + y1 + zn), vol.ld(x1 + y1 + zn), ox, fx);
-            const float yn = mix_e(a, b, oy, fy);
-            val = sgn ? mix_e(yn, ym0, o, f) : mix_e(ym1, yn, o, f);
-        }
-        zv[sgn] = val;
-    }
-    t.g.z = DR_SUB(zv[0], zv[1]);
-
-    // ---- y taps: y mixes and the z mix change
-    float yv[2];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        const Loc q = sgn ? t.ym : t.yp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float a, b;
-        if (q.lo == t.cy.lo) {
-            a = mix_e(xm00, xm10, o, f);
-            b = mix_e(xm01, xm11, o, f);
-        } else {
-            const uoff yn = offy(sgn ? q.lo : imin(q.lo + 1, L.my), L.sY);
-            const float n0 = mix_e(vol.ld(x0 + yn + z0), vol.ld(x1 + yn + z0), ox, fx);
-            const float n1 = mix_e(vol.ld(x0 + yn + z1), vol.ld(x1 + yn + z1), ox, fx);
-            a = sgn ? mix_e(n0, xm00, o, f) : mix_e(xm10, n0, o, f);
-            b = sgn ? mix_e(n1, xm01, o, f) : mix_e(xm11, n1, o, f);
-        }
-        yv[sgn] = mix_e(a, b, oz, fz);
-    }
-    t.g.y = DR_SUB(yv[0], yv[1]);
-
-    // ---- x taps: everything downstream of the corners changes
-    float xv[2];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        const Loc q = sgn ? t.xm : t.xp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float a00, a10, a01, a11;
-        if (q.lo == t.cx.lo) {
-            a00 = mix_e(v000, v100, o, f); a10 = mix_e(v010, v110, o, f);
-            a01 = mix_e(v001, v101, o, f); a11 = mix_e(v011, v111, o, f);
-        } else {
-            const uoff xn = offx(sgn ? q.lo : imin(q.lo + 1, L.mx));
-            const float n00 = vol.ld(xn + y0 + z0), n10 = vol.ld(xn + y1 + z0);
-            const float n01 = vol.ld(xn + y0 + z1), n11 = vol.ld(xn + y1 + z1);
-            if (sgn) {
-                a00 = mix_e(n00, v000, o, f); a10 = mix_e(n10, v010, o, f);
-                a01 = mix_e(n01, v001, o, f); a11 = mix_e(n11, v011, o, f);
-            } else {
-                a00 = mix_e(v100, n00, o, f); a10 = mix_e(v110, n10, o, f);
-                a01 = mix_e(v101, n01, o, f); a11 = mix_e(v111, n11, o, f);
-            }
-        }
-        const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);
-        xv[sgn] = mix_e(lo, hi, oz, fz);
-    }
-    t.g.x = DR_SUB(xv[0], xv[1]);
+    locate_centre(d, pos, c);
+    if (GENERIC) { c.I = trilinear_full_linear(d, vol.p, c.cx, c.cy, c.cz); return; }
+    typename AddrOf<VT, LAYOUT>::type ad;
+    ad.init(d, vol.p, L, c);
+    eval_centre(ad, c);
+}
+template <typename VT, int LAYOUT, bool GENERIC>
+DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, const Centre& c, Taps& t)
+{
+    if (GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
+    typename AddrOf<VT, LAYOUT>::type ad;
+    ad.init(d, vol.p, L, c);
+    eval_normals(d, ad, pos, c, t);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -705,23 +663,6 @@ DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int 
 // State per ray is O(1): A (accumulated premultiplied RGBA), K (active samples), Tprev (transmittance before
 // the last active sample).  Nothing per sample is stored (the reference stores 16*M bytes per ray, :82,102-103).
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool GENERIC>
-DR_HD void eval_sample(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Taps& t)
-{
-    if (LAYOUT == LAYOUT_LINEAR) eval_taps_linear<VT, GENERIC>(d, vol.p, pos, t);
-    else eval_taps<VT, GENERIC>(d, vol, L, pos, t);
-}
-
-// centre tap only (same operations as the centre of eval_taps*): lets the non-differentiable march test the TF alpha
-// before paying for the six normal taps (:330-335)
-template <typename VT, int LAYOUT>
-DR_HD float eval_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos)
-{
-    const Loc cx = locate(pos.x, d.scale[0]), cy = locate(pos.y, d.scale[1]), cz = locate(pos.z, d.scale[2]);
-    if (LAYOUT == LAYOUT_LINEAR) return trilinear_full_linear(d, vol.p, cx, cy, cz);
-    return trilinear_full(vol, L, cx, cy, cz);
-}
-
 template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
                          const Ray& r, F4& A, int& K, float& Tprev)
@@ -733,9 +674,10 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
     for (int s = 0; s < nn; ++s) {
         if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
         const F3 pos = sample_pos(r, cam, s);
-        Taps t;
+        Centre c;
+        sample_centre<VT, LAYOUT, GENERIC>(d, vol, L, pos, c);
         TfHit h;
-        apply_tf(d, tf, eval_centre<VT, LAYOUT>(d, vol, L, pos), h, false);
+        apply_tf(d, tf, c.I, h, false);
         if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334: skipped samples never evaluate the normal
         const float o = opacity(d, h.c.w);
         const float T = DR_SUB(1.0f, A.w);
@@ -747,7 +689,8 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
             ++K;
             continue;
         }
-        eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);   // centre again (L1-resident) + the six normal taps
+        Taps t;
+        sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);
         const float ko = sh.k * o;
@@ -777,8 +720,10 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
     float Tafter = 1.0f - Afinal.w;                     // transmittance after sample K-1
     for (int s = K - 1; s >= 0; --s) {
         const F3 pos = sample_pos(r, cam, s);
+        Centre c;
+        sample_centre<VT, LAYOUT, GENERIC>(d, vol, L, pos, c);
         Taps t;
-        eval_sample<VT, LAYOUT, GENERIC>(d, vol, L, pos, t);
+        sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
         TfHit h;
         apply_tf(d, tf, t.I, h, WANT_VOL);
         const float o = opacity(d, h.c.w);
