@@ -236,6 +236,9 @@ def run_ours(args, cfg):
     for _ in range(max(args.warmup, 3)):
         _, K, n_k = step(False)
     samples_per_step[0] = int(K.sum().item())
+    # diagnostic (untimed): how many of the active samples have non-zero opacity, i.e. are actually shaded
+    _, Ksh, _ = vr.march(vr.brick(vol_lin), tf_r4, cams, sr, jit, nondiff=mode == "nondiff", extra_flags=512)
+    shaded_fraction = float(Ksh.sum().item()) / max(samples_per_step[0], 1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -354,7 +357,8 @@ def run_ours(args, cfg):
                        "volume_layout": vr.resolve_layout(vol_lin), "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
                        "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
-                       "active_samples_per_step_per_gpu": s},
+                       "active_samples_per_step_per_gpu": s, "shaded_fraction_of_active_samples": round(shaded_fraction, 4),
+                       "note": "samples whose TF alpha is exactly 0 are composited exactly without evaluating their normal (DESIGN.md 4)"},
             "fwd": {"value": s / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "unit": "Gsamples/s", "ms": fwd_ms},
             "bwd": {"value": s / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "unit": "Gsamples/s", "ms": bwd_ms},
             "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},

@@ -10,10 +10,11 @@ LIB_PATH = os.environ.get("DIFFRENDER_LIB") or os.path.join(_PKG, "libdiffrender
 # include/diffrender.h
 DR_VERSION = 100
 VOX_F32, VOX_F16 = 0, 1
-F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM, F_LAYOUT_BRICK8 = 1, 2, 4, 8, 16, 32, 64, 128, 256
+F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM, F_LAYOUT_BRICK8, F_COUNT_SHADED = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
 EXPORTS = ("dr_version", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_forward",
-           "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad")
+           "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad", "dr_forward_mse", "dr_backward_mse",
+           "dr_momentum_step", "dr_ingest_u8")
 
 
 class DrDesc(ctypes.Structure):
@@ -52,6 +53,12 @@ def load():
     lib.dr_backward.argtypes = [dp] + [vp] * 11 + [ctypes.c_size_t, vp]; lib.dr_backward.restype = ctypes.c_int
     lib.dr_grad_cells_elems.argtypes = [dp]; lib.dr_grad_cells_elems.restype = ctypes.c_size_t
     lib.dr_gather_grad.argtypes = [dp, vp, vp, ctypes.c_int, vp]; lib.dr_gather_grad.restype = ctypes.c_int
+    lib.dr_forward_mse.argtypes = [dp] + [vp] * 10; lib.dr_forward_mse.restype = ctypes.c_int
+    lib.dr_backward_mse.argtypes = [dp] + [vp] * 5 + [ctypes.c_float] + [vp] * 6 + [ctypes.c_size_t, vp]
+    lib.dr_backward_mse.restype = ctypes.c_int
+    lib.dr_momentum_step.argtypes = [vp, vp, vp, ctypes.c_size_t] + [ctypes.c_float] * 5 + [vp]
+    lib.dr_momentum_step.restype = ctypes.c_int
+    lib.dr_ingest_u8.argtypes = [dp, vp, vp, ctypes.c_int, vp]; lib.dr_ingest_u8.restype = ctypes.c_int
     if lib.dr_version() != DR_VERSION:
         raise RuntimeError(f"differender_b200: libdiffrender.so version {lib.dr_version()} != binding {DR_VERSION}; rebuild")
     _lib = lib

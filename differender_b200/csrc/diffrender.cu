@@ -131,14 +131,17 @@ template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 __global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
-           float* __restrict__ outT, size_t vol_elems)
+           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     F4* s_tf = reinterpret_cast<F4*>(s_raw);
     const int b = blockIdx.z;
     stage_tf(d, tf, d.Btf == 1 ? 0 : b, s_tf);
     int i, j;
-    if (!pixel_of_thread(d, i, j)) return;
+    const bool valid = pixel_of_thread(d, i, j);
+    if (!valid && !target) return;
+    float sq = 0.0f;
+    if (valid) {
     const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;      // image orientation
     const F3 cam = { __ldg(camp + 3 * b), __ldg(camp + 3 * b + 1), __ldg(camp + 3 * b + 2) };
     const float jit = (d.flags & DR_F_HAS_JITTER) ? __ldg(jitter + pix) : 0.0f;
@@ -150,13 +153,32 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     march_forward<VT, LAYOUT, NONDIFF, GENERIC>(d, vol, L, s_tf, cam, r, A, K, Tp);
     if (d.flags & DR_F_OUT_IMAGE) {
         const size_t plane = (size_t)d.W * d.H;
-        float* o = out + (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
+        const size_t o0 = (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
+        float* o = out + o0;
         o[0] = A.x; o[plane] = A.y; o[2 * plane] = A.z; o[3 * plane] = A.w;
+        if (target) {
+            const float ex = A.x - __ldg(target + o0), ey = A.y - __ldg(target + o0 + plane);
+            const float ez = A.z - __ldg(target + o0 + 2 * plane), ew = A.w - __ldg(target + o0 + 3 * plane);
+            sq = ex * ex + ey * ey + ez * ez + ew * ew;
+        }
     } else {
-        reinterpret_cast<float4*>(out)[((size_t)b * d.W + i) * d.H + j] = make_float4(A.x, A.y, A.z, A.w);
+        const size_t o0 = ((size_t)b * d.W + i) * d.H + j;
+        reinterpret_cast<float4*>(out)[o0] = make_float4(A.x, A.y, A.z, A.w);
+        if (target) {
+            const float4 tg = __ldg(reinterpret_cast<const float4*>(target) + o0);
+            const float ex = A.x - tg.x, ey = A.y - tg.y, ez = A.z - tg.z, ew = A.w - tg.w;
+            sq = ex * ex + ey * ey + ez * ez + ew * ew;
+        }
     }
     if (outK) outK[pix] = K;
     if (outT) outT[pix] = Tp;
+    }
+    if (target) {
+        // fused loss (reference examples: torch mse_loss on output_rgba): one atomic per warp into this view's sum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum + b, sq);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -220,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, DR_BWD_MIN_BLOCKS)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
-           float4* __restrict__ tf_slots, size_t vol_elems)
+           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     F4* s_tf = reinterpret_cast<F4*>(s_raw);
@@ -248,6 +270,10 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(gout) + o);
         A = F4 { a4.x, a4.y, a4.z, a4.w };
         g = F4 { g4.x, g4.y, g4.z, g4.w };
+    }
+    if (d.flags & DR_F_FUSED_MSE) {
+        // `gout` holds the TARGET image: dL/dA = mse_scale * (A - target), never materialised in HBM
+        g.x = mse_scale * (A.x - g.x); g.y = mse_scale * (A.y - g.y); g.z = mse_scale * (A.z - g.z); g.w = mse_scale * (A.w - g.w);
     }
     if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;       // this ray's gradient is exactly zero
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
@@ -318,13 +344,13 @@ size_t vol_stride(const DrDesc* d)
 
 template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
 int launch_fwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, float* out,
-               int32_t* K, float* T, cudaStream_t st)
+               int32_t* K, float* T, cudaStream_t st, const float* target, float* loss_sum)
 {
     const size_t smem = (size_t)d->R * sizeof(F4);
     auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, GENERIC>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
-    kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, out, K, T, vol_stride(d));
+    kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, out, K, T, vol_stride(d), target, loss_sum);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
@@ -332,14 +358,14 @@ int launch_fwd(const DrDesc* d, const void* vol, const float* tf, const float* c
 template <typename VT, int LAYOUT, bool GENERIC, bool WV, bool WT, bool ACC>
 int launch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                const float* gout, const float* out, const int32_t* K, const float* T, float4* gvol, float4* slots,
-               cudaStream_t st)
+               cudaStream_t st, float mse_scale)
 {
     const size_t smem = (size_t)d->R * sizeof(F4);
     auto kern = bwd_kernel<VT, LAYOUT, GENERIC, WV, WT, ACC>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, st>>>(*d, static_cast<const VT*>(vol), tf, cam, jitter, gout, out, K, T, gvol, slots,
-                                       vol_stride(d));
+                                       vol_stride(d), mse_scale);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
 }
@@ -347,17 +373,116 @@ int launch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* c
 template <typename VT, int LAYOUT, bool GENERIC>
 int dispatch_bwd(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                  const float* gout, const float* out, const int32_t* K, const float* T, float4* gvol, float4* slots,
-                 cudaStream_t st)
+                 cudaStream_t st, float mse_scale)
 {
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
     const bool acc = !(d->flags & DR_F_NO_REG_ACCUM);
 #define DR_BWD(WV, WT)                                                                                              \
-    (acc ? launch_bwd<VT, LAYOUT, GENERIC, WV, WT, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st) \
-         : launch_bwd<VT, LAYOUT, GENERIC, WV, WT, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st))
+    (acc ? launch_bwd<VT, LAYOUT, GENERIC, WV, WT, true>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st, mse_scale) \
+         : launch_bwd<VT, LAYOUT, GENERIC, WV, WT, false>(d, vol, tf, cam, jitter, gout, out, K, T, gvol, slots, st, mse_scale))
     if (wv && wt) return DR_BWD(true, true);
     if (wv) return DR_BWD(true, false);
     return DR_BWD(false, true);
 #undef DR_BWD
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// caller-side steps either side of the march: optimiser update and raw-volume ingest.  Elementwise, HBM-bound.
+// ---------------------------------------------------------------------------------------------------------
+// momentum-SGD step of the reference's TF optimisation demo (examples/taichi_volume_raycaster.py:375-381):
+//   m = gamma*m + lr*clamp(g, -max_grad, max_grad);  p -= m;  p = clamp(p, lo, hi)
+// one rounding per operator (matches numpy float32 bit for bit)
+__global__ void __launch_bounds__(256) momentum_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                             size_t n, float lr, float gamma, float max_grad, float lo, float hi)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float gc = fminf(fmaxf(g[e], -max_grad), max_grad);
+    const float mv = __fadd_rn(__fmul_rn(gamma, m[e]), __fmul_rn(lr, gc));
+    m[e] = mv;
+    p[e] = fminf(fmaxf(__fsub_rn(p[e], mv), lo), hi);
+}
+
+// raw uint8 volume [A][B][C] -> linear voxel volume [Y][Z][X], value = u8 / 255 (fp32 division), optionally with the
+// reference's np.swapaxes(raw, 0, 1) (examples/taichi_volume_raycaster.py:548-550) fused into the read
+template <typename VT>
+__global__ void __launch_bounds__(256) ingest_u8_kernel(DrDesc d, const uint8_t* __restrict__ src, VT* __restrict__ dst, int swap01)
+{
+    const size_t n = (size_t)d.X * d.Y * d.Z;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int x = (int)(e % d.X);
+    const size_t r = e / d.X;
+    const int z = (int)(r % d.Z), y = (int)(r / d.Z);
+    // dst[y][z][x] = swap01 ? src[z][y][x] (src dims [Z][Y][X]) : src[y][z][x]
+    const size_t s = swap01 ? ((size_t)z * d.Y + y) * d.X + x : e;
+    dst[e] = VT(__fdiv_rn((float)src[s], 255.0f));
+}
+
+int forward_impl(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, float* out_rgba,
+                 int32_t* out_K, float* out_Tprev, const float* target, float* loss_sum, void* stream, const char* who)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!vol || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
+    if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_forward: DR_F_HAS_JITTER set but jitter is null");
+    if (!aligned(tf, 16) || !aligned(out_rgba, 16)) return fail(DR_EALIGN, "dr_forward: tf and out_rgba must be 16-byte aligned");
+    if (target && (!loss_sum || !aligned(target, 16))) return fail(DR_EINVAL, "dr_forward_mse: loss_sum is null or target is not 16-byte aligned");
+    (void)who;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool nd = d->flags & DR_F_NONDIFF, gen = d->tap_generic, brick = d->flags & DR_F_LAYOUT_BRICK8;
+#define DR_FWD1(VT, LAY, ND, GEN) launch_fwd<VT, LAY, ND, GEN>(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, st, target, loss_sum)
+#define DR_FWD(VT)                                                                                                  \
+    (brick ? (nd ? DR_FWD1(VT, LAYOUT_BRICK8, true, false) : DR_FWD1(VT, LAYOUT_BRICK8, false, false))              \
+           : (nd ? (gen ? DR_FWD1(VT, LAYOUT_LINEAR, true, true) : DR_FWD1(VT, LAYOUT_LINEAR, true, false))         \
+                 : (gen ? DR_FWD1(VT, LAYOUT_LINEAR, false, true) : DR_FWD1(VT, LAYOUT_LINEAR, false, false))))
+    return d->vox_dtype == DR_VOX_F32 ? DR_FWD(float) : DR_FWD(__half);
+#undef DR_FWD1
+#undef DR_FWD
+}
+
+int backward_impl(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+                  const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev, float* grad_vol_cells,
+                  float* grad_tf, void* workspace, size_t workspace_bytes, float mse_scale, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (d->flags & DR_F_NONDIFF) return fail(DR_EINVAL, "dr_backward: the non-differentiable march has no backward");
+    const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
+    if (!wv && !wt) return DR_OK;
+    if (!vol || !tf || !cam || !grad_out || !out_rgba || !K || !Tprev) return fail(DR_EINVAL, "dr_backward: null pointer");
+    if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_backward: DR_F_HAS_JITTER set but jitter is null");
+    if (wv && !grad_vol_cells) return fail(DR_EINVAL, "dr_backward: grad_vol_cells is null");
+    if (wv && !aligned(grad_vol_cells, 32)) return fail(DR_EALIGN, "dr_backward: grad_vol_cells must be 32-byte aligned");
+    if (wt && !grad_tf) return fail(DR_EINVAL, "dr_backward: grad_tf is null");
+    if (!aligned(tf, 16) || !aligned(out_rgba, 16) || !aligned(grad_out, 16))
+        return fail(DR_EALIGN, "dr_backward: tf, out_rgba and grad_out must be 16-byte aligned");
+    const size_t need = dr_workspace_bytes(d);
+    if (wt) {
+        if (!workspace || workspace_bytes < need) return fail(DR_EWORKSPACE, "dr_backward: workspace too small (dr_workspace_bytes)");
+        if (!aligned(workspace, 16)) return fail(DR_EALIGN, "dr_backward: workspace must be 16-byte aligned");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (wt) {
+        cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
+    }
+    float4* slots = static_cast<float4*>(workspace);
+    float4* gcells = reinterpret_cast<float4*>(grad_vol_cells);
+    int rc;
+    const bool brick = d->flags & DR_F_LAYOUT_BRICK8;
+#define DR_BWDL(VT, LAY, GEN) dispatch_bwd<VT, LAY, GEN>(d, vol, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st, mse_scale)
+#define DR_BWDV(VT) (brick ? DR_BWDL(VT, LAYOUT_BRICK8, false) : (d->tap_generic ? DR_BWDL(VT, LAYOUT_LINEAR, true) : DR_BWDL(VT, LAYOUT_LINEAR, false)))
+    rc = d->vox_dtype == DR_VOX_F32 ? DR_BWDV(float) : DR_BWDV(__half);
+#undef DR_BWDV
+#undef DR_BWDL
+    if (rc) return rc;
+    if (wt) {
+        dim3 grid((d->R * 4 + 255) / 256, d->Btf);
+        tf_reduce_kernel<<<grid, 256, 0, st>>>(*d, static_cast<const float*>(workspace), grad_tf);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(e, "tf_reduce_kernel launch");
+    }
+    return DR_OK;
 }
 
 }  // namespace
@@ -406,64 +531,58 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
 int dr_forward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream)
 {
-    if (int rc = check_desc(d)) return rc;
-    if (!vol || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
-    if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_forward: DR_F_HAS_JITTER set but jitter is null");
-    if (!aligned(tf, 16) || !aligned(out_rgba, 16)) return fail(DR_EALIGN, "dr_forward: tf and out_rgba must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool nd = d->flags & DR_F_NONDIFF, gen = d->tap_generic, brick = d->flags & DR_F_LAYOUT_BRICK8;
-#define DR_FWD1(VT, LAY, ND, GEN) launch_fwd<VT, LAY, ND, GEN>(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, st)
-#define DR_FWD(VT)                                                                                                  \
-    (brick ? (nd ? DR_FWD1(VT, LAYOUT_BRICK8, true, false) : DR_FWD1(VT, LAYOUT_BRICK8, false, false))              \
-           : (nd ? (gen ? DR_FWD1(VT, LAYOUT_LINEAR, true, true) : DR_FWD1(VT, LAYOUT_LINEAR, true, false))         \
-                 : (gen ? DR_FWD1(VT, LAYOUT_LINEAR, false, true) : DR_FWD1(VT, LAYOUT_LINEAR, false, false))))
-    return d->vox_dtype == DR_VOX_F32 ? DR_FWD(float) : DR_FWD(__half);
-#undef DR_FWD1
-#undef DR_FWD
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, nullptr, nullptr, stream, "dr_forward");
+}
+
+int dr_forward_mse(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+                   const float* target, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream)
+{
+    if (!target || !loss_sum) return fail(DR_EINVAL, "dr_forward_mse: target or loss_sum is null");
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, target, loss_sum, stream, "dr_forward_mse");
 }
 
 int dr_backward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                 const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev,
                 float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
 {
+    if (d && (d->flags & DR_F_FUSED_MSE)) return fail(DR_EINVAL, "dr_backward: DR_F_FUSED_MSE is set by dr_backward_mse only");
+    return backward_impl(d, vol, tf, cam, jitter, grad_out, out_rgba, K, Tprev, grad_vol_cells, grad_tf, workspace,
+                         workspace_bytes, 0.0f, stream);
+}
+
+int dr_backward_mse(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+                    const float* target, float scale, const float* out_rgba, const int32_t* K, const float* Tprev,
+                    float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!d) return fail(DR_EINVAL, "null descriptor");
+    DrDesc dd = *d;
+    dd.flags |= DR_F_FUSED_MSE;
+    return backward_impl(&dd, vol, tf, cam, jitter, target, out_rgba, K, Tprev, grad_vol_cells, grad_tf, workspace,
+                         workspace_bytes, scale, stream);
+}
+
+int dr_momentum_step(float* param, const float* grad, float* momentum, size_t n, float lr, float gamma, float max_grad,
+                     float lo, float hi, void* stream)
+{
+    if (!param || !grad || !momentum) return fail(DR_EINVAL, "dr_momentum_step: null pointer");
+    if (n == 0) return DR_OK;
+    momentum_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, momentum, n, lr, gamma,
+                                                                                                   max_grad, lo, hi);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "momentum_step_kernel launch");
+}
+
+int dr_ingest_u8(const DrDesc* d, const uint8_t* src, void* vol_linear, int swap_axes01, void* stream)
+{
     if (int rc = check_desc(d)) return rc;
-    if (d->flags & DR_F_NONDIFF) return fail(DR_EINVAL, "dr_backward: the non-differentiable march has no backward");
-    const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
-    if (!wv && !wt) return DR_OK;
-    if (!vol || !tf || !cam || !grad_out || !out_rgba || !K || !Tprev) return fail(DR_EINVAL, "dr_backward: null pointer");
-    if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_backward: DR_F_HAS_JITTER set but jitter is null");
-    if (wv && !grad_vol_cells) return fail(DR_EINVAL, "dr_backward: grad_vol_cells is null");
-    if (wv && !aligned(grad_vol_cells, 32)) return fail(DR_EALIGN, "dr_backward: grad_vol_cells must be 32-byte aligned");
-    if (wt && !grad_tf) return fail(DR_EINVAL, "dr_backward: grad_tf is null");
-    if (!aligned(tf, 16) || !aligned(out_rgba, 16) || !aligned(grad_out, 16))
-        return fail(DR_EALIGN, "dr_backward: tf, out_rgba and grad_out must be 16-byte aligned");
-    const size_t need = dr_workspace_bytes(d);
-    if (wt) {
-        if (!workspace || workspace_bytes < need) return fail(DR_EWORKSPACE, "dr_backward: workspace too small (dr_workspace_bytes)");
-        if (!aligned(workspace, 16)) return fail(DR_EALIGN, "dr_backward: workspace must be 16-byte aligned");
-    }
+    if (!src || !vol_linear) return fail(DR_EINVAL, "dr_ingest_u8: null pointer");
+    const size_t n = (size_t)d->X * d->Y * d->Z;
+    const unsigned grid = (unsigned)((n + 255) / 256);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (wt) {
-        cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
-        if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
-    }
-    float4* slots = static_cast<float4*>(workspace);
-    float4* gcells = reinterpret_cast<float4*>(grad_vol_cells);
-    int rc;
-    const bool brick = d->flags & DR_F_LAYOUT_BRICK8;
-#define DR_BWDL(VT, LAY, GEN) dispatch_bwd<VT, LAY, GEN>(d, vol, tf, cam, jitter, grad_out, out_rgba, K, Tprev, gcells, slots, st)
-#define DR_BWDV(VT) (brick ? DR_BWDL(VT, LAYOUT_BRICK8, false) : (d->tap_generic ? DR_BWDL(VT, LAYOUT_LINEAR, true) : DR_BWDL(VT, LAYOUT_LINEAR, false)))
-    rc = d->vox_dtype == DR_VOX_F32 ? DR_BWDV(float) : DR_BWDV(__half);
-#undef DR_BWDV
-#undef DR_BWDL
-    if (rc) return rc;
-    if (wt) {
-        dim3 grid((d->R * 4 + 255) / 256, d->Btf);
-        tf_reduce_kernel<<<grid, 256, 0, st>>>(*d, static_cast<const float*>(workspace), grad_tf);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return fail_cuda(e, "tf_reduce_kernel launch");
-    }
-    return DR_OK;
+    if (d->vox_dtype == DR_VOX_F32) ingest_u8_kernel<float><<<grid, 256, 0, st>>>(*d, src, static_cast<float*>(vol_linear), swap_axes01);
+    else ingest_u8_kernel<__half><<<grid, 256, 0, st>>>(*d, src, static_cast<__half*>(vol_linear), swap_axes01);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "ingest_u8_kernel launch");
 }
 
 size_t dr_grad_cells_elems(const DrDesc* d) { return d ? (size_t)d->X * d->Y * d->Z * 8 : 0; }

@@ -686,7 +686,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
             // C = (k*c*0, 0), so A_s = fma(T, 0, A_{s-1}) = A_{s-1} bit for bit whatever the Phong factor k is.  The
             // sample still counts as active (:303) but its six normal taps and shading are never evaluated.
             Tprev = T;
-            ++K;
+            if (!(d.flags & DR_F_COUNT_SHADED)) ++K;
             continue;
         }
         Taps t;

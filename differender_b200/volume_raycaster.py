@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, VOX_F16, VOX_F32)
 
-__all__ = ["VolumeRaycaster", "RaycastFunction", "Raycaster"]
+__all__ = ["VolumeRaycaster", "RaycastFunction", "RaycastMSEFunction", "Raycaster"]
 
 
 def _stream():
@@ -89,28 +89,37 @@ class VolumeRaycaster:
         _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
         return out
 
-    def march(self, bricked, tf_r4, cam, sampling_rate, jitter=None, nondiff=False, image_layout=True, want_aux=True):
-        """Forward of cam.shape[0] views.  Returns (out, K, Tprev)."""
+    def march(self, bricked, tf_r4, cam, sampling_rate, jitter=None, nondiff=False, image_layout=True, want_aux=True,
+              extra_flags=0, mse_target=None):
+        """Forward of cam.shape[0] views.  Returns (out, K, Tprev), or (out, K, Tprev, loss_sum[BS]) when `mse_target`
+        (same layout as out) is given: the squared-error sum is accumulated in the kernel's epilogue."""
         BS = cam.shape[0]
         w, h = self.resolution
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
-                self._lflag(bricked)
+                self._lflag(bricked) | extra_flags
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
         dev = bricked.device
         out = torch.empty((BS, 4, h, w) if image_layout else (BS, w, h, 4), dtype=torch.float32, device=dev)
         K = torch.empty((BS, h, w), dtype=torch.int32, device=dev) if want_aux else None
         Tp = torch.empty((BS, h, w), dtype=torch.float32, device=dev) if (want_aux and not nondiff) else None
+        if mse_target is not None:
+            loss_sum = torch.zeros((BS,), dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().dr_forward_mse(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                                  _lib.ptr(mse_target), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp), _lib.ptr(loss_sum),
+                                                  _stream()), "dr_forward_mse")
+            return out, K, Tp, loss_sum
         _lib.check(_lib.load().dr_forward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
                                           _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp), _stream()), "dr_forward")
         return out, K, Tp
 
     def march_backward(self, bricked, tf_r4, cam, sampling_rate, jitter, grad_out, out, K, Tprev, need_vol, need_tf,
-                       image_layout=True, grad_cells=None, extra_flags=0):
+                       image_layout=True, grad_cells=None, extra_flags=0, mse_scale=None):
         """Backward of cam.shape[0] views.  Returns (grad_vol_linear [Bvol,Y,Z,X] fp32 or None, grad_tf [Btf,R,4] or None).
         The volume gradient is scattered into a cell-major buffer [Bvol, X*Y*Z*8] (zeroed here) and gathered once.
         If `grad_cells` is given it is accumulated into and NOT gathered (it is returned instead), so that several calls
-        (e.g. chunks of a large view batch) share one buffer and one gather."""
+        (e.g. chunks of a large view batch) share one buffer and one gather.
+        With `mse_scale`, `grad_out` is the TARGET image and dL/d(out) = mse_scale*(out - target) is formed in the kernel."""
         BS = cam.shape[0]
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
@@ -124,10 +133,16 @@ class VolumeRaycaster:
         gtf = torch.zeros(tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
         ws_bytes = lib.dr_workspace_bytes(ctypes.byref(d))
         ws = torch.empty((max(ws_bytes, 16) + 3) // 4, dtype=torch.float32, device=dev)
-        _lib.check(lib.dr_backward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
-                                   _lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
-                                   _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
-                                   _stream()), "dr_backward")
+        if mse_scale is not None:
+            _lib.check(lib.dr_backward_mse(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                           _lib.ptr(grad_out), ctypes.c_float(mse_scale), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
+                                           _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
+                                           _stream()), "dr_backward_mse")
+        else:
+            _lib.check(lib.dr_backward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                       _lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
+                                       _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
+                                       _stream()), "dr_backward")
         if not need_vol:
             return None, gtf
         if keep_cells:
@@ -151,6 +166,89 @@ def _require_cuda(*tensors):
                                "There is no CPU fallback.")
 
 
+def _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor):
+    """Normalises the reference-style inputs (:395-410) to what the C ABI takes, without cloning shared inputs.
+    Returns (BS, vol_b, vol_lin [Bvol,Y,Z,X], tf_r4 [Btf,R,4], cam [BS,3], jit [BS,H,W] or None)."""
+    _require_cuda(volume, tf, look_from, jitter_tensor)
+    is_batched, bs = batched
+    BS = int(bs) if is_batched else 1
+    w, h = vr.resolution
+    vol_b = volume.ndim == 4
+    v = volume if vol_b else volume[None]
+    if vol_b and v.shape[0] > 1 and v.stride(0) == 0:
+        v = v[:1]                                          # an .expand()ed shared volume: do not clone it (:566)
+    if v.dtype not in (torch.float16, torch.float32):
+        v = v.float()                                      # set_volume's .float() (:119); fp16 is kept
+    vol_lin = v.permute(0, 2, 3, 1).contiguous()           # [Bvol, Y, Z, X] == torch (D, H, W); no-op for our views
+    if vol_lin.shape[0] not in (1, BS):
+        raise ValueError(f"volume batch {vol_lin.shape[0]} does not match batch size {BS}")
+    t = tf if tf.ndim == 3 else tf[None]
+    if t.shape[0] > 1 and t.stride(0) == 0:
+        t = t[:1]
+    tf_r4 = t.float().contiguous()                         # [Btf, R, 4]
+    if tf_r4.shape[-1] != 4 or tf_r4.shape[-2] != vr.tf_resolution:
+        raise ValueError(f"tf has shape {tuple(tf.shape)}, expected ([BS,] {vr.tf_resolution}, 4)")
+    if tf_r4.shape[0] not in (1, BS):
+        raise ValueError(f"tf batch {tf_r4.shape[0]} does not match batch size {BS}")
+    cam = look_from.float().reshape(-1, 3)
+    if cam.shape[0] == 1 and BS > 1:
+        cam = cam.expand(BS, 3)
+    cam = cam.contiguous()
+    if cam.shape[0] != BS:
+        raise ValueError(f"look_from batch {cam.shape[0]} does not match batch size {BS}")
+    jit = None
+    if jitter:
+        if jitter_tensor is None:
+            jit = torch.rand((BS, h, w), dtype=torch.float32, device=volume.device)     # replaces ti.random (:255)
+        else:
+            jit = jitter_tensor.float().reshape(-1, h, w)
+            if jit.shape[0] == 1 and BS > 1:
+                jit = jit.expand(BS, h, w)
+            jit = jit.contiguous()
+            if jit.shape[0] != BS:
+                raise ValueError(f"jitter_tensor batch {jit.shape[0]} does not match batch size {BS}")
+    return BS, vol_b, vol_lin, tf_r4, cam, jit
+
+
+def _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, image_layout):
+    vr.last_K = K
+    ctx.vr, ctx.sampling_rate, ctx.image_layout = vr, sampling_rate, image_layout
+    ctx.is_batched, ctx.vol_batched, ctx.tf_batched = batched[0], vol_b, tf.ndim == 3
+    ctx.vol_shape, ctx.tf_shape = tuple(volume.shape), tuple(tf.shape)
+    ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = tf_r4, cam, jit, out, K, Tp
+    if bricked.data_ptr() == volume.data_ptr():
+        ctx.save_for_backward(volume)          # zero-copy layout: let autograd detect in-place edits before backward
+        ctx.bricked = None
+    else:
+        ctx.save_for_backward()
+        ctx.bricked = bricked                  # our own copy (bricked layout, or a cast/contiguous copy)
+
+
+def _saved_volume(ctx):
+    if ctx.bricked is not None:
+        return ctx.bricked
+    (volume,) = ctx.saved_tensors
+    v = volume if ctx.vol_batched else volume[None]
+    if ctx.vol_batched and v.shape[0] > 1 and v.stride(0) == 0:
+        v = v[:1]
+    return v.permute(0, 2, 3, 1).contiguous()              # the same zero-copy view the forward read
+
+
+def _shape_grads(ctx, gvol, gtf, need_vol, need_tf):
+    gv = gt = None
+    if need_vol:
+        gv = gvol.permute(0, 3, 1, 2)                          # [Bvol, X, Y, Z] view (Taichi order, :447)
+        if not ctx.vol_batched:
+            gv = gv[0]
+        elif gv.shape[0] != ctx.vol_shape[0]:
+            gv = gv.expand(ctx.vol_shape)                      # caller passed an expanded shared volume
+    if need_tf:
+        gt = gtf if ctx.tf_batched else gtf[0]
+        if ctx.tf_batched and gt.shape[0] != ctx.tf_shape[0]:
+            gt = gt.expand(ctx.tf_shape)
+    return gv, gt
+
+
 class RaycastFunction(torch.autograd.Function):
     """Drop-in for the reference's autograd Function (:392-476); same positional arguments, two optional extras."""
 
@@ -161,58 +259,12 @@ class RaycastFunction(torch.autograd.Function):
         made when the underlying memory is the contiguous torch (D,H,W) tensor); tf ([BS,] R, 4); look_from ([BS,] 3).
         Returns ([BS,] W, H, 4) like the reference, or ([BS,] 4, H, W) already flipped when image_layout=True."""
         _require_cuda(volume, tf, look_from, jitter_tensor)
-        is_batched, bs = batched
-        BS = int(bs) if is_batched else 1
-        w, h = vr.resolution
         with torch.cuda.device(volume.device):
-            vol_b = volume.ndim == 4
-            v = volume if vol_b else volume[None]
-            if vol_b and v.shape[0] > 1 and v.stride(0) == 0:
-                v = v[:1]                                          # an .expand()ed shared volume: do not clone it (:566)
-            if v.dtype not in (torch.float16, torch.float32):
-                v = v.float()                                      # set_volume's .float() (:119); fp16 is kept
-            vol_lin = v.permute(0, 2, 3, 1).contiguous()           # [Bvol, Y, Z, X] == torch (D, H, W); no-op for our views
-            if vol_lin.shape[0] not in (1, BS):
-                raise ValueError(f"volume batch {vol_lin.shape[0]} does not match batch size {BS}")
-            t = tf if tf.ndim == 3 else tf[None]
-            if t.shape[0] > 1 and t.stride(0) == 0:
-                t = t[:1]
-            tf_r4 = t.float().contiguous()                         # [Btf, R, 4]
-            if tf_r4.shape[-1] != 4 or tf_r4.shape[-2] != vr.tf_resolution:
-                raise ValueError(f"tf has shape {tuple(tf.shape)}, expected ([BS,] {vr.tf_resolution}, 4)")
-            if tf_r4.shape[0] not in (1, BS):
-                raise ValueError(f"tf batch {tf_r4.shape[0]} does not match batch size {BS}")
-            cam = look_from.float().reshape(-1, 3)
-            if cam.shape[0] == 1 and BS > 1:
-                cam = cam.expand(BS, 3)
-            cam = cam.contiguous()
-            if cam.shape[0] != BS:
-                raise ValueError(f"look_from batch {cam.shape[0]} does not match batch size {BS}")
-            jit = None
-            if jitter:
-                if jitter_tensor is None:
-                    jit = torch.rand((BS, h, w), dtype=torch.float32, device=volume.device)     # replaces ti.random (:255)
-                else:
-                    jit = jitter_tensor.float().reshape(-1, h, w)
-                    if jit.shape[0] == 1 and BS > 1:
-                        jit = jit.expand(BS, h, w)
-                    jit = jit.contiguous()
-                    if jit.shape[0] != BS:
-                        raise ValueError(f"jitter_tensor batch {jit.shape[0]} does not match batch size {BS}")
+            BS, vol_b, vol_lin, tf_r4, cam, jit = _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor)
             bricked = vr.brick(vol_lin)
             out, K, Tp = vr.march(bricked, tf_r4, cam, sampling_rate, jit, nondiff=False, image_layout=image_layout)
-        vr.last_K = K
-        ctx.vr, ctx.sampling_rate, ctx.image_layout = vr, sampling_rate, image_layout
-        ctx.is_batched, ctx.vol_batched, ctx.tf_batched = is_batched, vol_b, tf.ndim == 3
-        ctx.vol_shape, ctx.tf_shape = tuple(volume.shape), tuple(tf.shape)
-        ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = tf_r4, cam, jit, out, K, Tp
-        if bricked.data_ptr() == volume.data_ptr():
-            ctx.save_for_backward(volume)          # zero-copy layout: let autograd detect in-place edits before backward
-            ctx.bricked = None
-        else:
-            ctx.save_for_backward()
-            ctx.bricked = bricked                  # our own copy (bricked layout, or a cast/contiguous copy)
-        return out if is_batched else out[0]
+        _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, image_layout)
+        return out if batched[0] else out[0]
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
@@ -220,30 +272,48 @@ class RaycastFunction(torch.autograd.Function):
         need_vol, need_tf = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         if not (need_vol or need_tf):
             return (None,) * 9
-        vr = ctx.vr
         with torch.cuda.device(grad_output.device):
             go = grad_output if ctx.is_batched else grad_output[None]
             go = go.float().contiguous()
-            bricked = ctx.bricked
-            if bricked is None:
-                (volume,) = ctx.saved_tensors
-                v = volume if ctx.vol_batched else volume[None]
-                if ctx.vol_batched and v.shape[0] > 1 and v.stride(0) == 0:
-                    v = v[:1]
-                bricked = v.permute(0, 2, 3, 1).contiguous()           # the same zero-copy view the forward read
-            gvol, gtf = vr.march_backward(bricked, ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, go, ctx.out, ctx.K,
-                                          ctx.Tp, need_vol, need_tf, image_layout=ctx.image_layout)
-        gv = gt = None
-        if need_vol:
-            gv = gvol.permute(0, 3, 1, 2)                          # [Bvol, X, Y, Z] view (Taichi order, :447)
-            if not ctx.vol_batched:
-                gv = gv[0]
-            elif gv.shape[0] != ctx.vol_shape[0]:
-                gv = gv.expand(ctx.vol_shape)                      # caller passed an expanded shared volume
-        if need_tf:
-            gt = gtf if ctx.tf_batched else gtf[0]
-            if ctx.tf_batched and gt.shape[0] != ctx.tf_shape[0]:
-                gt = gt.expand(ctx.tf_shape)
+            gvol, gtf = ctx.vr.march_backward(_saved_volume(ctx), ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, go, ctx.out,
+                                              ctx.K, ctx.Tp, need_vol, need_tf, image_layout=ctx.image_layout)
+        gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
+        return None, gv, gt, None, None, None, None, None, None
+
+
+class RaycastMSEFunction(torch.autograd.Function):
+    """Render + mean-squared-error against `target` in one pass each way: the loss is reduced in the
+    forward kernel's epilogue and dL/d(image) = 2 (image - target) / numel is formed inside the backward kernel, so
+    neither the residual nor the gradient image exists in HBM.  Equivalent to
+    `F.mse_loss(RaycastFunction.apply(..., image_layout=True), target)` (reference examples/test_opt_tf.py:70-72)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, vr, volume, tf, look_from, sampling_rate, batched, jitter, jitter_tensor, target):
+        _require_cuda(volume, tf, look_from, jitter_tensor, target)
+        with torch.cuda.device(volume.device):
+            BS, vol_b, vol_lin, tf_r4, cam, jit = _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor)
+            w, h = vr.resolution
+            tgt = target.float().reshape(BS, 4, h, w).contiguous()
+            bricked = vr.brick(vol_lin)
+            out, K, Tp, loss_sum = vr.march(bricked, tf_r4, cam, sampling_rate, jit, image_layout=True, mse_target=tgt)
+        _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, True)
+        ctx.tgt = tgt
+        img = out if batched[0] else out[0]
+        ctx.mark_non_differentiable(img)
+        return loss_sum.sum() / out.numel(), img
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_loss, _grad_img):
+        need_vol, need_tf = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_vol or need_tf):
+            return (None,) * 9
+        with torch.cuda.device(grad_loss.device):
+            scale = 2.0 * float(grad_loss) / ctx.out.numel()       # one scalar read; keeps the kernel argument a plain float
+            gvol, gtf = ctx.vr.march_backward(_saved_volume(ctx), ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, ctx.tgt,
+                                              ctx.out, ctx.K, ctx.Tp, need_vol, need_tf, image_layout=True, mse_scale=scale)
+        gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
         return None, gv, gt, None, None, None, None, None, None
 
 
@@ -291,6 +361,13 @@ class Raycaster(torch.nn.Module):
         batched, bs, vol_in, tf_in, lf_in = self._determine_batch(volume, tf, look_from)
         return RaycastFunction.apply(self.vr, vol_in, tf_in, lf_in, self.sampling_rate, (batched, bs), self.jitter,
                                      jitter_tensor, True)
+
+    def mse_loss(self, volume, tf, look_from, target, jitter_tensor=None):
+        """Fused render + MSE: returns (loss, image) with `loss == F.mse_loss(self(volume, tf, look_from), target)`;
+        the image is returned detached (gradients flow through the loss only)."""
+        batched, bs, vol_in, tf_in, lf_in = self._determine_batch(volume, tf, look_from)
+        return RaycastMSEFunction.apply(self.vr, vol_in, tf_in, lf_in, self.sampling_rate, (batched, bs), self.jitter,
+                                        jitter_tensor, target)
 
     def _determine_batch(self, volume, tf, look_from):
         """Same rule as the reference (:551-571): anything batched => batch size from the first batched input.

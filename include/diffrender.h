@@ -54,6 +54,8 @@ extern "C" {
 #define DR_F_TF_4R 32u         /* tf / grad_tf are [Btf][4][R] (torch layout; else the reference's [Btf][R][4], :567,571) */
 #define DR_F_GENERIC_TAPS 64u  /* force the 7x8-load tap path (always used when a normal tap can skip a whole cell) */
 #define DR_F_LAYOUT_BRICK8 256u /* `vol` is the 8x8x8-bricked copy made by dr_brick_volume; clear: `vol` is the caller's linear [Bvol][Y][Z][X] tensor, read in place */
+#define DR_F_FUSED_MSE 1024u    /* internal: set by dr_backward_mse (grad_out slot holds the target image) */
+#define DR_F_COUNT_SHADED 512u  /* diagnostic: out_K counts only samples with non-zero opacity (do not feed such a K to dr_backward) */
 #define DR_F_NO_REG_ACCUM 128u  /* tuning/debug: backward issues its reductions per sample instead of keeping the current cell / TF bin in registers */
 
 /* Plain-data description of one call.  Fill it with dr_desc_init(); do not hand-edit derived fields. */
@@ -146,6 +148,44 @@ int dr_backward(const DrDesc* d, const void* vol, const float* tf, const float* 
  * accumulate != 0 adds into grad_linear.
  */
 int dr_gather_grad(const DrDesc* d, const float* grad_vol_cells, float* grad_linear, int accumulate, void* stream);
+
+/* ---- caller-side steps either side of the march ------------------------------------------------ */
+
+/*
+ * dr_forward with the mean-squared-error loss of the reference's optimisation loops fused into the epilogue
+ * (torch.nn.functional.mse_loss(output_rgba, reference), examples/taichi_volume_raycaster.py:425-447;
+ * F.mse_loss(pred, targ), examples/test_opt_tf.py:70-72): besides everything dr_forward writes, loss_sum[b] +=
+ * sum over the view's pixels and 4 channels of (out - target)^2.  target has the layout of out_rgba; loss_sum is
+ * [BS] fp32, caller-zeroed.  The mean is the caller's division.
+ */
+int dr_forward_mse(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+                   const float* target, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream);
+
+/*
+ * dr_backward for that loss: dL/d(out) = scale * (out - target) is formed inside the kernel from out_rgba and target,
+ * so the gradient image never exists in HBM (replaces output_rgba.grad.from_torch, :436).  For the mean over
+ * BS*4*H*W elements pass scale = 2 / (BS*4*H*W) times the upstream gradient of the loss.
+ */
+int dr_backward_mse(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
+                    const float* target, float scale, const float* out_rgba, const int32_t* K, const float* Tprev,
+                    float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Momentum-SGD step with gradient clipping and projection, the reference's `apply_grad`
+ * (examples/taichi_volume_raycaster.py:375-381: tf_momentum = gamma*tf_momentum + lr*clamp(grad, +-max_grad);
+ * tf -= tf_momentum; tf = max(tf, 0)) generalised with an upper clamp so that it also covers the volume projection
+ * vol.clamp_(0, 1) of examples/test_opt_tf.py:86-88:
+ *   m = gamma*m + lr*clamp(g, -max_grad, max_grad);  p = clamp(p - m, lo, hi)      over n fp32 elements, in place.
+ */
+int dr_momentum_step(float* param, const float* grad, float* momentum, size_t n, float lr, float gamma, float max_grad,
+                     float lo, float hi, void* stream);
+
+/*
+ * Raw uint8 volume -> linear voxel volume [Y][Z][X] of d->vox_dtype with value = u8 / 255, as the reference ingests
+ * skull.raw (np.fromfile(uint8).reshape(256,256,256), swapaxes(0,1), / 255.0: examples/taichi_volume_raycaster.py:548-550).
+ * swap_axes01 != 0: src is [Z][Y][X] and the two slow axes are swapped on the fly; else src is already [Y][Z][X].
+ */
+int dr_ingest_u8(const DrDesc* d, const uint8_t* src, void* vol_linear, int swap_axes01, void* stream);
 
 #ifdef __cplusplus
 }
