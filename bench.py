@@ -289,19 +289,26 @@ def run_ours(args, cfg):
         h2d = sum(t.numel() * t.element_size() for t in (h_vol, h_tf, h_cams, h_target) + ((h_jit,) if h_jit is not None else ()))
         d2h = 4 + (h_gtf.numel() * 4 if need_tf else 0)
 
-        def e2e_step():
+        e2e_phase = {"h2d": 0.0, "forward": 0.0, "loss+backward": 0.0, "d2h+sync": 0.0}
+
+        def e2e_step(timed=False):
+            e = [ev() for _ in range(5)] if timed else None
             flush.zero_()
+            if timed: e[0].record()
             v = h_vol.to(dev, non_blocking=True)
             t = h_tf.to(dev, non_blocking=True)
             c = h_cams.to(dev, non_blocking=True)
             tg = h_target.to(dev, non_blocking=True)
             j = h_jit.to(dev, non_blocking=True) if h_jit is not None else None
+            if timed: e[1].record()
             if mode == "nondiff":
                 img = rc.raycast_nondiff(v, t, c, sampling_rate=sr)
+                if timed: e[2].record()
                 loss = ((img - tg) ** 2).mean()
             else:
                 v.requires_grad_(need_vol); t.requires_grad_(need_tf)
                 img = rc(v, t, c, j)
+                if timed: e[2].record()
                 loss = ((img - tg) ** 2).mean()
                 loss.backward()
                 if world > 1:
@@ -309,19 +316,27 @@ def run_ours(args, cfg):
                     dist.all_reduce(flat)
                 if need_tf:
                     h_gtf.copy_(t.grad, non_blocking=True)
+            if timed: e[3].record()
             h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            if timed: e[4].record()
             torch.cuda.synchronize()                                                  # the user reads the loss every step
+            if timed:
+                for name, x, y in (("h2d", 0, 1), ("forward", 1, 2), ("loss+backward", 2, 3), ("d2h+sync", 3, 4)):
+                    e2e_phase[name] += e[x].elapsed_time(e[y])
             return float(h_loss[0])
 
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             e2e_step()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = ev(), ev()
         a.record()
+        step_ms = []
         for _ in range(args.steps):
-            e2e_step()
+            t_s = time.perf_counter()
+            e2e_step(True)
+            step_ms.append(round(1e3 * (time.perf_counter() - t_s), 2))
         b.record()
         torch.cuda.synchronize()
         ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -329,6 +344,7 @@ def run_ours(args, cfg):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         e2e = {"value": all_samples * args.steps / (float(ms[0]) * 1e-3) / 1e9, "unit": "Gsamples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ms[0]) / args.steps,
+               "phase_ms_per_step": {k: v / args.steps for k, v in e2e_phase.items()}, "wall_ms_each_step": step_ms,
                "api": "differender_b200.Raycaster.forward + loss.backward()" if mode != "nondiff" else "Raycaster.raycast_nondiff"}
 
     if rank == 0:
