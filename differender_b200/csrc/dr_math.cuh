@@ -722,11 +722,14 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         const F3 pos = sample_pos(r, cam, s);
         Centre c;
         sample_centre<VT, LAYOUT, GENERIC>(d, vol, L, pos, c);
+        TfHit h;
+        apply_tf(d, tf, c.I, h, WANT_VOL);
+        const float o = opacity(d, h.c.w);
+        // Volume-only gradient: an exactly transparent sample whose two TF bins are both transparent (h.d.w == 0) has
+        // dc.rgb = k*o*dC = 0 and dI = tf_len * dc.w * h.d.w = 0, C = 0 (g.w unchanged) and T_{s-1} = T_s: nothing to do.
+        if (!WANT_TF && o == 0.0f && h.d.w == 0.0f) continue;
         Taps t;
         sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
-        TfHit h;
-        apply_tf(d, tf, t.I, h, WANT_VOL);
-        const float o = opacity(d, h.c.w);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, true, sh);
         const float T = (s == K - 1) ? Tprev : Tafter / (1.0f - o);

@@ -37,3 +37,21 @@ def test_device_math_nondiff_and_truncation():
     img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 40), max_samples=17, return_counts=True)
     out, K2, _, _ = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 40), max_samples=17)
     assert K.max() == 17 and np.array_equal(K, K2) and np.abs(img - out).max() <= 1e-6
+
+
+@pytest.mark.parametrize("want_vol,want_tf", [(True, False), (False, True)])
+def test_device_math_single_gradient_with_transparent_tf(want_vol, want_tf):
+    # tf1 is exactly transparent between its bumps: exercises the transparent-sample shortcuts of both marches
+    vol, tf, cams, jit = case_inputs((32, 32, 32), (40, 32), 128, seed=12, tf_name="tf1", jitter=True)
+    J = jit[0].numpy()
+    img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 32), jitter=J, max_samples=2048, return_counts=True)
+    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 32), jitter=J, max_samples=2048)
+    assert np.array_equal(K, K2) and np.array_equal(img[3], out[3]) and np.abs(img - out).max() <= 1e-6
+    go = np.random.default_rng(6).normal(size=img.shape).astype(np.float32)
+    gv, gt = co.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, (40, 32), jitter=J, max_samples=2048)
+    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, (40, 32), jitter=J, max_samples=2048,
+                           want_vol=want_vol, want_tf=want_tf)
+    if want_vol:
+        assert rel_l2(gv2, gv) <= 1e-4 and not gt2.any()
+    else:
+        assert rel_l2(gt2, gt) <= 1e-4 and not gv2.any()
