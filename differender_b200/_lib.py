@@ -12,7 +12,7 @@ DR_VERSION = 100
 VOX_F32, VOX_F16 = 0, 1
 F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM, F_LAYOUT_BRICK8, F_COUNT_SHADED = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
-EXPORTS = ("dr_version", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_forward",
+EXPORTS = ("dr_version", "dr_debug_oob_count", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_forward",
            "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad", "dr_forward_mse", "dr_backward_mse",
            "dr_momentum_step", "dr_ingest_u8")
 
@@ -43,6 +43,7 @@ def load():
     vp, cp = ctypes.c_void_p, ctypes.c_char_p
     dp = ctypes.POINTER(DrDesc)
     lib.dr_version.restype = ctypes.c_int
+    lib.dr_debug_oob_count.restype = ctypes.c_longlong
     lib.dr_last_error.restype = cp
     lib.dr_desc_init.argtypes = [dp] + [ctypes.c_int32] * 11 + [ctypes.c_uint32] + [ctypes.c_double] * 3
     lib.dr_desc_init.restype = ctypes.c_int

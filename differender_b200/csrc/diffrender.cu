@@ -19,6 +19,10 @@
 #include "dr_desc.h"
 #include "dr_math.cuh"
 
+#if defined(DR_BOUNDS_CHECK)
+__device__ unsigned long long dr_oob_counter = 0ULL;
+#endif
+
 using namespace dr;
 
 namespace {
@@ -190,8 +194,14 @@ template <bool ACCUM> struct CellVolSink {
     float4* g;
     int cur;
     float acc[8];
+#if defined(DR_BOUNDS_CHECK)
+    long long n_cells;
+#endif
     __device__ __forceinline__ void red(int cell, const float* v)
     {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(cell < 0 || cell >= n_cells);
+#endif
         float4* p = g + (size_t)cell * 2;
         atomicAdd(p, make_float4(v[0], v[1], v[2], v[3]));
         atomicAdd(p + 1, make_float4(v[4], v[5], v[6], v[7]));
@@ -282,6 +292,9 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     CellVolSink<ACCUM> vs;
     vs.g = WANT_VOL ? gcell + (d.Bvol == 1 ? 0 : (size_t)b * d.X * d.Y * d.Z * 2) : nullptr;
     vs.cur = -1;
+#if defined(DR_BOUNDS_CHECK)
+    vs.n_cells = (long long)d.X * d.Y * d.Z;
+#endif
     const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
     RedTfSink<ACCUM> ts;
     ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
@@ -493,6 +506,19 @@ int backward_impl(const DrDesc* d, const void* vol, const float* tf, const float
 extern "C" {
 
 int dr_version(void) { return DR_VERSION; }
+
+// number of out-of-range volume loads / gradient reductions seen so far; always 0 unless built with -DDR_BOUNDS_CHECK
+long long dr_debug_oob_count(void)
+{
+#if defined(DR_BOUNDS_CHECK)
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(&v, dr_oob_counter, sizeof(v)) != cudaSuccess) return -1;
+    return (long long)v;
+#else
+    return 0;
+#endif
+}
 
 const char* dr_last_error(void) { return g_err; }
 

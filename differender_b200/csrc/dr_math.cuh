@@ -48,6 +48,15 @@
 #define DR_SAT(a) fminf(1.0f, fmaxf(0.0f, (a)))
 #endif
 
+// Debug build (-DDR_BOUNDS_CHECK): every volume load and gradient reduction checks its index and counts violations
+// (compute-sanitizer is not available on the B200 pool).  Compiled out otherwise.
+#if defined(DR_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+extern __device__ unsigned long long dr_oob_counter;
+#define DR_OOB_IF(cond) do { if (cond) atomicAdd(&dr_oob_counter, 1ULL); } while (0)
+#else
+#define DR_OOB_IF(cond) do { } while (0)
+#endif
+
 namespace dr {
 
 DR_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -256,12 +265,24 @@ enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1 };
 template <typename VT> struct LinearAddr {
     typedef const VT* Row;
     const VT* vp; uoff sy, sz, i00;
+#if defined(DR_BOUNDS_CHECK)
+    long long n_elems;
+#endif
     DR_HD void init(const DrDesc& d, const VT* p, const Layout&, const Centre& c)
     {
         vp = p; sz = (uoff)d.X; sy = (uoff)(d.X * d.Z); i00 = (uoff)c.cidx;
+#if defined(DR_BOUNDS_CHECK)
+        n_elems = (long long)d.X * d.Y * d.Z;
+#endif
     }
     DR_HD Row row(int yi, int zi) const { return vp + (i00 + (uoff)yi * sy + (uoff)zi * sz); }   // wraps correctly for -1
-    DR_HD float ld(Row r, int xi) const { return load_vox(r, xi); }
+    DR_HD float ld(Row r, int xi) const
+    {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF((r + xi) - vp < 0 || (r + xi) - vp >= n_elems);
+#endif
+        return load_vox(r, xi);
+    }
 };
 template <typename VT> struct BrickAddr {
     typedef uoff Row;
@@ -271,7 +292,11 @@ template <typename VT> struct BrickAddr {
         vp = p; L = L_; lx = c.cx.lo; ly = c.cy.lo; lz = c.cz.lo;
     }
     DR_HD Row row(int yi, int zi) const { return offy(imin(ly + yi, L.my), L.sY) + offz(imin(lz + zi, L.mz), L.sZ); }
-    DR_HD float ld(Row r, int xi) const { return load_vox(vp, r + offx(imin(lx + xi, L.mx))); }
+    DR_HD float ld(Row r, int xi) const
+    {
+        DR_OOB_IF(lx + xi < 0 || (long long)(r + offx(imin(lx + xi, L.mx))) >= (long long)L.sZ * (((L.mz + 8) >> 3)));
+        return load_vox(vp, r + offx(imin(lx + xi, L.mx)));
+    }
 };
 template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };
 template <typename VT> struct AddrOf<VT, LAYOUT_BRICK8> { typedef BrickAddr<VT> type; };

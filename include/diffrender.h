@@ -85,6 +85,10 @@ typedef struct DrDesc {
 /* Library version (DR_VERSION of the build). */
 int dr_version(void);
 
+/* Debug aid: out-of-range volume loads / gradient reductions counted by a -DDR_BOUNDS_CHECK build (synchronises the
+ * device); always 0 in a normal build. */
+long long dr_debug_oob_count(void);
+
 /* Thread-local message of the last failure on this thread ("" if none). */
 const char* dr_last_error(void);
 
