@@ -27,7 +27,12 @@ using namespace dr;
 
 namespace {
 
-constexpr int kTileW = 16, kTileH = 8, kThreads = 128;
+// CTA = DR_CTA_WARPS warps, each an 8x4 pixel tile, laid out kWarpsX x kWarpsY
+#ifndef DR_CTA_WARPS
+#define DR_CTA_WARPS 4
+#endif
+constexpr int kWarpsX = DR_CTA_WARPS >= 2 ? 2 : 1, kWarpsY = DR_CTA_WARPS / kWarpsX;
+constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA_WARPS;
 // minimum resident CTAs per SM the compiler must allow (caps registers); tuned on B200, see DESIGN.md
 // (B200, C3: forward 6 CTAs/SM = 80 regs, no spills: +2 %; backward 5 CTAs/SM = 96 regs spills and loses 5 %, so 4.)
 #ifndef DR_FWD_MIN_BLOCKS
@@ -123,8 +128,8 @@ __device__ __forceinline__ void stage_tf(const DrDesc& d, const float* __restric
 __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
 {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    i = blockIdx.x * kTileW + (w & 1) * 8 + (l & 7);
-    j = blockIdx.y * kTileH + (w >> 1) * 4 + (l >> 3);
+    i = blockIdx.x * kTileW + (w % kWarpsX) * 8 + (l & 7);
+    j = blockIdx.y * kTileH + (w / kWarpsX) * 4 + (l >> 3);
     return i < d.W && j < d.H;
 }
 
