@@ -291,11 +291,12 @@ template <typename VT> struct BrickAddr {
     {
         vp = p; L = L_; lx = c.cx.lo; ly = c.cy.lo; lz = c.cz.lo;
     }
-    DR_HD Row row(int yi, int zi) const { return offy(imin(ly + yi, L.my), L.sY) + offz(imin(lz + zi, L.mz), L.sZ); }
+    // no clamps: in the corner-reuse path every index lo-1 .. lo+2 that is actually read is in range (see LinearAddr)
+    DR_HD Row row(int yi, int zi) const { return offy(ly + yi, L.sY) + offz(lz + zi, L.sZ); }
     DR_HD float ld(Row r, int xi) const
     {
-        DR_OOB_IF(lx + xi < 0 || (long long)(r + offx(imin(lx + xi, L.mx))) >= (long long)L.sZ * (((L.mz + 8) >> 3)));
-        return load_vox(vp, r + offx(imin(lx + xi, L.mx)));
+        DR_OOB_IF(lx + xi < 0 || lx + xi > L.mx || (long long)(r + offx(lx + xi)) >= (long long)L.sZ * (((L.mz + 8) >> 3)));
+        return load_vox(vp, r + offx(lx + xi));
     }
 };
 template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };

@@ -47,6 +47,12 @@ class VolumeRaycaster:
         self.ambient, self.diffuse, self.specular, self.shininess = 0.4, 0.8, 0.3, 32.0    # :91-94
         self.last_K = None           # per-ray active sample counts of the most recent forward ([BS,H,W] int32)
 
+    @property
+    def max_valid_sample_step_count(self):
+        """Largest number of active samples on any ray of the most recent forward -- the reference's diagnostic of the same
+        name (:89, :370-372; printed as "Max Samples: x / M" by its demo).  Synchronises."""
+        return 0 if self.last_K is None else int(self.last_K.max().item())
+
     # -- thin wrappers over the C ABI (one distinct volume is bricked once, not once per view) ---------------
     def desc(self, BS, Bvol, Btf, vox_dtype, flags, sampling_rate):
         X, Y, Z = self.volume_resolution
