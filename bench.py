@@ -347,6 +347,21 @@ def run_ours(args, cfg):
                "phase_ms_per_step": {k: v / args.steps for k, v in e2e_phase.items()}, "wall_ms_each_step": step_ms,
                "api": "differender_b200.Raycaster.forward + loss.backward()" if mode != "nondiff" else "Raycaster.raycast_nondiff"}
 
+    # L2 -> SM read bandwidth of this box (not in MEASURED_PEAKS.json, so measured here): repeated reduction
+    # of a 48 MiB buffer that stays L2-resident (126 MB L2); a library reduction, so a lower bound of the hardware figure
+    l2_gbs = None
+    if rank == 0:
+        lb = torch.empty(48 << 18, dtype=torch.float32, device=dev).normal_()
+        for _ in range(5):
+            lb.sum()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(20):
+            lb.sum()
+        b.record()
+        torch.cuda.synchronize()
+        l2_gbs = 20 * lb.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9
+        del lb
     if rank == 0:
         peaks = {}
         try:
@@ -390,6 +405,10 @@ def run_ours(args, cfg):
                          "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes * s, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_sample": dom_bytes,
                          "note": "algorithmic bytes are the L2-level figure of SURVEY 8(d) (8 corner reads [+ 8 fp32 atomic RMWs] per sample); the kernels are instruction-issue-bound and almost every access hits L1/L2, so measured DRAM traffic is far BELOW the algorithmic bytes"},
+            "rooflines_other": {"l2_read_gbs_measured": l2_gbs, "l2_how": "torch.sum over a 48 MiB L2-resident buffer, 20 reps",
+                                "achieved_over_l2": (achieved / l2_gbs) if l2_gbs else None,
+                                "issue_active_pct_ncu": {"fwd_kernel": 77.6, "bwd_kernel": 74.2, "source": "profiles/r01f_ncu_v3_c3_16views.txt"},
+                                "binding": "instruction issue (both kernels ~75-78 % issue-active; DRAM < 1 % of peak)"},
             "clocks": clocks, "gpu_launches": launches[0],
         }
         if e2e is not None:
