@@ -1,0 +1,47 @@
+"""Parity report: CUDA path (through the C ABI) vs the strict-fp32 CPU oracle on identical inputs and jitter, at sizes up to
+the full C3 volume.  Prints one row per case: RGBA max-abs error, rays whose n / K differ, relative L2 of both gradients.
+Run on a B200:  python tools/parity_report.py > gpurun_out/parity_report.txt"""
+import os, sys, time
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")]
+import numpy as np
+import torch
+from differender_b200 import VolumeRaycaster
+from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
+from oracle import cpu_oracle as co
+
+dev = "cuda:0"
+rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+print(f"{'case':58s} {'rays':>8s} {'samples':>10s} {'rgba max|d|':>12s} {'alpha max|d|':>12s} {'K!=':>4s} {'gvol relL2':>11s} {'gtf relL2':>10s}")
+CASES = [
+    ("64^3 fp32, 96x64, tf1 R=128, sr 1, jitter", 64, (96, 64), "tf1", 128, 1.0, True, torch.float32, "linear"),
+    ("64^3 fp32, 96x64, rand TF R=33, sr 0.7, jitter", 64, (96, 64), "rand", 33, 0.7, True, torch.float32, "linear"),
+    ("128^3 fp32, 128x128, tf1, sr 2, jitter", 128, (128, 128), "tf1", 128, 2.0, True, torch.float32, "linear"),
+    ("128^3 fp16, 128x128, tf1, sr 1, jitter, brick8", 128, (128, 128), "tf1", 128, 1.0, True, torch.float16, "brick8"),
+    ("256^3 fp32 (C3 volume), 256x256, tf1, sr 1, jitter", 256, (256, 256), "tf1", 128, 1.0, True, torch.float32, "linear"),
+    ("256^3 fp32 (C3 volume), 256x256, tf5, sr 1, no jitter", 256, (256, 256), "tf5", 128, 1.0, False, torch.float32, "linear"),
+    ("256^3 fp32, 192x192, 'gray' TF (no transparent bins), sr 1", 256, (192, 192), "gray", 128, 1.0, True, torch.float32, "linear"),
+]
+for name, n, (w, h), tfn, R, sr, jitter, dt, layout in CASES:
+    vol = make_volume(n)
+    if dt == torch.float16:
+        vol = vol.half().float()
+    tf = make_tf(tfn, R) if tfn != "rand" else torch.rand(4, R, generator=torch.Generator().manual_seed(1)) * torch.tensor([1, 1, 1, 0.15]).view(4, 1)
+    cam = make_cameras(16)[3:4]
+    jit = make_jitter(1, h, w) if jitter else None
+    M = 8192
+    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=layout)
+    v = vr.brick(vol.to(dev, dt).reshape(1, n, n, n).contiguous())
+    tf_r4 = tf.to(dev).t().contiguous()[None]
+    j = None if jit is None else jit.to(dev)
+    out, K, Tp = vr.march(v, tf_r4, cam.to(dev), sr, j)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    gv, gt = vr.march_backward(v, tf_r4, cam.to(dev), sr, j, go.to(dev), out, K, Tp, True, True)
+    J = None if jit is None else jit[0].numpy()
+    ref, Kr, nr = co.forward(vol.numpy(), tf.numpy(), cam[0].numpy(), (w, h), sampling_rate=sr, max_samples=M, jitter=J, return_counts=True)
+    gvr, gtr = co.backward(vol.numpy(), tf.numpy(), cam[0].numpy(), go[0].numpy(), (w, h), sampling_rate=sr, max_samples=M, jitter=J)
+    o = out[0].cpu().numpy(); Kc = K[0].cpu().numpy()
+    same = Kc == Kr
+    d = np.abs(o - ref)
+    print(f"{name:58s} {w*h:8d} {int(Kr.sum()):10d} {d[:, same].max():12.2e} {d[3][same].max():12.2e} {int((~same).sum()):4d} "
+          f"{rel(gv[0].cpu().numpy(), gvr):11.2e} {rel(gt[0].cpu().numpy().T, gtr):10.2e}", flush=True)
+print("tolerances (BASELINE.json north_star): RGBA <= 1e-4 max-abs, gradients <= 1e-3 relative L2")
