@@ -80,5 +80,5 @@ def make_desc(X, Y, Z, W, H, R, M, BS, Bvol, Btf, vox_dtype, flags, sampling_rat
 
 
 def ptr(t):
-    """Device pointer of a tensor (or None)."""
+    """Device pointer of a tensor-like (anything with data_ptr()) or None."""
     return None if t is None else ctypes.c_void_p(t.data_ptr())

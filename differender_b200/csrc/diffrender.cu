@@ -439,14 +439,13 @@ __global__ void __launch_bounds__(256) ingest_u8_kernel(DrDesc d, const uint8_t*
 }
 
 int forward_impl(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, float* out_rgba,
-                 int32_t* out_K, float* out_Tprev, const float* target, float* loss_sum, void* stream, const char* who)
+                 int32_t* out_K, float* out_Tprev, const float* target, float* loss_sum, void* stream)
 {
     if (int rc = check_desc(d)) return rc;
     if (!vol || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
     if ((d->flags & DR_F_HAS_JITTER) && !jitter) return fail(DR_EINVAL, "dr_forward: DR_F_HAS_JITTER set but jitter is null");
     if (!aligned(tf, 16) || !aligned(out_rgba, 16)) return fail(DR_EALIGN, "dr_forward: tf and out_rgba must be 16-byte aligned");
     if (target && (!loss_sum || !aligned(target, 16))) return fail(DR_EINVAL, "dr_forward_mse: loss_sum is null or target is not 16-byte aligned");
-    (void)who;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool nd = d->flags & DR_F_NONDIFF, gen = d->tap_generic, brick = d->flags & DR_F_LAYOUT_BRICK8;
 #define DR_FWD1(VT, LAY, ND, GEN) launch_fwd<VT, LAY, ND, GEN>(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, st, target, loss_sum)
@@ -562,14 +561,14 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
 int dr_forward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream)
 {
-    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, nullptr, nullptr, stream, "dr_forward");
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, nullptr, nullptr, stream);
 }
 
 int dr_forward_mse(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                    const float* target, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream)
 {
     if (!target || !loss_sum) return fail(DR_EINVAL, "dr_forward_mse: target or loss_sum is null");
-    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, target, loss_sum, stream, "dr_forward_mse");
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, target, loss_sum, stream);
 }
 
 int dr_backward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,

@@ -17,7 +17,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, VOX_F16, VOX_F32)
+from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, F_TF_4R, VOX_F16,
+                   VOX_F32)
 
 __all__ = ["VolumeRaycaster", "RaycastFunction", "RaycastMSEFunction", "Raycaster"]
 
@@ -98,8 +99,11 @@ class VolumeRaycaster:
     def march(self, bricked, tf_r4, cam, sampling_rate, jitter=None, nondiff=False, image_layout=True, want_aux=True,
               extra_flags=0, mse_target=None):
         """Forward of cam.shape[0] views.  Returns (out, K, Tprev), or (out, K, Tprev, loss_sum[BS]) when `mse_target`
-        (same layout as out) is given: the squared-error sum is accumulated in the kernel's epilogue."""
+        (same layout as out) is given: the squared-error sum is accumulated in the kernel's epilogue.
+        `tf_r4` is [Btf, R, 4] (the reference's order); pass extra_flags=F_TF_4R with a [Btf, 4, R] tensor (torch order)."""
         BS = cam.shape[0]
+        if extra_flags & F_TF_4R:
+            tf_r4 = _Tf4R(tf_r4)
         w, h = self.resolution
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
@@ -127,6 +131,8 @@ class VolumeRaycaster:
         (e.g. chunks of a large view batch) share one buffer and one gather.
         With `mse_scale`, `grad_out` is the TARGET image and dL/d(out) = mse_scale*(out - target) is formed in the kernel."""
         BS = cam.shape[0]
+        if extra_flags & F_TF_4R:
+            tf_r4 = _Tf4R(tf_r4)
         vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
         flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
                 (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags | self._lflag(bricked)
@@ -136,7 +142,7 @@ class VolumeRaycaster:
         keep_cells = grad_cells is not None
         if need_vol and grad_cells is None:
             grad_cells = torch.zeros((bricked.shape[0], lib.dr_grad_cells_elems(ctypes.byref(d))), dtype=torch.float32, device=dev)
-        gtf = torch.zeros(tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
+        gtf = torch.zeros(tf_r4.t.shape if isinstance(tf_r4, _Tf4R) else tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
         ws_bytes = lib.dr_workspace_bytes(ctypes.byref(d))
         ws = torch.empty((max(ws_bytes, 16) + 3) // 4, dtype=torch.float32, device=dev)
         if mse_scale is not None:
@@ -163,6 +169,17 @@ class VolumeRaycaster:
         gl = torch.empty((grad_cells.shape[0], Y, Z, X), dtype=torch.float32, device=grad_cells.device)
         _lib.check(_lib.load().dr_gather_grad(ctypes.byref(d), _lib.ptr(grad_cells), _lib.ptr(gl), 0, _stream()), "dr_gather_grad")
         return gl
+
+
+class _Tf4R:
+    """Adapter so that a [Btf, 4, R] transfer function reports the [Btf, R, 4] shape the wrappers size their buffers from."""
+
+    def __init__(self, t):
+        self.t = t
+        self.shape = (t.shape[0], t.shape[2], t.shape[1])
+
+    def data_ptr(self):
+        return self.t.data_ptr()
 
 
 def _require_cuda(*tensors):

@@ -165,3 +165,18 @@ def test_golden_fixtures_on_gpu():
                                    go.cuda().contiguous(), out, K, Tp, True, True)
         assert rel_l2(gv[0].cpu().numpy(), z["grad_volume"]) <= GRAD_TOL, f
         assert rel_l2(gt[0].cpu().numpy().T, z["grad_tf"]) <= GRAD_TOL, f
+
+
+def test_tf_in_torch_4xR_layout_equals_Rx4_layout():
+    from differender_b200._lib import F_TF_4R
+    vol, tf, cams, jit = case_inputs((32, 32, 32), (40, 24), 48, seed=17, tf_name="tf1", views=2)
+    vr, v, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (40, 24), jit)
+    tf_4r = tf.cuda().contiguous()[None]                                       # [1, 4, R]: the torch-side layout, no transpose copy
+    c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
+    out2, K2, Tp2 = vr.march(v, tf_4r, c, 1.0, j, extra_flags=F_TF_4R)
+    assert torch.equal(out, out2) and torch.equal(K, K2)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    gv, gt = vr.march_backward(v, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
+    gv2, gt2 = vr.march_backward(v, tf_4r, c, 1.0, j, go, out, K, Tp, True, True, extra_flags=F_TF_4R)
+    assert gt2.shape == (1, 4, 48)
+    assert rel_l2(gt2[0].t().cpu().numpy(), gt[0].cpu().numpy()) <= 1e-5 and rel_l2(gv2.cpu().numpy(), gv.cpu().numpy()) <= 1e-5
