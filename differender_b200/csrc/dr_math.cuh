@@ -127,12 +127,21 @@ DR_HD uoff offx(int x) { return (uoff)(((x >> 3) << 9) | (x & 7)); }
 DR_HD uoff offy(int y, int sY) { return (uoff)((y >> 3) * sY + ((y & 7) << 3)); }
 DR_HD uoff offz(int z, int sZ) { return (uoff)((z >> 3) * sZ + ((z & 7) << 6)); }
 
-DR_HD float load_vox(const float* p, uoff off)
+// pointer + unsigned element offset as ONE instruction (IMAD.WIDE.U32, FMA pipe).  Left to the compiler, a 2-byte element
+// type becomes four 64-bit IADD3/IADD3.X per address (base + off + off), which made integer adds 25 % of the fp16 kernels.
+// The element size comes from constant memory so that ptxas cannot strength-reduce the multiply back into LEA + LEA.HI.X.
+#if defined(__CUDACC__)
+static __constant__ unsigned dr_elem_size[3] = { 0u, 2u, 4u };     // indexed by sizeof(VT) / 2
+#endif
+template <typename VT>
+DR_HD const VT* ptr_add(const VT* p, uoff off)
 {
 #if defined(__CUDA_ARCH__)
-    return __ldg(p + off);
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(off), "r"(dr_elem_size[sizeof(VT) / 2]), "l"((unsigned long long)p));
+    return reinterpret_cast<const VT*>(a);
 #else
-    return p[off];
+    return p + off;
 #endif
 }
 DR_HD float load_vox(const float* p, int off)
@@ -143,15 +152,8 @@ DR_HD float load_vox(const float* p, int off)
     return p[off];
 #endif
 }
+DR_HD float load_vox(const float* p, uoff off) { return load_vox(ptr_add(p, off), 0); }
 #if defined(__CUDACC__)
-DR_HD float load_vox(const __half* p, uoff off)
-{
-#if defined(__CUDA_ARCH__)
-    return __half2float(__ldg(p + off));
-#else
-    return __half2float(p[off]);
-#endif
-}
 DR_HD float load_vox(const __half* p, int off)
 {
 #if defined(__CUDA_ARCH__)
@@ -160,6 +162,7 @@ DR_HD float load_vox(const __half* p, int off)
     return __half2float(p[off]);
 #endif
 }
+DR_HD float load_vox(const __half* p, uoff off) { return load_vox(ptr_add(p, off), 0); }
 #endif
 template <typename VT> struct VolView {
     const VT* p;
@@ -275,7 +278,7 @@ template <typename VT> struct LinearAddr {
         n_elems = (long long)d.X * d.Y * d.Z;
 #endif
     }
-    DR_HD Row row(int yi, int zi) const { return vp + (i00 + (uoff)yi * sy + (uoff)zi * sz); }   // wraps correctly for -1
+    DR_HD Row row(int yi, int zi) const { return ptr_add(vp, i00 + (uoff)yi * sy + (uoff)zi * sz); }   // wraps correctly for -1
     DR_HD float ld(Row r, int xi) const
     {
 #if defined(DR_BOUNDS_CHECK)
