@@ -201,6 +201,7 @@ def run_ours(args, cfg):
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     need_vol, need_tf = mode == "full", mode in ("full", "tf")
     momentum = torch.zeros_like(tf)
+    flat_grad = torch.empty(n ** 3 + R * 4, dtype=torch.float32, device=dev) if world > 1 else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
     phase_ms = {"brick": 0.0, "fwd": 0.0, "bwd": 0.0, "post": 0.0}
     samples_per_step = [0]
@@ -217,13 +218,21 @@ def run_ours(args, cfg):
         n_k = 2 if bricked.ndim == 2 else 1                                          # (brick_kernel +) fwd_kernel
         if mode != "nondiff":
             go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
-            gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf,
-                                          extra_flags=128 if args.no_reg_accum else 0)
+            xf = 128 if args.no_reg_accum else 0
+            if world > 1 and need_vol:
+                # the gather writes straight into the flat [volume grad | TF grad] buffer that is all-reduced (no concatenation copy)
+                cells = torch.zeros((1, n ** 3 * 8), dtype=torch.float32, device=dev)
+                _, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf, grad_cells=cells, extra_flags=xf)
+                gvol = vr.gather(cells, out=flat_grad[:n ** 3].view(1, n, n, n))
+                flat_grad[n ** 3:].copy_(gtf.reshape(-1))
+            else:
+                gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf, extra_flags=xf)
             if timed: e[3].record()
             n_k += 1 + (1 if need_tf else 0) + (1 if need_vol else 0)                 # bwd_kernel (+ tf_reduce_kernel) (+ gather_grad_kernel)
             if world > 1:
-                flat = torch.cat([t.reshape(-1) for t in (gvol, gtf) if t is not None])
-                dist.all_reduce(flat)
+                if not need_vol:
+                    flat_grad[:gtf.numel()].copy_(gtf.reshape(-1))
+                dist.all_reduce(flat_grad if need_vol else flat_grad[:gtf.numel()])      # ONE collective: NCCL over NVLink
             if mode == "tf":                                                         # C2: momentum update (reference example :375-381)
                 gt = gtf[0].t().clamp(-0.1, 0.1)
                 momentum.mul_(0.9).add_(gt, alpha=0.1)
@@ -409,6 +418,10 @@ def run_ours(args, cfg):
                                 "achieved_over_l2": (achieved / l2_gbs) if l2_gbs else None,
                                 "issue_active_pct_ncu": {"fwd_kernel": 77.6, "bwd_kernel": 74.2, "source": "profiles/r01f_ncu_v3_c3_16views.txt"},
                                 "binding": "instruction issue (both kernels ~75-78 % issue-active; DRAM < 1 % of peak)"},
+            "allreduce": None if world == 1 else {
+                "bytes": int((n ** 3 + R * 4) * 4 if need_vol else R * 16), "ms": phase_ms["post"] / args.steps,
+                "busbw_gbs": ((n ** 3 + R * 4) * 4 if need_vol else R * 16) * 2 * (world - 1) / world / (phase_ms["post"] / args.steps * 1e-3) / 1e9,
+                "nvlink_peak_gbs": 900.0, "note": "one all_reduce(SUM) of the flat [volume grad | TF grad] fp32 buffer, rank-0 CUDA-event time of the `post` phase"},
             "clocks": clocks, "gpu_launches": launches[0],
         }
         if e2e is not None:

@@ -161,12 +161,15 @@ class VolumeRaycaster:
             return grad_cells, gtf
         return self.gather(grad_cells), gtf
 
-    def gather(self, grad_cells):
-        """Cell-major gradient [Bvol, X*Y*Z*8] -> linear [Bvol, Y, Z, X] fp32 with nan_to_num."""
+    def gather(self, grad_cells, out=None):
+        """Cell-major gradient [Bvol, X*Y*Z*8] -> linear [Bvol, Y, Z, X] fp32 with nan_to_num (into `out` if given, e.g. a
+        slice of the flat buffer that is all-reduced across GPUs)."""
         X, Y, Z = self.volume_resolution
         d = self.desc(1, 1, 1, VOX_F32, 0, 1.0)
         d.Bvol = grad_cells.shape[0]
-        gl = torch.empty((grad_cells.shape[0], Y, Z, X), dtype=torch.float32, device=grad_cells.device)
+        gl = out if out is not None else torch.empty((grad_cells.shape[0], Y, Z, X), dtype=torch.float32, device=grad_cells.device)
+        if tuple(gl.shape) != (grad_cells.shape[0], Y, Z, X) or gl.dtype != torch.float32 or not gl.is_contiguous():
+            raise ValueError("gather: `out` must be a contiguous fp32 tensor of shape [Bvol, Y, Z, X]")
         _lib.check(_lib.load().dr_gather_grad(ctypes.byref(d), _lib.ptr(grad_cells), _lib.ptr(gl), 0, _stream()), "dr_gather_grad")
         return gl
 
