@@ -29,7 +29,7 @@ CONFIGS = {
     # name: volume N^3, dtype, image (w,h), views per GPU, mode
     "c1": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="nondiff", sr=16.0, M=1, jitter=False,
                desc="C1 forward-only nondiff render, 256^3 fp32, 512x512, 1 view, sr 16"),
-    "c2": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="tf", sr=1.0, M=2048, jitter=True,
+    "c2": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="tf", sr=1.0, M=2048, jitter=True, tf="black",
                desc="C2 TF optimisation step: fwd+bwd w.r.t. TF only + momentum update, 256^3 fp32, 512x512, 1 view"),
     "c3": dict(n=256, dtype="f32", res=(1024, 1024), views=16, mode="full", sr=1.0, M=2048, jitter=True,
                desc="C3 volume-gradient backprop: fwd+bwd (TF+volume grad), 256^3 fp32, 1024x1024, 16 views per GPU"),
@@ -51,6 +51,8 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--tf", default=None, help="transfer-function preset (reference utils.get_tf): tf1..tf5, gray, black, rand; "
+                                              "default tf1 (C2: its optimisation start `black`)")
     p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8"], help="volume layout read by the march kernels")
     p.add_argument("--no-reg-accum", action="store_true", help="tuning: backward without register accumulation (DR_F_NO_REG_ACCUM)")
     p.add_argument("--cuda-profiler-range", action="store_true",
@@ -116,7 +118,7 @@ def cpu_sample(cfg, budget_s=20.0):
     vol = make_volume(n).numpy()
     if cfg["dtype"] == "f16":
         vol = vol.astype(np.float16).astype(np.float32)
-    tf = make_tf("tf1", 128).numpy()
+    tf = make_tf(cfg.get("tf", "tf1"), 128).numpy()
     cam = make_cameras(max(cfg["views"], 1))[0].numpy()
     jit = make_jitter(1, h, w)[0].numpy() if cfg["jitter"] else None
     nondiff = cfg["mode"] == "nondiff"
@@ -188,7 +190,8 @@ def run_ours(args, cfg):
     mode = cfg["mode"]
     vdtype = torch.float16 if cfg["dtype"] == "f16" else torch.float32
     vol = make_volume(n, device=dev, dtype=vdtype)                                   # (1, D, H, W), replicated on every rank
-    tf = make_tf("tf1", R, device=dev)                                               # (4, R)
+    tf_name = args.tf or cfg.get("tf", "tf1")
+    tf = make_tf(tf_name, R, device=dev)                                             # (4, R)
     all_cams = make_cameras(views * world, device=dev)
     cams = all_cams[rank * views:(rank + 1) * views].contiguous()                   # this rank's shard of the view batch
     jit = make_jitter(views, h, w, seed=4321 + rank, device=dev) if cfg["jitter"] else None
@@ -402,7 +405,7 @@ def run_ours(args, cfg):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "volume": f"{n}^3 {cfg['dtype']}", "image": f"{w}x{h}", "views_per_gpu": views,
-                       "volume_layout": vr.resolve_layout(vol_lin), "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
+                       "volume_layout": vr.resolve_layout(vol_lin), "tf": tf_name, "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
                        "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
                        "active_samples_per_step_per_gpu": s, "shaded_fraction_of_active_samples": round(shaded_fraction, 4),
