@@ -39,6 +39,7 @@ CONFIGS = {
                desc="C5 large volume: fwd+bwd, 1024^3 fp16-stored, 2048x2048, jittered, 32 views per GPU (256 over 8 GPUs)"),
 }
 L2_FLUSH_BYTES = 256 << 20
+METRIC = {"full": "Gsamples/s fwd+bwd (TF+volume grad)", "tf": "Gsamples/s fwd+bwd (TF grad)", "nondiff": "Gsamples/s fwd"}
 
 
 def parse():
@@ -153,7 +154,7 @@ def run_reference(args, cfg):
     samples = sum(v["samples"] for v in vals)
     value = samples / secs / 1e9
     line = {
-        "impl": "reference", "metric": "Gsamples/s fwd+bwd (TF+volume grad)" if cfg["mode"] != "nondiff" else "Gsamples/s fwd",
+        "impl": "reference", "metric": METRIC[cfg["mode"]],
         "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -400,7 +401,7 @@ def run_ours(args, cfg):
         except (OSError, KeyError, ValueError):
             pass
         line = {
-            "metric": "Gsamples/s fwd+bwd (TF+volume grad)" if mode == "full" else ("Gsamples/s fwd+bwd (TF grad)" if mode == "tf" else "Gsamples/s fwd"),
+            "metric": METRIC[mode],
             "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
