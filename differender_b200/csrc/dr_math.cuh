@@ -36,6 +36,7 @@
 #define DR_SQRT(a) __fsqrt_rn((a))
 #define DR_RSQRT(a) rsqrtf((a))
 #define DR_SAT(a) __saturatef((a))
+#define DR_FAST_DIV(a, b) __fdividef((a), (b))
 #else
 // host build (tests/hostsim): compiled with -ffp-contract=off, so each operator is one IEEE operation
 #define DR_MUL(a, b) ((a) * (b))
@@ -46,6 +47,7 @@
 #define DR_SQRT(a) sqrtf((a))
 #define DR_RSQRT(a) (1.0f / sqrtf((a)))
 #define DR_SAT(a) fminf(1.0f, fmaxf(0.0f, (a)))
+#define DR_FAST_DIV(a, b) ((a) / (b))
 #endif
 
 // Debug build (-DDR_BOUNDS_CHECK): every volume load and gradient reduction checks its index and counts violations
@@ -761,7 +763,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, true, sh);
-        const float T = (s == K - 1) ? Tprev : Tafter / (1.0f - o);
+        const float T = (s == K - 1) ? Tprev : DR_FAST_DIV(Tafter, 1.0f - o);   // 1-o in (0.01, 1]: no IEEE slow path needed
         Tafter = T;
         SampleAdj a;
         const float Cg = sample_adjoint(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
