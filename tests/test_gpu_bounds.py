@@ -12,7 +12,16 @@ pytestmark = pytest.mark.gpu
 def test_no_out_of_range_access_in_debug_build():
     from differender_b200 import _lib
     if "dbg" not in os.path.basename(_lib.LIB_PATH):
-        pytest.skip("needs DIFFRENDER_LIB pointing at a -DDR_BOUNDS_CHECK build")
+        # the library is chosen at import time: re-run this very test in a child process bound to the debug build
+        import subprocess, sys
+        from differender_b200.build import DEBUG_LIB_PATH
+        if not os.path.exists(DEBUG_LIB_PATH):
+            pytest.skip("libdiffrender_dbg.so not built (__graft_entry__.build() builds it)")
+        env = dict(os.environ, DIFFRENDER_LIB=DEBUG_LIB_PATH)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__)], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        return
     from differender_b200 import VolumeRaycaster
     from differender_b200.synthetic import make_jitter, make_tf
     dev = "cuda:0"
