@@ -303,25 +303,35 @@ def run_ours(args, cfg):
         d2h = 4 + (h_gtf.numel() * 4 if need_tf else 0)
 
         e2e_phase = {"h2d": 0.0, "forward": 0.0, "loss+backward": 0.0, "d2h+sync": 0.0}
+        copy_stream = torch.cuda.Stream(device=dev)
+        d_target = torch.empty_like(target)
 
         def e2e_step(timed=False):
             e = [ev() for _ in range(5)] if timed else None
             flush.zero_()
             if timed: e[0].record()
+            # the target image is only needed by the loss: its copy (the largest input) runs on a second stream under the forward march
+            # (issued after the inputs of the march, so the copy engine serves those first; into a persistent device buffer)
+            main = torch.cuda.current_stream()
             v = h_vol.to(dev, non_blocking=True)
             t = h_tf.to(dev, non_blocking=True)
             c = h_cams.to(dev, non_blocking=True)
-            tg = h_target.to(dev, non_blocking=True)
             j = h_jit.to(dev, non_blocking=True) if h_jit is not None else None
             if timed: e[1].record()
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):
+                d_target.copy_(h_target, non_blocking=True)
+            tg = d_target
             if mode == "nondiff":
                 img = rc.raycast_nondiff(v, t, c, sampling_rate=sr)
                 if timed: e[2].record()
+                main.wait_stream(copy_stream)
                 loss = ((img - tg) ** 2).mean()
             else:
                 v.requires_grad_(need_vol); t.requires_grad_(need_tf)
                 img = rc(v, t, c, j)
                 if timed: e[2].record()
+                main.wait_stream(copy_stream)
                 loss = ((img - tg) ** 2).mean()
                 loss.backward()
                 if world > 1:
@@ -358,7 +368,8 @@ def run_ours(args, cfg):
         e2e = {"value": all_samples * args.steps / (float(ms[0]) * 1e-3) / 1e9, "unit": "Gsamples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ms[0]) / args.steps,
                "phase_ms_per_step": {k: v / args.steps for k, v in e2e_phase.items()}, "wall_ms_each_step": step_ms,
-               "api": "differender_b200.Raycaster.forward + loss.backward()" if mode != "nondiff" else "Raycaster.raycast_nondiff"}
+               "api": "differender_b200.Raycaster.forward + loss.backward()" if mode != "nondiff" else "Raycaster.raycast_nondiff",
+               "overlap": "the target image's H2D copy runs on a second stream under the forward march; `h2d` is the un-overlapped part (volume, TF, cameras, jitter)"}
 
     # L2 -> SM read bandwidth of this box (not in MEASURED_PEAKS.json, so measured here): repeated reduction
     # of a 48 MiB buffer that stays L2-resident (126 MB L2); a library reduction, so a lower bound of the hardware figure

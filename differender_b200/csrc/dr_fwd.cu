@@ -1,0 +1,25 @@
+// dr_fwd.cu -- instantiations of the forward march kernel (dr_kernels.cuh) and their dispatch.
+#include "dr_kernels.cuh"
+
+namespace dr {
+
+// The SR1 = false kernels are correct for any sampling rate (powf(x, 1) == x); the generic-tap path (volumes > ~2000 voxels
+// per axis, linear layout only) only has those.
+template <typename VT>
+static int forward_vt(const FwdArgs& a)
+{
+    const DrDesc* d = a.d;
+    const bool nd = d->flags & DR_F_NONDIFF, sr1 = d->inv_sr == 1.0f;
+#define DR_FWD_ND(LAY, GEN, SR1) (nd ? launch_fwd<VT, LAY, true, GEN, SR1>(a) : launch_fwd<VT, LAY, false, GEN, SR1>(a))
+    if (d->flags & DR_F_LAYOUT_BRICK8) return sr1 ? DR_FWD_ND(LAYOUT_BRICK8, false, true) : DR_FWD_ND(LAYOUT_BRICK8, false, false);
+    if (d->tap_generic) return DR_FWD_ND(LAYOUT_LINEAR, true, false);
+    return sr1 ? DR_FWD_ND(LAYOUT_LINEAR, false, true) : DR_FWD_ND(LAYOUT_LINEAR, false, false);
+#undef DR_FWD_ND
+}
+
+int launch_forward(const FwdArgs& a)
+{
+    return a.d->vox_dtype == DR_VOX_F32 ? forward_vt<float>(a) : forward_vt<__half>(a);
+}
+
+}  // namespace dr

@@ -1,0 +1,321 @@
+// dr_kernels.cuh -- the two march kernels (templates) and their launchers.  Included by dr_fwd.cu, dr_bwd_f32.cu and
+// dr_bwd_f16.cu, which instantiate them in separate translation units so the library builds in parallel.
+//
+//   fwd_kernel       ray set-up + march + compositing + final image          (reference :221-372)
+//   bwd_kernel       tape-free reverse march, TF + volume gradient scatter   (raycast.grad, :460-461)
+//
+// Thread mapping: one ray per thread; a warp is an 8x4 pixel tile, a CTA (4 warps) a 16x8 tile, so the 32 rays of
+// a warp traverse neighbouring voxels and their corner fetches fall into a few 128-byte lines of the same rows/bricks.
+// No tensor cores: nothing here is a dense contraction (north_star).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "diffrender.h"
+#include "dr_host.h"
+#include "dr_math.cuh"
+
+namespace dr {
+
+// CTA = DR_CTA_WARPS warps, each an 8x4 pixel tile, laid out kWarpsX x kWarpsY
+#ifndef DR_CTA_WARPS
+#define DR_CTA_WARPS 4
+#endif
+constexpr int kWarpsX = DR_CTA_WARPS >= 2 ? 2 : 1, kWarpsY = DR_CTA_WARPS / kWarpsX;
+constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA_WARPS;
+// minimum resident CTAs per SM the compiler must allow (caps registers); tuned on B200, see DESIGN.md
+// (B200, C3: forward 6 CTAs/SM = 80 regs, no spills: +2 %; backward 5 CTAs/SM = 96 regs spills and loses 5 %, so 4.)
+#ifndef DR_FWD_MIN_BLOCKS
+#define DR_FWD_MIN_BLOCKS 6
+#endif
+#ifndef DR_BWD_MIN_BLOCKS
+#define DR_BWD_MIN_BLOCKS 4
+#endif
+
+__host__ __device__ inline Layout make_layout(const DrDesc& d)
+{
+    Layout L;
+    L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
+    L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shared prologue: stage the view's transfer function in shared memory as R TfBin entries (32 bytes each: tf[r] and
+// what the lookup needs of tf[min(r+1, R-1)], see dr_math.cuh).  Returns the table accessor.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ TfTable stage_tf(const DrDesc& d, const float* __restrict__ tf, int tb, TfBin* s_tf)
+{
+    const float* src = tf + (size_t)tb * d.R * 4;
+    const int R = d.R;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int r1 = min(r + 1, R - 1);
+        F4 a, b;
+        if (d.flags & DR_F_TF_4R) {                              // [4][R]: a warp reads 32 consecutive bins of one channel
+            a = F4 { __ldg(src + r), __ldg(src + R + r), __ldg(src + 2 * R + r), __ldg(src + 3 * R + r) };
+            b = F4 { __ldg(src + r1), __ldg(src + R + r1), __ldg(src + 2 * R + r1), __ldg(src + 3 * R + r1) };
+        } else {
+            const float4 va = __ldg(reinterpret_cast<const float4*>(src) + r), vb = __ldg(reinterpret_cast<const float4*>(src) + r1);
+            a = F4 { va.x, va.y, va.z, va.w };
+            b = F4 { vb.x, vb.y, vb.z, vb.w };
+        }
+        s_tf[r] = make_tf_bin(a, b);
+    }
+    __syncthreads();
+    TfTable t;
+    t.base = (unsigned)__cvta_generic_to_shared(s_tf);
+    return t;
+}
+
+__device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
+{
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    i = blockIdx.x * kTileW + (w % kWarpsX) * 8 + (l & 7);
+    j = blockIdx.y * kTileH + (w / kWarpsX) * 4 + (l >> 3);
+    return i < d.W && j < d.H;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC, bool SR1>
+__global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
+fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
+           const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
+           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int b = blockIdx.z;
+    const TfTable s_tf = stage_tf(d, tf, d.Btf == 1 ? 0 : b, reinterpret_cast<TfBin*>(s_raw));
+    int i, j;
+    const bool valid = pixel_of_thread(d, i, j);
+    if (!valid && !target) return;
+    float sq = 0.0f;
+    if (valid) {
+    const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;      // image orientation
+    const F3 cam = { __ldg(camp + 3 * b), __ldg(camp + 3 * b + 1), __ldg(camp + 3 * b + 2) };
+    const float jit = (d.flags & DR_F_HAS_JITTER) ? __ldg(jitter + pix) : 0.0f;
+    Ray r;
+    setup_ray(d, cam, i, j, jit, r);
+    const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
+    const Layout L = make_layout(d);
+    F4 A; int K; float Tp;
+    march_forward<VT, LAYOUT, NONDIFF, GENERIC, SR1>(d, vol, L, s_tf, cam, r, A, K, Tp);
+    if (d.flags & DR_F_OUT_IMAGE) {
+        const size_t plane = (size_t)d.W * d.H;
+        const size_t o0 = (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
+        float* o = out + o0;
+        o[0] = A.x; o[plane] = A.y; o[2 * plane] = A.z; o[3 * plane] = A.w;
+        if (target) {
+            const float ex = A.x - __ldg(target + o0), ey = A.y - __ldg(target + o0 + plane);
+            const float ez = A.z - __ldg(target + o0 + 2 * plane), ew = A.w - __ldg(target + o0 + 3 * plane);
+            sq = ex * ex + ey * ey + ez * ez + ew * ew;
+        }
+    } else {
+        const size_t o0 = ((size_t)b * d.W + i) * d.H + j;
+        reinterpret_cast<float4*>(out)[o0] = make_float4(A.x, A.y, A.z, A.w);
+        if (target) {
+            const float4 tg = __ldg(reinterpret_cast<const float4*>(target) + o0);
+            const float ex = A.x - tg.x, ey = A.y - tg.y, ez = A.z - tg.z, ew = A.w - tg.w;
+            sq = ex * ex + ey * ey + ez * ez + ew * ew;
+        }
+    }
+    if (outK) outK[pix] = K;
+    if (outT) outT[pix] = Tp;
+    }
+    if (target) {
+        // fused loss (reference examples: torch mse_loss on output_rgba): one atomic per warp into this view's sum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum + b, sq);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+// Volume gradient: one cell = one 32-byte sector = two RED.E.ADD.F32x4.  The centre cell's 8-vector stays in registers
+// while consecutive samples of the ray fall into the same cell (about 3 samples per cell at sampling rate 1); the
+// per-sample weights are accumulated into it with FMAs (dr_math.cuh scatter_volume_grad).
+struct CellVolSink {
+    float4* g;
+    int cur;
+    float acc[8];
+#if defined(DR_BOUNDS_CHECK)
+    long long n_cells;
+#endif
+    __device__ __forceinline__ void red(int cell, const float* v)
+    {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(cell < 0 || cell >= n_cells);
+#endif
+        float4* p = g + (size_t)cell * 2;
+        atomicAdd(p, make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(p + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    __device__ __forceinline__ float* open(int cell)
+    {
+        if (cell != cur) {
+            if (cur >= 0) red(cur, acc);
+            cur = cell;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
+        }
+        return acc;
+    }
+    __device__ __forceinline__ void close() {}
+    __device__ __forceinline__ void direct(int cell, const float* v) { red(cell, v); }
+    __device__ __forceinline__ void flush() { if (cur >= 0) red(cur, acc); }
+};
+// TF gradient: two 16-byte vector reductions (bins lo, lo+1) into one of kTfSlots privatised copies of the table, summed by
+// tf_reduce_kernel.  Shared-memory fp32 atomicAdd is a CAS spin loop on sm_100a (ATOMS.CAST.SPIN) and measured 4x slower
+// than RED.F32x4 into L2 (profiles/r01_atomic_microbench.txt), so the privatised copies live in L2, not in shared memory.
+// While consecutive samples of the ray hit the same bin, S = sum dc and S1 = sum f*dc stay in registers (8 FP ops per
+// sample); the bin pair receives (S - S1, S1) when the bin changes.
+struct RedTfSink {
+    float4* g;      // [R] of this CTA's slot
+    int cur, Rm1;
+    float4 s, s1;
+    __device__ __forceinline__ void flush()
+    {
+        if (cur >= 0) {
+            atomicAdd(g + cur, make_float4(s.x - s1.x, s.y - s1.y, s.z - s1.z, s.w - s1.w));
+            atomicAdd(g + min(cur + 1, Rm1), s1);
+        }
+    }
+    __device__ __forceinline__ void add(int lo, float f, F4 dc)
+    {
+        if (lo != cur) {
+            flush();
+            cur = lo;
+            s = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s;
+        }
+        s.x += dc.x; s.y += dc.y; s.z += dc.z; s.w += dc.w;
+        s1.x += f * dc.x; s1.y += f * dc.y; s1.z += f * dc.z; s1.w += f * dc.w;
+    }
+};
+
+template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool SR1>
+__global__ void __launch_bounds__(kThreads, DR_BWD_MIN_BLOCKS)
+bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
+           const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
+           const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
+           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int b = blockIdx.z;
+    const int tb = d.Btf == 1 ? 0 : b;
+    const TfTable s_tf = stage_tf(d, tf, tb, reinterpret_cast<TfBin*>(s_raw));
+    int i, j;
+    if (!pixel_of_thread(d, i, j)) return;
+    const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;
+    const int K = __ldg(Kp + pix);
+    if (K <= 0) return;
+    const F3 cam = { __ldg(camp + 3 * b), __ldg(camp + 3 * b + 1), __ldg(camp + 3 * b + 2) };
+    const float jit = (d.flags & DR_F_HAS_JITTER) ? __ldg(jitter + pix) : 0.0f;
+    Ray r;
+    setup_ray(d, cam, i, j, jit, r);
+    F4 A, g;
+    if (d.flags & DR_F_OUT_IMAGE) {
+        const size_t plane = (size_t)d.W * d.H;
+        const size_t o = (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
+        A = F4 { __ldg(outp + o), __ldg(outp + o + plane), __ldg(outp + o + 2 * plane), __ldg(outp + o + 3 * plane) };
+        g = F4 { __ldg(gout + o), __ldg(gout + o + plane), __ldg(gout + o + 2 * plane), __ldg(gout + o + 3 * plane) };
+    } else {
+        const size_t o = ((size_t)b * d.W + i) * d.H + j;
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(outp) + o);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gout) + o);
+        A = F4 { a4.x, a4.y, a4.z, a4.w };
+        g = F4 { g4.x, g4.y, g4.z, g4.w };
+    }
+    if (d.flags & DR_F_FUSED_MSE) {
+        // `gout` holds the TARGET image: dL/dA = mse_scale * (A - target), never materialised in HBM
+        g.x = mse_scale * (A.x - g.x); g.y = mse_scale * (A.y - g.y); g.z = mse_scale * (A.z - g.z); g.w = mse_scale * (A.w - g.w);
+    }
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;       // this ray's gradient is exactly zero
+    const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
+    const VolView<VT> vol { volp + voff };
+    const Layout L = make_layout(d);
+    CellVolSink vs;
+    vs.g = WANT_VOL ? gcell + (d.Bvol == 1 ? 0 : (size_t)b * d.X * d.Y * d.Z * 2) : nullptr;
+    vs.cur = -1;
+#if defined(DR_BOUNDS_CHECK)
+    vs.n_cells = (long long)d.X * d.Y * d.Z;
+#endif
+    const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
+    RedTfSink ts;
+    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
+    ts.cur = -1; ts.Rm1 = d.R - 1;
+    march_backward<VT, LAYOUT, GENERIC, WANT_VOL, WANT_TF, SR1>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+template <typename K> int set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) {
+        if (bytes > kMaxTfSmem) return fail(DR_EINVAL, "tf resolution too large for shared memory staging (R <= 6400)");
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute");
+    }
+    return DR_OK;
+}
+
+inline size_t vol_stride(const DrDesc* d)
+{
+    return (d->flags & DR_F_LAYOUT_BRICK8) ? (size_t)d->nbx * d->nby * d->nbz * 512 : (size_t)d->X * d->Y * d->Z;
+}
+
+template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC, bool SR1>
+int launch_fwd(const FwdArgs& a)
+{
+    const DrDesc* d = a.d;
+    const size_t smem = (size_t)d->R * sizeof(TfBin);
+    auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, GENERIC, SR1>;
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
+    kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.out, a.K, a.T, vol_stride(d),
+                                         a.target, a.loss_sum);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
+}
+
+template <typename VT, int LAYOUT, bool GENERIC, bool WV, bool WT, bool SR1>
+int launch_bwd(const BwdArgs& a)
+{
+    const DrDesc* d = a.d;
+    const size_t smem = (size_t)d->R * sizeof(TfBin);
+    auto kern = bwd_kernel<VT, LAYOUT, GENERIC, WV, WT, SR1>;
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
+    kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
+                                         a.slots, vol_stride(d), a.mse_scale);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
+}
+
+// WANT_VOL / WANT_TF / sampling-rate dispatch of one (voxel type, layout, tap path).  The SR1 = false kernels are correct
+// for any sampling rate (powf(x, 1) == x); the generic-tap path (volumes > ~2000 voxels per axis) only has those.
+template <typename VT, int LAYOUT, bool GENERIC>
+int dispatch_bwd(const BwdArgs& a)
+{
+    const bool wv = a.d->flags & DR_F_NEEDS_VOL_GRAD, wt = a.d->flags & DR_F_NEEDS_TF_GRAD;
+    const bool sr1 = !GENERIC && a.d->inv_sr == 1.0f;
+#define DR_BWD(WV, WT) (sr1 ? launch_bwd<VT, LAYOUT, GENERIC, WV, WT, !GENERIC>(a) : launch_bwd<VT, LAYOUT, GENERIC, WV, WT, false>(a))
+    if (wv && wt) return DR_BWD(true, true);
+    if (wv) return DR_BWD(true, false);
+    return DR_BWD(false, true);
+#undef DR_BWD
+}
+
+template <typename VT>
+int dispatch_bwd_layout(const BwdArgs& a)
+{
+    if (a.d->flags & DR_F_LAYOUT_BRICK8) return dispatch_bwd<VT, LAYOUT_BRICK8, false>(a);
+    if (a.d->tap_generic) return dispatch_bwd<VT, LAYOUT_LINEAR, true>(a);
+    return dispatch_bwd<VT, LAYOUT_LINEAR, false>(a);
+}
+
+}  // namespace dr

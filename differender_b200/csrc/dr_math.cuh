@@ -36,7 +36,7 @@
 #define DR_SQRT(a) __fsqrt_rn((a))
 #define DR_RSQRT(a) rsqrtf((a))
 #define DR_SAT(a) __saturatef((a))
-#define DR_FAST_DIV(a, b) __fdividef((a), (b))
+#define DR_ALIGN16 __align__(16)
 #else
 // host build (tests/hostsim): compiled with -ffp-contract=off, so each operator is one IEEE operation
 #define DR_MUL(a, b) ((a) * (b))
@@ -47,7 +47,7 @@
 #define DR_SQRT(a) sqrtf((a))
 #define DR_RSQRT(a) (1.0f / sqrtf((a)))
 #define DR_SAT(a) fminf(1.0f, fmaxf(0.0f, (a)))
-#define DR_FAST_DIV(a, b) ((a) / (b))
+#define DR_ALIGN16 alignas(16)
 #endif
 
 // Debug build (-DDR_BOUNDS_CHECK): every volume load and gradient reduction checks its index and counts violations
@@ -62,6 +62,18 @@ extern __device__ unsigned long long dr_oob_counter;
 namespace dr {
 
 DR_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// 1/x for x well inside the normal range, off the exact path: one MUFU.RCP (no denormal/overflow fix-up code)
+DR_HD float fast_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 
 struct F3 { float x, y, z; };
 struct F4 { float x, y, z, w; };
@@ -88,29 +100,32 @@ DR_HD F3 normalized_e(F3 a)
     return r;
 }
 
-// floor of a value in [0, 2^22): returns floor as float, writes the integer.            low_high_frac :7-21
-DR_HD float floor_pos(float p, int& lo)
+// floor of a value in [0, 2^22): returns floor as float and writes the BIASED integer b = floor + kFloorBias (the bit
+// pattern of the float 2^23 + floor).  Cell comparisons use b directly; lo_of() gives the index.      low_high_frac :7-21
+constexpr int kFloorBias = 0x4B000000;
+DR_HD float floor_pos(float p, int& b)
 {
 #if defined(__CUDA_ARCH__)
     // p + 2^23 rounded toward -inf is exactly 2^23 + floor(p); all on the FMA/ALU pipes (no F2I/I2F)
     float r = __fadd_rd(p, 8388608.0f);
-    lo = __float_as_int(r) - 0x4B000000;
+    b = __float_as_int(r);
     return __fsub_rn(r, 8388608.0f);
 #else
     float l = floorf(p);
-    lo = (int)l;
+    b = (int)l + kFloorBias;
     return l;
 #endif
 }
 
-struct Loc { int lo; float f; };
+struct Loc { int b; float f; };      // b: biased floor index (see floor_pos), f: fraction
+DR_HD int lo_of(Loc q) { return q.b - kFloorBias; }
 
 // address part of sample_volume_trilinear for one axis                                   :163-172
 DR_HD Loc locate(float pos, float scale)
 {
     float p = DR_MUL(DR_SAT(DR_FMA(0.5f, pos, 0.5f)), scale);
     Loc r;
-    float l = floor_pos(p, r.lo);
+    float l = floor_pos(p, r.b);
     r.f = DR_SUB(p, l);
     return r;
 }
@@ -224,11 +239,9 @@ DR_HD void setup_ray(const DrDesc& d, F3 cam, int i, int j, float jit, Ray& r)
 // fast-math compiler emits for the reference's division; the oracle defines it the same way).  H3: n == 1 -> t = t0.
 DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
 {
-    float t = r.t0;
-    if (r.n > 1) {
-        float q = DR_MUL((float)s, r.inv_nm1);
-        t = mix_e(r.t0, r.texit, DR_SUB(1.0f, q), q);
-    }
+    // n <= 1: inv_nm1 = 0, so q = 0 and mix_e(t0, texit, 1, 0) = fma(t0, 1, texit*0) = t0 exactly (no branch)
+    const float q = DR_MUL((float)s, r.inv_nm1);
+    const float t = mix_e(r.t0, r.texit, DR_SUB(1.0f, q), q);
     F3 p = { DR_FMA(t, r.dir.x, cam.x), DR_FMA(t, r.dir.y, cam.y), DR_FMA(t, r.dir.z, cam.z) };
     return p;
 }
@@ -294,7 +307,7 @@ template <typename VT> struct BrickAddr {
     const VT* vp; Layout L; int lx, ly, lz;
     DR_HD void init(const DrDesc&, const VT* p, const Layout& L_, const Centre& c)
     {
-        vp = p; L = L_; lx = c.cx.lo; ly = c.cy.lo; lz = c.cz.lo;
+        vp = p; L = L_; lx = lo_of(c.cx); ly = lo_of(c.cy); lz = lo_of(c.cz);
     }
     // no clamps: in the corner-reuse path every index lo-1 .. lo+2 that is actually read is in range (see LinearAddr)
     DR_HD Row row(int yi, int zi) const { return offy(ly + yi, L.sY) + offz(lz + zi, L.sZ); }
@@ -312,7 +325,7 @@ DR_HD void locate_centre(const DrDesc& d, F3 pos, Centre& c)
     c.cx = locate(pos.x, d.scale[0]);
     c.cy = locate(pos.y, d.scale[1]);
     c.cz = locate(pos.z, d.scale[2]);
-    c.cidx = (c.cy.lo * d.Z + c.cz.lo) * d.X + c.cx.lo;
+    c.cidx = (lo_of(c.cy) * d.Z + lo_of(c.cz)) * d.X + lo_of(c.cx);
 }
 
 // centre tap                                                                                :173-189
@@ -353,7 +366,7 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
         const Loc q = sgn ? t.zm : t.zp;
         const float f = q.f, o = DR_SUB(1.0f, f);
         float val;
-        if (q.lo == c.cz.lo) {
+        if (q.b == c.cz.b) {
             val = mix_e(c.ym0, c.ym1, o, f);
         } else {
             // new plane: above the centre's high plane (+) or below its low plane (-)
@@ -372,7 +385,7 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
         const Loc q = sgn ? t.ym : t.yp;
         const float f = q.f, o = DR_SUB(1.0f, f);
         float a, b;
-        if (q.lo == c.cy.lo) {
+        if (q.b == c.cy.b) {
             a = mix_e(c.xm00, c.xm10, o, f);
             b = mix_e(c.xm01, c.xm11, o, f);
         } else {
@@ -391,7 +404,7 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
         const Loc q = sgn ? t.xm : t.xp;
         const float f = q.f, o = DR_SUB(1.0f, f);
         float a00, a10, a01, a11;
-        if (q.lo == c.cx.lo) {
+        if (q.b == c.cx.b) {
             a00 = mix_e(c.v000, c.v100, o, f); a10 = mix_e(c.v010, c.v110, o, f);
             a01 = mix_e(c.v001, c.v101, o, f); a11 = mix_e(c.v011, c.v111, o, f);
         } else {
@@ -417,9 +430,10 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
 template <typename VT>
 DR_HD float trilinear_full_linear(const DrDesc& d, const VT* p, Loc ax, Loc ay, Loc az)
 {
-    const int x0 = ax.lo, x1 = imin(ax.lo + 1, d.X - 1);
-    const int r00 = (ay.lo * d.Z + az.lo) * d.X, r10 = (imin(ay.lo + 1, d.Y - 1) * d.Z + az.lo) * d.X;
-    const int r01 = (ay.lo * d.Z + imin(az.lo + 1, d.Z - 1)) * d.X, r11 = (imin(ay.lo + 1, d.Y - 1) * d.Z + imin(az.lo + 1, d.Z - 1)) * d.X;
+    const int xl = lo_of(ax), yl = lo_of(ay), zl = lo_of(az);
+    const int x0 = xl, x1 = imin(xl + 1, d.X - 1);
+    const int r00 = (yl * d.Z + zl) * d.X, r10 = (imin(yl + 1, d.Y - 1) * d.Z + zl) * d.X;
+    const int r01 = (yl * d.Z + imin(zl + 1, d.Z - 1)) * d.X, r11 = (imin(yl + 1, d.Y - 1) * d.Z + imin(zl + 1, d.Z - 1)) * d.X;
     const float ox = DR_SUB(1.0f, ax.f), oy = DR_SUB(1.0f, ay.f), oz = DR_SUB(1.0f, az.f);
     float a = mix_e(load_vox(p, r00 + x0), load_vox(p, r00 + x1), ox, ax.f);
     float b = mix_e(load_vox(p, r10 + x0), load_vox(p, r10 + x1), ox, ax.f);
@@ -462,32 +476,66 @@ DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout&
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// transfer function lookup :205-219 (tf table: R float4 entries, in shared memory on the device)
+// transfer function lookup :205-219.  The table is staged (shared memory on the device) as one 32-byte TfBin per
+// bin r: a = tf[r], b = tf[min(r+1, R-1)] stored as (b.rgb - a.rgb, b.w).  Alpha is on the exact path and is evaluated
+// as mix_e(a.w, b.w, 1-f, f) like the reference; the colour only feeds the shading and is a.rgb + f*(b.rgb - a.rgb)
+// (one FMA per channel; the differences are what the adjoint needs anyway).
 // ---------------------------------------------------------------------------------------------------------
-struct TfHit { int lo, hi; float f, x; F4 c; F4 d; };   // c = colour, d = tf[hi] - tf[lo] (for dI)
+struct DR_ALIGN16 TfBin { F4 a; float dx, dy, dz, bw; };
 
-DR_HD void apply_tf(const DrDesc& d, const F4* tf, float intensity, TfHit& h, bool want_diff)
+DR_HD TfBin make_tf_bin(F4 a, F4 b)
+{
+    TfBin t;
+    t.a = a; t.dx = b.x - a.x; t.dy = b.y - a.y; t.dz = b.z - a.z; t.bw = b.w;
+    return t;
+}
+
+// table accessor: a plain pointer (host harness) or, on the device, a 32-bit shared-memory address kept in a register
+// (one LEA + two LDS.128 per lookup; a generic pointer costs three uniform-datapath instructions per lookup to re-form
+// the shared window base)
+struct TfTable {
+#if defined(__CUDACC__)
+    unsigned base;
+    DR_HD TfBin get(int r) const
+    {
+        TfBin t;
+#if defined(__CUDA_ARCH__)
+        const unsigned a = base + ((unsigned)r << 5);
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.a.x), "=f"(t.a.y), "=f"(t.a.z), "=f"(t.a.w) : "r"(a));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(t.dx), "=f"(t.dy), "=f"(t.dz), "=f"(t.bw) : "r"(a));
+#else
+        t = TfBin();        // nvcc's host pass only: the kernels are the sole callers
+#endif
+        return t;
+    }
+#else
+    const TfBin* p;
+    DR_HD TfBin get(int r) const { return p[r]; }
+#endif
+};
+
+struct TfHit { int lo; float f, x; F4 c; F4 d; };   // c = colour, d = tf[hi] - tf[lo] (for dI)
+
+DR_HD void apply_tf(const DrDesc& d, const TfTable& tf, float intensity, TfHit& h, bool want_diff)
 {
     float x = fmaxf(DR_MUL(intensity, d.tf_len), 0.0f);
     h.x = x;
-    int lo;
-    float l = floor_pos(x, lo);
+    int b;
+    float l = floor_pos(x, b);
     h.f = DR_SUB(x, l);
-    lo = imin(lo, d.R - 1);                      // H9
-    h.lo = lo;
-    h.hi = imin(lo + 1, d.R - 1);
-    const F4 a = tf[h.lo], b = tf[h.hi];
-    const float o = DR_SUB(1.0f, h.f);
-    h.c.x = mix_e(a.x, b.x, o, h.f); h.c.y = mix_e(a.y, b.y, o, h.f);
-    h.c.z = mix_e(a.z, b.z, o, h.f); h.c.w = mix_e(a.w, b.w, o, h.f);
-    if (want_diff) { h.d.x = b.x - a.x; h.d.y = b.y - a.y; h.d.z = b.z - a.z; h.d.w = b.w - a.w; }
+    h.lo = imin(b - kFloorBias, d.R - 1);        // H9
+    const TfBin t = tf.get(h.lo);
+    h.c.w = mix_e(t.a.w, t.bw, DR_SUB(1.0f, h.f), h.f);
+    h.c.x = t.a.x + h.f * t.dx; h.c.y = t.a.y + h.f * t.dy; h.c.z = t.a.z + h.f * t.dz;
+    if (want_diff) { h.d.x = t.dx; h.d.y = t.dy; h.d.z = t.dz; h.d.w = t.bw - t.a.w; }
 }
 
 // opacity = 1 - pow(1 - alpha, 1/sr)                                                       :284-285
+template <bool SR1>
 DR_HD float opacity(const DrDesc& d, float alpha)
 {
     float base = DR_SUB(1.0f, alpha);
-    if (d.inv_sr == 1.0f) return DR_SUB(1.0f, base);
+    if (SR1) return DR_SUB(1.0f, base);
     return DR_SUB(1.0f, powf(base, d.inv_sr));
 }
 
@@ -497,7 +545,7 @@ DR_HD float opacity(const DrDesc& d, float alpha)
 struct Shade {
     F3 N, l;
     float inv_g;       // 1/|g| (0 when flat)
-    float nl, rv, rdv, pw31, kraw, k;
+    float nl, rv, p32, kraw, k;       // p32 = max(rv,0)^32
 };
 
 DR_HD void shade(const DrDesc& d, F3 cam, F3 dir, F3 pos, F3 g, bool clamp_k, Shade& s)
@@ -515,11 +563,10 @@ DR_HD void shade(const DrDesc& d, F3 cam, F3 dir, F3 pos, F3 g, bool clamp_k, Sh
     float t2 = 2.0f * s.nl;
     float rx = s.l.x - t2 * s.N.x, ry = s.l.y - t2 * s.N.y, rz = s.l.z - t2 * s.N.z;   // reflect :293
     s.rv = flat ? 0.0f : -(rx * dir.x + ry * dir.y + rz * dir.z);                 // NaN normal -> max(NaN,0) = 0
-    s.rdv = fmaxf(s.rv, 0.0f);                                                     // :295
-    float p2 = s.rdv * s.rdv, p4 = p2 * p2, p8 = p4 * p4, p16 = p8 * p8;
-    float p32 = p16 * p16;                                                         // shininess 32 :296
-    s.pw31 = p16 * p8 * p4 * p2 * s.rdv;
-    s.kraw = d.diffuse * ndl + d.specular * p32 + d.ambient;
+    const float rdv = fmaxf(s.rv, 0.0f);                                           // :295
+    float p2 = rdv * rdv, p4 = p2 * p2, p8 = p4 * p4, p16 = p8 * p8;
+    s.p32 = p16 * p16;                                                             // shininess 32 :296
+    s.kraw = d.diffuse * ndl + d.specular * s.p32 + d.ambient;
     s.k = clamp_k ? fminf(1.0f, s.kraw) : s.kraw;                                  // :298 vs :345
 }
 
@@ -531,6 +578,7 @@ DR_HD void shade(const DrDesc& d, F3 cam, F3 dir, F3 pos, F3 g, bool clamp_k, Sh
 // ---------------------------------------------------------------------------------------------------------
 struct SampleAdj { F4 dc; float dI; F3 dg; bool has_dg; };
 
+template <bool SR1>
 DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, const Shade& s, float T, F4 g,
                            bool want_vol, SampleAdj& a)
 {
@@ -540,7 +588,7 @@ DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, con
     const float d_o = s.k * cd + T * g.w;
     const float dk = o * cd;
     float dpow = 1.0f;
-    if (d.inv_sr != 1.0f) dpow = d.inv_sr * powf(fmaxf(1.0f - h.c.w, 1e-12f), d.inv_sr - 1.0f);   // H8
+    if (!SR1) dpow = d.inv_sr * powf(fmaxf(1.0f - h.c.w, 1e-12f), d.inv_sr - 1.0f);   // H8
     const float kT = ko * T;
     a.dc.x = kT * g.x; a.dc.y = kT * g.y; a.dc.z = kT * g.z; a.dc.w = d_o * dpow;
     a.has_dg = false;
@@ -551,7 +599,8 @@ DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, con
         // dk == 0 (exactly transparent sample, or zero incoming gradient) makes every normal-path term exactly zero
         if (dk != 0.0f && s.inv_g > 0.0f && !(1.0f < s.kraw)) {
             const float d_ndl = (s.nl > 0.0f) ? d.diffuse * dk : 0.0f;
-            const float d_rdv = (s.rv > 0.0f) ? d.specular * 32.0f * s.pw31 * dk : 0.0f;
+            // d/d(rdv) rdv^32 = 32 rdv^31 = 32 p32 / rdv; below 1e-6 rdv^31 is exactly 0 in fp32 anyway
+            const float d_rdv = (s.rv > 1e-6f) ? d.specular * 32.0f * (s.p32 * fast_rcp(s.rv)) * dk : 0.0f;
             const float drx = -dir.x * d_rdv, dry = -dir.y * d_rdv, drz = -dir.z * d_rdv;
             const float drN = drx * s.N.x + dry * s.N.y + drz * s.N.z;
             const float cN = d_ndl - 2.0f * drN, c2 = 2.0f * s.nl;
@@ -572,9 +621,10 @@ DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, con
 // sector, so a tap's 8 trilinear weights go out as two 16-byte vector reductions (RED.E.ADD.F32x4) instead of 8
 // scalar ones -- measured 3.5x faster on B200 (profiles/r01_atomic_microbench.txt).  A gather pass
 // (gather_grad_kernel) sums the 8 slots that alias each voxel.
-//   * taps that stay in the centre cell are merged with the centre tap into one 8-vector (Sink::centre);
-//   * a tap that crossed a face goes to its own (neighbour) cell (Sink::direct);
-//   * Sink::centre may keep the 8-vector in registers while consecutive samples stay in the same cell.
+//   * taps that stay in the centre cell are merged with the centre tap into one 8-vector, added into the vector that
+//     Sink::open(cell) returns and committed by Sink::close() -- a sink may keep that vector in registers while
+//     consecutive samples stay in the same cell;
+//   * a tap that crossed a face goes to its own (neighbour) cell (Sink::direct).
 // ---------------------------------------------------------------------------------------------------------
 DR_HD int cell_index(const DrDesc& d, int cx, int cy, int cz) { return (cy * d.Z + cz) * d.X + cx; }
 
@@ -593,23 +643,24 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
     float v[8];
     const int cc = t.cidx;
     if (GENERIC) {
-        tap_weights(a.dI, t.cx, t.cy, t.cz, v); sink.centre(cc, v);
+        const int cx = lo_of(t.cx), cy = lo_of(t.cy), cz = lo_of(t.cz);
+        tap_weights(a.dI, t.cx, t.cy, t.cz, v); sink.direct(cc, v);
         if (a.has_dg) {
-            tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cell_index(d, t.xp.lo, t.cy.lo, t.cz.lo), v);
-            tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cell_index(d, t.xm.lo, t.cy.lo, t.cz.lo), v);
-            tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.yp.lo, t.cz.lo), v);
-            tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cell_index(d, t.cx.lo, t.ym.lo, t.cz.lo), v);
-            tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zp.lo), v);
-            tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cell_index(d, t.cx.lo, t.cy.lo, t.zm.lo), v);
+            tap_weights(a.dg.x, t.xp, t.cy, t.cz, v); sink.direct(cell_index(d, lo_of(t.xp), cy, cz), v);
+            tap_weights(-a.dg.x, t.xm, t.cy, t.cz, v); sink.direct(cell_index(d, lo_of(t.xm), cy, cz), v);
+            tap_weights(a.dg.y, t.cx, t.yp, t.cz, v); sink.direct(cell_index(d, cx, lo_of(t.yp), cz), v);
+            tap_weights(-a.dg.y, t.cx, t.ym, t.cz, v); sink.direct(cell_index(d, cx, lo_of(t.ym), cz), v);
+            tap_weights(a.dg.z, t.cx, t.cy, t.zp, v); sink.direct(cell_index(d, cx, cy, lo_of(t.zp)), v);
+            tap_weights(-a.dg.z, t.cx, t.cy, t.zm, v); sink.direct(cell_index(d, cx, cy, lo_of(t.zm)), v);
         }
         return;
     }
     const float wx0 = 1.0f - t.cx.f, wx1 = t.cx.f, wy0 = 1.0f - t.cy.f, wy1 = t.cy.f;
     const float wz0 = 1.0f - t.cz.f, wz1 = t.cz.f;
     // per axis: coefficients of the two voxel planes of the centre cell contributed by the taps that did NOT cross
-    const bool xpc = t.xp.lo != t.cx.lo, xmc = t.xm.lo != t.cx.lo;
-    const bool ypc = t.yp.lo != t.cy.lo, ymc = t.ym.lo != t.cy.lo;
-    const bool zpc = t.zp.lo != t.cz.lo, zmc = t.zm.lo != t.cz.lo;
+    const bool xpc = t.xp.b != t.cx.b, xmc = t.xm.b != t.cx.b;
+    const bool ypc = t.yp.b != t.cy.b, ymc = t.ym.b != t.cy.b;
+    const bool zpc = t.zp.b != t.cz.b, zmc = t.zm.b != t.cz.b;
     const float ex0 = a.dg.x * ((xpc ? 0.0f : 1.0f - t.xp.f) - (xmc ? 0.0f : 1.0f - t.xm.f));
     const float ex1 = a.dg.x * ((xpc ? 0.0f : t.xp.f) - (xmc ? 0.0f : t.xm.f));
     const float ey0 = a.dg.y * ((ypc ? 0.0f : 1.0f - t.yp.f) - (ymc ? 0.0f : 1.0f - t.ym.f));
@@ -621,15 +672,16 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
     const float xz00 = wx0 * wz0, xz10 = wx1 * wz0, xz01 = wx0 * wz1, xz11 = wx1 * wz1;
     const float xy00 = wx0 * wy0, xy10 = wx1 * wy0, xy01 = wx0 * wy1, xy11 = wx1 * wy1;
     // G[a][b][c] = wyz[b][c]*X_a + wxz[a][c]*ey_b + wxy[a][b]*ez_c
-    v[0] = yz00 * X0 + xz00 * ey0 + xy00 * ez0;
-    v[1] = yz00 * X1 + xz10 * ey0 + xy10 * ez0;
-    v[2] = yz10 * X0 + xz00 * ey1 + xy01 * ez0;
-    v[3] = yz10 * X1 + xz10 * ey1 + xy11 * ez0;
-    v[4] = yz01 * X0 + xz01 * ey0 + xy00 * ez1;
-    v[5] = yz01 * X1 + xz11 * ey0 + xy10 * ez1;
-    v[6] = yz11 * X0 + xz01 * ey1 + xy01 * ez1;
-    v[7] = yz11 * X1 + xz11 * ey1 + xy11 * ez1;
-    sink.centre(cc, v);
+    float* acc = sink.open(cc);         // three FMAs per slot, straight into the sink's (register-held) vector
+    acc[0] = yz00 * X0 + (xz00 * ey0 + (xy00 * ez0 + acc[0]));
+    acc[1] = yz00 * X1 + (xz10 * ey0 + (xy10 * ez0 + acc[1]));
+    acc[2] = yz10 * X0 + (xz00 * ey1 + (xy01 * ez0 + acc[2]));
+    acc[3] = yz10 * X1 + (xz10 * ey1 + (xy11 * ez0 + acc[3]));
+    acc[4] = yz01 * X0 + (xz01 * ey0 + (xy00 * ez1 + acc[4]));
+    acc[5] = yz01 * X1 + (xz11 * ey0 + (xy10 * ez1 + acc[5]));
+    acc[6] = yz11 * X0 + (xz01 * ey1 + (xy01 * ez1 + acc[6]));
+    acc[7] = yz11 * X1 + (xz11 * ey1 + (xy11 * ez1 + acc[7]));
+    sink.close();
     if (!a.has_dg) return;
     // a crossed tap lives in the face-neighbour cell: +-1 (x), +-X (z), +-X*Z (y) in the torch-linear cell order.  Its 8
     // weights reuse the centre's pair products: only the weight pair of the shifted axis differs.
@@ -694,8 +746,8 @@ DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int 
 // State per ray is O(1): A (accumulated premultiplied RGBA), K (active samples), Tprev (transmittance before
 // the last active sample).  Nothing per sample is stored (the reference stores 16*M bytes per ray, :82,102-103).
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC>
-DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
+template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC, bool SR1>
+DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const TfTable& tf, F3 cam,
                          const Ray& r, F4& A, int& K, float& Tprev)
 {
     A.x = A.y = A.z = A.w = 0.0f;                       // H1: tape[-1] = 0
@@ -710,7 +762,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         TfHit h;
         apply_tf(d, tf, c.I, h, false);
         if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334: skipped samples never evaluate the normal
-        const float o = opacity(d, h.c.w);
+        const float o = opacity<SR1>(d, h.c.w);
         const float T = DR_SUB(1.0f, A.w);
         if (o == 0.0f) {
             // Exactly transparent sample (TF alpha 0, the empty space between a transfer function's bumps):
@@ -741,11 +793,12 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
 // reconstructed as T_{s-1} = T_s / (1 - o_s); the last active sample uses the saved Tprev (so an opaque last
 // sample never divides by ~0), and 1 - o_s > 1 - ert for every earlier sample because sample s+1 was active.
 // dL/dA_s.rgb is constant along the ray (= grad_out.rgb); only dL/dA_s.w evolves: g.w -= C_s . g.
-// TfSink::add(lo, hi, f, dc) accumulates the TF gradient; VolSink::centre/direct(cell, v[8]) the volume gradient;
-// both may hold a partial sum in registers and are flushed at the end of the ray.
+// TfSink::add(lo, f, dc) accumulates the TF gradient ((1-f)*dc into bin lo, f*dc into bin min(lo+1, R-1));
+// VolSink::open/close/direct the volume gradient; both may hold a partial sum in registers and are flushed at the end
+// of the ray.
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, typename VolSink, typename TfSink>
-DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const F4* tf, F3 cam,
+template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool SR1, typename VolSink, typename TfSink>
+DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const TfTable& tf, F3 cam,
                           const Ray& r, F4 Afinal, int K, float Tprev, F4 g, VolSink& vsink, TfSink& tsink)
 {
     float Tafter = 1.0f - Afinal.w;                     // transmittance after sample K-1
@@ -755,7 +808,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         sample_centre<VT, LAYOUT, GENERIC>(d, vol, L, pos, c);
         TfHit h;
         apply_tf(d, tf, c.I, h, WANT_VOL);
-        const float o = opacity(d, h.c.w);
+        const float o = opacity<SR1>(d, h.c.w);
         // Volume-only gradient: an exactly transparent sample whose two TF bins are both transparent (h.d.w == 0) has
         // dc.rgb = k*o*dC = 0 and dI = tf_len * dc.w * h.d.w = 0, C = 0 (g.w unchanged) and T_{s-1} = T_s: nothing to do.
         if (!WANT_TF && o == 0.0f && h.d.w == 0.0f) continue;
@@ -763,12 +816,12 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, true, sh);
-        const float T = (s == K - 1) ? Tprev : DR_FAST_DIV(Tafter, 1.0f - o);   // 1-o in (0.01, 1]: no IEEE slow path needed
+        const float T = (s == K - 1) ? Tprev : Tafter * fast_rcp(1.0f - o);     // 1-o in (0.01, 1]: one MUFU.RCP, no fix-up code
         Tafter = T;
         SampleAdj a;
-        const float Cg = sample_adjoint(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
+        const float Cg = sample_adjoint<SR1>(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
         g.w -= Cg;
-        if (WANT_TF) tsink.add(h.lo, h.hi, h.f, a.dc);
+        if (WANT_TF) tsink.add(h.lo, h.f, a.dc);
         if (WANT_VOL && (a.has_dg || a.dI != 0.0f))          // exactly-zero contributions (transparent samples) are not scattered
             scatter_volume_grad<VolSink, GENERIC>(d, vsink, t, a);
     }

@@ -13,16 +13,19 @@
 using namespace dr;
 
 namespace {
-struct HostVolSink {          // cell-major [cell][8]; same interface as the device CellVolSink, no register accumulation
+struct HostVolSink {          // cell-major [cell][8]; same interface as the device CellVolSink, accumulates in place
     float* g;
-    void centre(int cell, const float* v) { for (int q = 0; q < 8; ++q) g[(size_t)cell * 8 + q] += v[q]; }
-    void direct(int cell, const float* v) { centre(cell, v); }
+    float* open(int cell) { return g + (size_t)cell * 8; }
+    void close() {}
+    void direct(int cell, const float* v) { for (int q = 0; q < 8; ++q) g[(size_t)cell * 8 + q] += v[q]; }
     void flush() {}
 };
 struct HostTfSink {
     float* g;   // [R][4]
-    void add(int lo, int hi, float f, F4 dc)
+    int Rm1;
+    void add(int lo, float f, F4 dc)
     {
+        const int hi = lo + 1 < Rm1 ? lo + 1 : Rm1;
         const float w0 = 1.0f - f, w1 = f;
         g[4 * lo + 0] += dc.x * w0; g[4 * lo + 1] += dc.y * w0; g[4 * lo + 2] += dc.z * w0; g[4 * lo + 3] += dc.w * w0;
         g[4 * hi + 0] += dc.x * w1; g[4 * hi + 1] += dc.y * w1; g[4 * hi + 2] += dc.z * w1; g[4 * hi + 3] += dc.w * w1;
@@ -35,6 +38,14 @@ Layout make_layout(const DrDesc& d)
     L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
     L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
     return L;
+}
+// the staged table the kernels build in shared memory (stage_tf in dr_kernels.cuh): bin r holds tf[r] and tf[min(r+1, R-1)]
+TfBin* make_tf_table(const DrDesc& d, const float* tf)
+{
+    const F4* t4 = (const F4*)tf;
+    TfBin* tab = (TfBin*)aligned_alloc(16, sizeof(TfBin) * (size_t)d.R);
+    for (int r = 0; r < d.R; ++r) tab[r] = make_tf_bin(t4[r], t4[r + 1 < d.R ? r + 1 : d.R - 1]);
+    return tab;
 }
 }  // namespace
 
@@ -69,9 +80,11 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
 {
     Layout L = make_layout(*d);
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
-    const F4* tf4 = (const F4*)tf;
+    TfBin* tab = make_tf_table(*d, tf);
+    const TfTable tf4 { tab };
     F3 cam = { cam3[0], cam3[1], cam3[2] };
     const size_t plane = (size_t)d->W * d->H;
+    const bool sr1 = d->inv_sr == 1.0f;
     for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {
         const size_t pix = (size_t)(d->H - 1 - j) * d->W + i;
         Ray r;
@@ -79,20 +92,21 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
         F4 A; int K; float Tp;
         const bool nd = d->flags & DR_F_NONDIFF;
         if (d->flags & DR_F_LAYOUT_BRICK8) {
-            if (nd) march_forward<float, LAYOUT_BRICK8, true, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
-            else march_forward<float, LAYOUT_BRICK8, false, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+#define FWD(LAY, ND, GEN) do { if (sr1 && !GEN) march_forward<float, LAY, ND, GEN, !GEN>(*d, vol, L, tf4, cam, r, A, K, Tp); \
+                               else march_forward<float, LAY, ND, GEN, false>(*d, vol, L, tf4, cam, r, A, K, Tp); } while (0)
+            if (nd) FWD(LAYOUT_BRICK8, true, false); else FWD(LAYOUT_BRICK8, false, false);
         } else if (d->tap_generic) {
-            if (nd) march_forward<float, LAYOUT_LINEAR, true, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
-            else march_forward<float, LAYOUT_LINEAR, false, true>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            if (nd) FWD(LAYOUT_LINEAR, true, true); else FWD(LAYOUT_LINEAR, false, true);
         } else {
-            if (nd) march_forward<float, LAYOUT_LINEAR, true, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
-            else march_forward<float, LAYOUT_LINEAR, false, false>(*d, vol, L, tf4, cam, r, A, K, Tp);
+            if (nd) FWD(LAYOUT_LINEAR, true, false); else FWD(LAYOUT_LINEAR, false, false);
         }
+#undef FWD
         out[pix] = A.x; out[plane + pix] = A.y; out[2 * plane + pix] = A.z; out[3 * plane + pix] = A.w;
         if (out_K) out_K[pix] = K;
         if (out_Tprev) out_Tprev[pix] = Tp;
         if (out_n) out_n[pix] = r.n;
     }
+    free(tab);
 }
 
 void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
@@ -101,11 +115,13 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
 {
     Layout L = make_layout(*d);
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
-    const F4* tf4 = (const F4*)tf;
+    TfBin* tab = make_tf_table(*d, tf);
+    const TfTable tf4 { tab };
     F3 cam = { cam3[0], cam3[1], cam3[2] };
     const size_t plane = (size_t)d->W * d->H;
     HostVolSink vs { gvol_cells };
-    HostTfSink ts { gtf };
+    HostTfSink ts { gtf, d->R - 1 };
+    const bool sr1 = d->inv_sr == 1.0f;
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
     for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {
         const size_t pix = (size_t)(d->H - 1 - j) * d->W + i;
@@ -115,7 +131,8 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
         F4 g = { grad_out[pix], grad_out[plane + pix], grad_out[2 * plane + pix], grad_out[3 * plane + pix] };
         const int K = Kin[pix];
         const float Tp = Tprev[pix];
-#define CALL(LAY, GEN, WV, WT) march_backward<float, LAY, GEN, WV, WT>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts)
+#define CALL(LAY, GEN, WV, WT) do { if (sr1 && !GEN) march_backward<float, LAY, GEN, WV, WT, !GEN>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); \
+                                    else march_backward<float, LAY, GEN, WV, WT, false>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); } while (0)
 #define CALL3(LAY, GEN) do { if (wv && wt) CALL(LAY, GEN, true, true); else if (wv) CALL(LAY, GEN, true, false); else if (wt) CALL(LAY, GEN, false, true); } while (0)
         if (d->flags & DR_F_LAYOUT_BRICK8) CALL3(LAYOUT_BRICK8, false);
         else if (d->tap_generic) CALL3(LAYOUT_LINEAR, true);
@@ -123,6 +140,7 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
 #undef CALL3
 #undef CALL
     }
+    free(tab);
 }
 
 }  // extern "C"
