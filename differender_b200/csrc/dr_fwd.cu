@@ -10,10 +10,13 @@ static int forward_vt(const FwdArgs& a)
 {
     const DrDesc* d = a.d;
     const bool nd = d->flags & DR_F_NONDIFF, sr1 = d->inv_sr == 1.0f;
-#define DR_FWD_ND(LAY, GEN, SR1) (nd ? launch_fwd<VT, LAY, true, GEN, SR1>(a) : launch_fwd<VT, LAY, false, GEN, SR1>(a))
-    if (d->flags & DR_F_LAYOUT_BRICK8) return sr1 ? DR_FWD_ND(LAYOUT_BRICK8, false, true) : DR_FWD_ND(LAYOUT_BRICK8, false, false);
-    if (d->tap_generic) return DR_FWD_ND(LAYOUT_LINEAR, true, false);
-    return sr1 ? DR_FWD_ND(LAYOUT_LINEAR, false, true) : DR_FWD_ND(LAYOUT_LINEAR, false, false);
+    const int taps = tap_mode(*d);
+#define DR_FWD_ND(LAY, TAPS, SR1) (nd ? launch_fwd<VT, LAY, true, TAPS, SR1>(a) : launch_fwd<VT, LAY, false, TAPS, SR1>(a))
+#define DR_FWD_SR(LAY, TAPS) (sr1 ? DR_FWD_ND(LAY, TAPS, true) : DR_FWD_ND(LAY, TAPS, false))
+    if (d->flags & DR_F_LAYOUT_BRICK8) return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_BRICK8, TAPS_ONE) : DR_FWD_SR(LAYOUT_BRICK8, TAPS_TWO);
+    if (taps == TAPS_GENERIC) return DR_FWD_ND(LAYOUT_LINEAR, TAPS_GENERIC, false);
+    return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_LINEAR, TAPS_ONE) : DR_FWD_SR(LAYOUT_LINEAR, TAPS_TWO);
+#undef DR_FWD_SR
 #undef DR_FWD_ND
 }
 

@@ -24,13 +24,18 @@ namespace dr {
 #endif
 constexpr int kWarpsX = DR_CTA_WARPS >= 2 ? 2 : 1, kWarpsY = DR_CTA_WARPS / kWarpsX;
 constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA_WARPS;
-// minimum resident CTAs per SM the compiler must allow (caps registers); tuned on B200, see DESIGN.md
-// (B200, C3: forward 6 CTAs/SM = 80 regs, no spills: +2 %; backward 5 CTAs/SM = 96 regs spills and loses 5 %, so 4.)
+// minimum resident CTAs per SM the compiler must allow (caps registers); tuned on B200 (profiles/r01_experiments.md):
+// forward 5 CTAs/SM = 96 registers without spills (6 = 80 registers spills 40 bytes once the taps are branch-free);
+// backward 5 CTAs/SM for the linear layout (96 registers, no spills, +3 %), 4 for brick8 (its addressing needs the
+// registers: 5 loses 6 % at C5).
 #ifndef DR_FWD_MIN_BLOCKS
-#define DR_FWD_MIN_BLOCKS 6
+#define DR_FWD_MIN_BLOCKS 5
 #endif
-#ifndef DR_BWD_MIN_BLOCKS
-#define DR_BWD_MIN_BLOCKS 4
+#ifndef DR_BWD_MIN_BLOCKS_LINEAR
+#define DR_BWD_MIN_BLOCKS_LINEAR 5
+#endif
+#ifndef DR_BWD_MIN_BLOCKS_BRICK
+#define DR_BWD_MIN_BLOCKS_BRICK 4
 #endif
 
 __host__ __device__ inline Layout make_layout(const DrDesc& d)
@@ -79,7 +84,7 @@ __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC, bool SR1>
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
 __global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
@@ -101,7 +106,7 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
     const Layout L = make_layout(d);
     F4 A; int K; float Tp;
-    march_forward<VT, LAYOUT, NONDIFF, GENERIC, SR1>(d, vol, L, s_tf, cam, r, A, K, Tp);
+    march_forward<VT, LAYOUT, NONDIFF, TAPS, SR1>(d, vol, L, s_tf, cam, r, A, K, Tp);
     if (d.flags & DR_F_OUT_IMAGE) {
         const size_t plane = (size_t)d.W * d.H;
         const size_t o0 = (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
@@ -194,10 +199,19 @@ struct RedTfSink {
         s.x += dc.x; s.y += dc.y; s.z += dc.z; s.w += dc.w;
         s1.x += f * dc.x; s1.y += f * dc.y; s1.z += f * dc.z; s1.w += f * dc.w;
     }
+    __device__ __forceinline__ void add_alpha(int lo, float f, float dcw)       // dc = (0, 0, 0, dcw)
+    {
+        if (lo != cur) {
+            flush();
+            cur = lo;
+            s = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s;
+        }
+        s.w += dcw; s1.w += f * dcw;
+    }
 };
 
-template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool SR1>
-__global__ void __launch_bounds__(kThreads, DR_BWD_MIN_BLOCKS)
+template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1>
+__global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_LINEAR ? DR_BWD_MIN_BLOCKS_LINEAR : DR_BWD_MIN_BLOCKS_BRICK)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
@@ -247,7 +261,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     RedTfSink ts;
     ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
     ts.cur = -1; ts.Rm1 = d.R - 1;
-    march_backward<VT, LAYOUT, GENERIC, WANT_VOL, WANT_TF, SR1>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
+    march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -268,12 +282,12 @@ inline size_t vol_stride(const DrDesc* d)
     return (d->flags & DR_F_LAYOUT_BRICK8) ? (size_t)d->nbx * d->nby * d->nbz * 512 : (size_t)d->X * d->Y * d->Z;
 }
 
-template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC, bool SR1>
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
 int launch_fwd(const FwdArgs& a)
 {
     const DrDesc* d = a.d;
     const size_t smem = (size_t)d->R * sizeof(TfBin);
-    auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, GENERIC, SR1>;
+    auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, TAPS, SR1>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.out, a.K, a.T, vol_stride(d),
@@ -282,12 +296,12 @@ int launch_fwd(const FwdArgs& a)
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
 
-template <typename VT, int LAYOUT, bool GENERIC, bool WV, bool WT, bool SR1>
+template <typename VT, int LAYOUT, int TAPS, bool WV, bool WT, bool SR1>
 int launch_bwd(const BwdArgs& a)
 {
     const DrDesc* d = a.d;
     const size_t smem = (size_t)d->R * sizeof(TfBin);
-    auto kern = bwd_kernel<VT, LAYOUT, GENERIC, WV, WT, SR1>;
+    auto kern = bwd_kernel<VT, LAYOUT, TAPS, WV, WT, SR1>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
@@ -296,14 +310,15 @@ int launch_bwd(const BwdArgs& a)
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
 }
 
-// WANT_VOL / WANT_TF / sampling-rate dispatch of one (voxel type, layout, tap path).  The SR1 = false kernels are correct
+// WANT_VOL / WANT_TF / sampling-rate dispatch of one (voxel type, layout, tap mode).  The SR1 = false kernels are correct
 // for any sampling rate (powf(x, 1) == x); the generic-tap path (volumes > ~2000 voxels per axis) only has those.
-template <typename VT, int LAYOUT, bool GENERIC>
+template <typename VT, int LAYOUT, int TAPS>
 int dispatch_bwd(const BwdArgs& a)
 {
     const bool wv = a.d->flags & DR_F_NEEDS_VOL_GRAD, wt = a.d->flags & DR_F_NEEDS_TF_GRAD;
-    const bool sr1 = !GENERIC && a.d->inv_sr == 1.0f;
-#define DR_BWD(WV, WT) (sr1 ? launch_bwd<VT, LAYOUT, GENERIC, WV, WT, !GENERIC>(a) : launch_bwd<VT, LAYOUT, GENERIC, WV, WT, false>(a))
+    constexpr bool kHasSr1 = TAPS != TAPS_GENERIC;
+    const bool sr1 = kHasSr1 && a.d->inv_sr == 1.0f;
+#define DR_BWD(WV, WT) (sr1 ? launch_bwd<VT, LAYOUT, TAPS, WV, WT, kHasSr1>(a) : launch_bwd<VT, LAYOUT, TAPS, WV, WT, false>(a))
     if (wv && wt) return DR_BWD(true, true);
     if (wv) return DR_BWD(true, false);
     return DR_BWD(false, true);
@@ -313,9 +328,10 @@ int dispatch_bwd(const BwdArgs& a)
 template <typename VT>
 int dispatch_bwd_layout(const BwdArgs& a)
 {
-    if (a.d->flags & DR_F_LAYOUT_BRICK8) return dispatch_bwd<VT, LAYOUT_BRICK8, false>(a);
-    if (a.d->tap_generic) return dispatch_bwd<VT, LAYOUT_LINEAR, true>(a);
-    return dispatch_bwd<VT, LAYOUT_LINEAR, false>(a);
+    const int taps = tap_mode(*a.d);
+    if (a.d->flags & DR_F_LAYOUT_BRICK8) return taps == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_BRICK8, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_BRICK8, TAPS_TWO>(a);
+    if (taps == TAPS_GENERIC) return dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_GENERIC>(a);
+    return taps == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_TWO>(a);
 }
 
 }  // namespace dr

@@ -181,6 +181,29 @@ DR_HD float load_vox(const __half* p, int off)
 }
 DR_HD float load_vox(const __half* p, uoff off) { return load_vox(ptr_add(p, off), 0); }
 #endif
+// predicated load (0 when !pred): ONE predicated LDG instead of a divergent branch around the load
+DR_HD float load_vox_if(const float* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    float v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}" : "=f"(v) : "l"(p), "r"((int)pred));
+    return v;
+#else
+    return pred ? *p : 0.0f;
+#endif
+}
+#if defined(__CUDACC__)
+DR_HD float load_vox_if(const __half* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned short h;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.b16 %0, 0;\n\t@q ld.global.nc.b16 %0, [%1];\n\t}" : "=h"(h) : "l"(p), "r"((int)pred));
+    return __half2float(__ushort_as_half(h));
+#else
+    return pred ? __half2float(*p) : 0.0f;
+#endif
+}
+#endif
 template <typename VT> struct VolView {
     const VT* p;
     DR_HD float ld(uoff off) const { return load_vox(p, off); }
@@ -279,6 +302,17 @@ struct Taps {
 //   axis (scale < dim-1 for dims <= 2000) and a crossed plane lo-1 / lo+2 is in range by construction.
 //   LAYOUT_BRICK8 reads the 8x8x8-bricked copy made by brick_kernel (separable offsets offx/offy/offz).
 enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1 };
+// How the six normal taps are evaluated (chosen per call from the volume dims, tap_mode() below):
+//   TAPS_ONE      corner reuse; at most one tap of an axis can leave the centre cell (tap offset < 1/2 voxel: dims <= ~1000)
+//   TAPS_TWO      corner reuse; both taps of an axis can leave it (1/2 <= offset < 1 voxel: dims <= ~2000)
+//   TAPS_GENERIC  a tap can skip a whole cell: seven full 8-load trilinear evaluations (linear layout only)
+enum { TAPS_ONE = 0, TAPS_TWO = 1, TAPS_GENERIC = 2 };
+inline int tap_mode(const DrDesc& d)
+{
+    if (d.tap_generic) return TAPS_GENERIC;
+    const float m = fmaxf(d.scale[0], fmaxf(d.scale[1], d.scale[2]));
+    return (0.5f * d.delta * m >= 0.499f) ? TAPS_TWO : TAPS_ONE;
+}
 
 template <typename VT> struct LinearAddr {
     typedef const VT* Row;
@@ -301,6 +335,16 @@ template <typename VT> struct LinearAddr {
 #endif
         return load_vox(r, xi);
     }
+    DR_HD float ld_if(Row r, int xi, bool pred) const
+    {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(pred && ((r + xi) - vp < 0 || (r + xi) - vp >= n_elems));
+#endif
+        return load_vox_if(r + xi, pred);
+    }
+    // row (yi, zi) where exactly one of them is `sel ? a : b` (the plane beyond the centre cell on that axis)
+    DR_HD Row row_sel_z(int yi, bool sel, int a, int b) const { return ptr_add(vp, i00 + (uoff)yi * sy + (sel ? (uoff)a : (uoff)b) * sz); }
+    DR_HD Row row_sel_y(bool sel, int a, int b, int zi) const { return ptr_add(vp, i00 + (sel ? (uoff)a : (uoff)b) * sy + (uoff)zi * sz); }
 };
 template <typename VT> struct BrickAddr {
     typedef uoff Row;
@@ -316,6 +360,13 @@ template <typename VT> struct BrickAddr {
         DR_OOB_IF(lx + xi < 0 || lx + xi > L.mx || (long long)(r + offx(lx + xi)) >= (long long)L.sZ * (((L.mz + 8) >> 3)));
         return load_vox(vp, r + offx(lx + xi));
     }
+    DR_HD float ld_if(Row r, int xi, bool pred) const
+    {
+        DR_OOB_IF(pred && (lx + xi < 0 || lx + xi > L.mx || (long long)(r + offx(lx + xi)) >= (long long)L.sZ * (((L.mz + 8) >> 3))));
+        return load_vox_if(ptr_add(vp, r + offx(lx + xi)), pred);
+    }
+    DR_HD Row row_sel_z(int yi, bool sel, int a, int b) const { return offy(ly + yi, L.sY) + offz(lz + (sel ? a : b), L.sZ); }
+    DR_HD Row row_sel_y(bool sel, int a, int b, int zi) const { return offy(ly + (sel ? a : b), L.sY) + offz(lz + zi, L.sZ); }
 };
 template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };
 template <typename VT> struct AddrOf<VT, LAYOUT_BRICK8> { typedef BrickAddr<VT> type; };
@@ -345,8 +396,13 @@ DR_HD void eval_centre(const A& ad, Centre& c)
     c.I = mix_e(c.ym0, c.ym1, oz, fz);
 }
 
-// the six normal taps on top of an evaluated centre
-template <typename A>
+// The six normal taps on top of an evaluated centre.  For y and z the code is branch-free in the common case: per axis the
+// ONE voxel plane beyond the centre cell that a crossed tap needs (lo+2 for the + tap, lo-1 for the - tap) is fetched with
+// four predicated loads and both taps pick their operands with selects -- the same mixes on the same values a branch per
+// tap would do, but a warp does not serialise through four divergent branches per sample (almost every warp has a lane
+// that crosses: P = 1-(1-0.13)^32 at 256^3).  Both taps of an axis leave the cell only when the tap offset exceeds half a
+// voxel (dims > 1000, TAPS_TWO); that case takes a branch for the second plane.
+template <int TAPS, typename A>
 DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, Taps& t)
 {
     t.cx = c.cx; t.cy = c.cy; t.cz = c.cz; t.cidx = c.cidx; t.I = c.I;
@@ -359,46 +415,41 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
     t.zm = locate(DR_SUB(pos.z, dl), d.scale[2]);
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
     const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
-    float zv[2], yv[2], xv[2];
-    // ---- z taps (+ then -): only the last mix changes
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        const Loc q = sgn ? t.zm : t.zp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float val;
-        if (q.b == c.cz.b) {
-            val = mix_e(c.ym0, c.ym1, o, f);
-        } else {
-            // new plane: above the centre's high plane (+) or below its low plane (-)
-            const typename A::Row n0 = ad.row(0, sgn ? -1 : 2), n1 = ad.row(1, sgn ? -1 : 2);
-            const float a = mix_e(ad.ld(n0, 0), ad.ld(n0, 1), ox, fx);
-            const float b = mix_e(ad.ld(n1, 0), ad.ld(n1, 1), ox, fx);
-            const float yn = mix_e(a, b, oy, fy);
-            val = sgn ? mix_e(yn, c.ym0, o, f) : mix_e(c.ym1, yn, o, f);
+    {   // ---- z taps
+        const bool cp = t.zp.b != c.cz.b, cm = t.zm.b != c.cz.b, any = cp | cm;
+        const typename A::Row n0 = ad.row_sel_z(0, cp, 2, -1), n1 = ad.row_sel_z(1, cp, 2, -1);
+        const float a = mix_e(ad.ld_if(n0, 0, any), ad.ld_if(n0, 1, any), ox, fx);
+        const float b = mix_e(ad.ld_if(n1, 0, any), ad.ld_if(n1, 1, any), ox, fx);
+        const float yn = mix_e(a, b, oy, fy);
+        const float fp = t.zp.f, fm = t.zm.f;
+        const float vp = mix_e(cp ? c.ym1 : c.ym0, cp ? yn : c.ym1, DR_SUB(1.0f, fp), fp);
+        float vm = mix_e(cm ? yn : c.ym0, cm ? c.ym0 : c.ym1, DR_SUB(1.0f, fm), fm);
+        if (TAPS == TAPS_TWO && (cp & cm)) {    // yn is plane lo+2; the - tap needs plane lo-1
+            const typename A::Row q0 = ad.row(0, -1), q1 = ad.row(1, -1);
+            const float a2 = mix_e(ad.ld(q0, 0), ad.ld(q0, 1), ox, fx), b2 = mix_e(ad.ld(q1, 0), ad.ld(q1, 1), ox, fx);
+            vm = mix_e(mix_e(a2, b2, oy, fy), c.ym0, DR_SUB(1.0f, fm), fm);
         }
-        zv[sgn] = val;
+        t.g.z = DR_SUB(vp, vm);
     }
-    t.g.z = DR_SUB(zv[0], zv[1]);
-    // ---- y taps: y mixes and the z mix change
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        const Loc q = sgn ? t.ym : t.yp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float a, b;
-        if (q.b == c.cy.b) {
-            a = mix_e(c.xm00, c.xm10, o, f);
-            b = mix_e(c.xm01, c.xm11, o, f);
-        } else {
-            const typename A::Row n0 = ad.row(sgn ? -1 : 2, 0), n1 = ad.row(sgn ? -1 : 2, 1);
-            const float m0 = mix_e(ad.ld(n0, 0), ad.ld(n0, 1), ox, fx);
-            const float m1 = mix_e(ad.ld(n1, 0), ad.ld(n1, 1), ox, fx);
-            a = sgn ? mix_e(m0, c.xm00, o, f) : mix_e(c.xm10, m0, o, f);
-            b = sgn ? mix_e(m1, c.xm01, o, f) : mix_e(c.xm11, m1, o, f);
+    {   // ---- y taps
+        const bool cp = t.yp.b != c.cy.b, cm = t.ym.b != c.cy.b, any = cp | cm;
+        const typename A::Row n0 = ad.row_sel_y(cp, 2, -1, 0), n1 = ad.row_sel_y(cp, 2, -1, 1);
+        const float m0 = mix_e(ad.ld_if(n0, 0, any), ad.ld_if(n0, 1, any), ox, fx);
+        const float m1 = mix_e(ad.ld_if(n1, 0, any), ad.ld_if(n1, 1, any), ox, fx);
+        const float fp = t.yp.f, op = DR_SUB(1.0f, fp), fm = t.ym.f, om = DR_SUB(1.0f, fm);
+        const float ap = mix_e(cp ? c.xm10 : c.xm00, cp ? m0 : c.xm10, op, fp);
+        const float bp = mix_e(cp ? c.xm11 : c.xm01, cp ? m1 : c.xm11, op, fp);
+        float am = mix_e(cm ? m0 : c.xm00, cm ? c.xm00 : c.xm10, om, fm);
+        float bm = mix_e(cm ? m1 : c.xm01, cm ? c.xm01 : c.xm11, om, fm);
+        if (TAPS == TAPS_TWO && (cp & cm)) {    // m0, m1 are row lo+2; the - tap needs row lo-1
+            const typename A::Row q0 = ad.row(-1, 0), q1 = ad.row(-1, 1);
+            am = mix_e(mix_e(ad.ld(q0, 0), ad.ld(q0, 1), ox, fx), c.xm00, om, fm);
+            bm = mix_e(mix_e(ad.ld(q1, 0), ad.ld(q1, 1), ox, fx), c.xm01, om, fm);
         }
-        yv[sgn] = mix_e(a, b, oz, fz);
+        t.g.y = DR_SUB(mix_e(ap, bp, oz, fz), mix_e(am, bm, oz, fz));
     }
-    t.g.y = DR_SUB(yv[0], yv[1]);
-    // ---- x taps: everything downstream of the corners changes
+    // ---- x taps: the rows are already formed; the compiler predicates the four neighbour loads itself
+    float xv[2];
 #pragma unroll
     for (int sgn = 0; sgn < 2; ++sgn) {
         const Loc q = sgn ? t.xm : t.xp;
@@ -457,22 +508,22 @@ DR_HD void eval_normals_generic(const DrDesc& d, const VT* vp, F3 pos, const Cen
 }
 
 // phase 1 / phase 2 dispatch on layout and tap path
-template <typename VT, int LAYOUT, bool GENERIC>
+template <typename VT, int LAYOUT, int TAPS>
 DR_HD void sample_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Centre& c)
 {
     locate_centre(d, pos, c);
-    if (GENERIC) { c.I = trilinear_full_linear(d, vol.p, c.cx, c.cy, c.cz); return; }
+    if (TAPS == TAPS_GENERIC) { c.I = trilinear_full_linear(d, vol.p, c.cx, c.cy, c.cz); return; }
     typename AddrOf<VT, LAYOUT>::type ad;
     ad.init(d, vol.p, L, c);
     eval_centre(ad, c);
 }
-template <typename VT, int LAYOUT, bool GENERIC>
+template <typename VT, int LAYOUT, int TAPS>
 DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, const Centre& c, Taps& t)
 {
-    if (GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
+    if (TAPS == TAPS_GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
     typename AddrOf<VT, LAYOUT>::type ad;
     ad.init(d, vol.p, L, c);
-    eval_normals(d, ad, pos, c, t);
+    eval_normals<TAPS>(d, ad, pos, c, t);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -637,7 +688,7 @@ DR_HD void tap_weights(float adj, Loc ax, Loc ay, Loc az, float v[8])
     v[4] = a01 * wx0; v[5] = a01 * wx1; v[6] = a11 * wx0; v[7] = a11 * wx1;
 }
 
-template <typename Sink, bool GENERIC>
+template <typename Sink, bool GENERIC, bool TWO>
 DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const SampleAdj& a)
 {
     float v[8];
@@ -684,42 +735,33 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
     sink.close();
     if (!a.has_dg) return;
     // a crossed tap lives in the face-neighbour cell: +-1 (x), +-X (z), +-X*Z (y) in the torch-linear cell order.  Its 8
-    // weights reuse the centre's pair products: only the weight pair of the shifted axis differs.
+    // weights reuse the centre's pair products: only the weight pair of the shifted axis differs.  One block per AXIS (the
+    // crossed tap is picked with selects; in a shaded warp some lane nearly always crossed on each axis, so a block per
+    // tap would cost twice the issue slots); both taps of an axis cross only under TAPS_TWO (second pass of the loop).
     const int sz = d.X, sy = d.X * d.Z;
-    if (xpc | xmc) {
 #pragma unroll
-        for (int sgn = 0; sgn < 2; ++sgn) {
-            if (sgn ? xmc : xpc) {
-                const Loc q = sgn ? t.xm : t.xp;
-                const float dg = sgn ? -a.dg.x : a.dg.x, q0 = dg * (1.0f - q.f), q1 = dg * q.f;
-                v[0] = q0 * yz00; v[1] = q1 * yz00; v[2] = q0 * yz10; v[3] = q1 * yz10;
-                v[4] = q0 * yz01; v[5] = q1 * yz01; v[6] = q0 * yz11; v[7] = q1 * yz11;
-                sink.direct(sgn ? cc - 1 : cc + 1, v);
-            }
+    for (int pass = 0; pass < (TWO ? 2 : 1); ++pass) {
+        const bool fx = pass ? (xpc & xmc) : (xpc | xmc), fy = pass ? (ypc & ymc) : (ypc | ymc), fz = pass ? (zpc & zmc) : (zpc | zmc);
+        if (fx) {
+            const bool m = pass ? true : !xpc;          // first pass: the + tap if it crossed, else the - tap
+            const float qf = m ? t.xm.f : t.xp.f, dg = m ? -a.dg.x : a.dg.x, q0 = dg * (1.0f - qf), q1 = dg * qf;
+            v[0] = q0 * yz00; v[1] = q1 * yz00; v[2] = q0 * yz10; v[3] = q1 * yz10;
+            v[4] = q0 * yz01; v[5] = q1 * yz01; v[6] = q0 * yz11; v[7] = q1 * yz11;
+            sink.direct(m ? cc - 1 : cc + 1, v);
         }
-    }
-    if (ypc | ymc) {
-#pragma unroll
-        for (int sgn = 0; sgn < 2; ++sgn) {
-            if (sgn ? ymc : ypc) {
-                const Loc q = sgn ? t.ym : t.yp;
-                const float dg = sgn ? -a.dg.y : a.dg.y, q0 = dg * (1.0f - q.f), q1 = dg * q.f;
-                v[0] = q0 * xz00; v[1] = q0 * xz10; v[2] = q1 * xz00; v[3] = q1 * xz10;
-                v[4] = q0 * xz01; v[5] = q0 * xz11; v[6] = q1 * xz01; v[7] = q1 * xz11;
-                sink.direct(sgn ? cc - sy : cc + sy, v);
-            }
+        if (fy) {
+            const bool m = pass ? true : !ypc;
+            const float qf = m ? t.ym.f : t.yp.f, dg = m ? -a.dg.y : a.dg.y, q0 = dg * (1.0f - qf), q1 = dg * qf;
+            v[0] = q0 * xz00; v[1] = q0 * xz10; v[2] = q1 * xz00; v[3] = q1 * xz10;
+            v[4] = q0 * xz01; v[5] = q0 * xz11; v[6] = q1 * xz01; v[7] = q1 * xz11;
+            sink.direct(m ? cc - sy : cc + sy, v);
         }
-    }
-    if (zpc | zmc) {
-#pragma unroll
-        for (int sgn = 0; sgn < 2; ++sgn) {
-            if (sgn ? zmc : zpc) {
-                const Loc q = sgn ? t.zm : t.zp;
-                const float dg = sgn ? -a.dg.z : a.dg.z, q0 = dg * (1.0f - q.f), q1 = dg * q.f;
-                v[0] = q0 * xy00; v[1] = q0 * xy10; v[2] = q0 * xy01; v[3] = q0 * xy11;
-                v[4] = q1 * xy00; v[5] = q1 * xy10; v[6] = q1 * xy01; v[7] = q1 * xy11;
-                sink.direct(sgn ? cc - sz : cc + sz, v);
-            }
+        if (fz) {
+            const bool m = pass ? true : !zpc;
+            const float qf = m ? t.zm.f : t.zp.f, dg = m ? -a.dg.z : a.dg.z, q0 = dg * (1.0f - qf), q1 = dg * qf;
+            v[0] = q0 * xy00; v[1] = q0 * xy10; v[2] = q0 * xy01; v[3] = q0 * xy11;
+            v[4] = q1 * xy00; v[5] = q1 * xy10; v[6] = q1 * xy01; v[7] = q1 * xy11;
+            sink.direct(m ? cc - sz : cc + sz, v);
         }
     }
 }
@@ -746,7 +788,7 @@ DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int 
 // State per ray is O(1): A (accumulated premultiplied RGBA), K (active samples), Tprev (transmittance before
 // the last active sample).  Nothing per sample is stored (the reference stores 16*M bytes per ray, :82,102-103).
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool NONDIFF, bool GENERIC, bool SR1>
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
 DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const TfTable& tf, F3 cam,
                          const Ray& r, F4& A, int& K, float& Tprev)
 {
@@ -758,7 +800,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
         const F3 pos = sample_pos(r, cam, s);
         Centre c;
-        sample_centre<VT, LAYOUT, GENERIC>(d, vol, L, pos, c);
+        sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
         TfHit h;
         apply_tf(d, tf, c.I, h, false);
         if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334: skipped samples never evaluate the normal
@@ -773,7 +815,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
             continue;
         }
         Taps t;
-        sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
+        sample_normals<VT, LAYOUT, TAPS>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);
         const float ko = sh.k * o;
@@ -797,7 +839,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
 // VolSink::open/close/direct the volume gradient; both may hold a partial sum in registers and are flushed at the end
 // of the ray.
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool GENERIC, bool WANT_VOL, bool WANT_TF, bool SR1, typename VolSink, typename TfSink>
+template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1, typename VolSink, typename TfSink>
 DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const TfTable& tf, F3 cam,
                           const Ray& r, F4 Afinal, int K, float Tprev, F4 g, VolSink& vsink, TfSink& tsink)
 {
@@ -805,7 +847,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
     for (int s = K - 1; s >= 0; --s) {
         const F3 pos = sample_pos(r, cam, s);
         Centre c;
-        sample_centre<VT, LAYOUT, GENERIC>(d, vol, L, pos, c);
+        sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
         TfHit h;
         apply_tf(d, tf, c.I, h, WANT_VOL);
         const float o = opacity<SR1>(d, h.c.w);
@@ -813,9 +855,28 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         // dc.rgb = k*o*dC = 0 and dI = tf_len * dc.w * h.d.w = 0, C = 0 (g.w unchanged) and T_{s-1} = T_s: nothing to do.
         if (!WANT_TF && o == 0.0f && h.d.w == 0.0f) continue;
         Taps t;
-        sample_normals<VT, LAYOUT, GENERIC>(d, vol, L, pos, c, t);
+        sample_normals<VT, LAYOUT, TAPS>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, true, sh);
+        if (o == 0.0f) {
+            // Exactly transparent sample (78 % of the active samples under the tf1 preset): C = 0, so g.w and the
+            // transmittance do not change (T_{s-1} = T_s; the forward saved Tprev = T for it too), dc.rgb = k*o*T*g = 0 and
+            // dk = 0 (no normal-path adjoint).  What is left of sample_adjoint is d(alpha) = k*(c.rgb . dC.rgb) + dC.w --
+            // it needs the Phong factor, which is why the normal was evaluated -- going to the alpha channel of the two TF
+            // bins and, where the bins' alphas differ, to the centre tap.
+            const float cd = Tafter * (h.c.x * g.x + h.c.y * g.y + h.c.z * g.z);
+            const float dcw = (sh.k * cd + Tafter * g.w) * (SR1 ? 1.0f : d.inv_sr);      // pow(1 - 0, 1/sr - 1) = 1
+            if (WANT_TF) tsink.add_alpha(h.lo, h.f, dcw);
+            if (WANT_VOL) {
+                SampleAdj a;
+                a.dI = (h.x > 0.0f) ? dcw * h.d.w * d.tf_len : 0.0f;
+                if (a.dI != 0.0f) {
+                    a.dg.x = a.dg.y = a.dg.z = 0.0f; a.has_dg = false;
+                    scatter_volume_grad<VolSink, TAPS == TAPS_GENERIC, TAPS == TAPS_TWO>(d, vsink, t, a);
+                }
+            }
+            continue;
+        }
         const float T = (s == K - 1) ? Tprev : Tafter * fast_rcp(1.0f - o);     // 1-o in (0.01, 1]: one MUFU.RCP, no fix-up code
         Tafter = T;
         SampleAdj a;
@@ -823,7 +884,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         g.w -= Cg;
         if (WANT_TF) tsink.add(h.lo, h.f, a.dc);
         if (WANT_VOL && (a.has_dg || a.dI != 0.0f))          // exactly-zero contributions (transparent samples) are not scattered
-            scatter_volume_grad<VolSink, GENERIC>(d, vsink, t, a);
+            scatter_volume_grad<VolSink, TAPS == TAPS_GENERIC, TAPS == TAPS_TWO>(d, vsink, t, a);
     }
     if (WANT_TF) tsink.flush();
     if (WANT_VOL) vsink.flush();

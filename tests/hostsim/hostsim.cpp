@@ -30,6 +30,7 @@ struct HostTfSink {
         g[4 * lo + 0] += dc.x * w0; g[4 * lo + 1] += dc.y * w0; g[4 * lo + 2] += dc.z * w0; g[4 * lo + 3] += dc.w * w0;
         g[4 * hi + 0] += dc.x * w1; g[4 * hi + 1] += dc.y * w1; g[4 * hi + 2] += dc.z * w1; g[4 * hi + 3] += dc.w * w1;
     }
+    void add_alpha(int lo, float f, float dcw) { add(lo, f, F4 { 0.0f, 0.0f, 0.0f, dcw }); }
     void flush() {}
 };
 Layout make_layout(const DrDesc& d)
@@ -85,6 +86,7 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
     F3 cam = { cam3[0], cam3[1], cam3[2] };
     const size_t plane = (size_t)d->W * d->H;
     const bool sr1 = d->inv_sr == 1.0f;
+    const int taps = tap_mode(*d);
     for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {
         const size_t pix = (size_t)(d->H - 1 - j) * d->W + i;
         Ray r;
@@ -92,14 +94,16 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
         F4 A; int K; float Tp;
         const bool nd = d->flags & DR_F_NONDIFF;
         if (d->flags & DR_F_LAYOUT_BRICK8) {
-#define FWD(LAY, ND, GEN) do { if (sr1 && !GEN) march_forward<float, LAY, ND, GEN, !GEN>(*d, vol, L, tf4, cam, r, A, K, Tp); \
-                               else march_forward<float, LAY, ND, GEN, false>(*d, vol, L, tf4, cam, r, A, K, Tp); } while (0)
-            if (nd) FWD(LAYOUT_BRICK8, true, false); else FWD(LAYOUT_BRICK8, false, false);
-        } else if (d->tap_generic) {
-            if (nd) FWD(LAYOUT_LINEAR, true, true); else FWD(LAYOUT_LINEAR, false, true);
+#define FWD2(LAY, ND, TAPS) do { if (sr1 && TAPS != TAPS_GENERIC) march_forward<float, LAY, ND, TAPS, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp); \
+                                else march_forward<float, LAY, ND, TAPS, false>(*d, vol, L, tf4, cam, r, A, K, Tp); } while (0)
+#define FWD(LAY, ND) do { if (taps == TAPS_ONE) FWD2(LAY, ND, TAPS_ONE); else FWD2(LAY, ND, TAPS_TWO); } while (0)
+            if (nd) FWD(LAYOUT_BRICK8, true); else FWD(LAYOUT_BRICK8, false);
+        } else if (taps == TAPS_GENERIC) {
+            if (nd) FWD2(LAYOUT_LINEAR, true, TAPS_GENERIC); else FWD2(LAYOUT_LINEAR, false, TAPS_GENERIC);
         } else {
-            if (nd) FWD(LAYOUT_LINEAR, true, false); else FWD(LAYOUT_LINEAR, false, false);
+            if (nd) FWD(LAYOUT_LINEAR, true); else FWD(LAYOUT_LINEAR, false);
         }
+#undef FWD2
 #undef FWD
         out[pix] = A.x; out[plane + pix] = A.y; out[2 * plane + pix] = A.z; out[3 * plane + pix] = A.w;
         if (out_K) out_K[pix] = K;
@@ -123,6 +127,7 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
     HostTfSink ts { gtf, d->R - 1 };
     const bool sr1 = d->inv_sr == 1.0f;
     const bool wv = d->flags & DR_F_NEEDS_VOL_GRAD, wt = d->flags & DR_F_NEEDS_TF_GRAD;
+    const int taps = tap_mode(*d);
     for (int j = 0; j < d->H; ++j) for (int i = 0; i < d->W; ++i) {
         const size_t pix = (size_t)(d->H - 1 - j) * d->W + i;
         Ray r;
@@ -131,12 +136,13 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
         F4 g = { grad_out[pix], grad_out[plane + pix], grad_out[2 * plane + pix], grad_out[3 * plane + pix] };
         const int K = Kin[pix];
         const float Tp = Tprev[pix];
-#define CALL(LAY, GEN, WV, WT) do { if (sr1 && !GEN) march_backward<float, LAY, GEN, WV, WT, !GEN>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); \
-                                    else march_backward<float, LAY, GEN, WV, WT, false>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); } while (0)
-#define CALL3(LAY, GEN) do { if (wv && wt) CALL(LAY, GEN, true, true); else if (wv) CALL(LAY, GEN, true, false); else if (wt) CALL(LAY, GEN, false, true); } while (0)
-        if (d->flags & DR_F_LAYOUT_BRICK8) CALL3(LAYOUT_BRICK8, false);
-        else if (d->tap_generic) CALL3(LAYOUT_LINEAR, true);
-        else CALL3(LAYOUT_LINEAR, false);
+#define CALL(LAY, TAPS, WV, WT) do { if (sr1 && TAPS != TAPS_GENERIC) march_backward<float, LAY, TAPS, WV, WT, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); \
+                                     else march_backward<float, LAY, TAPS, WV, WT, false>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); } while (0)
+#define CALL3(LAY, TAPS) do { if (wv && wt) CALL(LAY, TAPS, true, true); else if (wv) CALL(LAY, TAPS, true, false); else if (wt) CALL(LAY, TAPS, false, true); } while (0)
+        if (d->flags & DR_F_LAYOUT_BRICK8) { if (taps == TAPS_ONE) CALL3(LAYOUT_BRICK8, TAPS_ONE); else CALL3(LAYOUT_BRICK8, TAPS_TWO); }
+        else if (taps == TAPS_GENERIC) CALL3(LAYOUT_LINEAR, TAPS_GENERIC);
+        else if (taps == TAPS_ONE) CALL3(LAYOUT_LINEAR, TAPS_ONE);
+        else CALL3(LAYOUT_LINEAR, TAPS_TWO);
 #undef CALL3
 #undef CALL
     }

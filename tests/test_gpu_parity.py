@@ -34,6 +34,9 @@ CASES = [
     ((48, 48, 48), (64, 64), 128, 1, True, 0.7, 2048),
     ((40, 40, 40), (40, 40), 64, 1, True, 2.0, 4096),
     ((64, 64, 64), (64, 64), 128, 1, True, 1.0, 40),          # max_samples truncates the rays (H2)
+    ((1100, 6, 6), (24, 20), 32, 1, True, 1.0, 4096),         # an axis > 1000 voxels: both +-1e-3 taps of that axis can leave the cell
+    ((6, 1100, 6), (24, 20), 32, 1, True, 1.0, 4096),
+    ((6, 6, 1100), (24, 20), 32, 1, True, 1.0, 4096),
 ]
 
 

@@ -29,6 +29,24 @@ def test_device_math_matches_oracle(shape, out_shape, R, sr, jitter, generic, br
     assert rel_l2(gv2, gv) <= 1e-4 and rel_l2(gt2, gt) <= 1e-4
 
 
+@pytest.mark.parametrize("shape", [(1100, 6, 6), (6, 1100, 6), (6, 6, 1100)])
+@pytest.mark.parametrize("brick", [False, True])
+def test_device_math_both_taps_of_an_axis_cross(shape, brick):
+    # an axis longer than 1000 voxels: the +-1e-3 taps move more than half a voxel, so BOTH can leave the centre cell
+    # (the branch behind the select-based tap evaluation); still below the generic-tap threshold (~2000)
+    out_shape = (20, 16)
+    vol, tf, cams, jit = case_inputs(shape, out_shape, 32, seed=3, jitter=True)
+    J = jit[0].numpy()
+    img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, jitter=J, max_samples=4096, return_counts=True)
+    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, jitter=J, max_samples=4096, brick=brick)
+    assert n.max() > 1000 and np.array_equal(n, n2) and np.array_equal(K, K2)
+    assert np.array_equal(img[3], out[3]) and np.abs(img - out).max() <= 1e-6
+    go = np.random.default_rng(9).normal(size=img.shape).astype(np.float32)
+    gv, gt = co.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, jitter=J, max_samples=4096)
+    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, jitter=J, max_samples=4096, brick=brick)
+    assert rel_l2(gv2, gv) <= 1e-4 and rel_l2(gt2, gt) <= 1e-4
+
+
 def test_device_math_nondiff_and_truncation():
     vol, tf, cams, _ = case_inputs((32, 32, 32), (40, 40), 64, seed=8, tf_name="tf1", jitter=False)
     img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 40), sampling_rate=4.0, nondiff=True, return_counts=True)
