@@ -54,8 +54,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--tf", default=None, help="transfer-function preset (reference utils.get_tf): tf1..tf5, gray, black, rand; "
                                               "default tf1 (C2: its optimisation start `black`)")
-    p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8"], help="volume layout read by the march kernels")
-    p.add_argument("--no-reg-accum", action="store_true", help="tuning: backward without register accumulation (DR_F_NO_REG_ACCUM)")
+    p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8", "cell8"], help="volume layout read by the march kernels")
     p.add_argument("--cuda-profiler-range", action="store_true",
                    help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     return p.parse_args()
@@ -219,10 +218,10 @@ def run_ours(args, cfg):
         if timed: e[1].record()
         out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")
         if timed: e[2].record()
-        n_k = 2 if bricked.ndim == 2 else 1                                          # (brick_kernel +) fwd_kernel
+        n_k = 2 if bricked.ndim in (2, 3) else 1                                     # (brick_kernel / expand_cells_kernel +) fwd_kernel
         if mode != "nondiff":
             go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
-            xf = 128 if args.no_reg_accum else 0
+            xf = 0
             if world > 1 and need_vol:
                 # the gather writes straight into the flat [volume grad | TF grad] buffer that is all-reduced (no concatenation copy)
                 cells = torch.zeros((1, n ** 3 * 8), dtype=torch.float32, device=dev)

@@ -10,9 +10,9 @@ LIB_PATH = os.environ.get("DIFFRENDER_LIB") or os.path.join(_PKG, "libdiffrender
 # include/diffrender.h
 DR_VERSION = 100
 VOX_F32, VOX_F16 = 0, 1
-F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_NO_REG_ACCUM, F_LAYOUT_BRICK8, F_COUNT_SHADED = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_LAYOUT_BRICK8, F_COUNT_SHADED, F_LAYOUT_CELL8 = 1, 2, 4, 8, 16, 32, 64, 256, 512, 2048
 
-EXPORTS = ("dr_version", "dr_debug_oob_count", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_forward",
+EXPORTS = ("dr_version", "dr_debug_oob_count", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_expand_cells", "dr_forward",
            "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad", "dr_forward_mse", "dr_backward_mse",
            "dr_momentum_step", "dr_ingest_u8")
 
@@ -50,6 +50,7 @@ def load():
     lib.dr_bricked_elems.argtypes = [dp]; lib.dr_bricked_elems.restype = ctypes.c_size_t
     lib.dr_workspace_bytes.argtypes = [dp]; lib.dr_workspace_bytes.restype = ctypes.c_size_t
     lib.dr_brick_volume.argtypes = [dp, vp, vp, vp]; lib.dr_brick_volume.restype = ctypes.c_int
+    lib.dr_expand_cells.argtypes = [dp, vp, vp, vp]; lib.dr_expand_cells.restype = ctypes.c_int
     lib.dr_forward.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp]; lib.dr_forward.restype = ctypes.c_int
     lib.dr_backward.argtypes = [dp] + [vp] * 11 + [ctypes.c_size_t, vp]; lib.dr_backward.restype = ctypes.c_int
     lib.dr_grad_cells_elems.argtypes = [dp]; lib.dr_grad_cells_elems.restype = ctypes.c_size_t

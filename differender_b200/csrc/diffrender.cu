@@ -71,6 +71,27 @@ __global__ void __launch_bounds__(256) brick_kernel(DrDesc d, const VT* __restri
     br[(size_t)b * elems + e] = v;
 }
 
+// linear [Y][Z][X] volume -> cell-major records [cell][8] (LAYOUT_CELL8): slot a + 2b + 4c of cell (x,y,z) = voxel
+// (min(x+a,X-1), min(y+b,Y-1), min(z+c,Z-1)).  Write-bound: 8 * sizeof(voxel) bytes per voxel; the 8x re-read of the
+// input is served by L1/L2.
+template <typename VT>
+__global__ void __launch_bounds__(256) expand_cells_kernel(DrDesc d, const VT* __restrict__ lin, VT* __restrict__ cells)
+{
+    const size_t n = (size_t)d.X * d.Y * d.Z;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int b = blockIdx.y;
+    const int x = (int)(e % d.X);
+    const size_t r = e / d.X;
+    const int z = (int)(r % d.Z), y = (int)(r / d.Z);
+    const size_t dx = x + 1 < d.X ? 1 : 0, dz = z + 1 < d.Z ? (size_t)d.X : 0, dy = y + 1 < d.Y ? (size_t)d.X * d.Z : 0;
+    const VT* p = lin + (size_t)b * n + e;
+    struct alignas(16) Rec { VT v[8]; } rec;
+    rec.v[0] = p[0]; rec.v[1] = p[dx]; rec.v[2] = p[dy]; rec.v[3] = p[dy + dx];
+    rec.v[4] = p[dz]; rec.v[5] = p[dz + dx]; rec.v[6] = p[dz + dy]; rec.v[7] = p[dz + dy + dx];
+    reinterpret_cast<Rec*>(cells)[(size_t)b * n + e] = rec;
+}
+
 // cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 (HBM-bound: reads 32 B per voxel once, L2 serves the 8x reuse)
 __global__ void __launch_bounds__(256) gather_grad_kernel(DrDesc d, const float* __restrict__ gcell, float* __restrict__ lin, int accumulate)
 {
@@ -121,8 +142,9 @@ int check_desc(const DrDesc* d)
         return fail(DR_EINVAL, "descriptor brick counts inconsistent (use dr_desc_init)");
     if (d->vox_dtype != DR_VOX_F32 && d->vox_dtype != DR_VOX_F16) return fail(DR_EDTYPE, "unsupported voxel dtype");
     if (d->BS > 65535) return fail(DR_EINVAL, "more than 65535 views in one call");
-    if (d->tap_generic && (d->flags & DR_F_LAYOUT_BRICK8))
+    if (d->tap_generic && (d->flags & (DR_F_LAYOUT_BRICK8 | DR_F_LAYOUT_CELL8)))
         return fail(DR_EINVAL, "the generic tap path (volumes > ~2000 voxels per axis) needs the linear layout");
+    if ((d->flags & DR_F_LAYOUT_BRICK8) && (d->flags & DR_F_LAYOUT_CELL8)) return fail(DR_EINVAL, "two volume layouts selected");
     return DR_OK;
 }
 
@@ -267,6 +289,22 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
         brick_kernel<__half><<<grid, 256, 0, st>>>(*d, static_cast<const __half*>(vol_linear), static_cast<__half*>(vol_bricked), elems);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "brick_kernel launch");
+}
+
+int dr_expand_cells(const DrDesc* d, const void* vol_linear, void* vol_cells, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!vol_linear || !vol_cells) return fail(DR_EINVAL, "dr_expand_cells: null pointer");
+    if ((reinterpret_cast<uintptr_t>(vol_cells) & 31) != 0) return fail(DR_EALIGN, "dr_expand_cells: vol_cells must be 32-byte aligned");
+    const size_t n = (size_t)d->X * d->Y * d->Z;
+    dim3 grid((unsigned)((n + 255) / 256), d->Bvol);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->vox_dtype == DR_VOX_F32)
+        expand_cells_kernel<float><<<grid, 256, 0, st>>>(*d, static_cast<const float*>(vol_linear), static_cast<float*>(vol_cells));
+    else
+        expand_cells_kernel<__half><<<grid, 256, 0, st>>>(*d, static_cast<const __half*>(vol_linear), static_cast<__half*>(vol_cells));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "expand_cells_kernel launch");
 }
 
 int dr_forward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,

@@ -13,6 +13,7 @@ static int forward_vt(const FwdArgs& a)
     const int taps = tap_mode(*d);
 #define DR_FWD_ND(LAY, TAPS, SR1) (nd ? launch_fwd<VT, LAY, true, TAPS, SR1>(a) : launch_fwd<VT, LAY, false, TAPS, SR1>(a))
 #define DR_FWD_SR(LAY, TAPS) (sr1 ? DR_FWD_ND(LAY, TAPS, true) : DR_FWD_ND(LAY, TAPS, false))
+    if (d->flags & DR_F_LAYOUT_CELL8) return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_CELL8, TAPS_ONE) : DR_FWD_SR(LAYOUT_CELL8, TAPS_TWO);
     if (d->flags & DR_F_LAYOUT_BRICK8) return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_BRICK8, TAPS_ONE) : DR_FWD_SR(LAYOUT_BRICK8, TAPS_TWO);
     if (taps == TAPS_GENERIC) return DR_FWD_ND(LAYOUT_LINEAR, TAPS_GENERIC, false);
     return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_LINEAR, TAPS_ONE) : DR_FWD_SR(LAYOUT_LINEAR, TAPS_TWO);

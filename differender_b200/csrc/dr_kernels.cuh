@@ -211,7 +211,7 @@ struct RedTfSink {
 };
 
 template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1>
-__global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_LINEAR ? DR_BWD_MIN_BLOCKS_LINEAR : DR_BWD_MIN_BLOCKS_BRICK)
+__global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN_BLOCKS_BRICK : DR_BWD_MIN_BLOCKS_LINEAR)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
@@ -279,6 +279,7 @@ template <typename K> int set_smem(K kernel, size_t bytes)
 
 inline size_t vol_stride(const DrDesc* d)
 {
+    if (d->flags & DR_F_LAYOUT_CELL8) return (size_t)d->X * d->Y * d->Z * 8;
     return (d->flags & DR_F_LAYOUT_BRICK8) ? (size_t)d->nbx * d->nby * d->nbz * 512 : (size_t)d->X * d->Y * d->Z;
 }
 
@@ -329,6 +330,7 @@ template <typename VT>
 int dispatch_bwd_layout(const BwdArgs& a)
 {
     const int taps = tap_mode(*a.d);
+    if (a.d->flags & DR_F_LAYOUT_CELL8) return taps == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_CELL8, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_CELL8, TAPS_TWO>(a);
     if (a.d->flags & DR_F_LAYOUT_BRICK8) return taps == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_BRICK8, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_BRICK8, TAPS_TWO>(a);
     if (taps == TAPS_GENERIC) return dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_GENERIC>(a);
     return taps == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_TWO>(a);

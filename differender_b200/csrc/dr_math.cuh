@@ -204,6 +204,85 @@ DR_HD float load_vox_if(const __half* p, bool pred)
 #endif
 }
 #endif
+// ---- cell-major records (LAYOUT_CELL8): 8 consecutive elements per cell ---------------------------------
+#if defined(__CUDACC__)
+static __constant__ unsigned dr_rec_size[3] = { 0u, 16u, 32u };    // bytes per record, indexed by sizeof(VT) / 2
+#endif
+template <typename VT>
+DR_HD const VT* rec_add(const VT* p, uoff cell)                     // p + 8*cell as ONE IMAD.WIDE.U32 (64-bit result)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cell), "r"(dr_rec_size[sizeof(VT) / 2]), "l"((unsigned long long)p));
+    return reinterpret_cast<const VT*>(a);
+#else
+    return p + (size_t)cell * 8;
+#endif
+}
+DR_HD void load_vox8(const float* r, float v[8])
+{
+#if defined(__CUDA_ARCH__)
+    const float4 a = __ldg(reinterpret_cast<const float4*>(r)), b = __ldg(reinterpret_cast<const float4*>(r) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#else
+    for (int q = 0; q < 8; ++q) v[q] = r[q];
+#endif
+}
+DR_HD void load_vox4_if(const float* r, bool pred, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\t"
+        "mov.f32 %3, 0f00000000;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(r), "r"((int)pred));
+#else
+    for (int q = 0; q < 4; ++q) n[q] = pred ? r[q] : 0.0f;
+#endif
+}
+DR_HD void load_vox2_if(const float* r, bool pred, float n[2])
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+        "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}" : "=f"(n[0]), "=f"(n[1]) : "l"(r), "r"((int)pred));
+#else
+    for (int q = 0; q < 2; ++q) n[q] = pred ? r[q] : 0.0f;
+#endif
+}
+#if defined(__CUDACC__)
+DR_HD void load_vox8(const __half* r, float v[8])
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(r));
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&a.z)), p3 = __half22float2(*reinterpret_cast<const __half2*>(&a.w));
+    v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+#else
+    for (int q = 0; q < 8; ++q) v[q] = __half2float(r[q]);
+#endif
+}
+DR_HD void load_vox4_if(const __half* r, bool pred, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned lo, hi;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t@q ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
+        : "=r"(lo), "=r"(hi) : "l"(r), "r"((int)pred));
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    n[0] = p0.x; n[1] = p0.y; n[2] = p1.x; n[3] = p1.y;
+#else
+    for (int q = 0; q < 4; ++q) n[q] = pred ? __half2float(r[q]) : 0.0f;
+#endif
+}
+DR_HD void load_vox2_if(const __half* r, bool pred, float n[2])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned w;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(w) : "l"(r), "r"((int)pred));
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    n[0] = p0.x; n[1] = p0.y;
+#else
+    for (int q = 0; q < 2; ++q) n[q] = pred ? __half2float(r[q]) : 0.0f;
+#endif
+}
+#endif
 template <typename VT> struct VolView {
     const VT* p;
     DR_HD float ld(uoff off) const { return load_vox(p, off); }
@@ -294,14 +373,23 @@ struct Taps {
     F3 g;                         // (f(x+d)-f(x-d), ...), un-normalised                     :197-202
 };
 
-// Volume storage layouts, as addressing policies.  row(yi, zi) names the voxel row (y0+yi, z0+zi) and ld(row, xi) reads
-// voxel x0+xi of it, with xi, yi, zi in {-1, 0, 1, 2} relative to the centre cell's low corner (only plus-shaped
-// combinations occur: at most one coordinate outside {0, 1}).
+// Volume storage layouts, as fetch policies.  A policy is initialised for one centre cell and provides
+//   centre(v)                 the cell's 8 corners, v[a + 2b + 4c] = voxel (x0+a, y0+b, z0+c)
+//   plane_z(plus, pred, n)    the voxel plane beyond the cell along z (z0+2 if plus else z0-1), predicated:
+//                             n = (x0,y0) (x1,y0) (x0,y1) (x1,y1)
+//   plane_y(plus, pred, n)    likewise along y: n = (x0,z0) (x1,z0) (x0,z1) (x1,z1)
+//   plane_x(minus, n)         likewise along x (x0-1 if minus else x0+2): n = (y0,z0) (y1,z0) (y0,z1) (y1,z1)
+// No index clamps: in the corner-reuse path lo <= dim-2 on every axis (scale < dim-1 for dims <= 2000) and a plane beyond
+// the cell is only fetched by a tap that crossed into it, so it is in range by construction.
 //   LAYOUT_LINEAR reads the caller's contiguous torch tensor [y][z][x] in place (zero copy): a row is a pointer
-//   (one IMAD.WIDE.U32), x-neighbours are immediate offsets.  No clamps: in the corner-reuse path lo <= dim-2 on every
-//   axis (scale < dim-1 for dims <= 2000) and a crossed plane lo-1 / lo+2 is in range by construction.
-//   LAYOUT_BRICK8 reads the 8x8x8-bricked copy made by brick_kernel (separable offsets offx/offy/offz).
-enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1 };
+//     (one IMAD.WIDE.U32), x-neighbours are immediate offsets.  8 scalar loads per cell.
+//   LAYOUT_BRICK8 reads the 8x8x8-bricked copy made by dr_brick_volume (separable offsets offx/offy/offz).
+//   LAYOUT_CELL8  reads the cell-major copy made by dr_expand_cells: record `cell` (the torch-linear index of the cell's
+//     low corner) holds the cell's 8 corners contiguously (32 bytes fp32 = one sector, 16 bytes fp16), so a cell is ONE
+//     address and two (fp16: one) 16-byte loads instead of four rows and eight 4-byte loads that touch ~5 sectors each
+//     across a warp -- the L1 data pipe, which bounds the forward in the linear layout, sees a quarter of the wavefronts.
+//     A plane beyond the cell is half / two quarters / four eighths of the neighbour's record.  Costs 8x the volume's bytes.
+enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1, LAYOUT_CELL8 = 2 };
 // How the six normal taps are evaluated (chosen per call from the volume dims, tap_mode() below):
 //   TAPS_ONE      corner reuse; at most one tap of an axis can leave the centre cell (tap offset < 1/2 voxel: dims <= ~1000)
 //   TAPS_TWO      corner reuse; both taps of an axis can leave it (1/2 <= offset < 1 voxel: dims <= ~2000)
@@ -342,9 +430,30 @@ template <typename VT> struct LinearAddr {
 #endif
         return load_vox_if(r + xi, pred);
     }
-    // row (yi, zi) where exactly one of them is `sel ? a : b` (the plane beyond the centre cell on that axis)
-    DR_HD Row row_sel_z(int yi, bool sel, int a, int b) const { return ptr_add(vp, i00 + (uoff)yi * sy + (sel ? (uoff)a : (uoff)b) * sz); }
-    DR_HD Row row_sel_y(bool sel, int a, int b, int zi) const { return ptr_add(vp, i00 + (sel ? (uoff)a : (uoff)b) * sy + (uoff)zi * sz); }
+    DR_HD void centre(float v[8]) const
+    {
+        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
+        v[0] = ld(r00, 0); v[1] = ld(r00, 1); v[2] = ld(r10, 0); v[3] = ld(r10, 1);
+        v[4] = ld(r01, 0); v[5] = ld(r01, 1); v[6] = ld(r11, 0); v[7] = ld(r11, 1);
+    }
+    DR_HD void plane_z(bool plus, bool pred, float n[4]) const
+    {
+        const uoff zo = (plus ? (uoff)2 : (uoff)-1) * sz;
+        const Row n0 = ptr_add(vp, i00 + zo), n1 = ptr_add(vp, i00 + sy + zo);
+        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
+    }
+    DR_HD void plane_y(bool plus, bool pred, float n[4]) const
+    {
+        const uoff yo = (plus ? (uoff)2 : (uoff)-1) * sy;
+        const Row n0 = ptr_add(vp, i00 + yo), n1 = ptr_add(vp, i00 + yo + sz);
+        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
+    }
+    DR_HD void plane_x(bool minus, float n[4]) const
+    {
+        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
+        const int xi = minus ? -1 : 2;
+        n[0] = ld(r00, xi); n[1] = ld(r10, xi); n[2] = ld(r01, xi); n[3] = ld(r11, xi);
+    }
 };
 template <typename VT> struct BrickAddr {
     typedef uoff Row;
@@ -353,7 +462,6 @@ template <typename VT> struct BrickAddr {
     {
         vp = p; L = L_; lx = lo_of(c.cx); ly = lo_of(c.cy); lz = lo_of(c.cz);
     }
-    // no clamps: in the corner-reuse path every index lo-1 .. lo+2 that is actually read is in range (see LinearAddr)
     DR_HD Row row(int yi, int zi) const { return offy(ly + yi, L.sY) + offz(lz + zi, L.sZ); }
     DR_HD float ld(Row r, int xi) const
     {
@@ -365,11 +473,79 @@ template <typename VT> struct BrickAddr {
         DR_OOB_IF(pred && (lx + xi < 0 || lx + xi > L.mx || (long long)(r + offx(lx + xi)) >= (long long)L.sZ * (((L.mz + 8) >> 3))));
         return load_vox_if(ptr_add(vp, r + offx(lx + xi)), pred);
     }
-    DR_HD Row row_sel_z(int yi, bool sel, int a, int b) const { return offy(ly + yi, L.sY) + offz(lz + (sel ? a : b), L.sZ); }
-    DR_HD Row row_sel_y(bool sel, int a, int b, int zi) const { return offy(ly + (sel ? a : b), L.sY) + offz(lz + zi, L.sZ); }
+    DR_HD void centre(float v[8]) const
+    {
+        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
+        v[0] = ld(r00, 0); v[1] = ld(r00, 1); v[2] = ld(r10, 0); v[3] = ld(r10, 1);
+        v[4] = ld(r01, 0); v[5] = ld(r01, 1); v[6] = ld(r11, 0); v[7] = ld(r11, 1);
+    }
+    DR_HD void plane_z(bool plus, bool pred, float n[4]) const
+    {
+        const int zi = plus ? 2 : -1;
+        const Row n0 = row(0, zi), n1 = row(1, zi);
+        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
+    }
+    DR_HD void plane_y(bool plus, bool pred, float n[4]) const
+    {
+        const int yi = plus ? 2 : -1;
+        const Row n0 = row(yi, 0), n1 = row(yi, 1);
+        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
+    }
+    DR_HD void plane_x(bool minus, float n[4]) const
+    {
+        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
+        const int xi = minus ? -1 : 2;
+        n[0] = ld(r00, xi); n[1] = ld(r10, xi); n[2] = ld(r01, xi); n[3] = ld(r11, xi);
+    }
+};
+template <typename VT> struct CellAddr {
+    const VT* vp; uoff cell, sy, sz;
+#if defined(DR_BOUNDS_CHECK)
+    long long n_cells;
+#endif
+    DR_HD void init(const DrDesc& d, const VT* p, const Layout&, const Centre& c)
+    {
+        vp = p; cell = (uoff)c.cidx; sz = (uoff)d.X; sy = (uoff)(d.X * d.Z);
+#if defined(DR_BOUNDS_CHECK)
+        n_cells = (long long)d.X * d.Y * d.Z;
+#endif
+    }
+    DR_HD const VT* rec(uoff c) const
+    {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF((long long)c >= n_cells);
+#endif
+        return rec_add(vp, c);
+    }
+    DR_HD void centre(float v[8]) const { load_vox8(rec(cell), v); }
+    DR_HD void plane_z(bool plus, bool pred, float n[4]) const
+    {
+        // the + neighbour's upper half (slots 4..7 = plane z0+2) or the - neighbour's lower half (slots 0..3 = plane z0-1)
+        const VT* r = rec_add(vp, plus ? cell + sz : cell - sz) + (plus ? 4 : 0);
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(pred && (long long)(plus ? cell + sz : cell - sz) >= n_cells);
+#endif
+        load_vox4_if(r, pred, n);
+    }
+    DR_HD void plane_y(bool plus, bool pred, float n[4]) const
+    {
+        // b = 1 slots {2,3} {6,7} of the + neighbour, b = 0 slots {0,1} {4,5} of the - neighbour
+        const VT* r = rec_add(vp, plus ? cell + sy : cell - sy) + (plus ? 2 : 0);
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(pred && (long long)(plus ? cell + sy : cell - sy) >= n_cells);
+#endif
+        load_vox2_if(r, pred, n); load_vox2_if(r + 4, pred, n + 2);
+    }
+    DR_HD void plane_x(bool minus, float n[4]) const
+    {
+        // a = 0 slots {0,2,4,6} of the - neighbour, a = 1 slots {1,3,5,7} of the + neighbour
+        const VT* r = rec(minus ? cell - 1 : cell + 1) + (minus ? 0 : 1);
+        n[0] = load_vox(r, 0); n[1] = load_vox(r, 2); n[2] = load_vox(r, 4); n[3] = load_vox(r, 6);
+    }
 };
 template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };
 template <typename VT> struct AddrOf<VT, LAYOUT_BRICK8> { typedef BrickAddr<VT> type; };
+template <typename VT> struct AddrOf<VT, LAYOUT_CELL8> { typedef CellAddr<VT> type; };
 
 DR_HD void locate_centre(const DrDesc& d, F3 pos, Centre& c)
 {
@@ -383,11 +559,10 @@ DR_HD void locate_centre(const DrDesc& d, F3 pos, Centre& c)
 template <typename A>
 DR_HD void eval_centre(const A& ad, Centre& c)
 {
-    const typename A::Row r00 = ad.row(0, 0), r10 = ad.row(1, 0), r01 = ad.row(0, 1), r11 = ad.row(1, 1);
-    c.v000 = ad.ld(r00, 0); c.v100 = ad.ld(r00, 1);
-    c.v010 = ad.ld(r10, 0); c.v110 = ad.ld(r10, 1);
-    c.v001 = ad.ld(r01, 0); c.v101 = ad.ld(r01, 1);
-    c.v011 = ad.ld(r11, 0); c.v111 = ad.ld(r11, 1);
+    float v[8];
+    ad.centre(v);
+    c.v000 = v[0]; c.v100 = v[1]; c.v010 = v[2]; c.v110 = v[3];
+    c.v001 = v[4]; c.v101 = v[5]; c.v011 = v[6]; c.v111 = v[7];
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
     const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
     c.xm00 = mix_e(c.v000, c.v100, ox, fx); c.xm10 = mix_e(c.v010, c.v110, ox, fx);
@@ -398,7 +573,7 @@ DR_HD void eval_centre(const A& ad, Centre& c)
 
 // The six normal taps on top of an evaluated centre.  For y and z the code is branch-free in the common case: per axis the
 // ONE voxel plane beyond the centre cell that a crossed tap needs (lo+2 for the + tap, lo-1 for the - tap) is fetched with
-// four predicated loads and both taps pick their operands with selects -- the same mixes on the same values a branch per
+// predicated loads and both taps pick their operands with selects -- the same mixes on the same values a branch per
 // tap would do, but a warp does not serialise through four divergent branches per sample (almost every warp has a lane
 // that crosses: P = 1-(1-0.13)^32 at 256^3).  Both taps of an axis leave the cell only when the tap offset exceeds half a
 // voxel (dims > 1000, TAPS_TWO); that case takes a branch for the second plane.
@@ -416,39 +591,37 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
     const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
     {   // ---- z taps
-        const bool cp = t.zp.b != c.cz.b, cm = t.zm.b != c.cz.b, any = cp | cm;
-        const typename A::Row n0 = ad.row_sel_z(0, cp, 2, -1), n1 = ad.row_sel_z(1, cp, 2, -1);
-        const float a = mix_e(ad.ld_if(n0, 0, any), ad.ld_if(n0, 1, any), ox, fx);
-        const float b = mix_e(ad.ld_if(n1, 0, any), ad.ld_if(n1, 1, any), ox, fx);
-        const float yn = mix_e(a, b, oy, fy);
+        const bool cp = t.zp.b != c.cz.b, cm = t.zm.b != c.cz.b;
+        float n[4];
+        ad.plane_z(cp, cp | cm, n);
+        const float yn = mix_e(mix_e(n[0], n[1], ox, fx), mix_e(n[2], n[3], ox, fx), oy, fy);
         const float fp = t.zp.f, fm = t.zm.f;
         const float vp = mix_e(cp ? c.ym1 : c.ym0, cp ? yn : c.ym1, DR_SUB(1.0f, fp), fp);
         float vm = mix_e(cm ? yn : c.ym0, cm ? c.ym0 : c.ym1, DR_SUB(1.0f, fm), fm);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // yn is plane lo+2; the - tap needs plane lo-1
-            const typename A::Row q0 = ad.row(0, -1), q1 = ad.row(1, -1);
-            const float a2 = mix_e(ad.ld(q0, 0), ad.ld(q0, 1), ox, fx), b2 = mix_e(ad.ld(q1, 0), ad.ld(q1, 1), ox, fx);
-            vm = mix_e(mix_e(a2, b2, oy, fy), c.ym0, DR_SUB(1.0f, fm), fm);
+            ad.plane_z(false, true, n);
+            vm = mix_e(mix_e(mix_e(n[0], n[1], ox, fx), mix_e(n[2], n[3], ox, fx), oy, fy), c.ym0, DR_SUB(1.0f, fm), fm);
         }
         t.g.z = DR_SUB(vp, vm);
     }
     {   // ---- y taps
-        const bool cp = t.yp.b != c.cy.b, cm = t.ym.b != c.cy.b, any = cp | cm;
-        const typename A::Row n0 = ad.row_sel_y(cp, 2, -1, 0), n1 = ad.row_sel_y(cp, 2, -1, 1);
-        const float m0 = mix_e(ad.ld_if(n0, 0, any), ad.ld_if(n0, 1, any), ox, fx);
-        const float m1 = mix_e(ad.ld_if(n1, 0, any), ad.ld_if(n1, 1, any), ox, fx);
+        const bool cp = t.yp.b != c.cy.b, cm = t.ym.b != c.cy.b;
+        float n[4];
+        ad.plane_y(cp, cp | cm, n);
+        const float m0 = mix_e(n[0], n[1], ox, fx), m1 = mix_e(n[2], n[3], ox, fx);
         const float fp = t.yp.f, op = DR_SUB(1.0f, fp), fm = t.ym.f, om = DR_SUB(1.0f, fm);
         const float ap = mix_e(cp ? c.xm10 : c.xm00, cp ? m0 : c.xm10, op, fp);
         const float bp = mix_e(cp ? c.xm11 : c.xm01, cp ? m1 : c.xm11, op, fp);
         float am = mix_e(cm ? m0 : c.xm00, cm ? c.xm00 : c.xm10, om, fm);
         float bm = mix_e(cm ? m1 : c.xm01, cm ? c.xm01 : c.xm11, om, fm);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // m0, m1 are row lo+2; the - tap needs row lo-1
-            const typename A::Row q0 = ad.row(-1, 0), q1 = ad.row(-1, 1);
-            am = mix_e(mix_e(ad.ld(q0, 0), ad.ld(q0, 1), ox, fx), c.xm00, om, fm);
-            bm = mix_e(mix_e(ad.ld(q1, 0), ad.ld(q1, 1), ox, fx), c.xm01, om, fm);
+            ad.plane_y(false, true, n);
+            am = mix_e(mix_e(n[0], n[1], ox, fx), c.xm00, om, fm);
+            bm = mix_e(mix_e(n[2], n[3], ox, fx), c.xm01, om, fm);
         }
         t.g.y = DR_SUB(mix_e(ap, bp, oz, fz), mix_e(am, bm, oz, fz));
     }
-    // ---- x taps: the rows are already formed; the compiler predicates the four neighbour loads itself
+    // ---- x taps: everything downstream of the corners changes; the compiler predicates the neighbour loads itself
     float xv[2];
 #pragma unroll
     for (int sgn = 0; sgn < 2; ++sgn) {
@@ -459,15 +632,14 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
             a00 = mix_e(c.v000, c.v100, o, f); a10 = mix_e(c.v010, c.v110, o, f);
             a01 = mix_e(c.v001, c.v101, o, f); a11 = mix_e(c.v011, c.v111, o, f);
         } else {
-            const typename A::Row r00 = ad.row(0, 0), r10 = ad.row(1, 0), r01 = ad.row(0, 1), r11 = ad.row(1, 1);
-            const int xi = sgn ? -1 : 2;
-            const float n00 = ad.ld(r00, xi), n10 = ad.ld(r10, xi), n01 = ad.ld(r01, xi), n11 = ad.ld(r11, xi);
+            float n[4];
+            ad.plane_x(sgn != 0, n);
             if (sgn) {
-                a00 = mix_e(n00, c.v000, o, f); a10 = mix_e(n10, c.v010, o, f);
-                a01 = mix_e(n01, c.v001, o, f); a11 = mix_e(n11, c.v011, o, f);
+                a00 = mix_e(n[0], c.v000, o, f); a10 = mix_e(n[1], c.v010, o, f);
+                a01 = mix_e(n[2], c.v001, o, f); a11 = mix_e(n[3], c.v011, o, f);
             } else {
-                a00 = mix_e(c.v100, n00, o, f); a10 = mix_e(c.v110, n10, o, f);
-                a01 = mix_e(c.v101, n01, o, f); a11 = mix_e(c.v111, n11, o, f);
+                a00 = mix_e(c.v100, n[0], o, f); a10 = mix_e(c.v110, n[1], o, f);
+                a01 = mix_e(c.v101, n[2], o, f); a11 = mix_e(c.v111, n[3], o, f);
             }
         }
         const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);

@@ -17,7 +17,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, F_TF_4R, VOX_F16,
+from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_LAYOUT_CELL8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, F_TF_4R, VOX_F16,
                    VOX_F32)
 
 __all__ = ["VolumeRaycaster", "RaycastFunction", "RaycastMSEFunction", "Raycaster"]
@@ -36,8 +36,9 @@ class VolumeRaycaster:
 
     def __init__(self, volume_resolution, render_resolution, max_samples=512, tf_resolution=128, fov=30.0,
                  nearfar=(0.1, 100.0), layout="auto"):
-        if layout not in ("auto", "linear", "brick8"):
-            raise ValueError("layout must be 'auto', 'linear' (read the torch tensor in place) or 'brick8' (8x8x8-bricked copy)")
+        if layout not in ("auto", "linear", "brick8", "cell8"):
+            raise ValueError("layout must be 'auto', 'linear' (read the torch tensor in place), 'brick8' (8x8x8-bricked copy) "
+                             "or 'cell8' (cell-major copy, 8x the volume's bytes)")
         self.layout = layout
         self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
         self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
@@ -61,10 +62,11 @@ class VolumeRaycaster:
         return _lib.make_desc(X, Y, Z, w, h, self.tf_resolution, self.max_samples, BS, Bvol, Btf, vox_dtype, flags,
                               sampling_rate, self.fov_deg, self.near)
 
-    # Measured on B200: the linear layout wins while the volume is small relative to the rays' footprint
-    # (C3 256^3: forward 77 vs 54 Gsamples/s) and ties at 512^3; the bricked copy wins once the volume is far larger than
-    # L2 and a warp's corner fetches spread over many 128-byte rows (C5 1024^3 fp16: forward 48 vs 29 Gsamples/s).
-    AUTO_BRICK_BYTES = 1 << 30
+    # Measured on B200 (profiles/r01_experiments.md): the cell-major copy wins at every benchmark size
+    # (forward +18 % at 256^3, +61 % at 512^3, +48 % at 1024^3 fp16 over the previous best layout; backward +0..21 %) because a
+    # cell is one sector and two 16-byte loads instead of eight 4-byte loads spread over ~5 sectors each.  It costs 8x the
+    # volume's bytes, so `auto` falls back to the 8x8x8-bricked copy (1x) above AUTO_CELL_BYTES of cell-major data.
+    AUTO_CELL_BYTES = 48 << 30
 
     def resolve_layout(self, vol_lin):
         if self.layout != "auto":
@@ -72,26 +74,33 @@ class VolumeRaycaster:
         X, Y, Z = self.volume_resolution
         if max(X, Y, Z) > 2000:
             return "linear"                      # the generic tap path exists for the linear layout only
-        return "brick8" if X * Y * Z * vol_lin.element_size() > self.AUTO_BRICK_BYTES else "linear"
+        return "cell8" if X * Y * Z * 8 * vol_lin.element_size() * vol_lin.shape[0] <= self.AUTO_CELL_BYTES else "brick8"
 
     def _lflag(self, vol):
-        """Layout flag for a tensor returned by brick(): a 2-D tensor is a bricked copy, a 4-D one the linear volume."""
-        return F_LAYOUT_BRICK8 if vol.ndim == 2 else 0
+        """Layout flag for a tensor returned by brick(): a 2-D tensor is a bricked copy, a 3-D one [Bvol, cells, 8] the
+        cell-major copy, a 4-D one the linear volume."""
+        return F_LAYOUT_BRICK8 if vol.ndim == 2 else (F_LAYOUT_CELL8 if vol.ndim == 3 else 0)
 
     def brick(self, vol_lin):
         """[Bvol, Y, Z, X] contiguous fp32/fp16 CUDA tensor -> what the march kernels read: the tensor itself for the
-        default 'linear' layout (zero copy), or a bricked copy [Bvol, elems] of the same dtype for 'brick8'."""
+        'linear' layout (zero copy), a bricked copy [Bvol, elems] for 'brick8', or the cell-major copy [Bvol, X*Y*Z, 8]
+        for 'cell8' (same dtype)."""
         X, Y, Z = self.volume_resolution
         if tuple(vol_lin.shape[1:]) != (Y, Z, X):
             raise ValueError(f"volume has spatial shape {tuple(vol_lin.shape[1:])}, raycaster was built for (D,H,W)={(Y, Z, X)}")
         if not vol_lin.is_contiguous():
             raise ValueError("volume must be contiguous")
-        if self.resolve_layout(vol_lin) == "linear":
+        layout = self.resolve_layout(vol_lin)
+        if layout == "linear":
             return vol_lin
         vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
         d = self.desc(1, 1, 1, vox, 0, 1.0)
         d.Bvol = vol_lin.shape[0]
         lib = _lib.load()
+        if layout == "cell8":
+            out = torch.empty((vol_lin.shape[0], X * Y * Z, 8), dtype=vol_lin.dtype, device=vol_lin.device)
+            _lib.check(lib.dr_expand_cells(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_expand_cells")
+            return out
         out = torch.empty((vol_lin.shape[0], lib.dr_bricked_elems(ctypes.byref(d))), dtype=vol_lin.dtype, device=vol_lin.device)
         _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
         return out

@@ -54,9 +54,10 @@ extern "C" {
 #define DR_F_TF_4R 32u         /* tf / grad_tf are [Btf][4][R] (torch layout; else the reference's [Btf][R][4], :567,571) */
 #define DR_F_GENERIC_TAPS 64u  /* force the 7x8-load tap path (always used when a normal tap can skip a whole cell) */
 #define DR_F_LAYOUT_BRICK8 256u /* `vol` is the 8x8x8-bricked copy made by dr_brick_volume; clear: `vol` is the caller's linear [Bvol][Y][Z][X] tensor, read in place */
+#define DR_F_LAYOUT_CELL8 2048u /* `vol` is the cell-major copy made by dr_expand_cells: [Bvol][X*Y*Z][8], record c = the 8 corners of the cell whose low corner has torch-linear index c (8x the volume's bytes; one address and two 16-byte loads per cell) */
 #define DR_F_FUSED_MSE 1024u    /* internal: set by dr_backward_mse (grad_out slot holds the target image) */
 #define DR_F_COUNT_SHADED 512u  /* diagnostic: out_K counts only samples with non-zero opacity (do not feed such a K to dr_backward) */
-#define DR_F_NO_REG_ACCUM 128u  /* tuning/debug: backward issues its reductions per sample instead of keeping the current cell / TF bin in registers */
+/* 128u: reserved (was DR_F_NO_REG_ACCUM, a tuning flag of early builds; ignored) */
 
 /* Plain-data description of one call.  Fill it with dr_desc_init(); do not hand-edit derived fields. */
 typedef struct DrDesc {
@@ -112,11 +113,19 @@ size_t dr_bricked_elems(const DrDesc* d);
 int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, void* stream);
 
 /*
+ * Cell-major copy of the volume for DR_F_LAYOUT_CELL8 (same role as dr_brick_volume; replaces set_volume's from_torch
+ * into the reference's 4x4x4-blocked field, :97-101, :118-119): vol_cells is [Bvol][X*Y*Z][8] of the volume's dtype
+ * (dr_grad_cells_elems(d) elements per volume, 32-byte aligned); record c holds the 8 corners of the cell whose low corner
+ * has torch-linear index c, slot a + 2b + 4c = voxel (min(x+a,X-1), min(y+b,Y-1), min(z+c,Z-1)).
+ */
+int dr_expand_cells(const DrDesc* d, const void* vol_linear, void* vol_cells, void* stream);
+
+/*
  * Forward march of BS views.  Replaces, per view: set_cam_pos/set_tf_tex (:121-125), clear_framebuffer
  * (:374-382), compute_entry_exit (:221-259), raycast (:261-306) or raycast_nondiff (:308-351), and
  * get_final_image (:363-372) or get_final_image_nondiff (:353-361), i.e. the body of
  * RaycastFunction.forward (:418-438) and Raycaster.raycast_nondiff (:502-523).
- *   vol [Bvol] volumes: linear [Y][Z][X] (default, zero copy) or bricked (DR_F_LAYOUT_BRICK8), fp32/fp16
+ *   vol [Bvol] volumes: linear [Y][Z][X] (default, zero copy), bricked (DR_F_LAYOUT_BRICK8) or cell-major (DR_F_LAYOUT_CELL8), fp32/fp16
  *   tf [Btf][R][4] or [Btf][4][R]     cam [BS][3]
  *   jitter [BS][H][W] uniform [0,1) or NULL (replaces ti.random, :255)
  *   out_rgba  see layout note            out_K [BS][H][W] active samples per ray (valid_sample_step_count-1,

@@ -68,6 +68,18 @@ void sim_brick(const DrDesc* d, const float* lin, float* bricked)
     for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
         bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)] = lin[((size_t)y * d->Z + z) * d->X + x];
 }
+// linear [Y][Z][X] -> cell-major records [cell][8] (what dr_expand_cells builds)
+void sim_expand(const DrDesc* d, const float* lin, float* cells)
+{
+    for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x) {
+        const size_t c = ((size_t)y * d->Z + z) * d->X + x;
+        for (int q = 0; q < 8; ++q) {
+            const int xx = x + (q & 1) < d->X ? x + (q & 1) : d->X - 1, yy = y + ((q >> 1) & 1) < d->Y ? y + ((q >> 1) & 1) : d->Y - 1;
+            const int zz = z + (q >> 2) < d->Z ? z + (q >> 2) : d->Z - 1;
+            cells[c * 8 + q] = lin[((size_t)yy * d->Z + zz) * d->X + xx];
+        }
+    }
+}
 // cell-major gradient [Y*Z*X][8] -> linear [Y][Z][X]
 void sim_gather(const DrDesc* d, const float* gcell, float* lin)
 {
@@ -93,10 +105,12 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
         setup_ray(*d, cam, i, j, jitter ? jitter[pix] : 0.0f, r);
         F4 A; int K; float Tp;
         const bool nd = d->flags & DR_F_NONDIFF;
-        if (d->flags & DR_F_LAYOUT_BRICK8) {
 #define FWD2(LAY, ND, TAPS) do { if (sr1 && TAPS != TAPS_GENERIC) march_forward<float, LAY, ND, TAPS, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp); \
                                 else march_forward<float, LAY, ND, TAPS, false>(*d, vol, L, tf4, cam, r, A, K, Tp); } while (0)
 #define FWD(LAY, ND) do { if (taps == TAPS_ONE) FWD2(LAY, ND, TAPS_ONE); else FWD2(LAY, ND, TAPS_TWO); } while (0)
+        if (d->flags & DR_F_LAYOUT_CELL8) {
+            if (nd) FWD(LAYOUT_CELL8, true); else FWD(LAYOUT_CELL8, false);
+        } else if (d->flags & DR_F_LAYOUT_BRICK8) {
             if (nd) FWD(LAYOUT_BRICK8, true); else FWD(LAYOUT_BRICK8, false);
         } else if (taps == TAPS_GENERIC) {
             if (nd) FWD2(LAYOUT_LINEAR, true, TAPS_GENERIC); else FWD2(LAYOUT_LINEAR, false, TAPS_GENERIC);
@@ -139,7 +153,8 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
 #define CALL(LAY, TAPS, WV, WT) do { if (sr1 && TAPS != TAPS_GENERIC) march_backward<float, LAY, TAPS, WV, WT, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); \
                                      else march_backward<float, LAY, TAPS, WV, WT, false>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); } while (0)
 #define CALL3(LAY, TAPS) do { if (wv && wt) CALL(LAY, TAPS, true, true); else if (wv) CALL(LAY, TAPS, true, false); else if (wt) CALL(LAY, TAPS, false, true); } while (0)
-        if (d->flags & DR_F_LAYOUT_BRICK8) { if (taps == TAPS_ONE) CALL3(LAYOUT_BRICK8, TAPS_ONE); else CALL3(LAYOUT_BRICK8, TAPS_TWO); }
+        if (d->flags & DR_F_LAYOUT_CELL8) { if (taps == TAPS_ONE) CALL3(LAYOUT_CELL8, TAPS_ONE); else CALL3(LAYOUT_CELL8, TAPS_TWO); }
+        else if (d->flags & DR_F_LAYOUT_BRICK8) { if (taps == TAPS_ONE) CALL3(LAYOUT_BRICK8, TAPS_ONE); else CALL3(LAYOUT_BRICK8, TAPS_TWO); }
         else if (taps == TAPS_GENERIC) CALL3(LAYOUT_LINEAR, TAPS_GENERIC);
         else if (taps == TAPS_ONE) CALL3(LAYOUT_LINEAR, TAPS_ONE);
         else CALL3(LAYOUT_LINEAR, TAPS_TWO);

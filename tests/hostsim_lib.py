@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "hostsim", "build", "libhostsim.so")
 
 # flag values of include/diffrender.h
-F_NONDIFF, F_VOL, F_TF, F_JIT, F_IMG, F_TF4R, F_GENERIC, F_BRICK8 = 1, 2, 4, 8, 16, 32, 64, 256
+F_NONDIFF, F_VOL, F_TF, F_JIT, F_IMG, F_TF4R, F_GENERIC, F_BRICK8, F_CELL8 = 1, 2, 4, 8, 16, 32, 64, 256, 2048
 
 
 class DrDesc(ctypes.Structure):
@@ -59,18 +59,27 @@ def make_desc(vol_shape_dhw, output_shape, R, max_samples, flags, sr=1.0, fov=30
     return d
 
 
-def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, jitter=None, nondiff=False, generic=False,
-            brick=False):
-    vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
-    tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
-    flags = (F_NONDIFF if nondiff else 0) | (F_JIT if jitter is not None else 0) | (F_GENERIC if generic else 0) | F_IMG | \
-            (F_BRICK8 if brick else 0)
-    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate)
-    L = lib()
-    br = vol
+def _layout_data(L, d, vol, brick, cell):
     if brick:
         br = np.zeros(L.sim_bricked_elems(ctypes.byref(d)), np.float32)
         L.sim_brick(ctypes.byref(d), _p(vol), _p(br))
+        return br
+    if cell:
+        ce = np.zeros(vol.size * 8, np.float32)
+        L.sim_expand(ctypes.byref(d), _p(vol), _p(ce))
+        return ce
+    return vol
+
+
+def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, jitter=None, nondiff=False, generic=False,
+            brick=False, cell=False):
+    vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
+    tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
+    flags = (F_NONDIFF if nondiff else 0) | (F_JIT if jitter is not None else 0) | (F_GENERIC if generic else 0) | F_IMG | \
+            (F_BRICK8 if brick else 0) | (F_CELL8 if cell else 0)
+    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate)
+    L = lib()
+    br = _layout_data(L, d, vol, brick, cell)
     w, h = output_shape
     out = np.zeros((4, h, w), np.float32); K = np.zeros((h, w), np.int32); Tp = np.zeros((h, w), np.float32)
     n = np.zeros((h, w), np.int32)
@@ -82,18 +91,15 @@ def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, j
 
 
 def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_samples=512, jitter=None,
-             want_vol=True, want_tf=True, generic=False, brick=False):
+             want_vol=True, want_tf=True, generic=False, brick=False, cell=False):
     vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
     tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
-    out, K, Tp, _ = forward(volume, tf, cam, output_shape, sampling_rate, max_samples, jitter, False, generic, brick)
+    out, K, Tp, _ = forward(volume, tf, cam, output_shape, sampling_rate, max_samples, jitter, False, generic, brick, cell)
     flags = (F_JIT if jitter is not None else 0) | (F_GENERIC if generic else 0) | F_IMG | (F_BRICK8 if brick else 0) | \
-            (F_VOL if want_vol else 0) | (F_TF if want_tf else 0)
+            (F_CELL8 if cell else 0) | (F_VOL if want_vol else 0) | (F_TF if want_tf else 0)
     d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate)
     L = lib()
-    br = vol
-    if brick:
-        br = np.zeros(L.sim_bricked_elems(ctypes.byref(d)), np.float32)
-        L.sim_brick(ctypes.byref(d), _p(vol), _p(br))
+    br = _layout_data(L, d, vol, brick, cell)
     gbr = np.zeros(vol.size * 8, np.float32); gtf = np.zeros_like(tf_r4)
     cam = np.ascontiguousarray(cam, np.float32)
     jit = None if jitter is None else np.ascontiguousarray(jitter, np.float32)

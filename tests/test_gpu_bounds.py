@@ -29,7 +29,7 @@ def test_no_out_of_range_access_in_debug_build():
     assert lib.dr_debug_oob_count() == 0
     g = torch.Generator().manual_seed(0)
     cams = torch.tensor([[1.2, 0.7, 2.2], [0.3, 0.2, 0.4], [-2.0, 1.5, 0.1], [0.0, 0.7, 2.5]], device=dev)   # incl. a camera inside the box
-    for layout in ("linear", "brick8"):
+    for layout in ("linear", "brick8", "cell8"):
         for (D, H, W) in ((2, 2, 2), (5, 9, 3), (16, 16, 16), (21, 18, 27)):
             for dtype in (torch.float32, torch.float16):
                 vol = torch.rand((1, D, H, W), generator=g).to(dev, dtype)

@@ -124,19 +124,37 @@ def test_generic_tap_path_equals_corner_reuse_path():
     assert rel_l2(gv2.cpu().numpy(), gv.cpu().numpy()) <= 1e-4 and rel_l2(gt2.cpu().numpy(), gt.cpu().numpy()) <= 1e-4
 
 
-def test_bricked_layout_is_bit_identical_to_linear_layout():
+@pytest.mark.parametrize("layout,dtype", [("brick8", torch.float32), ("cell8", torch.float32), ("cell8", torch.float16), ("brick8", torch.float16)])
+def test_copied_layouts_are_bit_identical_to_linear_layout(layout, dtype):
     vol, tf, cams, jit = case_inputs((37, 29, 45), (56, 40), 64, seed=13, views=2)
-    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (56, 40), jit)
-    vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (56, 40), jit, layout="brick8")
-    assert vlin.shape == (1, 37, 29, 45) and bricked.shape == (1, 5 * 4 * 6 * 512)       # zero-copy view vs bricked copy
+    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (56, 40), jit, dtype=dtype)
+    vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (56, 40), jit, layout=layout, dtype=dtype)
+    # zero-copy view vs bricked / cell-major copy
+    assert vlin.shape == (1, 37, 29, 45) and bricked.dtype == dtype
+    assert bricked.shape == ((1, 5 * 4 * 6 * 512) if layout == "brick8" else (1, 37 * 29 * 45, 8))
     assert torch.equal(out, out_b) and torch.equal(K, K_b) and torch.equal(Tp, Tp_b)     # same arithmetic, same order
     go = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).cuda()
     c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
     gv, gt = vr.march_backward(vlin, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
     gv_b, gt_b = vb.march_backward(bricked, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
     assert rel_l2(gv_b.cpu().numpy(), gv.cpu().numpy()) <= 1e-5 and rel_l2(gt_b.cpu().numpy(), gt.cpu().numpy()) <= 1e-5
-    ref, Kr, _ = oracle_forward_views(vol, tf, cams, (56, 40), jit, max_samples=2048)
-    assert np.array_equal(K_b.cpu().numpy(), Kr) and np.abs(out_b.cpu().numpy() - ref).max() <= RGBA_TOL
+    if dtype == torch.float32:
+        ref, Kr, _ = oracle_forward_views(vol, tf, cams, (56, 40), jit, max_samples=2048)
+        assert np.array_equal(K_b.cpu().numpy(), Kr) and np.abs(out_b.cpu().numpy() - ref).max() <= RGBA_TOL
+
+
+@pytest.mark.parametrize("shape", [(1100, 6, 6), (6, 1100, 6), (6, 6, 1100)])
+@pytest.mark.parametrize("layout", ["brick8", "cell8"])
+def test_copied_layouts_with_both_taps_crossing(shape, layout):
+    vol, tf, cams, jit = case_inputs(shape, (24, 20), 32, seed=5, views=1)
+    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096)
+    vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096, layout=layout)
+    assert torch.equal(out, out_b) and torch.equal(K, K_b) and torch.equal(Tp, Tp_b)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).cuda()
+    c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
+    gv, gt = vr.march_backward(vlin, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
+    gv_b, gt_b = vb.march_backward(bricked, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
+    assert rel_l2(gv_b.cpu().numpy(), gv.cpu().numpy()) <= 1e-5 and rel_l2(gt_b.cpu().numpy(), gt.cpu().numpy()) <= 1e-5
 
 
 def test_raw_layout_equals_image_layout():

@@ -14,36 +14,37 @@ from oracle import cpu_oracle as co
     ((37, 29, 45), (33, 29), 128, 1.0, False),
     ((24, 24, 24), (32, 32), 32, 0.7, True),
 ])
-@pytest.mark.parametrize("generic,brick", [(False, False), (True, False), (False, True)])
-def test_device_math_matches_oracle(shape, out_shape, R, sr, jitter, generic, brick):
+@pytest.mark.parametrize("generic,brick,cell", [(False, False, False), (True, False, False), (False, True, False), (False, False, True)])
+def test_device_math_matches_oracle(shape, out_shape, R, sr, jitter, generic, brick, cell):
     vol, tf, cams, jit = case_inputs(shape, out_shape, R, seed=R, jitter=jitter)
     J = None if jit is None else jit[0].numpy()
     img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, jitter=J, return_counts=True)
-    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, jitter=J, generic=generic, brick=brick)
+    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, jitter=J, generic=generic, brick=brick, cell=cell)
     assert np.array_equal(n, n2) and np.array_equal(K, K2)
     assert np.array_equal(img[3], out[3])                      # alpha path: bit-identical by construction
     assert np.abs(img - out).max() <= 1e-6
     go = np.random.default_rng(5).normal(size=img.shape).astype(np.float32)
     gv, gt = co.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, jitter=J)
-    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, jitter=J, generic=generic, brick=brick)
+    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, jitter=J, generic=generic, brick=brick, cell=cell)
     assert rel_l2(gv2, gv) <= 1e-4 and rel_l2(gt2, gt) <= 1e-4
 
 
 @pytest.mark.parametrize("shape", [(1100, 6, 6), (6, 1100, 6), (6, 6, 1100)])
-@pytest.mark.parametrize("brick", [False, True])
-def test_device_math_both_taps_of_an_axis_cross(shape, brick):
+@pytest.mark.parametrize("layout", ["linear", "brick8", "cell8"])
+def test_device_math_both_taps_of_an_axis_cross(shape, layout):
+    brick, cell = layout == "brick8", layout == "cell8"
     # an axis longer than 1000 voxels: the +-1e-3 taps move more than half a voxel, so BOTH can leave the centre cell
     # (the branch behind the select-based tap evaluation); still below the generic-tap threshold (~2000)
     out_shape = (20, 16)
     vol, tf, cams, jit = case_inputs(shape, out_shape, 32, seed=3, jitter=True)
     J = jit[0].numpy()
     img, K, n = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, jitter=J, max_samples=4096, return_counts=True)
-    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, jitter=J, max_samples=4096, brick=brick)
+    out, K2, Tp, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, jitter=J, max_samples=4096, brick=brick, cell=cell)
     assert n.max() > 1000 and np.array_equal(n, n2) and np.array_equal(K, K2)
     assert np.array_equal(img[3], out[3]) and np.abs(img - out).max() <= 1e-6
     go = np.random.default_rng(9).normal(size=img.shape).astype(np.float32)
     gv, gt = co.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, jitter=J, max_samples=4096)
-    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, jitter=J, max_samples=4096, brick=brick)
+    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, jitter=J, max_samples=4096, brick=brick, cell=cell)
     assert rel_l2(gv2, gv) <= 1e-4 and rel_l2(gt2, gt) <= 1e-4
 
 
