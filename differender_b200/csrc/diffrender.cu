@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) brick_kernel(DrDesc d, const VT* __restri
     br[(size_t)b * elems + e] = v;
 }
 
-// linear [Y][Z][X] volume -> cell-major records [cell][8] (LAYOUT_CELL8): slot a + 2b + 4c of cell (x,y,z) = voxel
+// linear [Y][Z][X] volume -> cell-major records [cell][8] (LAYOUT_CELL8): slot c + 2a + 4b of cell (x,y,z) = voxel
 // (min(x+a,X-1), min(y+b,Y-1), min(z+c,Z-1)).  Write-bound: 8 * sizeof(voxel) bytes per voxel; the 8x re-read of the
 // input is served by L1/L2.
 template <typename VT>
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(256) expand_cells_kernel(DrDesc d, const VT* _
     const size_t dx = x + 1 < d.X ? 1 : 0, dz = z + 1 < d.Z ? (size_t)d.X : 0, dy = y + 1 < d.Y ? (size_t)d.X * d.Z : 0;
     const VT* p = lin + (size_t)b * n + e;
     struct alignas(16) Rec { VT v[8]; } rec;
-    rec.v[0] = p[0]; rec.v[1] = p[dx]; rec.v[2] = p[dy]; rec.v[3] = p[dy + dx];
-    rec.v[4] = p[dz]; rec.v[5] = p[dz + dx]; rec.v[6] = p[dz + dy]; rec.v[7] = p[dz + dy + dx];
+    rec.v[0] = p[0]; rec.v[1] = p[dz]; rec.v[2] = p[dx]; rec.v[3] = p[dx + dz];
+    rec.v[4] = p[dy]; rec.v[5] = p[dy + dz]; rec.v[6] = p[dy + dx]; rec.v[7] = p[dy + dx + dz];
     reinterpret_cast<Rec*>(cells)[(size_t)b * n + e] = rec;
 }
 

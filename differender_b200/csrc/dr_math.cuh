@@ -83,6 +83,67 @@ struct F4 { float x, y, z, w; };
 // ---------------------------------------------------------------------------------------------------------
 // taichi_glsl.mix(x, y, a) = x*(1-a) + y*a, rounded as fma(x, 1-a, y*a)  (omt = 1-a precomputed)
 DR_HD float mix_e(float a, float b, float omt, float t) { return DR_FMA(a, omt, DR_MUL(b, t)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed pairs.  sm_100a has two-wide fp32 instructions (FMUL2 / FFMA2 / FADD2 on 64-bit register pairs: PTX
+// mul/fma/add .f32x2): each lane is rounded exactly like the scalar instruction (IEEE rn, no ftz), the FMA pipe is busy
+// for two cycles, but the pair costs ONE issue slot -- and issue slots are what bounds these kernels
+// (profiles/r01_f32x2_microbench.txt: 8 FFMA + 16 integer instructions 16.6 ms, 4 FFMA2 + the same integer work 13.6 ms).
+// The trilinear mixes come in natural pairs (the same fraction applied to two rows of voxels), so the sample evaluation
+// is written on F2.  On the host (tests/hostsim) an F2 operation is two scalar operations with the same rounding.
+// ---------------------------------------------------------------------------------------------------------
+struct F2 { float x, y; };
+DR_HD F2 f2(float x, float y) { F2 r = { x, y }; return r; }
+DR_HD F2 splat(float a) { F2 r = { a, a }; return r; }
+DR_HD F2 sel2(bool c, F2 a, F2 b) { F2 r = { c ? a.x : b.x, c ? a.y : b.y }; return r; }
+DR_HD F2 mul2(F2 a, F2 b)
+{
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tmul.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+#else
+    return f2(DR_MUL(a.x, b.x), DR_MUL(a.y, b.y));
+#endif
+}
+DR_HD F2 fma2(F2 a, F2 b, F2 c)
+{
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .b64 pa, pb, pc;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tmov.b64 pc, {%6, %7};\n\t"
+        "fma.rn.f32x2 pa, pa, pb, pc;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+#else
+    return f2(DR_FMA(a.x, b.x, c.x), DR_FMA(a.y, b.y, c.y));
+#endif
+}
+DR_HD F2 add2(F2 a, F2 b)
+{
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tadd.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+#else
+    return f2(DR_ADD(a.x, b.x), DR_ADD(a.y, b.y));
+#endif
+}
+DR_HD F2 sub2(F2 a, F2 b)
+{
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tsub.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+#else
+    return f2(DR_SUB(a.x, b.x), DR_SUB(a.y, b.y));
+#endif
+}
+// two mixes with per-lane fractions: (a.x*(1-t.x) + b.x*t.x, a.y*(1-t.y) + b.y*t.y), each rounded like mix_e
+DR_HD F2 mix2(F2 a, F2 b, F2 omt, F2 t) { return fma2(a, omt, mul2(b, t)); }
+
 DR_HD float dot_e(F3 a, F3 b) { return DR_ADD(DR_ADD(DR_MUL(a.x, b.x), DR_MUL(a.y, b.y)), DR_MUL(a.z, b.z)); }
 DR_HD F3 cross_e(F3 a, F3 b)
 {
@@ -128,6 +189,25 @@ DR_HD Loc locate(float pos, float scale)
     float l = floor_pos(p, r.b);
     r.f = DR_SUB(p, l);
     return r;
+}
+
+// locate() of the two taps pos + delta and pos - delta of one axis, on packed pairs (same operations per lane)
+DR_HD void locate_pair(float pos, float delta, float scale, Loc& plus, Loc& minus)
+{
+    const F2 p = mul2(f2(DR_SAT(DR_FMA(0.5f, DR_ADD(pos, delta), 0.5f)), DR_SAT(DR_FMA(0.5f, DR_SUB(pos, delta), 0.5f))), splat(scale));
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %4};\n\tadd.rm.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(p.x), "f"(p.y), "f"(8388608.0f));
+    plus.b = __float_as_int(r.x); minus.b = __float_as_int(r.y);
+    const F2 f = sub2(p, sub2(r, splat(8388608.0f)));
+    plus.f = f.x; minus.f = f.y;
+#else
+    float l = floor_pos(p.x, plus.b);
+    plus.f = DR_SUB(p.x, l);
+    l = floor_pos(p.y, minus.b);
+    minus.f = DR_SUB(p.y, l);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -360,9 +440,10 @@ DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
 struct Centre {
     Loc cx, cy, cz;               // centre cell
     int cidx;                     // torch-linear index (cy*Z + cz)*X + cx of the centre cell's low corner
-    float v000, v100, v010, v110, v001, v101, v011, v111;   // its 8 corners
-    float xm00, xm10, xm01, xm11; // x mixes at (y0,z0) (y1,z0) (y0,z1) (y1,z1)
-    float ym0, ym1;               // y mixes at z0, z1
+    // the 8 corners as pairs over z: A = voxels at x0, B = voxels at x1; suffix = y;  A0 = (v[x0,y0,z0], v[x0,y0,z1]) ...
+    F2 A0, B0, A1, B1;
+    F2 xm0, xm1;                  // x mixes at y0 and y1, each a pair over (z0, z1)
+    F2 ym;                        // y mixes at (z0, z1)
     float I;                      // centre intensity
 };
 struct Taps {
@@ -373,22 +454,23 @@ struct Taps {
     F3 g;                         // (f(x+d)-f(x-d), ...), un-normalised                     :197-202
 };
 
-// Volume storage layouts, as fetch policies.  A policy is initialised for one centre cell and provides
-//   centre(v)                 the cell's 8 corners, v[a + 2b + 4c] = voxel (x0+a, y0+b, z0+c)
-//   plane_z(plus, pred, n)    the voxel plane beyond the cell along z (z0+2 if plus else z0-1), predicated:
-//                             n = (x0,y0) (x1,y0) (x0,y1) (x1,y1)
-//   plane_y(plus, pred, n)    likewise along y: n = (x0,z0) (x1,z0) (x0,z1) (x1,z1)
-//   plane_x(minus, n)         likewise along x (x0-1 if minus else x0+2): n = (y0,z0) (y1,z0) (y0,z1) (y1,z1)
+// Volume storage layouts, as fetch policies.  A policy is initialised for one centre cell and provides, as pairs over z
+// (x = the voxel at z0, y = the voxel at z1) unless stated:
+//   centre(A0, B0, A1, B1)        the cell's 8 corners: A = x0, B = x1, suffix = y0 / y1
+//   plane_x(plus, pred, N0, N1)   the voxel plane beyond the cell along x (x0+2 if plus else x0-1), predicated: N0 = row y0, N1 = row y1
+//   plane_y(plus, pred, N0, N1)   likewise along y (y0+2 / y0-1): N0 = x0, N1 = x1
+//   plane_z(plus, pred, N0, N1)   likewise along z (z0+2 / z0-1): N0 = x0, N1 = x1, each a pair over (y0, y1)
 // No index clamps: in the corner-reuse path lo <= dim-2 on every axis (scale < dim-1 for dims <= 2000) and a plane beyond
-// the cell is only fetched by a tap that crossed into it, so it is in range by construction.
+// the cell is only fetched (pred) by a tap that crossed into it, so it is in range by construction.
 //   LAYOUT_LINEAR reads the caller's contiguous torch tensor [y][z][x] in place (zero copy): a row is a pointer
 //     (one IMAD.WIDE.U32), x-neighbours are immediate offsets.  8 scalar loads per cell.
 //   LAYOUT_BRICK8 reads the 8x8x8-bricked copy made by dr_brick_volume (separable offsets offx/offy/offz).
 //   LAYOUT_CELL8  reads the cell-major copy made by dr_expand_cells: record `cell` (the torch-linear index of the cell's
-//     low corner) holds the cell's 8 corners contiguously (32 bytes fp32 = one sector, 16 bytes fp16), so a cell is ONE
-//     address and two (fp16: one) 16-byte loads instead of four rows and eight 4-byte loads that touch ~5 sectors each
-//     across a warp -- the L1 data pipe, which bounds the forward in the linear layout, sees a quarter of the wavefronts.
-//     A plane beyond the cell is half / two quarters / four eighths of the neighbour's record.  Costs 8x the volume's bytes.
+//     low corner) holds the cell's 8 corners contiguously (32 bytes fp32 = one sector, 16 bytes fp16), slot c + 2a + 4b =
+//     voxel (x0+a, y0+b, z0+c), so a cell is ONE address and two (fp16: one) 16-byte loads that land directly in the
+//     register pairs above -- instead of four rows and eight 4-byte loads that touch ~5 sectors each across a warp: the
+//     L1 data pipe, which bounds the forward in the linear layout, sees a quarter of the wavefronts.  A plane beyond the
+//     cell is half (y) / two quarters (x) / four eighths (z) of the neighbour's record.  Costs 8x the volume's bytes.
 enum { LAYOUT_LINEAR = 0, LAYOUT_BRICK8 = 1, LAYOUT_CELL8 = 2 };
 // How the six normal taps are evaluated (chosen per call from the volume dims, tap_mode() below):
 //   TAPS_ONE      corner reuse; at most one tap of an axis can leave the centre cell (tap offset < 1/2 voxel: dims <= ~1000)
@@ -402,7 +484,37 @@ inline int tap_mode(const DrDesc& d)
     return (0.5f * d.delta * m >= 0.499f) ? TAPS_TWO : TAPS_ONE;
 }
 
-template <typename VT> struct LinearAddr {
+// rows of voxels: what the linear and bricked layouts have in common
+template <typename Derived> struct RowFetch {
+    DR_HD const Derived& self() const { return *static_cast<const Derived*>(this); }
+    DR_HD void centre(F2& A0, F2& B0, F2& A1, F2& B1) const
+    {
+        const Derived& t = self();
+        const typename Derived::Row r00 = t.row(0, 0), r10 = t.row(1, 0), r01 = t.row(0, 1), r11 = t.row(1, 1);
+        A0 = f2(t.ld(r00, 0), t.ld(r01, 0)); B0 = f2(t.ld(r00, 1), t.ld(r01, 1));
+        A1 = f2(t.ld(r10, 0), t.ld(r11, 0)); B1 = f2(t.ld(r10, 1), t.ld(r11, 1));
+    }
+    DR_HD void plane_x(bool plus, bool pred, F2& N0, F2& N1) const
+    {
+        const Derived& t = self();
+        const typename Derived::Row r00 = t.row(0, 0), r10 = t.row(1, 0), r01 = t.row(0, 1), r11 = t.row(1, 1);
+        N0 = f2(t.ld_sel(r00, plus, pred), t.ld_sel(r01, plus, pred));
+        N1 = f2(t.ld_sel(r10, plus, pred), t.ld_sel(r11, plus, pred));
+    }
+    DR_HD void plane_y(bool plus, bool pred, F2& N0, F2& N1) const
+    {
+        const Derived& t = self();
+        const typename Derived::Row n0 = t.row_y(plus, 0), n1 = t.row_y(plus, 1);
+        N0 = f2(t.ld_if(n0, 0, pred), t.ld_if(n1, 0, pred)); N1 = f2(t.ld_if(n0, 1, pred), t.ld_if(n1, 1, pred));
+    }
+    DR_HD void plane_z(bool plus, bool pred, F2& N0, F2& N1) const
+    {
+        const Derived& t = self();
+        const typename Derived::Row n0 = t.row_z(0, plus), n1 = t.row_z(1, plus);
+        N0 = f2(t.ld_if(n0, 0, pred), t.ld_if(n1, 0, pred)); N1 = f2(t.ld_if(n0, 1, pred), t.ld_if(n1, 1, pred));
+    }
+};
+template <typename VT> struct LinearAddr : RowFetch<LinearAddr<VT> > {
     typedef const VT* Row;
     const VT* vp; uoff sy, sz, i00;
 #if defined(DR_BOUNDS_CHECK)
@@ -416,6 +528,8 @@ template <typename VT> struct LinearAddr {
 #endif
     }
     DR_HD Row row(int yi, int zi) const { return ptr_add(vp, i00 + (uoff)yi * sy + (uoff)zi * sz); }   // wraps correctly for -1
+    DR_HD Row row_y(bool plus, int zi) const { return ptr_add(vp, i00 + (plus ? (uoff)2 : (uoff)-1) * sy + (uoff)zi * sz); }
+    DR_HD Row row_z(int yi, bool plus) const { return ptr_add(vp, i00 + (uoff)yi * sy + (plus ? (uoff)2 : (uoff)-1) * sz); }
     DR_HD float ld(Row r, int xi) const
     {
 #if defined(DR_BOUNDS_CHECK)
@@ -430,32 +544,9 @@ template <typename VT> struct LinearAddr {
 #endif
         return load_vox_if(r + xi, pred);
     }
-    DR_HD void centre(float v[8]) const
-    {
-        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
-        v[0] = ld(r00, 0); v[1] = ld(r00, 1); v[2] = ld(r10, 0); v[3] = ld(r10, 1);
-        v[4] = ld(r01, 0); v[5] = ld(r01, 1); v[6] = ld(r11, 0); v[7] = ld(r11, 1);
-    }
-    DR_HD void plane_z(bool plus, bool pred, float n[4]) const
-    {
-        const uoff zo = (plus ? (uoff)2 : (uoff)-1) * sz;
-        const Row n0 = ptr_add(vp, i00 + zo), n1 = ptr_add(vp, i00 + sy + zo);
-        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
-    }
-    DR_HD void plane_y(bool plus, bool pred, float n[4]) const
-    {
-        const uoff yo = (plus ? (uoff)2 : (uoff)-1) * sy;
-        const Row n0 = ptr_add(vp, i00 + yo), n1 = ptr_add(vp, i00 + yo + sz);
-        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
-    }
-    DR_HD void plane_x(bool minus, float n[4]) const
-    {
-        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
-        const int xi = minus ? -1 : 2;
-        n[0] = ld(r00, xi); n[1] = ld(r10, xi); n[2] = ld(r01, xi); n[3] = ld(r11, xi);
-    }
+    DR_HD float ld_sel(Row r, bool plus, bool pred) const { return ld_if(r + (plus ? 2 : -1), 0, pred); }
 };
-template <typename VT> struct BrickAddr {
+template <typename VT> struct BrickAddr : RowFetch<BrickAddr<VT> > {
     typedef uoff Row;
     const VT* vp; Layout L; int lx, ly, lz;
     DR_HD void init(const DrDesc&, const VT* p, const Layout& L_, const Centre& c)
@@ -463,6 +554,8 @@ template <typename VT> struct BrickAddr {
         vp = p; L = L_; lx = lo_of(c.cx); ly = lo_of(c.cy); lz = lo_of(c.cz);
     }
     DR_HD Row row(int yi, int zi) const { return offy(ly + yi, L.sY) + offz(lz + zi, L.sZ); }
+    DR_HD Row row_y(bool plus, int zi) const { return offy(ly + (plus ? 2 : -1), L.sY) + offz(lz + zi, L.sZ); }
+    DR_HD Row row_z(int yi, bool plus) const { return offy(ly + yi, L.sY) + offz(lz + (plus ? 2 : -1), L.sZ); }
     DR_HD float ld(Row r, int xi) const
     {
         DR_OOB_IF(lx + xi < 0 || lx + xi > L.mx || (long long)(r + offx(lx + xi)) >= (long long)L.sZ * (((L.mz + 8) >> 3)));
@@ -473,30 +566,7 @@ template <typename VT> struct BrickAddr {
         DR_OOB_IF(pred && (lx + xi < 0 || lx + xi > L.mx || (long long)(r + offx(lx + xi)) >= (long long)L.sZ * (((L.mz + 8) >> 3))));
         return load_vox_if(ptr_add(vp, r + offx(lx + xi)), pred);
     }
-    DR_HD void centre(float v[8]) const
-    {
-        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
-        v[0] = ld(r00, 0); v[1] = ld(r00, 1); v[2] = ld(r10, 0); v[3] = ld(r10, 1);
-        v[4] = ld(r01, 0); v[5] = ld(r01, 1); v[6] = ld(r11, 0); v[7] = ld(r11, 1);
-    }
-    DR_HD void plane_z(bool plus, bool pred, float n[4]) const
-    {
-        const int zi = plus ? 2 : -1;
-        const Row n0 = row(0, zi), n1 = row(1, zi);
-        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
-    }
-    DR_HD void plane_y(bool plus, bool pred, float n[4]) const
-    {
-        const int yi = plus ? 2 : -1;
-        const Row n0 = row(yi, 0), n1 = row(yi, 1);
-        n[0] = ld_if(n0, 0, pred); n[1] = ld_if(n0, 1, pred); n[2] = ld_if(n1, 0, pred); n[3] = ld_if(n1, 1, pred);
-    }
-    DR_HD void plane_x(bool minus, float n[4]) const
-    {
-        const Row r00 = row(0, 0), r10 = row(1, 0), r01 = row(0, 1), r11 = row(1, 1);
-        const int xi = minus ? -1 : 2;
-        n[0] = ld(r00, xi); n[1] = ld(r10, xi); n[2] = ld(r01, xi); n[3] = ld(r11, xi);
-    }
+    DR_HD float ld_sel(Row r, bool plus, bool pred) const { return ld_if(r, plus ? 2 : -1, pred); }
 };
 template <typename VT> struct CellAddr {
     const VT* vp; uoff cell, sy, sz;
@@ -510,37 +580,41 @@ template <typename VT> struct CellAddr {
         n_cells = (long long)d.X * d.Y * d.Z;
 #endif
     }
-    DR_HD const VT* rec(uoff c) const
+    DR_HD const VT* rec(uoff c, bool pred) const
     {
 #if defined(DR_BOUNDS_CHECK)
-        DR_OOB_IF((long long)c >= n_cells);
+        DR_OOB_IF(pred && (long long)c >= n_cells);
 #endif
         return rec_add(vp, c);
     }
-    DR_HD void centre(float v[8]) const { load_vox8(rec(cell), v); }
-    DR_HD void plane_z(bool plus, bool pred, float n[4]) const
+    DR_HD void centre(F2& A0, F2& B0, F2& A1, F2& B1) const
     {
-        // the + neighbour's upper half (slots 4..7 = plane z0+2) or the - neighbour's lower half (slots 0..3 = plane z0-1)
-        const VT* r = rec_add(vp, plus ? cell + sz : cell - sz) + (plus ? 4 : 0);
-#if defined(DR_BOUNDS_CHECK)
-        DR_OOB_IF(pred && (long long)(plus ? cell + sz : cell - sz) >= n_cells);
-#endif
-        load_vox4_if(r, pred, n);
+        float v[8];
+        load_vox8(rec(cell, true), v);
+        A0 = f2(v[0], v[1]); B0 = f2(v[2], v[3]); A1 = f2(v[4], v[5]); B1 = f2(v[6], v[7]);
     }
-    DR_HD void plane_y(bool plus, bool pred, float n[4]) const
+    DR_HD void plane_x(bool plus, bool pred, F2& N0, F2& N1) const
     {
-        // b = 1 slots {2,3} {6,7} of the + neighbour, b = 0 slots {0,1} {4,5} of the - neighbour
-        const VT* r = rec_add(vp, plus ? cell + sy : cell - sy) + (plus ? 2 : 0);
-#if defined(DR_BOUNDS_CHECK)
-        DR_OOB_IF(pred && (long long)(plus ? cell + sy : cell - sy) >= n_cells);
-#endif
+        // a = 1 quarters {2,3} {6,7} of the + neighbour, a = 0 quarters {0,1} {4,5} of the - neighbour
+        const VT* r = rec(plus ? cell + 1 : cell - 1, pred) + (plus ? 2 : 0);
+        float n[4];
         load_vox2_if(r, pred, n); load_vox2_if(r + 4, pred, n + 2);
+        N0 = f2(n[0], n[1]); N1 = f2(n[2], n[3]);
     }
-    DR_HD void plane_x(bool minus, float n[4]) const
+    DR_HD void plane_y(bool plus, bool pred, F2& N0, F2& N1) const
     {
-        // a = 0 slots {0,2,4,6} of the - neighbour, a = 1 slots {1,3,5,7} of the + neighbour
-        const VT* r = rec(minus ? cell - 1 : cell + 1) + (minus ? 0 : 1);
-        n[0] = load_vox(r, 0); n[1] = load_vox(r, 2); n[2] = load_vox(r, 4); n[3] = load_vox(r, 6);
+        // the + neighbour's b = 1 half (slots 4..7 = row y0+2) or the - neighbour's b = 0 half (slots 0..3 = row y0-1)
+        const VT* r = rec(plus ? cell + sy : cell - sy, pred) + (plus ? 4 : 0);
+        float n[4];
+        load_vox4_if(r, pred, n);
+        N0 = f2(n[0], n[1]); N1 = f2(n[2], n[3]);
+    }
+    DR_HD void plane_z(bool plus, bool pred, F2& N0, F2& N1) const
+    {
+        // c = 1 slots {1,3,5,7} of the + neighbour, c = 0 slots {0,2,4,6} of the - neighbour
+        const VT* r = rec(plus ? cell + sz : cell - sz, pred) + (plus ? 1 : 0);
+        N0 = f2(load_vox_if(r, pred), load_vox_if(r + 4, pred));
+        N1 = f2(load_vox_if(r + 2, pred), load_vox_if(r + 6, pred));
     }
 };
 template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };
@@ -555,97 +629,81 @@ DR_HD void locate_centre(const DrDesc& d, F3 pos, Centre& c)
     c.cidx = (lo_of(c.cy) * d.Z + lo_of(c.cz)) * d.X + lo_of(c.cx);
 }
 
-// centre tap                                                                                :173-189
+// centre tap: x mixes, y mixes, z mix                                                      :173-189
 template <typename A>
 DR_HD void eval_centre(const A& ad, Centre& c)
 {
-    float v[8];
-    ad.centre(v);
-    c.v000 = v[0]; c.v100 = v[1]; c.v010 = v[2]; c.v110 = v[3];
-    c.v001 = v[4]; c.v101 = v[5]; c.v011 = v[6]; c.v111 = v[7];
+    ad.centre(c.A0, c.B0, c.A1, c.B1);
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
-    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
-    c.xm00 = mix_e(c.v000, c.v100, ox, fx); c.xm10 = mix_e(c.v010, c.v110, ox, fx);
-    c.xm01 = mix_e(c.v001, c.v101, ox, fx); c.xm11 = mix_e(c.v011, c.v111, ox, fx);
-    c.ym0 = mix_e(c.xm00, c.xm10, oy, fy); c.ym1 = mix_e(c.xm01, c.xm11, oy, fy);
-    c.I = mix_e(c.ym0, c.ym1, oz, fz);
+    const F2 fx2 = splat(fx), ox2 = splat(DR_SUB(1.0f, fx));
+    c.xm0 = mix2(c.A0, c.B0, ox2, fx2);
+    c.xm1 = mix2(c.A1, c.B1, ox2, fx2);
+    c.ym = mix2(c.xm0, c.xm1, splat(DR_SUB(1.0f, fy)), splat(fy));
+    c.I = mix_e(c.ym.x, c.ym.y, DR_SUB(1.0f, fz), fz);
 }
 
-// The six normal taps on top of an evaluated centre.  For y and z the code is branch-free in the common case: per axis the
-// ONE voxel plane beyond the centre cell that a crossed tap needs (lo+2 for the + tap, lo-1 for the - tap) is fetched with
-// predicated loads and both taps pick their operands with selects -- the same mixes on the same values a branch per
-// tap would do, but a warp does not serialise through four divergent branches per sample (almost every warp has a lane
-// that crosses: P = 1-(1-0.13)^32 at 256^3).  Both taps of an axis leave the cell only when the tap offset exceeds half a
-// voxel (dims > 1000, TAPS_TWO); that case takes a branch for the second plane.
+// The six normal taps on top of an evaluated centre, branch-free in the common case: per axis the ONE voxel plane beyond
+// the centre cell that a crossed tap needs (lo+2 for the + tap, lo-1 for the - tap) is fetched with predicated loads and
+// both taps pick their operands with selects -- the same mixes on the same values a branch per tap would do, but a warp
+// does not serialise through six divergent branches per sample (almost every warp has a lane that crosses:
+// P = 1-(1-0.13)^32 at 256^3).  Both taps of an axis leave the cell only when the tap offset exceeds half a voxel
+// (dims > 1000, TAPS_TWO); that case takes a branch for the second plane.  Mixes run as packed pairs (F2).
 template <int TAPS, typename A>
 DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, Taps& t)
 {
     t.cx = c.cx; t.cy = c.cy; t.cz = c.cz; t.cidx = c.cidx; t.I = c.I;
-    const float dl = d.delta;
-    t.xp = locate(DR_ADD(pos.x, dl), d.scale[0]);
-    t.xm = locate(DR_SUB(pos.x, dl), d.scale[0]);
-    t.yp = locate(DR_ADD(pos.y, dl), d.scale[1]);
-    t.ym = locate(DR_SUB(pos.y, dl), d.scale[1]);
-    t.zp = locate(DR_ADD(pos.z, dl), d.scale[2]);
-    t.zm = locate(DR_SUB(pos.z, dl), d.scale[2]);
+    locate_pair(pos.x, d.delta, d.scale[0], t.xp, t.xm);
+    locate_pair(pos.y, d.delta, d.scale[1], t.yp, t.ym);
+    locate_pair(pos.z, d.delta, d.scale[2], t.zp, t.zm);
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f;
-    const float ox = DR_SUB(1.0f, fx), oy = DR_SUB(1.0f, fy), oz = DR_SUB(1.0f, fz);
-    {   // ---- z taps
+    const float oz = DR_SUB(1.0f, fz);
+    const F2 fx2 = splat(fx), ox2 = splat(DR_SUB(1.0f, fx)), fy2 = splat(fy), oy2 = splat(DR_SUB(1.0f, fy));
+    {   // ---- z taps: only the last mix changes; both taps in one packed mix
         const bool cp = t.zp.b != c.cz.b, cm = t.zm.b != c.cz.b;
-        float n[4];
-        ad.plane_z(cp, cp | cm, n);
-        const float yn = mix_e(mix_e(n[0], n[1], ox, fx), mix_e(n[2], n[3], ox, fx), oy, fy);
-        const float fp = t.zp.f, fm = t.zm.f;
-        const float vp = mix_e(cp ? c.ym1 : c.ym0, cp ? yn : c.ym1, DR_SUB(1.0f, fp), fp);
-        float vm = mix_e(cm ? yn : c.ym0, cm ? c.ym0 : c.ym1, DR_SUB(1.0f, fm), fm);
+        F2 N0, N1;
+        ad.plane_z(cp, cp | cm, N0, N1);
+        const F2 xn = mix2(N0, N1, ox2, fx2);                               // x mixes of the new plane at (y0, y1)
+        const float yn = mix_e(xn.x, xn.y, oy2.x, fy);
+        const F2 f = f2(t.zp.f, t.zm.f), o = sub2(splat(1.0f), f);
+        F2 v = mix2(f2(cp ? c.ym.y : c.ym.x, cm ? yn : c.ym.x), f2(cp ? yn : c.ym.y, cm ? c.ym.x : c.ym.y), o, f);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // yn is plane lo+2; the - tap needs plane lo-1
-            ad.plane_z(false, true, n);
-            vm = mix_e(mix_e(mix_e(n[0], n[1], ox, fx), mix_e(n[2], n[3], ox, fx), oy, fy), c.ym0, DR_SUB(1.0f, fm), fm);
+            ad.plane_z(false, true, N0, N1);
+            const F2 xq = mix2(N0, N1, ox2, fx2);
+            v.y = mix_e(mix_e(xq.x, xq.y, oy2.x, fy), c.ym.x, o.y, f.y);
         }
-        t.g.z = DR_SUB(vp, vm);
+        t.g.z = DR_SUB(v.x, v.y);
     }
-    {   // ---- y taps
+    {   // ---- y taps: y mixes (a pair over z per tap) and the z mix change
         const bool cp = t.yp.b != c.cy.b, cm = t.ym.b != c.cy.b;
-        float n[4];
-        ad.plane_y(cp, cp | cm, n);
-        const float m0 = mix_e(n[0], n[1], ox, fx), m1 = mix_e(n[2], n[3], ox, fx);
-        const float fp = t.yp.f, op = DR_SUB(1.0f, fp), fm = t.ym.f, om = DR_SUB(1.0f, fm);
-        const float ap = mix_e(cp ? c.xm10 : c.xm00, cp ? m0 : c.xm10, op, fp);
-        const float bp = mix_e(cp ? c.xm11 : c.xm01, cp ? m1 : c.xm11, op, fp);
-        float am = mix_e(cm ? m0 : c.xm00, cm ? c.xm00 : c.xm10, om, fm);
-        float bm = mix_e(cm ? m1 : c.xm01, cm ? c.xm01 : c.xm11, om, fm);
-        if (TAPS == TAPS_TWO && (cp & cm)) {    // m0, m1 are row lo+2; the - tap needs row lo-1
-            ad.plane_y(false, true, n);
-            am = mix_e(mix_e(n[0], n[1], ox, fx), c.xm00, om, fm);
-            bm = mix_e(mix_e(n[2], n[3], ox, fx), c.xm01, om, fm);
+        F2 N0, N1;
+        ad.plane_y(cp, cp | cm, N0, N1);
+        const F2 m = mix2(N0, N1, ox2, fx2);                                // x mixes of the new row at (z0, z1)
+        const F2 fp = splat(t.yp.f), op = splat(DR_SUB(1.0f, t.yp.f)), fm = splat(t.ym.f), om = splat(DR_SUB(1.0f, t.ym.f));
+        const F2 yp = mix2(sel2(cp, c.xm1, c.xm0), sel2(cp, m, c.xm1), op, fp);
+        F2 ym = mix2(sel2(cm, m, c.xm0), sel2(cm, c.xm0, c.xm1), om, fm);
+        if (TAPS == TAPS_TWO && (cp & cm)) {    // m is row lo+2; the - tap needs row lo-1
+            ad.plane_y(false, true, N0, N1);
+            ym = mix2(mix2(N0, N1, ox2, fx2), c.xm0, om, fm);
         }
-        t.g.y = DR_SUB(mix_e(ap, bp, oz, fz), mix_e(am, bm, oz, fz));
+        t.g.y = DR_SUB(mix_e(yp.x, yp.y, oz, fz), mix_e(ym.x, ym.y, oz, fz));
     }
-    // ---- x taps: everything downstream of the corners changes; the compiler predicates the neighbour loads itself
-    float xv[2];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        const Loc q = sgn ? t.xm : t.xp;
-        const float f = q.f, o = DR_SUB(1.0f, f);
-        float a00, a10, a01, a11;
-        if (q.b == c.cx.b) {
-            a00 = mix_e(c.v000, c.v100, o, f); a10 = mix_e(c.v010, c.v110, o, f);
-            a01 = mix_e(c.v001, c.v101, o, f); a11 = mix_e(c.v011, c.v111, o, f);
-        } else {
-            float n[4];
-            ad.plane_x(sgn != 0, n);
-            if (sgn) {
-                a00 = mix_e(n[0], c.v000, o, f); a10 = mix_e(n[1], c.v010, o, f);
-                a01 = mix_e(n[2], c.v001, o, f); a11 = mix_e(n[3], c.v011, o, f);
-            } else {
-                a00 = mix_e(c.v100, n[0], o, f); a10 = mix_e(c.v110, n[1], o, f);
-                a01 = mix_e(c.v101, n[2], o, f); a11 = mix_e(c.v111, n[3], o, f);
-            }
+    {   // ---- x taps: everything downstream of the corners changes
+        const bool cp = t.xp.b != c.cx.b, cm = t.xm.b != c.cx.b;
+        F2 N0, N1;
+        ad.plane_x(cp, cp | cm, N0, N1);
+        const F2 fp = splat(t.xp.f), op = splat(DR_SUB(1.0f, t.xp.f)), fm = splat(t.xm.f), om = splat(DR_SUB(1.0f, t.xm.f));
+        const F2 p0 = mix2(sel2(cp, c.B0, c.A0), sel2(cp, N0, c.B0), op, fp);          // row y0, pair over z
+        const F2 p1 = mix2(sel2(cp, c.B1, c.A1), sel2(cp, N1, c.B1), op, fp);          // row y1
+        F2 m0 = mix2(sel2(cm, N0, c.A0), sel2(cm, c.A0, c.B0), om, fm);
+        F2 m1 = mix2(sel2(cm, N1, c.A1), sel2(cm, c.A1, c.B1), om, fm);
+        if (TAPS == TAPS_TWO && (cp & cm)) {    // N0, N1 are plane lo+2; the - tap needs plane lo-1
+            ad.plane_x(false, true, N0, N1);
+            m0 = mix2(N0, c.A0, om, fm);
+            m1 = mix2(N1, c.A1, om, fm);
         }
-        const float lo = mix_e(a00, a10, oy, fy), hi = mix_e(a01, a11, oy, fy);
-        xv[sgn] = mix_e(lo, hi, oz, fz);
+        const F2 yp = mix2(p0, p1, oy2, fy2), ym = mix2(m0, m1, oy2, fy2);
+        t.g.x = DR_SUB(mix_e(yp.x, yp.y, oz, fz), mix_e(ym.x, ym.y, oz, fz));
     }
-    t.g.x = DR_SUB(xv[0], xv[1]);
 }
 
 // Generic path (a normal tap can skip a whole cell: dims > ~2000; linear layout only): every tap is a full 8-load

@@ -116,7 +116,8 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
  * Cell-major copy of the volume for DR_F_LAYOUT_CELL8 (same role as dr_brick_volume; replaces set_volume's from_torch
  * into the reference's 4x4x4-blocked field, :97-101, :118-119): vol_cells is [Bvol][X*Y*Z][8] of the volume's dtype
  * (dr_grad_cells_elems(d) elements per volume, 32-byte aligned); record c holds the 8 corners of the cell whose low corner
- * has torch-linear index c, slot a + 2b + 4c = voxel (min(x+a,X-1), min(y+b,Y-1), min(z+c,Z-1)).
+ * has torch-linear index c, slot c + 2a + 4b = voxel (min(x+a,X-1), min(y+b,Y-1), min(z+c,Z-1)) -- z pairs adjacent, so the two
+ * 16-byte loads of a record land in the register pairs the packed (f32x2) trilinear mixes work on.
  */
 int dr_expand_cells(const DrDesc* d, const void* vol_linear, void* vol_cells, void* stream);
 

@@ -72,11 +72,11 @@ void sim_brick(const DrDesc* d, const float* lin, float* bricked)
 void sim_expand(const DrDesc* d, const float* lin, float* cells)
 {
     for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x) {
-        const size_t c = ((size_t)y * d->Z + z) * d->X + x;
+        const size_t cell = ((size_t)y * d->Z + z) * d->X + x;
         for (int q = 0; q < 8; ++q) {
-            const int xx = x + (q & 1) < d->X ? x + (q & 1) : d->X - 1, yy = y + ((q >> 1) & 1) < d->Y ? y + ((q >> 1) & 1) : d->Y - 1;
-            const int zz = z + (q >> 2) < d->Z ? z + (q >> 2) : d->Z - 1;
-            cells[c * 8 + q] = lin[((size_t)yy * d->Z + zz) * d->X + xx];
+            const int a = (q >> 1) & 1, b = q >> 2, c = q & 1;                    // slot = c + 2a + 4b
+            const int xx = x + a < d->X ? x + a : d->X - 1, yy = y + b < d->Y ? y + b : d->Y - 1, zz = z + c < d->Z ? z + c : d->Z - 1;
+            cells[cell * 8 + q] = lin[((size_t)yy * d->Z + zz) * d->X + xx];
         }
     }
 }

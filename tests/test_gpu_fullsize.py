@@ -93,7 +93,7 @@ def test_c4_512cube_1024sq():
 
 def test_c5_1024cube_fp16_2048sq():
     vr, vol, tf, tf_r4, cams, jit, bricked = _setup(1024, (2048, 2048), 1, dtype=torch.float16, M=8192)
-    assert bricked.dtype == torch.float16 and bricked.numel() == 1024 ** 3
+    assert bricked.dtype == torch.float16 and bricked.numel() == 8 * 1024 ** 3       # `auto` = cell-major copy (16 GiB)
     out, K, Tp = vr.march(bricked, tf_r4, cams, 1.0, jit)
     assert torch.isfinite(out).all() and K.max().item() <= 8192 and out[:, 3].max().item() <= 1.0 + 1e-5
     g1 = torch.randn(out.shape, generator=torch.Generator(device=DEV).manual_seed(1), device=DEV)
