@@ -38,14 +38,6 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 #define DR_BWD_MIN_BLOCKS_BRICK 4
 #endif
 
-__host__ __device__ inline Layout make_layout(const DrDesc& d)
-{
-    Layout L;
-    L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
-    L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
-    return L;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // shared prologue: stage the view's transfer function in shared memory as R TfBin entries (32 bytes each: tf[r] and
 // what the lookup needs of tf[min(r+1, R-1)], see dr_math.cuh).  Returns the table accessor.

@@ -34,7 +34,7 @@
 #define DR_FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #define DR_DIV(a, b) __fdiv_rn((a), (b))
 #define DR_SQRT(a) __fsqrt_rn((a))
-#define DR_RSQRT(a) rsqrtf((a))
+#define DR_RSQRT(a) dr::rsqrt_fast((a))
 #define DR_SAT(a) __saturatef((a))
 #define DR_ALIGN16 __align__(16)
 #else
@@ -63,6 +63,17 @@ namespace dr {
 
 DR_HD int imin(int a, int b) { return a < b ? a : b; }
 
+// 1/sqrt(x) off the exact path: one MUFU.RSQ for normal x (rsqrtf() adds denormal-scaling code around it); the rare
+// denormal / zero argument takes the library path so that the result stays finite exactly where rsqrtf()'s is
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float rsqrt_fast(float x)
+{
+    float r;
+    if (x >= 1.17549435e-38f) asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    else r = rsqrtf(x);
+    return r;
+}
+#endif
 // 1/x for x well inside the normal range, off the exact path: one MUFU.RCP (no denormal/overflow fix-up code)
 DR_HD float fast_rcp(float x)
 {
@@ -217,6 +228,7 @@ DR_HD void locate_pair(float pos, float delta, float scale, Loc& plus, Loc& minu
 struct Layout {
     int sY, sZ;           // element strides between bricks along y and z: nbx*512, nbx*nby*512
     int mx, my, mz;       // dim - 1 (index clamps)
+    unsigned cbias;       // (kFloorBias*Z + kFloorBias)*X + kFloorBias mod 2^32: turns biased floor indices into a cell index
 };
 // Offsets are UNSIGNED so that `pointer + offset` is one IMAD.WIDE.U32 (a signed int needs LEA + LEA.HI.X.SX32).
 typedef unsigned int uoff;
@@ -261,12 +273,14 @@ DR_HD float load_vox(const __half* p, int off)
 }
 DR_HD float load_vox(const __half* p, uoff off) { return load_vox(ptr_add(p, off), 0); }
 #endif
-// predicated load (0 when !pred): ONE predicated LDG instead of a divergent branch around the load
+// predicated load: ONE predicated LDG instead of a divergent branch around the load.  When !pred the result is UNDEFINED on
+// the device (the register is left as it is -- a zero-initialising MOV per value cost 25 issue slots per sample); every
+// caller discards it with a select.  The host build returns 0.
 DR_HD float load_vox_if(const float* p, bool pred)
 {
 #if defined(__CUDA_ARCH__)
     float v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}" : "=f"(v) : "l"(p), "r"((int)pred));
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}" : "=f"(v) : "l"(p), "r"((int)pred));
     return v;
 #else
     return pred ? *p : 0.0f;
@@ -277,7 +291,7 @@ DR_HD float load_vox_if(const __half* p, bool pred)
 {
 #if defined(__CUDA_ARCH__)
     unsigned short h;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.b16 %0, 0;\n\t@q ld.global.nc.b16 %0, [%1];\n\t}" : "=h"(h) : "l"(p), "r"((int)pred));
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.b16 %0, [%1];\n\t}" : "=h"(h) : "l"(p), "r"((int)pred));
     return __half2float(__ushort_as_half(h));
 #else
     return pred ? __half2float(*p) : 0.0f;
@@ -311,8 +325,8 @@ DR_HD void load_vox8(const float* r, float v[8])
 DR_HD void load_vox4_if(const float* r, bool pred, float n[4])
 {
 #if defined(__CUDA_ARCH__)
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\t"
-        "mov.f32 %3, 0f00000000;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t"
+        "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
         : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(r), "r"((int)pred));
 #else
     for (int q = 0; q < 4; ++q) n[q] = pred ? r[q] : 0.0f;
@@ -321,7 +335,7 @@ DR_HD void load_vox4_if(const float* r, bool pred, float n[4])
 DR_HD void load_vox2_if(const float* r, bool pred, float n[2])
 {
 #if defined(__CUDA_ARCH__)
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t"
         "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}" : "=f"(n[0]), "=f"(n[1]) : "l"(r), "r"((int)pred));
 #else
     for (int q = 0; q < 2; ++q) n[q] = pred ? r[q] : 0.0f;
@@ -343,7 +357,7 @@ DR_HD void load_vox4_if(const __half* r, bool pred, float n[4])
 {
 #if defined(__CUDA_ARCH__)
     unsigned lo, hi;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t@q ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
         : "=r"(lo), "=r"(hi) : "l"(r), "r"((int)pred));
     const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     n[0] = p0.x; n[1] = p0.y; n[2] = p1.x; n[3] = p1.y;
@@ -355,7 +369,7 @@ DR_HD void load_vox2_if(const __half* r, bool pred, float n[2])
 {
 #if defined(__CUDA_ARCH__)
     unsigned w;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(w) : "l"(r), "r"((int)pred));
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(w) : "l"(r), "r"((int)pred));
     const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&w));
     n[0] = p0.x; n[1] = p0.y;
 #else
@@ -621,12 +635,35 @@ template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; 
 template <typename VT> struct AddrOf<VT, LAYOUT_BRICK8> { typedef BrickAddr<VT> type; };
 template <typename VT> struct AddrOf<VT, LAYOUT_CELL8> { typedef CellAddr<VT> type; };
 
-DR_HD void locate_centre(const DrDesc& d, F3 pos, Centre& c)
+DR_HD Layout make_layout(const DrDesc& d)
 {
-    c.cx = locate(pos.x, d.scale[0]);
-    c.cy = locate(pos.y, d.scale[1]);
+    Layout L;
+    L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
+    L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
+    L.cbias = ((unsigned)kFloorBias * (unsigned)d.Z + (unsigned)kFloorBias) * (unsigned)d.X + (unsigned)kFloorBias;
+    return L;
+}
+
+DR_HD void locate_centre(const DrDesc& d, const Layout& L, F3 pos, Centre& c)
+{
+    // x and y as one packed pair (same operations per lane as locate()), z scalar
+    const F2 p = mul2(f2(DR_SAT(DR_FMA(0.5f, pos.x, 0.5f)), DR_SAT(DR_FMA(0.5f, pos.y, 0.5f))), f2(d.scale[0], d.scale[1]));
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %4};\n\tadd.rm.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(p.x), "f"(p.y), "f"(8388608.0f));
+    c.cx.b = __float_as_int(r.x); c.cy.b = __float_as_int(r.y);
+    const F2 f = sub2(p, sub2(r, splat(8388608.0f)));
+    c.cx.f = f.x; c.cy.f = f.y;
+#else
+    float l = floor_pos(p.x, c.cx.b);
+    c.cx.f = DR_SUB(p.x, l);
+    l = floor_pos(p.y, c.cy.b);
+    c.cy.f = DR_SUB(p.y, l);
+#endif
     c.cz = locate(pos.z, d.scale[2]);
-    c.cidx = (lo_of(c.cy) * d.Z + lo_of(c.cz)) * d.X + lo_of(c.cx);
+    // (lo_y*Z + lo_z)*X + lo_x from the biased indices: the three bias subtractions fold into one constant (mod 2^32)
+    c.cidx = (int)(((unsigned)c.cy.b * (unsigned)d.Z + (unsigned)c.cz.b) * (unsigned)d.X + (unsigned)c.cx.b - L.cbias);
 }
 
 // centre tap: x mixes, y mixes, z mix                                                      :173-189
@@ -741,7 +778,7 @@ DR_HD void eval_normals_generic(const DrDesc& d, const VT* vp, F3 pos, const Cen
 template <typename VT, int LAYOUT, int TAPS>
 DR_HD void sample_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Centre& c)
 {
-    locate_centre(d, pos, c);
+    locate_centre(d, L, pos, c);
     if (TAPS == TAPS_GENERIC) { c.I = trilinear_full_linear(d, vol.p, c.cx, c.cy, c.cz); return; }
     typename AddrOf<VT, LAYOUT>::type ad;
     ad.init(d, vol.p, L, c);
@@ -795,9 +832,10 @@ struct TfTable {
 #endif
 };
 
-struct TfHit { int lo; float f, x; F4 c; F4 d; };   // c = colour, d = tf[hi] - tf[lo] (for dI)
+struct TfHit { int lo; float f, x; F4 c; F4 d; TfBin t; };   // c = colour, d = tf[hi] - tf[lo] (for dI), t = the bin
 
-DR_HD void apply_tf(const DrDesc& d, const TfTable& tf, float intensity, TfHit& h, bool want_diff)
+// alpha only (the exact path); tf_colour() adds the colour and, for the adjoint, the bin differences
+DR_HD void apply_tf(const DrDesc& d, const TfTable& tf, float intensity, TfHit& h)
 {
     float x = fmaxf(DR_MUL(intensity, d.tf_len), 0.0f);
     h.x = x;
@@ -805,8 +843,12 @@ DR_HD void apply_tf(const DrDesc& d, const TfTable& tf, float intensity, TfHit& 
     float l = floor_pos(x, b);
     h.f = DR_SUB(x, l);
     h.lo = imin(b - kFloorBias, d.R - 1);        // H9
-    const TfBin t = tf.get(h.lo);
-    h.c.w = mix_e(t.a.w, t.bw, DR_SUB(1.0f, h.f), h.f);
+    h.t = tf.get(h.lo);
+    h.c.w = mix_e(h.t.a.w, h.t.bw, DR_SUB(1.0f, h.f), h.f);
+}
+DR_HD void tf_colour(TfHit& h, bool want_diff)
+{
+    const TfBin& t = h.t;
     h.c.x = t.a.x + h.f * t.dx; h.c.y = t.a.y + h.f * t.dy; h.c.z = t.a.z + h.f * t.dz;
     if (want_diff) { h.d.x = t.dx; h.d.y = t.dy; h.d.z = t.dz; h.d.w = t.bw - t.a.w; }
 }
@@ -1024,6 +1066,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
 {
     A.x = A.y = A.z = A.w = 0.0f;                       // H1: tape[-1] = 0
     K = 0;
+    int Kshaded = 0;                                    // diagnostic (DR_F_COUNT_SHADED): samples with non-zero opacity
     Tprev = 1.0f;
     const int nn = NONDIFF ? r.n : imin(r.n, d.M);      // :267-269 (s < max_samples only in the diff kernel)
     for (int s = 0; s < nn; ++s) {
@@ -1032,7 +1075,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         Centre c;
         sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
         TfHit h;
-        apply_tf(d, tf, c.I, h, false);
+        apply_tf(d, tf, c.I, h);
         if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334: skipped samples never evaluate the normal
         const float o = opacity<SR1>(d, h.c.w);
         const float T = DR_SUB(1.0f, A.w);
@@ -1041,9 +1084,10 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
             // C = (k*c*0, 0), so A_s = fma(T, 0, A_{s-1}) = A_{s-1} bit for bit whatever the Phong factor k is.  The
             // sample still counts as active (:303) but its six normal taps and shading are never evaluated.
             Tprev = T;
-            if (!(d.flags & DR_F_COUNT_SHADED)) ++K;
+            ++K;
             continue;
         }
+        tf_colour(h, false);
         Taps t;
         sample_normals<VT, LAYOUT, TAPS>(d, vol, L, pos, c, t);
         Shade sh;
@@ -1055,7 +1099,9 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         A.z = DR_FMA(T, ko * h.c.z, A.z);
         A.w = DR_FMA(T, o, A.w);                        // :300-302
         ++K;                                            // :303
+        ++Kshaded;
     }
+    if (d.flags & DR_F_COUNT_SHADED) K = Kshaded;
     if (NONDIFF) { A.x = fminf(1.0f, A.x); A.y = fminf(1.0f, A.y); A.z = fminf(1.0f, A.z); A.w = fminf(1.0f, A.w); }   // :358
 }
 
@@ -1079,7 +1125,8 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         Centre c;
         sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
         TfHit h;
-        apply_tf(d, tf, c.I, h, WANT_VOL);
+        apply_tf(d, tf, c.I, h);
+        tf_colour(h, WANT_VOL);
         const float o = opacity<SR1>(d, h.c.w);
         // Volume-only gradient: an exactly transparent sample whose two TF bins are both transparent (h.d.w == 0) has
         // dc.rgb = k*o*dC = 0 and dI = tf_len * dc.w * h.d.w = 0, C = 0 (g.w unchanged) and T_{s-1} = T_s: nothing to do.

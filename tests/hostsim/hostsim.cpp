@@ -33,13 +33,6 @@ struct HostTfSink {
     void add_alpha(int lo, float f, float dcw) { add(lo, f, F4 { 0.0f, 0.0f, 0.0f, dcw }); }
     void flush() {}
 };
-Layout make_layout(const DrDesc& d)
-{
-    Layout L;
-    L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
-    L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
-    return L;
-}
 // the staged table the kernels build in shared memory (stage_tf in dr_kernels.cuh): bin r holds tf[r] and tf[min(r+1, R-1)]
 TfBin* make_tf_table(const DrDesc& d, const float* tf)
 {
