@@ -250,7 +250,11 @@ def _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, ca
     ctx.vr, ctx.sampling_rate, ctx.image_layout = vr, sampling_rate, image_layout
     ctx.is_batched, ctx.vol_batched, ctx.tf_batched = batched[0], vol_b, tf.ndim == 3
     ctx.vol_shape, ctx.tf_shape = tuple(volume.shape), tuple(tf.shape)
-    ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = tf_r4, cam, jit, out, K, Tp
+    # `out` is also the tensor the Function returns: keeping that very object on ctx would close a reference cycle
+    # (out.grad_fn -> ctx -> out) and leave every buffer of the step (the cell-major volume copy, K, Tprev ...) to Python's
+    # cyclic collector -- the caching allocator then cudaMallocs ~1 GiB of fresh blocks per step (measured: 50-300 ms
+    # stalls).  A detached alias shares the storage and has no grad_fn.
+    ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = tf_r4, cam, jit, out.detach(), K, Tp
     if bricked.data_ptr() == volume.data_ptr():
         ctx.save_for_backward(volume)          # zero-copy layout: let autograd detect in-place edits before backward
         ctx.bricked = None
