@@ -404,10 +404,15 @@ def run_ours(args, cfg):
         achieved = dom_bytes * s / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         # DRAM bytes of the dominant kernel per launch, from the committed `ncu --set full` capture of this very workload
         traffic = None
+        ncu_note = {"source": None}
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
             if tj["config"] == args.config and tj["views_per_gpu"] == views and tj["layout"] == vr.resolve_layout(vol_lin):
                 traffic = tj["kernels"][dominant]["traffic_bytes_per_launch"]
+                ncu_note = {"source": tj["source"],
+                            "issue_active_pct": {k: round(v["issue_active_pct"], 1) for k, v in tj["kernels"].items()},
+                            "l1tex_throughput_pct": {k: round(v["l1tex_throughput_pct"], 1) for k, v in tj["kernels"].items()},
+                            "lts_throughput_pct": {k: round(v["lts_throughput_pct"], 1) for k, v in tj["kernels"].items()}}
         except (OSError, KeyError, ValueError):
             pass
         line = {
@@ -427,11 +432,12 @@ def run_ours(args, cfg):
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes * s, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_sample": dom_bytes,
-                         "note": "algorithmic bytes are the L2-level figure of SURVEY 8(d) (8 corner reads [+ 8 fp32 atomic RMWs] per sample); the kernels are instruction-issue-bound and almost every access hits L1/L2, so measured DRAM traffic is far BELOW the algorithmic bytes"},
+                         "note": "algorithmic bytes are the L2-level figure of SURVEY 8(d) (8 corner reads [+ 8 fp32 atomic RMWs] per sample); the kernels are instruction-issue-bound and most accesses hit L1/L2, so measured DRAM traffic (`traffic`) is far BELOW the algorithmic bytes"},
             "rooflines_other": {"l2_read_gbs_measured": l2_gbs, "l2_how": "torch.sum over a 48 MiB L2-resident buffer, 20 reps",
                                 "achieved_over_l2": (achieved / l2_gbs) if l2_gbs else None,
-                                "issue_active_pct_ncu": {"fwd_kernel": 77.6, "bwd_kernel": 74.2, "source": "profiles/r01f_ncu_v3_c3_16views.txt"},
-                                "binding": "instruction issue (both kernels ~75-78 % issue-active; DRAM < 1 % of peak)"},
+                                "ncu": ncu_note,
+                                "binding": "instruction issue (backward 78 % issue-active with the ALU pipe at 61 %; forward 64 % issue-active and "
+                                           "latency-exposed, L1TEX 60 %); DRAM < 2 % of peak"},
             "allreduce": None if world == 1 else {
                 "bytes": int((n ** 3 + R * 4) * 4 if need_vol else R * 16), "ms": phase_ms["post"] / args.steps,
                 "busbw_gbs": ((n ** 3 + R * 4) * 4 if need_vol else R * 16) * 2 * (world - 1) / world / (phase_ms["post"] / args.steps * 1e-3) / 1e9,
