@@ -63,15 +63,15 @@ namespace dr {
 
 DR_HD int imin(int a, int b) { return a < b ? a : b; }
 
-// 1/sqrt(x) off the exact path: one MUFU.RSQ for normal x (rsqrtf() adds denormal-scaling code around it); the rare
-// denormal / zero argument takes the library path so that the result stays finite exactly where rsqrtf()'s is
+// 1/sqrt(x) off the exact path as FMUL + MUFU.RSQ + FMUL, branch-free: rsqrtf() wraps the MUFU in compare / predicate /
+// rescale code for denormal arguments (11 issue slots once if-converted).  Scaling the argument by 2^40 (exact) keeps
+// every positive fp32 up to 2^87 inside MUFU.RSQ's normal range, and the result is scaled back by 2^20 (exact).
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ float rsqrt_fast(float x)
 {
     float r;
-    if (x >= 1.17549435e-38f) asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    else r = rsqrtf(x);
-    return r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1099511627776.0f));
+    return r * 1048576.0f;
 }
 #endif
 // 1/x for x well inside the normal range, off the exact path: one MUFU.RCP (no denormal/overflow fix-up code)
@@ -377,6 +377,98 @@ DR_HD void load_vox2_if(const __half* r, bool pred, float n[2])
 #endif
 }
 #endif
+// Plane beyond the centre cell from the face neighbours' records (LAYOUT_CELL8), as TWO loads under complementary-use
+// predicates: `rm` (the - neighbour) under bm != bc, then `rp` (the + neighbour) under bp != bc, into the same registers
+// (when both taps crossed the + plane wins; TAPS_TWO fetches the other one separately).  The predicates are formed inside
+// the asm from the biased floor indices, so no boolean is materialised in a register and no address is selected: the
+// ALU pipe, the busiest of the backward, does nothing for the fetch but the two address IMADs.  Undefined when neither
+// tap crossed (every caller discards the values with a select); the host build returns 0 then.
+#define DR_PM_PRED4 "{\n\t.reg .pred p, m;\n\tsetp.ne.s32 p, %6, %8;\n\tsetp.ne.s32 m, %7, %8;\n\t"     /* 4 outputs: rp %4, rm %5, bp %6, bm %7, bc %8 */
+#define DR_PM_PRED2 "{\n\t.reg .pred p, m;\n\tsetp.ne.s32 p, %4, %6;\n\tsetp.ne.s32 m, %5, %6;\n\t"     /* 2 outputs: rp %2, rm %3, bp %4, bm %5, bc %6 */
+DR_HD void cell_plane_y(const float* rp, const float* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    asm(DR_PM_PRED4 "@m ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+16];\n\t}"
+        : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+#else
+    const float* r = bp != bc ? rp + 4 : rm;
+    for (int q = 0; q < 4; ++q) n[q] = (bp != bc || bm != bc) ? r[q] : 0.0f;
+#endif
+}
+DR_HD void cell_plane_x(const float* rp, const float* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    asm(DR_PM_PRED4 "@m ld.global.nc.v2.f32 {%0, %1}, [%5];\n\t@m ld.global.nc.v2.f32 {%2, %3}, [%5+16];\n\t"
+        "@p ld.global.nc.v2.f32 {%0, %1}, [%4+8];\n\t@p ld.global.nc.v2.f32 {%2, %3}, [%4+24];\n\t}"
+        : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+#else
+    const float* r = bp != bc ? rp + 2 : rm;
+    const bool any = bp != bc || bm != bc;
+    n[0] = any ? r[0] : 0.0f; n[1] = any ? r[1] : 0.0f; n[2] = any ? r[4] : 0.0f; n[3] = any ? r[5] : 0.0f;
+#endif
+}
+// n = slots (c), (c+4), (c+2), (c+6) with c = 1 for the + neighbour, 0 for the - neighbour: (x0,y0) (x0,y1) (x1,y0) (x1,y1)
+DR_HD void cell_plane_z(const float* rp, const float* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    asm(DR_PM_PRED4 "@m ld.global.nc.f32 %0, [%5];\n\t@m ld.global.nc.f32 %1, [%5+16];\n\t@m ld.global.nc.f32 %2, [%5+8];\n\t"
+        "@m ld.global.nc.f32 %3, [%5+24];\n\t@p ld.global.nc.f32 %0, [%4+4];\n\t@p ld.global.nc.f32 %1, [%4+20];\n\t"
+        "@p ld.global.nc.f32 %2, [%4+12];\n\t@p ld.global.nc.f32 %3, [%4+28];\n\t}"
+        : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+#else
+    const float* r = bp != bc ? rp + 1 : rm;
+    const bool any = bp != bc || bm != bc;
+    n[0] = any ? r[0] : 0.0f; n[1] = any ? r[4] : 0.0f; n[2] = any ? r[2] : 0.0f; n[3] = any ? r[6] : 0.0f;
+#endif
+}
+#if defined(__CUDACC__)
+DR_HD void cell_plane_y(const __half* rp, const __half* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned lo, hi;
+    asm(DR_PM_PRED2 "@m ld.global.nc.v2.b32 {%0, %1}, [%3];\n\t@p ld.global.nc.v2.b32 {%0, %1}, [%2+8];\n\t}"
+        : "=r"(lo), "=r"(hi) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    n[0] = p0.x; n[1] = p0.y; n[2] = p1.x; n[3] = p1.y;
+#else
+    const __half* r = bp != bc ? rp + 4 : rm;
+    for (int q = 0; q < 4; ++q) n[q] = (bp != bc || bm != bc) ? __half2float(r[q]) : 0.0f;
+#endif
+}
+DR_HD void cell_plane_x(const __half* rp, const __half* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned lo, hi;
+    asm(DR_PM_PRED2 "@m ld.global.nc.b32 %0, [%3];\n\t@m ld.global.nc.b32 %1, [%3+8];\n\t"
+        "@p ld.global.nc.b32 %0, [%2+4];\n\t@p ld.global.nc.b32 %1, [%2+12];\n\t}"
+        : "=r"(lo), "=r"(hi) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    n[0] = p0.x; n[1] = p0.y; n[2] = p1.x; n[3] = p1.y;
+#else
+    const __half* r = bp != bc ? rp + 2 : rm;
+    const bool any = bp != bc || bm != bc;
+    n[0] = any ? __half2float(r[0]) : 0.0f; n[1] = any ? __half2float(r[1]) : 0.0f;
+    n[2] = any ? __half2float(r[4]) : 0.0f; n[3] = any ? __half2float(r[5]) : 0.0f;
+#endif
+}
+DR_HD void cell_plane_z(const __half* rp, const __half* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned short h0, h1, h2, h3;
+    asm(DR_PM_PRED4 "@m ld.global.nc.b16 %0, [%5];\n\t@m ld.global.nc.b16 %1, [%5+8];\n\t@m ld.global.nc.b16 %2, [%5+4];\n\t"
+        "@m ld.global.nc.b16 %3, [%5+12];\n\t@p ld.global.nc.b16 %0, [%4+2];\n\t@p ld.global.nc.b16 %1, [%4+10];\n\t"
+        "@p ld.global.nc.b16 %2, [%4+6];\n\t@p ld.global.nc.b16 %3, [%4+14];\n\t}"
+        : "=h"(h0), "=h"(h1), "=h"(h2), "=h"(h3) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    n[0] = __half2float(__ushort_as_half(h0)); n[1] = __half2float(__ushort_as_half(h1));
+    n[2] = __half2float(__ushort_as_half(h2)); n[3] = __half2float(__ushort_as_half(h3));
+#else
+    const __half* r = bp != bc ? rp + 1 : rm;
+    const bool any = bp != bc || bm != bc;
+    n[0] = any ? __half2float(r[0]) : 0.0f; n[1] = any ? __half2float(r[4]) : 0.0f;
+    n[2] = any ? __half2float(r[2]) : 0.0f; n[3] = any ? __half2float(r[6]) : 0.0f;
+#endif
+}
+#endif
 template <typename VT> struct VolView {
     const VT* p;
     DR_HD float ld(uoff off) const { return load_vox(p, off); }
@@ -508,21 +600,24 @@ template <typename Derived> struct RowFetch {
         A0 = f2(t.ld(r00, 0), t.ld(r01, 0)); B0 = f2(t.ld(r00, 1), t.ld(r01, 1));
         A1 = f2(t.ld(r10, 0), t.ld(r11, 0)); B1 = f2(t.ld(r10, 1), t.ld(r11, 1));
     }
-    DR_HD void plane_x(bool plus, bool pred, F2& N0, F2& N1) const
+    DR_HD void plane_x(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
+        const bool plus = bp != bc, pred = plus | (bm != bc);
         const Derived& t = self();
         const typename Derived::Row r00 = t.row(0, 0), r10 = t.row(1, 0), r01 = t.row(0, 1), r11 = t.row(1, 1);
         N0 = f2(t.ld_sel(r00, plus, pred), t.ld_sel(r01, plus, pred));
         N1 = f2(t.ld_sel(r10, plus, pred), t.ld_sel(r11, plus, pred));
     }
-    DR_HD void plane_y(bool plus, bool pred, F2& N0, F2& N1) const
+    DR_HD void plane_y(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
+        const bool plus = bp != bc, pred = plus | (bm != bc);
         const Derived& t = self();
         const typename Derived::Row n0 = t.row_y(plus, 0), n1 = t.row_y(plus, 1);
         N0 = f2(t.ld_if(n0, 0, pred), t.ld_if(n1, 0, pred)); N1 = f2(t.ld_if(n0, 1, pred), t.ld_if(n1, 1, pred));
     }
-    DR_HD void plane_z(bool plus, bool pred, F2& N0, F2& N1) const
+    DR_HD void plane_z(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
+        const bool plus = bp != bc, pred = plus | (bm != bc);
         const Derived& t = self();
         const typename Derived::Row n0 = t.row_z(0, plus), n1 = t.row_z(1, plus);
         N0 = f2(t.ld_if(n0, 0, pred), t.ld_if(n1, 0, pred)); N1 = f2(t.ld_if(n0, 1, pred), t.ld_if(n1, 1, pred));
@@ -582,7 +677,11 @@ template <typename VT> struct BrickAddr : RowFetch<BrickAddr<VT> > {
     }
     DR_HD float ld_sel(Row r, bool plus, bool pred) const { return ld_if(r, plus ? 2 : -1, pred); }
 };
-template <typename VT> struct CellAddr {
+// DUAL: fetch a plane beyond the cell with one load per neighbour (cell_plane_*: no address select, no materialised
+// predicate) instead of one load from a selected address.  Twice the load instructions for fewer ALU instructions: it pays
+// in the ALU-bound backward while at most one tap of an axis crosses (C3: backward +7 %), and costs where loads matter
+// (forward -6 %) or crossings are frequent (C5, TAPS_TWO: backward -15 %), so only the TAPS_ONE backward uses it.
+template <typename VT, bool DUAL> struct CellAddr {
     const VT* vp; uoff cell, sy, sz;
 #if defined(DR_BOUNDS_CHECK)
     long long n_cells;
@@ -607,33 +706,63 @@ template <typename VT> struct CellAddr {
         load_vox8(rec(cell, true), v);
         A0 = f2(v[0], v[1]); B0 = f2(v[2], v[3]); A1 = f2(v[4], v[5]); B1 = f2(v[6], v[7]);
     }
-    DR_HD void plane_x(bool plus, bool pred, F2& N0, F2& N1) const
+    // the records of the two face neighbours along an axis with cell stride `st`
+    DR_HD void nbr(uoff st, int bp, int bm, int bc, const VT*& rp, const VT*& rm) const
+    {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(bp != bc && (long long)(cell + st) >= n_cells);
+        DR_OOB_IF(bm != bc && (long long)(cell - st) >= n_cells);
+#endif
+        rp = rec_add(vp, cell + st); rm = rec_add(vp, cell - st);
+    }
+    DR_HD void plane_x(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
         // a = 1 quarters {2,3} {6,7} of the + neighbour, a = 0 quarters {0,1} {4,5} of the - neighbour
-        const VT* r = rec(plus ? cell + 1 : cell - 1, pred) + (plus ? 2 : 0);
         float n[4];
-        load_vox2_if(r, pred, n); load_vox2_if(r + 4, pred, n + 2);
+        if (DUAL) {
+            const VT *rp, *rm;
+            nbr(1u, bp, bm, bc, rp, rm);
+            cell_plane_x(rp, rm, bp, bm, bc, n);
+        } else {
+            const bool plus = bp != bc, pred = plus | (bm != bc);
+            const VT* r = rec(plus ? cell + 1 : cell - 1, pred) + (plus ? 2 : 0);
+            load_vox2_if(r, pred, n); load_vox2_if(r + 4, pred, n + 2);
+        }
         N0 = f2(n[0], n[1]); N1 = f2(n[2], n[3]);
     }
-    DR_HD void plane_y(bool plus, bool pred, F2& N0, F2& N1) const
+    DR_HD void plane_y(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
         // the + neighbour's b = 1 half (slots 4..7 = row y0+2) or the - neighbour's b = 0 half (slots 0..3 = row y0-1)
-        const VT* r = rec(plus ? cell + sy : cell - sy, pred) + (plus ? 4 : 0);
         float n[4];
-        load_vox4_if(r, pred, n);
+        if (DUAL) {
+            const VT *rp, *rm;
+            nbr(sy, bp, bm, bc, rp, rm);
+            cell_plane_y(rp, rm, bp, bm, bc, n);
+        } else {
+            const bool plus = bp != bc, pred = plus | (bm != bc);
+            load_vox4_if(rec(plus ? cell + sy : cell - sy, pred) + (plus ? 4 : 0), pred, n);
+        }
         N0 = f2(n[0], n[1]); N1 = f2(n[2], n[3]);
     }
-    DR_HD void plane_z(bool plus, bool pred, F2& N0, F2& N1) const
+    DR_HD void plane_z(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
-        // c = 1 slots {1,3,5,7} of the + neighbour, c = 0 slots {0,2,4,6} of the - neighbour
-        const VT* r = rec(plus ? cell + sz : cell - sz, pred) + (plus ? 1 : 0);
-        N0 = f2(load_vox_if(r, pred), load_vox_if(r + 4, pred));
-        N1 = f2(load_vox_if(r + 2, pred), load_vox_if(r + 6, pred));
+        // c = 1 slots {1,5} {3,7} of the + neighbour, c = 0 slots {0,4} {2,6} of the - neighbour
+        float n[4];
+        if (DUAL) {
+            const VT *rp, *rm;
+            nbr(sz, bp, bm, bc, rp, rm);
+            cell_plane_z(rp, rm, bp, bm, bc, n);
+        } else {
+            const bool plus = bp != bc, pred = plus | (bm != bc);
+            const VT* r = rec(plus ? cell + sz : cell - sz, pred) + (plus ? 1 : 0);
+            n[0] = load_vox_if(r, pred); n[1] = load_vox_if(r + 4, pred); n[2] = load_vox_if(r + 2, pred); n[3] = load_vox_if(r + 6, pred);
+        }
+        N0 = f2(n[0], n[1]); N1 = f2(n[2], n[3]);
     }
 };
-template <typename VT, int LAYOUT> struct AddrOf { typedef LinearAddr<VT> type; };
-template <typename VT> struct AddrOf<VT, LAYOUT_BRICK8> { typedef BrickAddr<VT> type; };
-template <typename VT> struct AddrOf<VT, LAYOUT_CELL8> { typedef CellAddr<VT> type; };
+template <typename VT, int LAYOUT, bool DUAL> struct AddrOf { typedef LinearAddr<VT> type; };
+template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_BRICK8, DUAL> { typedef BrickAddr<VT> type; };
+template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_CELL8, DUAL> { typedef CellAddr<VT, DUAL> type; };
 
 DR_HD Layout make_layout(const DrDesc& d)
 {
@@ -698,13 +827,13 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
     {   // ---- z taps: only the last mix changes; both taps in one packed mix
         const bool cp = t.zp.b != c.cz.b, cm = t.zm.b != c.cz.b;
         F2 N0, N1;
-        ad.plane_z(cp, cp | cm, N0, N1);
+        ad.plane_z(t.zp.b, t.zm.b, c.cz.b, N0, N1);
         const F2 xn = mix2(N0, N1, ox2, fx2);                               // x mixes of the new plane at (y0, y1)
         const float yn = mix_e(xn.x, xn.y, oy2.x, fy);
         const F2 f = f2(t.zp.f, t.zm.f), o = sub2(splat(1.0f), f);
         F2 v = mix2(f2(cp ? c.ym.y : c.ym.x, cm ? yn : c.ym.x), f2(cp ? yn : c.ym.y, cm ? c.ym.x : c.ym.y), o, f);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // yn is plane lo+2; the - tap needs plane lo-1
-            ad.plane_z(false, true, N0, N1);
+            ad.plane_z(c.cz.b, t.zm.b, c.cz.b, N0, N1);
             const F2 xq = mix2(N0, N1, ox2, fx2);
             v.y = mix_e(mix_e(xq.x, xq.y, oy2.x, fy), c.ym.x, o.y, f.y);
         }
@@ -713,13 +842,13 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
     {   // ---- y taps: y mixes (a pair over z per tap) and the z mix change
         const bool cp = t.yp.b != c.cy.b, cm = t.ym.b != c.cy.b;
         F2 N0, N1;
-        ad.plane_y(cp, cp | cm, N0, N1);
+        ad.plane_y(t.yp.b, t.ym.b, c.cy.b, N0, N1);
         const F2 m = mix2(N0, N1, ox2, fx2);                                // x mixes of the new row at (z0, z1)
         const F2 fp = splat(t.yp.f), op = splat(DR_SUB(1.0f, t.yp.f)), fm = splat(t.ym.f), om = splat(DR_SUB(1.0f, t.ym.f));
         const F2 yp = mix2(sel2(cp, c.xm1, c.xm0), sel2(cp, m, c.xm1), op, fp);
         F2 ym = mix2(sel2(cm, m, c.xm0), sel2(cm, c.xm0, c.xm1), om, fm);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // m is row lo+2; the - tap needs row lo-1
-            ad.plane_y(false, true, N0, N1);
+            ad.plane_y(c.cy.b, t.ym.b, c.cy.b, N0, N1);
             ym = mix2(mix2(N0, N1, ox2, fx2), c.xm0, om, fm);
         }
         t.g.y = DR_SUB(mix_e(yp.x, yp.y, oz, fz), mix_e(ym.x, ym.y, oz, fz));
@@ -727,14 +856,14 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
     {   // ---- x taps: everything downstream of the corners changes
         const bool cp = t.xp.b != c.cx.b, cm = t.xm.b != c.cx.b;
         F2 N0, N1;
-        ad.plane_x(cp, cp | cm, N0, N1);
+        ad.plane_x(t.xp.b, t.xm.b, c.cx.b, N0, N1);
         const F2 fp = splat(t.xp.f), op = splat(DR_SUB(1.0f, t.xp.f)), fm = splat(t.xm.f), om = splat(DR_SUB(1.0f, t.xm.f));
         const F2 p0 = mix2(sel2(cp, c.B0, c.A0), sel2(cp, N0, c.B0), op, fp);          // row y0, pair over z
         const F2 p1 = mix2(sel2(cp, c.B1, c.A1), sel2(cp, N1, c.B1), op, fp);          // row y1
         F2 m0 = mix2(sel2(cm, N0, c.A0), sel2(cm, c.A0, c.B0), om, fm);
         F2 m1 = mix2(sel2(cm, N1, c.A1), sel2(cm, c.A1, c.B1), om, fm);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // N0, N1 are plane lo+2; the - tap needs plane lo-1
-            ad.plane_x(false, true, N0, N1);
+            ad.plane_x(c.cx.b, t.xm.b, c.cx.b, N0, N1);
             m0 = mix2(N0, c.A0, om, fm);
             m1 = mix2(N1, c.A1, om, fm);
         }
@@ -775,20 +904,20 @@ DR_HD void eval_normals_generic(const DrDesc& d, const VT* vp, F3 pos, const Cen
 }
 
 // phase 1 / phase 2 dispatch on layout and tap path
-template <typename VT, int LAYOUT, int TAPS>
+template <typename VT, int LAYOUT, int TAPS, bool DUAL = false>
 DR_HD void sample_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Centre& c)
 {
     locate_centre(d, L, pos, c);
     if (TAPS == TAPS_GENERIC) { c.I = trilinear_full_linear(d, vol.p, c.cx, c.cy, c.cz); return; }
-    typename AddrOf<VT, LAYOUT>::type ad;
+    typename AddrOf<VT, LAYOUT, DUAL>::type ad;
     ad.init(d, vol.p, L, c);
     eval_centre(ad, c);
 }
-template <typename VT, int LAYOUT, int TAPS>
+template <typename VT, int LAYOUT, int TAPS, bool DUAL>
 DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, const Centre& c, Taps& t)
 {
     if (TAPS == TAPS_GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
-    typename AddrOf<VT, LAYOUT>::type ad;
+    typename AddrOf<VT, LAYOUT, DUAL>::type ad;
     ad.init(d, vol.p, L, c);
     eval_normals<TAPS>(d, ad, pos, c, t);
 }
@@ -1089,7 +1218,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         }
         tf_colour(h, false);
         Taps t;
-        sample_normals<VT, LAYOUT, TAPS>(d, vol, L, pos, c, t);
+        sample_normals<VT, LAYOUT, TAPS, false>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);
         const float ko = sh.k * o;
@@ -1132,7 +1261,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         // dc.rgb = k*o*dC = 0 and dI = tf_len * dc.w * h.d.w = 0, C = 0 (g.w unchanged) and T_{s-1} = T_s: nothing to do.
         if (!WANT_TF && o == 0.0f && h.d.w == 0.0f) continue;
         Taps t;
-        sample_normals<VT, LAYOUT, TAPS>(d, vol, L, pos, c, t);
+        sample_normals<VT, LAYOUT, TAPS, TAPS == TAPS_ONE>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, cam, r.dir, pos, t.g, true, sh);
         if (o == 0.0f) {
