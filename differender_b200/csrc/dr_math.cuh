@@ -107,6 +107,21 @@ struct F2 { float x, y; };
 DR_HD F2 f2(float x, float y) { F2 r = { x, y }; return r; }
 DR_HD F2 splat(float a) { F2 r = { a, a }; return r; }
 DR_HD F2 sel2(bool c, F2 a, F2 b) { F2 r = { c ? a.x : b.x, c ? a.y : b.y }; return r; }
+// (x != y) ? a : b on a register pair: the predicate is formed inside the asm (no boolean materialised) and the pair is
+// selected as one 64-bit selp, which ptxas lowers to two SELs instead of the four predicated MOVs it emits for sel2 when
+// the destination has to be an aligned pair
+DR_HD F2 sel2_ne(int x, int y, F2 a, F2 b)
+{
+#if defined(__CUDA_ARCH__)
+    F2 r;
+    asm("{\n\t.reg .pred q;\n\t.reg .b64 pa, pb;\n\tsetp.ne.s32 q, %6, %7;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\t"
+        "selp.b64 pa, pa, pb, q;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "r"(x), "r"(y));
+    return r;
+#else
+    return x != y ? a : b;
+#endif
+}
 DR_HD F2 mul2(F2 a, F2 b)
 {
 #if defined(__CUDA_ARCH__)
@@ -845,8 +860,8 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
         ad.plane_y(t.yp.b, t.ym.b, c.cy.b, N0, N1);
         const F2 m = mix2(N0, N1, ox2, fx2);                                // x mixes of the new row at (z0, z1)
         const F2 fp = splat(t.yp.f), op = splat(DR_SUB(1.0f, t.yp.f)), fm = splat(t.ym.f), om = splat(DR_SUB(1.0f, t.ym.f));
-        const F2 yp = mix2(sel2(cp, c.xm1, c.xm0), sel2(cp, m, c.xm1), op, fp);
-        F2 ym = mix2(sel2(cm, m, c.xm0), sel2(cm, c.xm0, c.xm1), om, fm);
+        const F2 yp = mix2(sel2_ne(t.yp.b, c.cy.b, c.xm1, c.xm0), sel2_ne(t.yp.b, c.cy.b, m, c.xm1), op, fp);
+        F2 ym = mix2(sel2_ne(t.ym.b, c.cy.b, m, c.xm0), sel2_ne(t.ym.b, c.cy.b, c.xm0, c.xm1), om, fm);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // m is row lo+2; the - tap needs row lo-1
             ad.plane_y(c.cy.b, t.ym.b, c.cy.b, N0, N1);
             ym = mix2(mix2(N0, N1, ox2, fx2), c.xm0, om, fm);
@@ -858,10 +873,11 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
         F2 N0, N1;
         ad.plane_x(t.xp.b, t.xm.b, c.cx.b, N0, N1);
         const F2 fp = splat(t.xp.f), op = splat(DR_SUB(1.0f, t.xp.f)), fm = splat(t.xm.f), om = splat(DR_SUB(1.0f, t.xm.f));
-        const F2 p0 = mix2(sel2(cp, c.B0, c.A0), sel2(cp, N0, c.B0), op, fp);          // row y0, pair over z
-        const F2 p1 = mix2(sel2(cp, c.B1, c.A1), sel2(cp, N1, c.B1), op, fp);          // row y1
-        F2 m0 = mix2(sel2(cm, N0, c.A0), sel2(cm, c.A0, c.B0), om, fm);
-        F2 m1 = mix2(sel2(cm, N1, c.A1), sel2(cm, c.A1, c.B1), om, fm);
+        const int bp = t.xp.b, bm = t.xm.b, bc = c.cx.b;
+        const F2 p0 = mix2(sel2_ne(bp, bc, c.B0, c.A0), sel2_ne(bp, bc, N0, c.B0), op, fp);       // row y0, pair over z
+        const F2 p1 = mix2(sel2_ne(bp, bc, c.B1, c.A1), sel2_ne(bp, bc, N1, c.B1), op, fp);       // row y1
+        F2 m0 = mix2(sel2_ne(bm, bc, N0, c.A0), sel2_ne(bm, bc, c.A0, c.B0), om, fm);
+        F2 m1 = mix2(sel2_ne(bm, bc, N1, c.A1), sel2_ne(bm, bc, c.A1, c.B1), om, fm);
         if (TAPS == TAPS_TWO && (cp & cm)) {    // N0, N1 are plane lo+2; the - tap needs plane lo-1
             ad.plane_x(c.cx.b, t.xm.b, c.cx.b, N0, N1);
             m0 = mix2(N0, c.A0, om, fm);
