@@ -80,7 +80,7 @@ template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
 __global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
-           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum)
+           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum, unsigned cbias)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.z;
@@ -96,7 +96,7 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     Ray r;
     setup_ray(d, cam, i, j, jit, r);
     const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
-    const Layout L = make_layout(d);
+    const Layout L = make_layout(d, cbias);
     F4 A; int K; float Tp;
     march_forward<VT, LAYOUT, NONDIFF, TAPS, SR1>(d, vol, L, s_tf, cam, r, A, K, Tp);
     if (d.flags & DR_F_OUT_IMAGE) {
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
-           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale)
+           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale, unsigned cbias)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.z;
@@ -242,7 +242,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;       // this ray's gradient is exactly zero
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
     const VolView<VT> vol { volp + voff };
-    const Layout L = make_layout(d);
+    const Layout L = make_layout(d, cbias);
     CellVolSink vs;
     vs.g = WANT_VOL ? gcell + (d.Bvol == 1 ? 0 : (size_t)b * d.X * d.Y * d.Z * 2) : nullptr;
     vs.cur = -1;
@@ -284,7 +284,7 @@ int launch_fwd(const FwdArgs& a)
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.out, a.K, a.T, vol_stride(d),
-                                         a.target, a.loss_sum);
+                                         a.target, a.loss_sum, cell_bias(*d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
@@ -298,7 +298,7 @@ int launch_bwd(const BwdArgs& a)
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
-                                         a.slots, vol_stride(d), a.mse_scale);
+                                         a.slots, vol_stride(d), a.mse_scale, cell_bias(*d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
 }

@@ -410,14 +410,17 @@ DR_HD void cell_plane_y(const float* rp, const float* rm, int bp, int bm, int bc
     for (int q = 0; q < 4; ++q) n[q] = (bp != bc || bm != bc) ? r[q] : 0.0f;
 #endif
 }
-DR_HD void cell_plane_x(const float* rp, const float* rm, int bp, int bm, int bc, float n[4])
+// the x neighbours are the adjacent records: rc is the CENTRE record and the loads use immediate offsets from it (+ neighbour
+// at +32 bytes: quarters {2,3} {6,7}; - neighbour at -32 bytes: quarters {0,1} {4,5}) -- no address arithmetic at all
+DR_HD void cell_plane_x(const float* rc, int bp, int bm, int bc, float n[4])
 {
 #if defined(__CUDA_ARCH__)
-    asm(DR_PM_PRED4 "@m ld.global.nc.v2.f32 {%0, %1}, [%5];\n\t@m ld.global.nc.v2.f32 {%2, %3}, [%5+16];\n\t"
-        "@p ld.global.nc.v2.f32 {%0, %1}, [%4+8];\n\t@p ld.global.nc.v2.f32 {%2, %3}, [%4+24];\n\t}"
-        : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    asm("{\n\t.reg .pred p, m;\n\tsetp.ne.s32 p, %5, %7;\n\tsetp.ne.s32 m, %6, %7;\n\t"
+        "@m ld.global.nc.v2.f32 {%0, %1}, [%4+-32];\n\t@m ld.global.nc.v2.f32 {%2, %3}, [%4+-16];\n\t"
+        "@p ld.global.nc.v2.f32 {%0, %1}, [%4+40];\n\t@p ld.global.nc.v2.f32 {%2, %3}, [%4+56];\n\t}"
+        : "=f"(n[0]), "=f"(n[1]), "=f"(n[2]), "=f"(n[3]) : "l"(rc), "r"(bp), "r"(bm), "r"(bc));
 #else
-    const float* r = bp != bc ? rp + 2 : rm;
+    const float* r = bp != bc ? rc + 8 + 2 : rc - 8;
     const bool any = bp != bc || bm != bc;
     n[0] = any ? r[0] : 0.0f; n[1] = any ? r[1] : 0.0f; n[2] = any ? r[4] : 0.0f; n[3] = any ? r[5] : 0.0f;
 #endif
@@ -450,17 +453,18 @@ DR_HD void cell_plane_y(const __half* rp, const __half* rm, int bp, int bm, int 
     for (int q = 0; q < 4; ++q) n[q] = (bp != bc || bm != bc) ? __half2float(r[q]) : 0.0f;
 #endif
 }
-DR_HD void cell_plane_x(const __half* rp, const __half* rm, int bp, int bm, int bc, float n[4])
+DR_HD void cell_plane_x(const __half* rc, int bp, int bm, int bc, float n[4])      // records are 16 bytes
 {
 #if defined(__CUDA_ARCH__)
     unsigned lo, hi;
-    asm(DR_PM_PRED2 "@m ld.global.nc.b32 %0, [%3];\n\t@m ld.global.nc.b32 %1, [%3+8];\n\t"
-        "@p ld.global.nc.b32 %0, [%2+4];\n\t@p ld.global.nc.b32 %1, [%2+12];\n\t}"
-        : "=r"(lo), "=r"(hi) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    asm("{\n\t.reg .pred p, m;\n\tsetp.ne.s32 p, %3, %5;\n\tsetp.ne.s32 m, %4, %5;\n\t"
+        "@m ld.global.nc.b32 %0, [%2+-16];\n\t@m ld.global.nc.b32 %1, [%2+-8];\n\t"
+        "@p ld.global.nc.b32 %0, [%2+20];\n\t@p ld.global.nc.b32 %1, [%2+28];\n\t}"
+        : "=r"(lo), "=r"(hi) : "l"(rc), "r"(bp), "r"(bm), "r"(bc));
     const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     n[0] = p0.x; n[1] = p0.y; n[2] = p1.x; n[3] = p1.y;
 #else
-    const __half* r = bp != bc ? rp + 2 : rm;
+    const __half* r = bp != bc ? rc + 8 + 2 : rc - 8;
     const bool any = bp != bc || bm != bc;
     n[0] = any ? __half2float(r[0]) : 0.0f; n[1] = any ? __half2float(r[1]) : 0.0f;
     n[2] = any ? __half2float(r[4]) : 0.0f; n[3] = any ? __half2float(r[5]) : 0.0f;
@@ -735,9 +739,11 @@ template <typename VT, bool DUAL> struct CellAddr {
         // a = 1 quarters {2,3} {6,7} of the + neighbour, a = 0 quarters {0,1} {4,5} of the - neighbour
         float n[4];
         if (DUAL) {
-            const VT *rp, *rm;
-            nbr(1u, bp, bm, bc, rp, rm);
-            cell_plane_x(rp, rm, bp, bm, bc, n);
+#if defined(DR_BOUNDS_CHECK)
+            DR_OOB_IF(bp != bc && (long long)(cell + 1) >= n_cells);
+            DR_OOB_IF(bm != bc && (long long)(cell - 1) >= n_cells);
+#endif
+            cell_plane_x(rec_add(vp, cell), bp, bm, bc, n);
         } else {
             const bool plus = bp != bc, pred = plus | (bm != bc);
             const VT* r = rec(plus ? cell + 1 : cell - 1, pred) + (plus ? 2 : 0);
@@ -779,12 +785,18 @@ template <typename VT, int LAYOUT, bool DUAL> struct AddrOf { typedef LinearAddr
 template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_BRICK8, DUAL> { typedef BrickAddr<VT> type; };
 template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_CELL8, DUAL> { typedef CellAddr<VT, DUAL> type; };
 
-DR_HD Layout make_layout(const DrDesc& d)
+// cell-index bias of locate_centre; computed on the host and passed to the kernels as an argument (a constant-bank operand:
+// left to the device, the compiler re-derived it inside the march loop, 5 issue slots per sample)
+inline unsigned cell_bias(const DrDesc& d)
+{
+    return ((unsigned)kFloorBias * (unsigned)d.Z + (unsigned)kFloorBias) * (unsigned)d.X + (unsigned)kFloorBias;
+}
+DR_HD Layout make_layout(const DrDesc& d, unsigned cbias)
 {
     Layout L;
     L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
     L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
-    L.cbias = ((unsigned)kFloorBias * (unsigned)d.Z + (unsigned)kFloorBias) * (unsigned)d.X + (unsigned)kFloorBias;
+    L.cbias = cbias;
     return L;
 }
 

@@ -56,7 +56,7 @@ size_t sim_bricked_elems(const DrDesc* d) { return (size_t)d->nbx * d->nby * d->
 // linear [Y][Z][X] -> bricked
 void sim_brick(const DrDesc* d, const float* lin, float* bricked)
 {
-    Layout L = make_layout(*d);
+    Layout L = make_layout(*d, cell_bias(*d));
     memset(bricked, 0, sizeof(float) * sim_bricked_elems(d));
     for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
         bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)] = lin[((size_t)y * d->Z + z) * d->X + x];
@@ -84,7 +84,7 @@ void sim_gather(const DrDesc* d, const float* gcell, float* lin)
 void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
                  float* out, int* out_K, float* out_Tprev, int* out_n)
 {
-    Layout L = make_layout(*d);
+    Layout L = make_layout(*d, cell_bias(*d));
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
     TfBin* tab = make_tf_table(*d, tf);
     const TfTable tf4 { tab };
@@ -124,7 +124,7 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
                   const float* grad_out, const float* out, const int* Kin, const float* Tprev,
                   float* gvol_cells, float* gtf)
 {
-    Layout L = make_layout(*d);
+    Layout L = make_layout(*d, cell_bias(*d));
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
     TfBin* tab = make_tf_table(*d, tf);
     const TfTable tf4 { tab };
