@@ -106,10 +106,9 @@ DR_HD float mix_e(float a, float b, float omt, float t) { return DR_FMA(a, omt, 
 struct F2 { float x, y; };
 DR_HD F2 f2(float x, float y) { F2 r = { x, y }; return r; }
 DR_HD F2 splat(float a) { F2 r = { a, a }; return r; }
-DR_HD F2 sel2(bool c, F2 a, F2 b) { F2 r = { c ? a.x : b.x, c ? a.y : b.y }; return r; }
 // (x != y) ? a : b on a register pair: the predicate is formed inside the asm (no boolean materialised) and the pair is
-// selected as one 64-bit selp, which ptxas lowers to two SELs instead of the four predicated MOVs it emits for sel2 when
-// the destination has to be an aligned pair
+// selected as one 64-bit selp, which ptxas lowers to two SELs (two scalar selects written into an aligned pair became
+// four predicated MOVs)
 DR_HD F2 sel2_ne(int x, int y, F2 a, F2 b)
 {
 #if defined(__CUDA_ARCH__)
@@ -143,17 +142,6 @@ DR_HD F2 fma2(F2 a, F2 b, F2 c)
     return r;
 #else
     return f2(DR_FMA(a.x, b.x, c.x), DR_FMA(a.y, b.y, c.y));
-#endif
-}
-DR_HD F2 add2(F2 a, F2 b)
-{
-#if defined(__CUDA_ARCH__)
-    F2 r;
-    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tadd.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-#else
-    return f2(DR_ADD(a.x, b.x), DR_ADD(a.y, b.y));
 #endif
 }
 DR_HD F2 sub2(F2 a, F2 b)

@@ -67,6 +67,8 @@ def test_entry_points_validate_pointers_without_touching_the_gpu(lib):
     assert lib.dr_forward(ctypes.byref(d), None, None, None, None, None, None, None, None) == -1
     assert b"null pointer" in lib.dr_last_error()
     assert lib.dr_brick_volume(ctypes.byref(d), None, None, None) == -1
+    assert lib.dr_expand_cells(ctypes.byref(d), None, None, None) == -1 and b"dr_expand_cells" in lib.dr_last_error()
+    assert lib.dr_expand_cells(ctypes.byref(d), ctypes.c_void_p(0x1000), ctypes.c_void_p(0x1010), None) == -3      # 32-byte alignment
     assert lib.dr_gather_grad(ctypes.byref(d), None, None, 0, None) == -1
     assert lib.dr_grad_cells_elems(ctypes.byref(d)) == 32 ** 3 * 8
     d.flags = _lib.F_NEEDS_TF_GRAD
@@ -75,6 +77,12 @@ def test_entry_points_validate_pointers_without_touching_the_gpu(lib):
     assert rc == -5 and b"workspace" in lib.dr_last_error()
     d.flags = _lib.F_NONDIFF
     assert lib.dr_backward(ctypes.byref(d), fake, fake, fake, None, fake, fake, fake, fake, None, None, None, 0, None) == -1
+    two = _lib.make_desc(32, 32, 32, 16, 16, 16, 64, 1, 1, 1, 0, _lib.F_LAYOUT_BRICK8 | _lib.F_LAYOUT_CELL8, 1.0, 30.0, 0.1)
+    assert lib.dr_forward(ctypes.byref(two), fake, fake, fake, None, fake, None, None, None) == -1
+    assert b"two volume layouts" in lib.dr_last_error()
+    gen = _lib.make_desc(2304, 8, 8, 16, 16, 16, 64, 1, 1, 1, 0, _lib.F_LAYOUT_CELL8, 1.0, 30.0, 0.1)
+    assert lib.dr_forward(ctypes.byref(gen), fake, fake, fake, None, fake, None, None, None) == -1
+    assert b"linear layout" in lib.dr_last_error()                 # the generic tap path exists for the linear layout only
     zero = _lib.DrDesc()
     assert lib.dr_forward(ctypes.byref(zero), fake, fake, fake, None, fake, None, None, None) == -1
     assert b"dr_desc_init" in lib.dr_last_error()
