@@ -55,6 +55,7 @@ def parse():
     p.add_argument("--tf", default=None, help="transfer-function preset (reference utils.get_tf): tf1..tf5, gray, black, rand; "
                                               "default tf1 (C2: its optimisation start `black`)")
     p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8", "cell8"], help="volume layout read by the march kernels")
+    p.add_argument("--no-skip", action="store_true", help="march every sample (no exact empty-space skip grid in the forward)")
     p.add_argument("--cuda-profiler-range", action="store_true",
                    help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     return p.parse_args()
@@ -198,7 +199,7 @@ def run_ours(args, cfg):
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     target = torch.rand((views, 4, h, w), generator=g, device=dev)
 
-    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=args.layout)
+    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=args.layout, skip_empty=not args.no_skip)
     vol_lin = vol.reshape(1, n, n, n)
     tf_r4 = tf.t().contiguous()[None]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
@@ -218,7 +219,7 @@ def run_ours(args, cfg):
         if timed: e[1].record()
         out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")
         if timed: e[2].record()
-        n_k = 2 if bricked.ndim in (2, 3) else 1                                     # (brick_kernel / expand_cells_kernel +) fwd_kernel
+        n_k = (2 if bricked.ndim in (2, 3) else 1) + (0 if args.no_skip else 2)      # (brick_kernel / expand_cells_kernel +) (skip_minmax + skip_classify +) fwd_kernel
         if mode != "nondiff":
             go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
             xf = 0
@@ -292,7 +293,7 @@ def run_ours(args, cfg):
     # ---- end-to-end through the public autograd API, inputs from pinned host memory every step ---------------------
     e2e = None
     if not args.no_e2e:
-        rc = Raycaster((n, n, n), (w, h), R, sampling_rate=sr, jitter=cfg["jitter"], max_samples=M, layout=args.layout)
+        rc = Raycaster((n, n, n), (w, h), R, sampling_rate=sr, jitter=cfg["jitter"], max_samples=M, layout=args.layout, skip_empty=not args.no_skip)
         pin = lambda t: t.detach().cpu().pin_memory()
         h_vol, h_tf, h_cams, h_target = pin(vol), pin(tf), pin(cams), pin(target)
         h_jit = pin(jit) if jit is not None else None
@@ -425,7 +426,9 @@ def run_ours(args, cfg):
                        "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
                        "active_samples_per_step_per_gpu": s, "shaded_fraction_of_active_samples": round(shaded_fraction, 4),
-                       "note": "samples whose TF alpha is exactly 0 are composited exactly without evaluating their normal (DESIGN.md 4)"},
+                       "empty_space_skipping": not args.no_skip,
+                       "note": "samples whose TF alpha is exactly 0 are composited exactly without evaluating their normal, and runs of them inside "
+                               "macro-cells that are transparent under the TF are counted without being marched (exact; DESIGN.md 4)"},
             "fwd": {"value": s / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "unit": "Gsamples/s", "ms": fwd_ms},
             "bwd": {"value": s / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "unit": "Gsamples/s", "ms": bwd_ms},
             "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},

@@ -14,6 +14,7 @@ F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R
 
 EXPORTS = ("dr_version", "dr_debug_oob_count", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_expand_cells", "dr_forward",
            "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad", "dr_forward_mse", "dr_backward_mse",
+           "dr_skip_minmax_bytes", "dr_skip_grid_bytes", "dr_build_skip_grid", "dr_forward_ex",
            "dr_momentum_step", "dr_ingest_u8")
 
 
@@ -56,6 +57,10 @@ def load():
     lib.dr_grad_cells_elems.argtypes = [dp]; lib.dr_grad_cells_elems.restype = ctypes.c_size_t
     lib.dr_gather_grad.argtypes = [dp, vp, vp, ctypes.c_int, vp]; lib.dr_gather_grad.restype = ctypes.c_int
     lib.dr_forward_mse.argtypes = [dp] + [vp] * 10; lib.dr_forward_mse.restype = ctypes.c_int
+    lib.dr_forward_ex.argtypes = [dp] + [vp] * 11; lib.dr_forward_ex.restype = ctypes.c_int
+    lib.dr_skip_minmax_bytes.argtypes = [dp]; lib.dr_skip_minmax_bytes.restype = ctypes.c_size_t
+    lib.dr_skip_grid_bytes.argtypes = [dp]; lib.dr_skip_grid_bytes.restype = ctypes.c_size_t
+    lib.dr_build_skip_grid.argtypes = [dp, vp, vp, vp, ctypes.c_int, vp, vp]; lib.dr_build_skip_grid.restype = ctypes.c_int
     lib.dr_backward_mse.argtypes = [dp] + [vp] * 5 + [ctypes.c_float] + [vp] * 6 + [ctypes.c_size_t, vp]
     lib.dr_backward_mse.restype = ctypes.c_int
     lib.dr_momentum_step.argtypes = [vp, vp, vp, ctypes.c_size_t] + [ctypes.c_float] * 5 + [vp]

@@ -2,13 +2,13 @@
 //
 // Kernels (DESIGN.md has the roofline of each):
 //   brick_kernel     linear [Y][Z][X] volume -> 8x8x8 bricks                 (set_volume, reference :118-119)
-//   fwd_kernel       ray set-up + march + compositing + final image          (:221-372)   dr_kernels.cuh / dr_fwd.cu
+//   fwd_kernel       ray set-up + march + compositing + final image          (:221-372)   dr_kernels.cuh / dr_fwd_f32.cu, dr_fwd_f16.cu
 //   bwd_kernel       tape-free reverse march, TF + volume gradient scatter   (raycast.grad, :460-461)   dr_bwd_f32.cu / dr_bwd_f16.cu
 //   tf_reduce_kernel sums the privatised TF-gradient copies                  (tf_tex.grad.to_torch, :464,475)
 //   gather_grad_kernel cell-major fp32 gradient -> linear, nan_to_num        (volume.grad.to_torch, :463,474)
 //   momentum_step_kernel, ingest_u8_kernel                                   (the caller's steps either side of the march)
 //
-// The march kernels are instantiated in three other translation units so that the library builds in parallel; the
+// The march kernels are instantiated in four other translation units so that the library builds in parallel; the
 // bounds-checking debug build (-DDR_BOUNDS_CHECK -DDR_UNITY_BUILD) compiles everything as one unit instead, because its
 // device-side violation counter is one __device__ variable.
 #include <cuda_fp16.h>
@@ -19,13 +19,15 @@
 #include "diffrender.h"
 #include "dr_desc.h"
 #include "dr_host.h"
+#include "dr_kernels.cuh"
 #include "dr_math.cuh"
 
 #if defined(DR_BOUNDS_CHECK)
 __device__ unsigned long long dr_oob_counter = 0ULL;
 #endif
 #if defined(DR_UNITY_BUILD)
-#include "dr_fwd.cu"
+#include "dr_fwd_f32.cu"
+#include "dr_fwd_f16.cu"
 #include "dr_bwd_f32.cu"
 #include "dr_bwd_f16.cu"
 #endif
@@ -90,6 +92,51 @@ __global__ void __launch_bounds__(256) expand_cells_kernel(DrDesc d, const VT* _
     rec.v[0] = p[0]; rec.v[1] = p[dz]; rec.v[2] = p[dx]; rec.v[3] = p[dx + dz];
     rec.v[4] = p[dy]; rec.v[5] = p[dy + dz]; rec.v[6] = p[dy + dx]; rec.v[7] = p[dy + dx + dz];
     reinterpret_cast<Rec*>(cells)[(size_t)b * n + e] = rec;
+}
+
+// skip grid, step 1: voxel min / max of every macro-cell (8x8x8 cells = the 9x9x9 voxels its cells' corners touch).
+// One warp per macro-cell; depends on the volume only.
+template <typename VT>
+__global__ void __launch_bounds__(256) skip_minmax_kernel(DrDesc d, const VT* __restrict__ lin, float2* __restrict__ mm)
+{
+    const size_t cells = (size_t)d.nbx * d.nby * d.nbz;
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= cells) return;
+    const int lane = threadIdx.x & 31, b = blockIdx.y;
+    const int mx_ = (int)(w % d.nbx), mz_ = (int)((w / d.nbx) % d.nbz), my_ = (int)(w / ((size_t)d.nbx * d.nbz));
+    const VT* v = lin + (size_t)b * d.X * d.Y * d.Z;
+    float mn = 3.4e38f, mx = -3.4e38f;
+    bool bad = false;
+    for (int e = lane; e < 729; e += 32) {
+        const int x = min(mx_ * 8 + e % 9, d.X - 1), z = min(mz_ * 8 + (e / 9) % 9, d.Z - 1), y = min(my_ * 8 + e / 81, d.Y - 1);
+        const float f = (float)v[((size_t)y * d.Z + z) * d.X + x];
+        bad |= (f != f);
+        mn = fminf(mn, f); mx = fmaxf(mx, f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) mm[(size_t)b * cells + w] = bad ? make_float2(1.0f, -1.0f) : make_float2(mn, mx);     // NaN inside: mn > mx = never skip
+}
+
+// skip grid, step 2: classify every macro-cell against the view's transfer function (dr_math.cuh skip_classify)
+__global__ void __launch_bounds__(256) skip_classify_kernel(DrDesc d, const float2* __restrict__ mm, const float* __restrict__ tf,
+                                                            unsigned char* __restrict__ grid, int views)
+{
+    const size_t cells = (size_t)d.nbx * d.nby * d.nbz;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const bool live = e < cells;
+    const float2 r = live ? mm[(size_t)(d.Bvol == 1 ? 0 : b) * cells + e] : make_float2(1.0f, -1.0f);
+    const float* t = tf + (size_t)(d.Btf == 1 ? 0 : b) * d.R * 4;
+    const bool t4r = d.flags & DR_F_TF_4R;
+    const unsigned char c = !live ? 0 : skip_classify(d, r.x, r.y, t4r ? t + 3 * (size_t)d.R : t + 3, t4r ? 1 : 4);
+    if (live) grid[kSkipHeader + (size_t)b * cells + e] = c;
+    const int n = __syncthreads_count(c);                       // header: total number of empty macro-cells
+    if (threadIdx.x == 0 && n) atomicAdd(reinterpret_cast<unsigned*>(grid), (unsigned)n);
 }
 
 // cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 (HBM-bound: reads 32 B per voxel once, L2 serves the 8x reuse)
@@ -184,7 +231,7 @@ __global__ void __launch_bounds__(256) ingest_u8_kernel(DrDesc d, const uint8_t*
 }
 
 int forward_impl(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, float* out_rgba,
-                 int32_t* out_K, float* out_Tprev, const float* target, float* loss_sum, void* stream)
+                 int32_t* out_K, float* out_Tprev, const float* target, float* loss_sum, const unsigned char* skip_grid, void* stream)
 {
     if (int rc = check_desc(d)) return rc;
     if (!vol || !tf || !cam || !out_rgba) return fail(DR_EINVAL, "dr_forward: null pointer");
@@ -192,8 +239,9 @@ int forward_impl(const DrDesc* d, const void* vol, const float* tf, const float*
     if (!aligned(tf, 16) || !aligned(out_rgba, 16)) return fail(DR_EALIGN, "dr_forward: tf and out_rgba must be 16-byte aligned");
     if (target && (!loss_sum || !aligned(target, 16))) return fail(DR_EINVAL, "dr_forward_mse: loss_sum is null or target is not 16-byte aligned");
     if ((size_t)d->R * 32 > kMaxTfSmem) return fail(DR_EINVAL, "tf resolution too large for shared memory staging (R <= 6400)");
-    const FwdArgs a { d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, static_cast<cudaStream_t>(stream), target, loss_sum };
-    return launch_forward(a);
+    if (skip_grid && d->tap_generic) skip_grid = nullptr;          // the generic tap path marches every sample
+    const FwdArgs a { d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, static_cast<cudaStream_t>(stream), target, loss_sum, skip_grid };
+    return d->vox_dtype == DR_VOX_F32 ? launch_forward_f32(a) : launch_forward_f16(a);
 }
 
 int backward_impl(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
@@ -310,14 +358,51 @@ int dr_expand_cells(const DrDesc* d, const void* vol_linear, void* vol_cells, vo
 int dr_forward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                float* out_rgba, int32_t* out_K, float* out_Tprev, void* stream)
 {
-    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, nullptr, nullptr, stream);
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, nullptr, nullptr, nullptr, stream);
 }
 
 int dr_forward_mse(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                    const float* target, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream)
 {
     if (!target || !loss_sum) return fail(DR_EINVAL, "dr_forward_mse: target or loss_sum is null");
-    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, target, loss_sum, stream);
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, target, loss_sum, nullptr, stream);
+}
+
+int dr_forward_ex(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, const float* target,
+                  const uint8_t* skip_grid, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream)
+{
+    if (target && !loss_sum) return fail(DR_EINVAL, "dr_forward_ex: target given but loss_sum is null");
+    return forward_impl(d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, target, target ? loss_sum : nullptr, skip_grid, stream);
+}
+
+size_t dr_skip_minmax_bytes(const DrDesc* d) { return d ? (size_t)d->Bvol * skip_cells(d) * sizeof(float2) : 0; }
+
+size_t dr_skip_grid_bytes(const DrDesc* d) { return d ? kSkipHeader + (size_t)skip_views(d) * skip_cells(d) : 0; }
+
+int dr_build_skip_grid(const DrDesc* d, const void* vol_linear, const float* tf, void* minmax, int minmax_valid, uint8_t* skip_grid,
+                       void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!tf || !minmax || !skip_grid || (!minmax_valid && !vol_linear)) return fail(DR_EINVAL, "dr_build_skip_grid: null pointer");
+    if (!aligned(minmax, 8)) return fail(DR_EALIGN, "dr_build_skip_grid: minmax must be 8-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t cells = skip_cells(d);
+    if (!minmax_valid) {
+        dim3 grid((unsigned)((cells * 32 + 255) / 256), d->Bvol);
+        if (d->vox_dtype == DR_VOX_F32)
+            skip_minmax_kernel<float><<<grid, 256, 0, st>>>(*d, static_cast<const float*>(vol_linear), static_cast<float2*>(minmax));
+        else
+            skip_minmax_kernel<__half><<<grid, 256, 0, st>>>(*d, static_cast<const __half*>(vol_linear), static_cast<float2*>(minmax));
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(e, "skip_minmax_kernel launch");
+    }
+    if (!aligned(skip_grid, 4)) return fail(DR_EALIGN, "dr_build_skip_grid: skip_grid must be 4-byte aligned");
+    cudaError_t em = cudaMemsetAsync(skip_grid, 0, kSkipHeader, st);
+    if (em != cudaSuccess) return fail_cuda(em, "cudaMemsetAsync(skip grid header)");
+    dim3 grid((unsigned)((cells + 255) / 256), skip_views(d));
+    skip_classify_kernel<<<grid, 256, 0, st>>>(*d, static_cast<const float2*>(minmax), tf, skip_grid, skip_views(d));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "skip_classify_kernel launch");
 }
 
 int dr_backward(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,

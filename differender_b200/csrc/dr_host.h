@@ -22,6 +22,7 @@ DR_INTERNAL int fail_cuda(cudaError_t e, const char* where);
 struct FwdArgs {
     const DrDesc* d; const void* vol; const float* tf; const float* cam; const float* jitter;
     float* out; int32_t* K; float* T; cudaStream_t st; const float* target; float* loss_sum;
+    const unsigned char* skip_grid;      // [1 or BS][nbz*nby*nbx] bytes from dr_build_skip_grid, or null
 };
 struct BwdArgs {
     const DrDesc* d; const void* vol; const float* tf; const float* cam; const float* jitter;
@@ -29,7 +30,8 @@ struct BwdArgs {
     cudaStream_t st; float mse_scale;
 };
 
-DR_INTERNAL int launch_forward(const FwdArgs& a);          // dr_fwd.cu
+DR_INTERNAL int launch_forward_f32(const FwdArgs& a);      // dr_fwd_f32.cu
+DR_INTERNAL int launch_forward_f16(const FwdArgs& a);      // dr_fwd_f16.cu
 DR_INTERNAL int launch_backward_f32(const BwdArgs& a);     // dr_bwd_f32.cu
 DR_INTERNAL int launch_backward_f16(const BwdArgs& a);     // dr_bwd_f16.cu
 

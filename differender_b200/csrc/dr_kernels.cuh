@@ -1,5 +1,5 @@
-// dr_kernels.cuh -- the two march kernels (templates) and their launchers.  Included by dr_fwd.cu, dr_bwd_f32.cu and
-// dr_bwd_f16.cu, which instantiate them in separate translation units so the library builds in parallel.
+// dr_kernels.cuh -- the two march kernels (templates) and their launchers.  Included by dr_fwd_f32.cu, dr_fwd_f16.cu,
+// dr_bwd_f32.cu and dr_bwd_f16.cu, which instantiate them in separate translation units so the library builds in parallel.
 //
 //   fwd_kernel       ray set-up + march + compositing + final image          (reference :221-372)
 //   bwd_kernel       tape-free reverse march, TF + volume gradient scatter   (raycast.grad, :460-461)
@@ -37,6 +37,11 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 #ifndef DR_BWD_MIN_BLOCKS_BRICK
 #define DR_BWD_MIN_BLOCKS_BRICK 4
 #endif
+
+// skip grid: one byte per macro-cell; shared by all views when the volume and the TF are, else one grid per view
+constexpr size_t kSkipHeader = 16;      // bytes before the grid: uint32 number of empty macro-cells (+ padding)
+inline size_t skip_cells(const DrDesc* d) { return (size_t)d->nbx * d->nby * d->nbz; }
+inline int skip_views(const DrDesc* d) { return (d->Bvol == 1 && d->Btf == 1) ? 1 : d->BS; }
 
 // ---------------------------------------------------------------------------------------------------------
 // shared prologue: stage the view's transfer function in shared memory as R TfBin entries (32 bytes each: tf[r] and
@@ -76,11 +81,12 @@ __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1, bool SKIP>
 __global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
-           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum, unsigned cbias)
+           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum, unsigned cbias,
+           const unsigned char* __restrict__ skip_grid, size_t skip_stride)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.z;
@@ -98,7 +104,10 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
     const Layout L = make_layout(d, cbias);
     F4 A; int K; float Tp;
-    march_forward<VT, LAYOUT, NONDIFF, TAPS, SR1>(d, vol, L, s_tf, cam, r, A, K, Tp);
+    // skip grid: a 16-byte header (the number of empty macro-cells: nothing to skip -> march as if there were no grid) + the bytes
+    const unsigned char* grid = nullptr;
+    if (SKIP && __ldg(reinterpret_cast<const unsigned*>(skip_grid)) != 0u) grid = skip_grid + kSkipHeader + (size_t)b * skip_stride;
+    march_forward<VT, LAYOUT, NONDIFF, TAPS, SR1, SKIP>(d, vol, L, s_tf, cam, r, A, K, Tp, grid);
     if (d.flags & DR_F_OUT_IMAGE) {
         const size_t plane = (size_t)d.W * d.H;
         const size_t o0 = (size_t)b * 4 * plane + (size_t)(d.H - 1 - j) * d.W + i;
@@ -275,16 +284,16 @@ inline size_t vol_stride(const DrDesc* d)
     return (d->flags & DR_F_LAYOUT_BRICK8) ? (size_t)d->nbx * d->nby * d->nbz * 512 : (size_t)d->X * d->Y * d->Z;
 }
 
-template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
-int launch_fwd(const FwdArgs& a)
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1, bool SKIP>
+int launch_fwd_skip(const FwdArgs& a)
 {
     const DrDesc* d = a.d;
     const size_t smem = (size_t)d->R * sizeof(TfBin);
-    auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, TAPS, SR1>;
+    auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, TAPS, SR1, SKIP>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.out, a.K, a.T, vol_stride(d),
-                                         a.target, a.loss_sum, cell_bias(*d));
+                                         a.target, a.loss_sum, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
@@ -301,6 +310,15 @@ int launch_bwd(const BwdArgs& a)
                                          a.slots, vol_stride(d), a.mse_scale, cell_bias(*d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
+}
+
+// with or without the skip grid (the kernels without it carry none of the skip code); the generic tap path never skips
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
+int launch_fwd(const FwdArgs& a)
+{
+    constexpr bool kCanSkip = TAPS != TAPS_GENERIC;
+    if (kCanSkip && a.skip_grid) return launch_fwd_skip<VT, LAYOUT, NONDIFF, TAPS, SR1, kCanSkip>(a);
+    return launch_fwd_skip<VT, LAYOUT, NONDIFF, TAPS, SR1, false>(a);
 }
 
 // WANT_VOL / WANT_TF / sampling-rate dispatch of one (voxel type, layout, tap mode).  The SR1 = false kernels are correct
@@ -327,5 +345,24 @@ int dispatch_bwd_layout(const BwdArgs& a)
     if (taps == TAPS_GENERIC) return dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_GENERIC>(a);
     return taps == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_LINEAR, TAPS_TWO>(a);
 }
+
+// The SR1 = false kernels are correct for any sampling rate (powf(x, 1) == x); the generic-tap path (volumes > ~2000 voxels
+// per axis, linear layout only) only has those.
+template <typename VT>
+int forward_vt(const FwdArgs& a)
+{
+    const DrDesc* d = a.d;
+    const bool nd = d->flags & DR_F_NONDIFF, sr1 = d->inv_sr == 1.0f;
+    const int taps = tap_mode(*d);
+#define DR_FWD_ND(LAY, TAPS, SR1) (nd ? launch_fwd<VT, LAY, true, TAPS, SR1>(a) : launch_fwd<VT, LAY, false, TAPS, SR1>(a))
+#define DR_FWD_SR(LAY, TAPS) (sr1 ? DR_FWD_ND(LAY, TAPS, true) : DR_FWD_ND(LAY, TAPS, false))
+    if (d->flags & DR_F_LAYOUT_CELL8) return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_CELL8, TAPS_ONE) : DR_FWD_SR(LAYOUT_CELL8, TAPS_TWO);
+    if (d->flags & DR_F_LAYOUT_BRICK8) return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_BRICK8, TAPS_ONE) : DR_FWD_SR(LAYOUT_BRICK8, TAPS_TWO);
+    if (taps == TAPS_GENERIC) return DR_FWD_ND(LAYOUT_LINEAR, TAPS_GENERIC, false);
+    return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_LINEAR, TAPS_ONE) : DR_FWD_SR(LAYOUT_LINEAR, TAPS_TWO);
+#undef DR_FWD_SR
+#undef DR_FWD_ND
+}
+
 
 }  // namespace dr

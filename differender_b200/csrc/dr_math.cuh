@@ -1201,24 +1201,116 @@ DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Exact empty-space skipping (forward).  The skip grid has one byte per MACRO-CELL (8x8x8 cells, the brick counts nbx,
+// nby, nbz of the descriptor): 1 when every cell whose low corner lies in the macro-cell is exactly transparent under the
+// call's transfer function, i.e. every TF bin that a trilinear value of the cell's corners can select has alpha 0 (built
+// by skip_classify below from per-macro-cell voxel min/max with a rounding margin).  A sample in such a cell has TF alpha
+// fma(0, 1-f, 0*f) = 0, hence o = 0 and A_s = A_{s-1} bit for bit: it only counts (K, :303) -- so a run of samples that
+// stays inside one empty macro-cell is replaced by K += m.  m is conservative: the ray's exit from the macro-cell is
+// computed in voxel space against a box shrunk by kSkipMargin voxels (fp32 position error is < 2e-4 voxel at 1024^3) and
+// one more sample is left to the normal path.  Images, K and Tprev are bit-identical with and without the grid.
+// ---------------------------------------------------------------------------------------------------------
+constexpr float kSkipMargin = 0.02f;
+
+DR_HD unsigned char load_u8(const unsigned char* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+DR_HD size_t macro_index(const DrDesc& d, int cx, int cy, int cz)       // cell low corner -> macro-cell, [y][z][x] order
+{
+    return ((size_t)(cy >> 3) * d.nbz + (cz >> 3)) * d.nbx + (cx >> 3);
+}
+
+// number of consecutive samples s, s+1, ... (at least 1: sample s itself is known to be inside) whose cells stay in the
+// macro-cell of sample s's cell (cx, cy, cz); never more than nn - s
+DR_HD int skip_run(const DrDesc& d, const Ray& r, F3 cam, int s, int nn, int cx, int cy, int cz)
+{
+    if (r.n < 2) return 1;
+    // voxel-space position along the ray: p_a(t) = P_a + t * D_a   (locate() without the clamp, which only acts on the faces)
+    const float Px = (0.5f * cam.x + 0.5f) * d.scale[0], Dx = 0.5f * r.dir.x * d.scale[0];
+    const float Py = (0.5f * cam.y + 0.5f) * d.scale[1], Dy = 0.5f * r.dir.y * d.scale[1];
+    const float Pz = (0.5f * cam.z + 0.5f) * d.scale[2], Dz = 0.5f * r.dir.z * d.scale[2];
+    const float bx = (float)(cx & ~7), by = (float)(cy & ~7), bz = (float)(cz & ~7);
+    // exit parameter per axis (the face the ray moves towards, shrunk by the margin); an axis the ray does not move along never exits
+    float tout = 3.0e38f;
+    // (approximate reciprocals: their 1e-7 relative error moves a position by far less than the margin)
+    if (fabsf(Dx) > 1e-20f) tout = fminf(tout, ((Dx > 0.0f ? bx + (8.0f - kSkipMargin) : bx + kSkipMargin) - Px) * fast_rcp(Dx));
+    if (fabsf(Dy) > 1e-20f) tout = fminf(tout, ((Dy > 0.0f ? by + (8.0f - kSkipMargin) : by + kSkipMargin) - Py) * fast_rcp(Dy));
+    if (fabsf(Dz) > 1e-20f) tout = fminf(tout, ((Dz > 0.0f ? bz + (8.0f - kSkipMargin) : bz + kSkipMargin) - Pz) * fast_rcp(Dz));
+    // samples sit at t(s') = t0 + (texit - t0) * s'/(n-1): the last one strictly before tout, minus one for safety
+    const float dt = (r.texit - r.t0) * r.inv_nm1;
+    if (!(dt > 1e-20f)) return 1;
+    const float last = floorf((tout - r.t0) * fast_rcp(dt)) - 1.0f;
+    int m = (last < (float)s) ? 1 : (last > (float)(nn - 1) ? nn - s : (int)last - s + 1);
+    return m < 1 ? 1 : m;
+}
+
+// 1 when every TF bin reachable from voxel values in [mn, mx] has alpha 0 (tf is the staged bin table's source: alpha of bin
+// r is tf_alpha[r * tf_stride]).  The range is widened by the rounding slack of three fp32 mix levels and of the bin scale.
+DR_HD unsigned char skip_classify(const DrDesc& d, float mn, float mx, const float* tf_alpha, int tf_stride)
+{
+    if (!(mn <= mx)) return 0;                                   // NaN anywhere: never skip
+    const float slack = 4e-6f * fmaxf(fabsf(mn), fabsf(mx)) + 1e-30f;
+    const float lo = fmaxf((mn - slack) * d.tf_len, 0.0f), hi = fmaxf((mx + slack) * d.tf_len, 0.0f);
+    if (!(hi < 16777216.0f)) return 0;
+    int b0 = (int)floorf(lo), b1 = (int)floorf(hi) + 1;          // + 1: the lookup also reads bin lo + 1
+    if (b0 > d.R - 1) b0 = d.R - 1;
+    if (b1 > d.R - 1) b1 = d.R - 1;
+    for (int b = b0; b <= b1; ++b)
+        if (tf_alpha[(size_t)b * tf_stride] != 0.0f) return 0;   // (also false for NaN alpha: NaN != 0)
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Per-ray forward march: raycast :261-306 / raycast_nondiff :308-351 + get_final_image(_nondiff) :353-372.
 // State per ray is O(1): A (accumulated premultiplied RGBA), K (active samples), Tprev (transmittance before
 // the last active sample).  Nothing per sample is stored (the reference stores 16*M bytes per ray, :82,102-103).
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1>
+template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1, bool SKIP = false>
 DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const TfTable& tf, F3 cam,
-                         const Ray& r, F4& A, int& K, float& Tprev)
+                         const Ray& r, F4& A, int& K, float& Tprev, const unsigned char* skip_grid = nullptr)
 {
     A.x = A.y = A.z = A.w = 0.0f;                       // H1: tape[-1] = 0
     K = 0;
     int Kshaded = 0;                                    // diagnostic (DR_F_COUNT_SHADED): samples with non-zero opacity
     Tprev = 1.0f;
     const int nn = NONDIFF ? r.n : imin(r.n, d.M);      // :267-269 (s < max_samples only in the diff kernel)
+    // SKIP: whether the sample's cell left the macro-cell of the previous sample costs two LOP3 and a compare on the
+    // biased floor indices (the bias is a multiple of 8); the grid byte is loaded and a run skipped only on such a change
+    int pbx = -1, pby = -1, pbz = -1;                   // biased cell indices of the sample examined last
+    bool in_empty = false;                              // ... and whether its macro-cell is empty
     for (int s = 0; s < nn; ++s) {
         if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
         const F3 pos = sample_pos(r, cam, s);
         Centre c;
-        sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
+        if (SKIP && TAPS != TAPS_GENERIC && skip_grid) {
+            locate_centre(d, L, pos, c);
+            if ((((c.cx.b ^ pbx) | (c.cy.b ^ pby) | (c.cz.b ^ pbz)) & ~7) != 0) {
+                pbx = c.cx.b; pby = c.cy.b; pbz = c.cz.b;
+                const int cx = lo_of(c.cx), cy = lo_of(c.cy), cz = lo_of(c.cz);
+                in_empty = load_u8(skip_grid + macro_index(d, cx, cy, cz)) != 0;
+                if (in_empty) {
+                    // an exactly transparent run: the samples only count (diff march) / are skipped (nondiff, alpha <= 1e-3)
+                    const int m = skip_run(d, r, cam, s, nn, cx, cy, cz);
+                    if (!NONDIFF) { K += m; Tprev = DR_SUB(1.0f, A.w); }
+                    s += m - 1;
+                    continue;
+                }
+            } else if (in_empty) {                      // the conservative run ended a sample or two before the macro-cell does
+                if (!NONDIFF) { ++K; Tprev = DR_SUB(1.0f, A.w); }
+                continue;
+            }
+            typename AddrOf<VT, LAYOUT, false>::type ad;
+            ad.init(d, vol.p, L, c);
+            eval_centre(ad, c);
+        } else {
+            sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
+        }
         TfHit h;
         apply_tf(d, tf, c.I, h);
         if (NONDIFF && !(h.c.w > d.alpha_skip)) continue;      // :334: skipped samples never evaluate the normal

@@ -35,11 +35,14 @@ class VolumeRaycaster:
     """
 
     def __init__(self, volume_resolution, render_resolution, max_samples=512, tf_resolution=128, fov=30.0,
-                 nearfar=(0.1, 100.0), layout="auto"):
+                 nearfar=(0.1, 100.0), layout="auto", skip_empty=True):
         if layout not in ("auto", "linear", "brick8", "cell8"):
             raise ValueError("layout must be 'auto', 'linear' (read the torch tensor in place), 'brick8' (8x8x8-bricked copy) "
                              "or 'cell8' (cell-major copy, 8x the volume's bytes)")
         self.layout = layout
+        self.skip_empty = bool(skip_empty)   # exact empty-space skipping in the forward march (dr_build_skip_grid / dr_forward_ex)
+        self._skip_ring, self._skip_pending, self._skip_use = None, [], True     # asynchronous read-back of the grids' empty counts
+        self._skip_calls, self._skip_minmax = 0, None
         self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
         self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
         self.max_samples = int(max_samples)
@@ -93,6 +96,7 @@ class VolumeRaycaster:
         layout = self.resolve_layout(vol_lin)
         if layout == "linear":
             return vol_lin
+        # (the copies below remember the linear tensor they were made from: the forward builds its skip grid from it)
         vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
         d = self.desc(1, 1, 1, vox, 0, 1.0)
         d.Bvol = vol_lin.shape[0]
@@ -100,16 +104,59 @@ class VolumeRaycaster:
         if layout == "cell8":
             out = torch.empty((vol_lin.shape[0], X * Y * Z, 8), dtype=vol_lin.dtype, device=vol_lin.device)
             _lib.check(lib.dr_expand_cells(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_expand_cells")
+            out.dr_source = vol_lin
             return out
         out = torch.empty((vol_lin.shape[0], lib.dr_bricked_elems(ctypes.byref(d))), dtype=vol_lin.dtype, device=vol_lin.device)
         _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
+        out.dr_source = vol_lin
         return out
 
+    def skip_grid(self, d, bricked, tf_r4):
+        """Macro-cell emptiness bytes for this call (exact empty-space skipping), or None when skipping is off, the volume's
+        linear tensor is not known (a copy not made by brick()) or the generic tap path is in use."""
+        src = bricked if bricked.ndim == 4 else getattr(bricked, "dr_source", None)
+        if not self.skip_empty or src is None or d.tap_generic:
+            return None
+        self._skip_calls += 1
+        if not self._skip_use and self._skip_calls % self.SKIP_RETRY:
+            return None                          # not worth it lately: look again every SKIP_RETRY-th call
+        lib = _lib.load()
+        # the per-macro-cell min / max depends on the volume only: reused while the same tensor has not been written to
+        key = (src.data_ptr(), src._version, tuple(src.shape), src.dtype)
+        mm_valid = self._skip_minmax is not None and self._skip_minmax[0] == key
+        mm = self._skip_minmax[1] if mm_valid else \
+            torch.empty(max(lib.dr_skip_minmax_bytes(ctypes.byref(d)) // 4, 2), dtype=torch.float32, device=src.device)
+        grid = torch.empty(max(lib.dr_skip_grid_bytes(ctypes.byref(d)), 1), dtype=torch.uint8, device=src.device)
+        _lib.check(lib.dr_build_skip_grid(ctypes.byref(d), _lib.ptr(src), _lib.ptr(tf_r4), _lib.ptr(mm), int(mm_valid), _lib.ptr(grid),
+                                          _stream()), "dr_build_skip_grid")
+        self._skip_minmax = (key, mm)
+        # Performance hint only (results are bit-identical either way): with (almost) no empty macro-cells the skip kernels'
+        # bookkeeping costs ~5 % of the forward, so they are not used while the PREVIOUS call's grid -- its count is read back
+        # asynchronously, never waited for -- had fewer than MIN_EMPTY_FRACTION of its macro-cells empty.
+        if self._skip_ring is None:
+            self._skip_ring = torch.zeros(self.SKIP_RING, dtype=torch.int32).pin_memory()
+        while self._skip_pending and self._skip_pending[0][1].query():           # newest completed read-back decides
+            slot, _, total = self._skip_pending.pop(0)
+            self._skip_use = int(self._skip_ring[slot]) >= self.MIN_EMPTY_FRACTION * total
+        if len(self._skip_pending) < self.SKIP_RING:                             # (a full ring just skips this call's read-back)
+            used = {p[0] for p in self._skip_pending}
+            slot = next(i for i in range(self.SKIP_RING) if i not in used)
+            self._skip_ring[slot:slot + 1].copy_(grid[:4].view(torch.int32), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._skip_pending.append((slot, ev, grid.numel() - 16))
+        return grid if self._skip_use else None
+
+    MIN_EMPTY_FRACTION = 0.05
+    SKIP_RING = 8
+    SKIP_RETRY = 16
+
     def march(self, bricked, tf_r4, cam, sampling_rate, jitter=None, nondiff=False, image_layout=True, want_aux=True,
-              extra_flags=0, mse_target=None):
+              extra_flags=0, mse_target=None, skip=None):
         """Forward of cam.shape[0] views.  Returns (out, K, Tprev), or (out, K, Tprev, loss_sum[BS]) when `mse_target`
         (same layout as out) is given: the squared-error sum is accumulated in the kernel's epilogue.
-        `tf_r4` is [Btf, R, 4] (the reference's order); pass extra_flags=F_TF_4R with a [Btf, 4, R] tensor (torch order)."""
+        `tf_r4` is [Btf, R, 4] (the reference's order); pass extra_flags=F_TF_4R with a [Btf, 4, R] tensor (torch order).
+        `skip` = False marches every sample; None / True use the exact empty-space skip grid when `skip_empty` is set."""
         BS = cam.shape[0]
         if extra_flags & F_TF_4R:
             tf_r4 = _Tf4R(tf_r4)
@@ -122,14 +169,13 @@ class VolumeRaycaster:
         out = torch.empty((BS, 4, h, w) if image_layout else (BS, w, h, 4), dtype=torch.float32, device=dev)
         K = torch.empty((BS, h, w), dtype=torch.int32, device=dev) if want_aux else None
         Tp = torch.empty((BS, h, w), dtype=torch.float32, device=dev) if (want_aux and not nondiff) else None
+        grid = self.skip_grid(d, bricked, tf_r4) if skip is None or skip else None
+        loss_sum = torch.zeros((BS,), dtype=torch.float32, device=dev) if mse_target is not None else None
+        _lib.check(_lib.load().dr_forward_ex(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                             _lib.ptr(mse_target), _lib.ptr(grid), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp),
+                                             _lib.ptr(loss_sum), _stream()), "dr_forward_ex")
         if mse_target is not None:
-            loss_sum = torch.zeros((BS,), dtype=torch.float32, device=dev)
-            _lib.check(_lib.load().dr_forward_mse(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
-                                                  _lib.ptr(mse_target), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp), _lib.ptr(loss_sum),
-                                                  _stream()), "dr_forward_mse")
             return out, K, Tp, loss_sum
-        _lib.check(_lib.load().dr_forward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
-                                          _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp), _stream()), "dr_forward")
         return out, K, Tp
 
     def march_backward(self, bricked, tf_r4, cam, sampling_rate, jitter, grad_out, out, K, Tprev, need_vol, need_tf,
@@ -360,7 +406,7 @@ class Raycaster(torch.nn.Module):
     """Same constructor and methods as the reference's `Raycaster` (:478-574)."""
 
     def __init__(self, volume_shape, output_shape, tf_shape, sampling_rate=1.0, jitter=True, max_samples=512, fov=30.0,
-                 near=0.1, far=100.0, ti_kwargs={}, layout="auto"):
+                 near=0.1, far=100.0, ti_kwargs={}, layout="auto", skip_empty=True):
         super().__init__()
         self.volume_shape = (volume_shape[2], volume_shape[0], volume_shape[1])       # torch (D,H,W) -> Taichi (W,D,H) :481
         self.output_shape = output_shape
@@ -370,7 +416,7 @@ class Raycaster(torch.nn.Module):
         self.ti_kwargs = dict(ti_kwargs)      # accepted for signature compatibility; there is no Taichi runtime to configure
         _lib.load()                           # fail loudly at construction if the CUDA library is missing
         self.vr = VolumeRaycaster(self.volume_shape, output_shape, max_samples=max_samples, tf_resolution=tf_shape,
-                                  fov=fov, nearfar=(near, far), layout=layout)
+                                  fov=fov, nearfar=(near, far), layout=layout, skip_empty=skip_empty)
 
     def raycast_nondiff(self, volume, tf, look_from, sampling_rate=None):
         """Non-differentiable render (:490-523): alpha-skip, no shading clamp, output clamped to 1, jitter off,

@@ -176,6 +176,27 @@ int dr_forward_mse(const DrDesc* d, const void* vol, const float* tf, const floa
                    const float* target, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream);
 
 /*
+ * Exact empty-space skipping for the forward march (no counterpart in the reference, which marches every sample of every ray,
+ * :264-306).  dr_build_skip_grid classifies every MACRO-CELL (8x8x8 cells; nbx*nby*nbz of them per volume) as "exactly
+ * transparent under this call's transfer function": every TF bin that a trilinear value of the macro-cell's voxels can select
+ * has alpha 0.  A sample there has opacity exactly 0 and leaves the accumulated colour bit-identical, so dr_forward_ex replaces
+ * runs of such samples by their count: images, out_K and out_Tprev are bit-identical with and without the grid.
+ *   minmax     [Bvol][nbz*nby*nbx] float2 workspace (dr_skip_minmax_bytes): per-macro-cell voxel min / max.  It depends on the
+ *              volume only: pass minmax_valid = 1 to reuse it while only the transfer function changes (vol_linear may be NULL).
+ *   skip_grid  dr_skip_grid_bytes(d) bytes, 4-byte aligned: a 16-byte header (uint32 number of empty macro-cells; 0 makes
+ *              dr_forward_ex march as if no grid were given) followed by [1 or BS][nbz*nby*nbx] bytes, one grid per view unless
+ *              volume and TF are shared.
+ * dr_forward_ex is dr_forward (target == NULL) or dr_forward_mse (target, loss_sum != NULL) with an optional skip_grid
+ * (NULL = march every sample).  The grid must have been built from the same volume, transfer function and descriptor.
+ */
+size_t dr_skip_minmax_bytes(const DrDesc* d);
+size_t dr_skip_grid_bytes(const DrDesc* d);
+int dr_build_skip_grid(const DrDesc* d, const void* vol_linear, const float* tf, void* minmax, int minmax_valid, uint8_t* skip_grid,
+                       void* stream);
+int dr_forward_ex(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, const float* target,
+                  const uint8_t* skip_grid, float* out_rgba, int32_t* out_K, float* out_Tprev, float* loss_sum, void* stream);
+
+/*
  * dr_backward for that loss: dL/d(out) = scale * (out - target) is formed inside the kernel from out_rgba and target,
  * so the gradient image never exists in HBM (replaces output_rgba.grad.from_torch, :436).  For the mean over
  * BS*4*H*W elements pass scale = 2 / (BS*4*H*W) times the upstream gradient of the loss.

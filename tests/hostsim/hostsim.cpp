@@ -73,6 +73,22 @@ void sim_expand(const DrDesc* d, const float* lin, float* cells)
         }
     }
 }
+// skip grid (what dr_build_skip_grid builds): per-macro-cell voxel min / max, then skip_classify; tf is [R][4]
+void sim_skip_grid(const DrDesc* d, const float* lin, const float* tf, unsigned char* grid)
+{
+    for (int my = 0; my < d->nby; ++my) for (int mz = 0; mz < d->nbz; ++mz) for (int mx = 0; mx < d->nbx; ++mx) {
+        float mn = 3.4e38f, mxv = -3.4e38f;
+        bool bad = false;
+        for (int e = 0; e < 729; ++e) {
+            const int x = mx * 8 + e % 9 < d->X ? mx * 8 + e % 9 : d->X - 1, z = mz * 8 + (e / 9) % 9 < d->Z ? mz * 8 + (e / 9) % 9 : d->Z - 1;
+            const int y = my * 8 + e / 81 < d->Y ? my * 8 + e / 81 : d->Y - 1;
+            const float f = lin[((size_t)y * d->Z + z) * d->X + x];
+            bad |= (f != f);
+            mn = f < mn ? f : mn; mxv = f > mxv ? f : mxv;
+        }
+        grid[((size_t)my * d->nbz + mz) * d->nbx + mx] = bad ? 0 : skip_classify(*d, mn, mxv, tf + 3, 4);
+    }
+}
 // cell-major gradient [Y*Z*X][8] -> linear [Y][Z][X]
 void sim_gather(const DrDesc* d, const float* gcell, float* lin)
 {
@@ -82,7 +98,7 @@ void sim_gather(const DrDesc* d, const float* gcell, float* lin)
 
 // one view; vol_data is linear [Y][Z][X] or bricked (DR_F_LAYOUT_BRICK8); tf is [R][4]; jitter/out_K/out_Tprev are [H][W] image orientation; out is [4][H][W]
 void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
-                 float* out, int* out_K, float* out_Tprev, int* out_n)
+                 float* out, int* out_K, float* out_Tprev, int* out_n, const unsigned char* skip_grid)
 {
     Layout L = make_layout(*d, cell_bias(*d));
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
@@ -98,8 +114,8 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
         setup_ray(*d, cam, i, j, jitter ? jitter[pix] : 0.0f, r);
         F4 A; int K; float Tp;
         const bool nd = d->flags & DR_F_NONDIFF;
-#define FWD2(LAY, ND, TAPS) do { if (sr1 && TAPS != TAPS_GENERIC) march_forward<float, LAY, ND, TAPS, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp); \
-                                else march_forward<float, LAY, ND, TAPS, false>(*d, vol, L, tf4, cam, r, A, K, Tp); } while (0)
+#define FWD2(LAY, ND, TAPS) do { if (sr1 && TAPS != TAPS_GENERIC) march_forward<float, LAY, ND, TAPS, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp, skip_grid); \
+                                else march_forward<float, LAY, ND, TAPS, false>(*d, vol, L, tf4, cam, r, A, K, Tp, skip_grid); } while (0)
 #define FWD(LAY, ND) do { if (taps == TAPS_ONE) FWD2(LAY, ND, TAPS_ONE); else FWD2(LAY, ND, TAPS_TWO); } while (0)
         if (d->flags & DR_F_LAYOUT_CELL8) {
             if (nd) FWD(LAYOUT_CELL8, true); else FWD(LAYOUT_CELL8, false);

@@ -71,8 +71,18 @@ def _layout_data(L, d, vol, brick, cell):
     return vol
 
 
+def skip_grid(volume, tf, output_shape, sampling_rate=1.0, max_samples=512):
+    """The macro-cell emptiness bytes dr_build_skip_grid would produce for (volume, tf): array [nby][nbz][nbx] of 0/1."""
+    vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
+    tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
+    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, 0, sampling_rate)
+    g = np.zeros((d.nby, d.nbz, d.nbx), np.uint8)
+    lib().sim_skip_grid(ctypes.byref(d), _p(vol), _p(tf_r4), _p(g, ctypes.c_ubyte))
+    return g
+
+
 def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, jitter=None, nondiff=False, generic=False,
-            brick=False, cell=False):
+            brick=False, cell=False, skip=False):
     vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
     tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
     flags = (F_NONDIFF if nondiff else 0) | (F_JIT if jitter is not None else 0) | (F_GENERIC if generic else 0) | F_IMG | \
@@ -85,8 +95,12 @@ def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, j
     n = np.zeros((h, w), np.int32)
     cam = np.ascontiguousarray(cam, np.float32)
     jit = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
+    grid = None
+    if skip:
+        grid = np.zeros((d.nby, d.nbz, d.nbx), np.uint8)
+        L.sim_skip_grid(ctypes.byref(d), _p(vol), _p(tf_r4), _p(grid, ctypes.c_ubyte))
     L.sim_forward(ctypes.byref(d), _p(br), _p(tf_r4), _p(cam), _p(jit), _p(out), _p(K, ctypes.c_int32), _p(Tp),
-                  _p(n, ctypes.c_int32))
+                  _p(n, ctypes.c_int32), _p(grid, ctypes.c_ubyte))
     return out, K, Tp, n
 
 

@@ -1,0 +1,77 @@
+"""Exact empty-space skipping (dr_build_skip_grid / dr_forward_ex): the forward with the skip grid must reproduce the forward
+without it bit for bit -- image, active-sample counts K and Tprev -- in every layout, dtype and march variant, and the grid the
+device builds must equal the one the host restatement of the same functions builds."""
+import numpy as np
+import pytest
+import torch
+
+import hostsim_lib as hs
+from helpers import case_inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _march(vol, tf, cams, jit, out_shape, layout, skip, dtype=torch.float32, sr=1.0, nondiff=False, M=4096, batched_tf=False):
+    from differender_b200 import VolumeRaycaster
+    D, H, W = vol.shape[-3:]
+    vr = VolumeRaycaster((W, D, H), out_shape, max_samples=M, tf_resolution=tf.shape[-1], layout=layout, skip_empty=skip)
+    bricked = vr.brick(vol.to(DEV, dtype).reshape(1, D, H, W).contiguous())
+    tf_r4 = tf.to(DEV).t().contiguous()[None]
+    if batched_tf:                                           # one TF per view: view 1 gets a shifted copy
+        tf_r4 = torch.cat([tf_r4, torch.roll(tf_r4, 7, dims=1)]).contiguous()
+    return vr.march(bricked, tf_r4, cams.to(DEV).contiguous(), sr, None if jit is None else jit.to(DEV).contiguous(), nondiff=nondiff)
+
+
+@pytest.mark.parametrize("layout", ["linear", "brick8", "cell8"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_skip_is_bit_identical(layout, dtype):
+    vol, tf, cams, jit = case_inputs((72, 64, 80), (96, 64), 128, seed=31, tf_name="tf1", views=2)
+    a = _march(vol, tf, cams, jit, (96, 64), layout, False, dtype)
+    b = _march(vol, tf, cams, jit, (96, 64), layout, True, dtype)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert a[1].sum().item() > 0
+
+
+@pytest.mark.parametrize("kw", [dict(sr=0.7), dict(sr=4.0, nondiff=True), dict(batched_tf=True), dict(tf_name="tf5"), dict(tf_name="gray")])
+def test_skip_variants_are_bit_identical(kw):
+    kw = dict(kw)
+    tf_name = kw.pop("tf_name", "tf1")
+    vol, tf, cams, jit = case_inputs((64, 64, 64), (80, 56), 128, seed=17, tf_name=tf_name, views=2)
+    a = _march(vol, tf, cams, jit, (80, 56), "cell8", False, **kw)
+    b = _march(vol, tf, cams, jit, (80, 56), "cell8", True, **kw)
+    for x, y in zip(a, b):
+        assert (x is None and y is None) or torch.equal(x, y)
+
+
+def test_long_axis_and_gradients_unchanged():
+    # an axis of 1100 voxels (TAPS_TWO) through the autograd API: skipping only touches the forward, gradients must not move
+    from differender_b200 import Raycaster
+    vol, tf, cams, jit = case_inputs((9, 1100, 9), (32, 24), 64, seed=9, tf_name="tf1", views=1)
+    res = []
+    for skip in (False, True):
+        rc = Raycaster((9, 1100, 9), (32, 24), 64, max_samples=4096, skip_empty=skip)
+        v = vol.to(DEV).requires_grad_(True); t = tf.to(DEV).requires_grad_(True)
+        img = rc(v, t, cams[0].to(DEV), jit[0].to(DEV))
+        (img * torch.linspace(0, 1, img.numel(), device=DEV).reshape(img.shape)).sum().backward()
+        res.append((img.detach(), v.grad.clone(), t.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    for x, y in zip(res[0][1:], res[1][1:]):               # float atomics: the summation order differs from run to run
+        assert rel_l2(y.cpu().numpy(), x.cpu().numpy()) <= 1e-5
+
+
+def test_device_grid_equals_host_grid():
+    import ctypes
+    from differender_b200 import VolumeRaycaster, _lib
+    vol, tf, _, _ = case_inputs((40, 56, 72), (8, 8), 64, seed=4, tf_name="tf3", jitter=False)
+    vr = VolumeRaycaster((72, 40, 56), (8, 8), max_samples=64, tf_resolution=64)
+    lin = vol.to(DEV).reshape(1, 40, 56, 72).contiguous()
+    tf_r4 = tf.to(DEV).t().contiguous()[None]
+    d = vr.desc(1, 1, 1, _lib.VOX_F32, 0, 1.0)
+    grid = vr.skip_grid(d, lin, tf_r4)
+    ref = hs.skip_grid(vol.numpy(), tf.numpy(), (8, 8), max_samples=64)
+    g = grid.cpu().numpy()
+    assert g.size == 16 + ref.size and ref.size == 5 * 7 * 9
+    assert np.array_equal(g[16:].reshape(ref.shape), ref) and 0 < ref.mean() < 1
+    assert int(g[:4].view(np.uint32)[0]) == int(ref.sum())          # header: number of empty macro-cells

@@ -74,3 +74,38 @@ def test_device_math_single_gradient_with_transparent_tf(want_vol, want_tf):
         assert rel_l2(gv2, gv) <= 1e-4 and not gt2.any()
     else:
         assert rel_l2(gt2, gt) <= 1e-4 and not gv2.any()
+
+
+@pytest.mark.parametrize("shape,tf_name,sr,nondiff", [((64, 64, 64), "tf1", 1.0, False), ((40, 56, 72), "tf5", 1.0, False),
+                                                     ((64, 64, 64), "tf1", 0.7, False), ((48, 48, 48), "tf1", 4.0, True),
+                                                     ((1100, 9, 9), "tf1", 1.0, False)])
+@pytest.mark.parametrize("layout", ["linear", "cell8"])
+def test_empty_space_skipping_is_exact(shape, tf_name, sr, nondiff, layout):
+    # transparent macro-cells are skipped as whole runs of samples: image, K and Tprev must not change by one bit
+    out_shape = (40, 32)
+    vol, tf, cams, jit = case_inputs(shape, out_shape, 128, seed=21, tf_name=tf_name, jitter=True)
+    J = jit[0].numpy()
+    grid = hs.skip_grid(vol.numpy(), tf.numpy(), out_shape, sampling_rate=sr, max_samples=4096)
+    assert 0.02 < grid.mean() < 1.0                        # the case does have empty macro-cells, and non-empty ones
+    kw = dict(sampling_rate=sr, max_samples=4096, jitter=J, nondiff=nondiff, cell=layout == "cell8")
+    out, K, Tp, n = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, **kw)
+    out2, K2, Tp2, n2 = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, skip=True, **kw)
+    assert np.array_equal(out, out2) and np.array_equal(K, K2) and np.array_equal(Tp, Tp2) and np.array_equal(n, n2)
+    ref, Kr, _ = co.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), out_shape, sampling_rate=sr, max_samples=4096, jitter=J, nondiff=nondiff,
+                            return_counts=True)
+    assert np.array_equal(K2, Kr) and np.array_equal(ref[3], out2[3])
+
+
+def test_skip_grid_never_marks_a_cell_that_can_be_opaque():
+    # brute force: every voxel whose TF bins (its own and the next) have non-zero alpha must lie in a non-empty macro-cell
+    vol, tf, _, _ = case_inputs((40, 56, 72), (8, 8), 64, seed=4, tf_name="tf3", jitter=False)
+    g = hs.skip_grid(vol.numpy(), tf.numpy(), (8, 8))
+    v = vol.numpy().reshape(40, 56, 72)                    # [y][z][x]
+    a = tf.numpy()[3]
+    lo = np.minimum(np.floor(np.maximum(v, 0) * 63).astype(int), 63)
+    opaque = (a[lo] != 0) | (a[np.minimum(lo + 1, 63)] != 0)
+    ys, zs, xs = np.nonzero(opaque)
+    for dy in (0, -1):                                     # a voxel is a corner of cells in its own and the previous macro-cell row
+        for dz in (0, -1):
+            for dx in (0, -1):
+                assert not g[np.maximum(ys + dy, 0) // 8, np.maximum(zs + dz, 0) // 8, np.maximum(xs + dx, 0) // 8].any()
