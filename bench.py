@@ -215,6 +215,8 @@ def run_ours(args, cfg):
         e = [ev() for _ in range(5)] if timed else None
         flush.zero_()                                                                # L2 flush between steps
         if timed: e[0].record()
+        if need_vol:
+            vr.forget_volume()                                                       # a volume-gradient loop changes the volume every step: rebuild the skip grid's min/max too
         bricked = vr.brick(vol_lin)
         if timed: e[1].record()
         out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")

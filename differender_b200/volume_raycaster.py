@@ -111,6 +111,11 @@ class VolumeRaycaster:
         out.dr_source = vol_lin
         return out
 
+    def forget_volume(self):
+        """Drops the cached per-macro-cell min / max (it is keyed on the volume tensor's pointer and version counter, so this is
+        only needed when the memory was changed behind PyTorch's back -- or by a benchmark that wants it rebuilt every step)."""
+        self._skip_minmax = None
+
     def skip_grid(self, d, bricked, tf_r4):
         """Macro-cell emptiness bytes for this call (exact empty-space skipping), or None when skipping is off, the volume's
         linear tensor is not known (a copy not made by brick()) or the generic tap path is in use."""
