@@ -180,14 +180,15 @@ struct CellVolSink {
 // While consecutive samples of the ray hit the same bin, S = sum dc and S1 = sum f*dc stay in registers (8 FP ops per
 // sample); the bin pair receives (S - S1, S1) when the bin changes.
 struct RedTfSink {
-    float4* g;      // [R] of this CTA's slot
+    float4* g;      // [R + 1] of this CTA's slot (bin R is folded into R - 1 by tf_reduce_kernel: no index clamp here)
     int cur, Rm1;
     float4 s, s1;
     __device__ __forceinline__ void flush()
     {
         if (cur >= 0) {
-            atomicAdd(g + cur, make_float4(s.x - s1.x, s.y - s1.y, s.z - s1.z, s.w - s1.w));
-            atomicAdd(g + min(cur + 1, Rm1), s1);
+            float4* p = g + cur;
+            atomicAdd(p, make_float4(s.x - s1.x, s.y - s1.y, s.z - s1.z, s.w - s1.w));
+            atomicAdd(p + 1, s1);
         }
     }
     __device__ __forceinline__ void add(int lo, float f, F4 dc)
@@ -260,7 +261,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
 #endif
     const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
     RedTfSink ts;
-    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
+    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * (d.R + 1) : nullptr;
     ts.cur = -1; ts.Rm1 = d.R - 1;
     march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
 }
