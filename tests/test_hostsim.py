@@ -109,3 +109,17 @@ def test_skip_grid_never_marks_a_cell_that_can_be_opaque():
         for dz in (0, -1):
             for dx in (0, -1):
                 assert not g[np.maximum(ys + dy, 0) // 8, np.maximum(zs + dz, 0) // 8, np.maximum(xs + dx, 0) // 8].any()
+
+
+def test_empty_space_skipping_respects_max_samples_and_views_without_hits():
+    # max_samples cuts the rays inside an empty run; a camera far to the side leaves most rays without samples
+    vol, tf, cams, jit = case_inputs((64, 64, 64), (40, 32), 128, seed=2, tf_name="tf1", jitter=True)
+    J = jit[0].numpy()
+    for M in (1, 7, 33):
+        a = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 32), max_samples=M, jitter=J)
+        b = hs.forward(vol.numpy(), tf.numpy(), cams[0].numpy(), (40, 32), max_samples=M, jitter=J, skip=True)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and a[1].max() == M
+    cam = np.array([9.0, 0.3, 0.2], np.float32)
+    a = hs.forward(vol.numpy(), tf.numpy(), cam, (40, 32), max_samples=2048, jitter=J)
+    b = hs.forward(vol.numpy(), tf.numpy(), cam, (40, 32), max_samples=2048, jitter=J, skip=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
