@@ -164,18 +164,11 @@ __global__ void __launch_bounds__(256) tf_reduce_kernel(DrDesc d, const float* _
     const int e = blockIdx.x * blockDim.x + threadIdx.x;       // r*4 + c
     const int tb = blockIdx.y;
     if (e >= d.R * 4) return;
-    // each copy has R + 1 bins: bin R only ever receives the "lo + 1" half of bin R - 1 (the reference clamps that index,
-    // :216-218) and is folded back into R - 1 here, so that the scatter needs no clamp and no second address
-    const size_t copy = (size_t)(d.R + 1) * 4;
-    const float* p = slots + (size_t)tb * kTfSlots * copy + e;
-    const bool last = (e >> 2) == d.R - 1;
+    const float* p = slots + (size_t)tb * kTfSlots * d.R * 4 + e;
     float acc[4] = { 0.f, 0.f, 0.f, 0.f };
     for (int s = 0; s < kTfSlots; s += 4) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            acc[u] += __ldg(p + (size_t)(s + u) * copy);
-            if (last) acc[u] += __ldg(p + (size_t)(s + u) * copy + 4);
-        }
+        for (int u = 0; u < 4; ++u) acc[u] += __ldg(p + (size_t)(s + u) * d.R * 4);
     }
     float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     if (v != v) v = 0.0f;                                      // torch.nan_to_num (:464, :475)
@@ -328,7 +321,7 @@ size_t dr_bricked_elems(const DrDesc* d) { return d ? (size_t)d->nbx * d->nby * 
 size_t dr_workspace_bytes(const DrDesc* d)
 {
     if (!d || !(d->flags & DR_F_NEEDS_TF_GRAD)) return 0;
-    return (size_t)d->Btf * kTfSlots * (d->R + 1) * sizeof(float4);
+    return (size_t)d->Btf * kTfSlots * d->R * sizeof(float4);
 }
 
 int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, void* stream)

@@ -180,34 +180,41 @@ struct CellVolSink {
 // While consecutive samples of the ray hit the same bin, S = sum dc and S1 = sum f*dc stay in registers (8 FP ops per
 // sample); the bin pair receives (S - S1, S1) when the bin changes.
 struct RedTfSink {
-    float4* g;      // [R + 1] of this CTA's slot (bin R is folded into R - 1 by tf_reduce_kernel: no index clamp here)
+    float4* g;      // [R] of this CTA's slot
     int cur, Rm1;
     float4 s, s1;
+    bool rgb;       // a shaded sample went into the current bin; otherwise the colour sums are exactly zero and stay home
     __device__ __forceinline__ void flush()
     {
         if (cur >= 0) {
             float4* p = g + cur;
-            atomicAdd(p, make_float4(s.x - s1.x, s.y - s1.y, s.z - s1.z, s.w - s1.w));
-            atomicAdd(p + 1, s1);
+            float4* q = g + min(cur + 1, Rm1);           // the reference clamps the upper bin (:216-218)
+            if (rgb) {
+                atomicAdd(p, make_float4(s.x - s1.x, s.y - s1.y, s.z - s1.z, s.w - s1.w));
+                atomicAdd(q, s1);
+            } else {                                     // a run of transparent samples only moves alpha: two scalar REDs
+                atomicAdd(&p->w, s.w - s1.w);
+                atomicAdd(&q->w, s1.w);
+            }
         }
+    }
+    __device__ __forceinline__ void next(int lo)
+    {
+        flush();
+        cur = lo;
+        s.w = 0.f; s1.w = 0.f;
+        if (rgb) { s.x = s.y = s.z = 0.f; s1.x = s1.y = s1.z = 0.f; rgb = false; }
     }
     __device__ __forceinline__ void add(int lo, float f, F4 dc)
     {
-        if (lo != cur) {
-            flush();
-            cur = lo;
-            s = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s;
-        }
+        if (lo != cur) next(lo);
+        rgb = true;
         s.x += dc.x; s.y += dc.y; s.z += dc.z; s.w += dc.w;
         s1.x += f * dc.x; s1.y += f * dc.y; s1.z += f * dc.z; s1.w += f * dc.w;
     }
     __device__ __forceinline__ void add_alpha(int lo, float f, float dcw)       // dc = (0, 0, 0, dcw)
     {
-        if (lo != cur) {
-            flush();
-            cur = lo;
-            s = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s;
-        }
+        if (lo != cur) next(lo);
         s.w += dcw; s1.w += f * dcw;
     }
 };
@@ -261,8 +268,9 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
 #endif
     const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
     RedTfSink ts;
-    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * (d.R + 1) : nullptr;
-    ts.cur = -1; ts.Rm1 = d.R - 1;
+    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
+    ts.cur = -1; ts.Rm1 = d.R - 1; ts.rgb = false;
+    ts.s = make_float4(0.f, 0.f, 0.f, 0.f); ts.s1 = ts.s;
     march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
 }
 
