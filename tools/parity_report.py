@@ -1,5 +1,6 @@
 """Parity report: CUDA path (through the C ABI) vs the strict-fp32 CPU oracle on identical inputs and jitter, at sizes up to
-the full C3 volume.  Prints one row per case: RGBA max-abs error, rays whose n / K differ, relative L2 of both gradients.
+the full C3 volume (layout "auto" = the cell-major copy with the exact empty-space skip grid, i.e. the default product path).
+Prints one row per case: RGBA max-abs error, rays whose n / K differ, relative L2 of both gradients.
 Run on a B200:  python tools/parity_report.py > gpurun_out/parity_report.txt"""
 import os, sys, time
 sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")]
@@ -13,13 +14,14 @@ dev = "cuda:0"
 rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
 print(f"{'case':58s} {'rays':>8s} {'samples':>10s} {'rgba max|d|':>12s} {'alpha max|d|':>12s} {'K!=':>4s} {'gvol relL2':>11s} {'gtf relL2':>10s}")
 CASES = [
-    ("64^3 fp32, 96x64, tf1 R=128, sr 1, jitter", 64, (96, 64), "tf1", 128, 1.0, True, torch.float32, "linear"),
-    ("64^3 fp32, 96x64, rand TF R=33, sr 0.7, jitter", 64, (96, 64), "rand", 33, 0.7, True, torch.float32, "linear"),
-    ("128^3 fp32, 128x128, tf1, sr 2, jitter", 128, (128, 128), "tf1", 128, 2.0, True, torch.float32, "linear"),
+    ("64^3 fp32, 96x64, tf1 R=128, sr 1, jitter, linear", 64, (96, 64), "tf1", 128, 1.0, True, torch.float32, "linear"),
+    ("64^3 fp32, 96x64, rand TF R=33, sr 0.7, jitter", 64, (96, 64), "rand", 33, 0.7, True, torch.float32, "auto"),
+    ("128^3 fp32, 128x128, tf1, sr 2, jitter", 128, (128, 128), "tf1", 128, 2.0, True, torch.float32, "auto"),
+    ("128^3 fp16, 128x128, tf1, sr 1, jitter", 128, (128, 128), "tf1", 128, 1.0, True, torch.float16, "auto"),
     ("128^3 fp16, 128x128, tf1, sr 1, jitter, brick8", 128, (128, 128), "tf1", 128, 1.0, True, torch.float16, "brick8"),
-    ("256^3 fp32 (C3 volume), 256x256, tf1, sr 1, jitter", 256, (256, 256), "tf1", 128, 1.0, True, torch.float32, "linear"),
-    ("256^3 fp32 (C3 volume), 256x256, tf5, sr 1, no jitter", 256, (256, 256), "tf5", 128, 1.0, False, torch.float32, "linear"),
-    ("256^3 fp32, 192x192, 'gray' TF (no transparent bins), sr 1", 256, (192, 192), "gray", 128, 1.0, True, torch.float32, "linear"),
+    ("256^3 fp32 (C3 volume), 256x256, tf1, sr 1, jitter", 256, (256, 256), "tf1", 128, 1.0, True, torch.float32, "auto"),
+    ("256^3 fp32 (C3 volume), 256x256, tf5, sr 1, no jitter", 256, (256, 256), "tf5", 128, 1.0, False, torch.float32, "auto"),
+    ("256^3 fp32, 192x192, 'gray' TF (no transparent bins), sr 1", 256, (192, 192), "gray", 128, 1.0, True, torch.float32, "auto"),
 ]
 for name, n, (w, h), tfn, R, sr, jitter, dt, layout in CASES:
     vol = make_volume(n)
