@@ -4,12 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-One "step" = one pass of the hot path over one batch of views: brick the volume, forward march, backward march
-(TF + volume gradients), gather the cell-major gradient (and, for N > 1, all-reduce [volume grad | TF grad]).  A "sample" is one
-ACTIVE ray-march step; the count is the sum of the forward kernel's per-ray K.
+One "step" = one pass of the hot path over one batch of views: cell-major copy of the volume, skip grid (per-macro-cell
+min/max + TF classification), forward march, backward march (TF + volume gradients), gather of the cell-major gradient (and,
+for N > 1, all-reduce [volume grad | TF grad]).  A "sample" is one ACTIVE ray-march step; the count is the sum
+of the forward kernel's per-ray K -- identical with and without the exact empty-space skipping (--no-skip).
 
 Prints ONE JSON line on rank 0.  `value` = device-resident throughput through the C ABI; `e2e` = the same metric through
-the public `Raycaster` autograd API with inputs coming from pinned host memory every step.
+the public `Raycaster` autograd API with all inputs copied from pinned host memory every step (double-buffered: step i+1's
+copies run on a second stream under step i's compute).
 `--impl reference` times the CPU oracle (oracle/cpu_ref.c, kind "port": the real reference needs Taichi, which is not
 installable here) on the host cores on a bounded sample of the same workload.
 """
