@@ -413,6 +413,29 @@ DR_HD void cell_plane_x(const float* rc, int bp, int bm, int bc, float n[4])
     n[0] = any ? r[0] : 0.0f; n[1] = any ? r[1] : 0.0f; n[2] = any ? r[4] : 0.0f; n[3] = any ? r[5] : 0.0f;
 #endif
 }
+// The corners of an x tap's OWN cell: the centre's (already in a0..b1) unless the tap crossed (bt != bc), in which case the
+// face neighbour's whole record -- which is exactly the tap cell's (A0, B0, A1, B1) in the same slot order -- overwrites them
+// with two predicated 16-byte loads at an immediate offset from the centre record.  No selects at all, and both taps of
+// an axis may cross independently (no TAPS_TWO case).  fp32 records only.
+template <bool PLUS>
+DR_HD void cell_tap_x(const float* rc, int bt, int bc, F2& a0, F2& b0, F2& a1, F2& b1)
+{
+#if defined(__CUDA_ARCH__)
+    if (PLUS)
+        asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %9, %10;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%8+32];\n\t"
+            "@q ld.global.nc.v4.f32 {%4, %5, %6, %7}, [%8+48];\n\t}"
+            : "+f"(a0.x), "+f"(a0.y), "+f"(b0.x), "+f"(b0.y), "+f"(a1.x), "+f"(a1.y), "+f"(b1.x), "+f"(b1.y) : "l"(rc), "r"(bt), "r"(bc));
+    else
+        asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %9, %10;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%8+-32];\n\t"
+            "@q ld.global.nc.v4.f32 {%4, %5, %6, %7}, [%8+-16];\n\t}"
+            : "+f"(a0.x), "+f"(a0.y), "+f"(b0.x), "+f"(b0.y), "+f"(a1.x), "+f"(a1.y), "+f"(b1.x), "+f"(b1.y) : "l"(rc), "r"(bt), "r"(bc));
+#else
+    if (bt != bc) {
+        const float* r = PLUS ? rc + 8 : rc - 8;
+        a0 = f2(r[0], r[1]); b0 = f2(r[2], r[3]); a1 = f2(r[4], r[5]); b1 = f2(r[6], r[7]);
+    }
+#endif
+}
 // n = slots (c), (c+4), (c+2), (c+6) with c = 1 for the + neighbour, 0 for the - neighbour: (x0,y0) (x0,y1) (x1,y0) (x1,y1)
 DR_HD void cell_plane_z(const float* rp, const float* rm, int bp, int bm, int bc, float n[4])
 {
@@ -599,6 +622,7 @@ inline int tap_mode(const DrDesc& d)
 
 // rows of voxels: what the linear and bricked layouts have in common
 template <typename Derived> struct RowFetch {
+    static constexpr bool kRecordTapsX = false;
     DR_HD const Derived& self() const { return *static_cast<const Derived*>(this); }
     DR_HD void centre(F2& A0, F2& B0, F2& A1, F2& B1) const
     {
@@ -689,7 +713,15 @@ template <typename VT> struct BrickAddr : RowFetch<BrickAddr<VT> > {
 // in the ALU-bound backward while at most one tap of an axis crosses (C3: backward +7 %), and costs where loads matter
 // (forward -6 %) or crossings are frequent (C5, TAPS_TWO: backward -15 %), so only the TAPS_ONE backward uses it.
 template <typename VT, bool DUAL> struct CellAddr {
+    static constexpr bool kRecordTapsX = sizeof(VT) == 4;      // x taps read their own cell's record (cell_tap_x)
     const VT* vp; uoff cell, sy, sz;
+    template <bool PLUS> DR_HD void tap_x(int bt, int bc, F2& a0, F2& b0, F2& a1, F2& b1) const
+    {
+#if defined(DR_BOUNDS_CHECK)
+        DR_OOB_IF(bt != bc && (long long)(PLUS ? cell + 1 : cell - 1) >= n_cells);
+#endif
+        cell_tap_x<PLUS>(reinterpret_cast<const float*>(rec_add(vp, cell)), bt, bc, a0, b0, a1, b1);
+    }
 #if defined(DR_BOUNDS_CHECK)
     long long n_cells;
 #endif
@@ -868,7 +900,17 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
         }
         t.g.y = DR_SUB(mix_e(yp.x, yp.y, oz, fz), mix_e(ym.x, ym.y, oz, fz));
     }
-    {   // ---- x taps: everything downstream of the corners changes
+    if constexpr (A::kRecordTapsX) {   // ---- x taps, cell-major fp32 records: each tap mixes the corners of its own cell
+        const F2 fp = splat(t.xp.f), op = splat(DR_SUB(1.0f, t.xp.f)), fm = splat(t.xm.f), om = splat(DR_SUB(1.0f, t.xm.f));
+        F2 a0 = c.A0, b0 = c.B0, a1 = c.A1, b1 = c.B1;
+        ad.template tap_x<false>(t.xm.b, c.cx.b, a0, b0, a1, b1);
+        const F2 m0 = mix2(a0, b0, om, fm), m1 = mix2(a1, b1, om, fm);
+        a0 = c.A0; b0 = c.B0; a1 = c.A1; b1 = c.B1;
+        ad.template tap_x<true>(t.xp.b, c.cx.b, a0, b0, a1, b1);
+        const F2 p0 = mix2(a0, b0, op, fp), p1 = mix2(a1, b1, op, fp);
+        const F2 yp = mix2(p0, p1, oy2, fy2), ym = mix2(m0, m1, oy2, fy2);
+        t.g.x = DR_SUB(mix_e(yp.x, yp.y, oz, fz), mix_e(ym.x, ym.y, oz, fz));
+    } else {   // ---- x taps: everything downstream of the corners changes
         const bool cp = t.xp.b != c.cx.b, cm = t.xm.b != c.cx.b;
         F2 N0, N1;
         ad.plane_x(t.xp.b, t.xm.b, c.cx.b, N0, N1);
