@@ -456,8 +456,8 @@ def run_ours(args, cfg):
             "rooflines_other": {"l2_read_gbs_measured": l2_gbs, "l2_how": "torch.sum over a 48 MiB L2-resident buffer, 20 reps",
                                 "achieved_over_l2": (achieved / l2_gbs) if l2_gbs else None,
                                 "ncu": ncu_note,
-                                "binding": "instruction issue (backward 74 % issue-active, FMA pipe 54 %, ALU 45 %; forward 69 % issue-active and "
-                                           "latency-exposed, L1TEX 39 %); DRAM < 2 % of peak"},
+                                "binding": "instruction issue (backward 75 % issue-active, FMA pipe 56 %, ALU 41 %; forward 69 % issue-active and "
+                                           "latency-exposed, L1TEX 43 %); DRAM < 2 % of peak"},
             "allreduce": None if world == 1 else {
                 "bytes": int((n ** 3 + R * 4) * 4 if need_vol else R * 16), "ms": phase_ms["post"] / args.steps,
                 "busbw_gbs": ((n ** 3 + R * 4) * 4 if need_vol else R * 16) * 2 * (world - 1) / world / (phase_ms["post"] / args.steps * 1e-3) / 1e9,
