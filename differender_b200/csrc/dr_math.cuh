@@ -568,8 +568,9 @@ DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
 // One sample: centre tap + the six normal taps of get_volume_normal (:191-203) with corner reuse.
 // A tap whose cell equals the centre cell is the same trilinear polynomial at a shifted fraction, so only the
 // mixes downstream of the shifted axis are redone (x: 7, y: 3, z: 1) on register-held values.  A tap that
-// crosses a cell face (|dlo| == 1) fetches the 4 corners of the one new voxel plane.  Both give exactly the
-// value a full 8-load trilinear evaluation would give (same operations, same order).
+// crosses a cell face (|dlo| == 1) fetches the 4 corners of the one new voxel plane (cell8 fp32, x axis: the 8
+// corners of the tap's own cell record, one predicated 32-byte fetch -- cell_tap_x).  All give exactly the value
+// a full 8-load trilinear evaluation would give (same operations, same order).
 // The evaluation is split in two phases so that the forward can stop after the centre tap when the sample turns
 // out to be exactly transparent: eval_centre (8 corner loads, 7 mixes) and eval_normals (the six taps).
 // ---------------------------------------------------------------------------------------------------------
