@@ -37,6 +37,9 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 #ifndef DR_BWD_MIN_BLOCKS_BRICK
 #define DR_BWD_MIN_BLOCKS_BRICK 4
 #endif
+#ifndef DR_BWD_MIN_BLOCKS_TWO       // two-neighbour taps (an axis of 1001..2000 voxels) with both gradients: 114 registers, spills at 96 (C5 backward +7.5 % at 4)
+#define DR_BWD_MIN_BLOCKS_TWO 4
+#endif
 
 // skip grid: one byte per macro-cell; shared by all views when the volume and the TF are, else one grid per view
 constexpr size_t kSkipHeader = 16;      // bytes before the grid: uint32 number of empty macro-cells (+ padding)
@@ -220,7 +223,8 @@ struct RedTfSink {
 };
 
 template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1>
-__global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN_BLOCKS_BRICK : DR_BWD_MIN_BLOCKS_LINEAR)
+__global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN_BLOCKS_BRICK
+                                              : (TAPS == TAPS_TWO && WANT_VOL && WANT_TF) ? DR_BWD_MIN_BLOCKS_TWO : DR_BWD_MIN_BLOCKS_LINEAR)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
