@@ -89,3 +89,23 @@ def test_shard_views_partitions_exactly():
             parts = [shard_views(n, r, world) for r in range(world)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_auto_layout_policy():
+    # layout="auto": cell-major copy while it stays below AUTO_CELL_BYTES (8x the volume), the 8^3-bricked copy above,
+    # the linear tensor in place when an axis is long enough for the generic taps (> 2000 voxels)
+    def pick(shape_xyz, dtype, layout="auto", bvol=1):
+        X, Y, Z = shape_xyz
+        vr = VolumeRaycaster(shape_xyz, (64, 64), layout=layout)
+        return vr.resolve_layout(torch.empty(bvol, Y, Z, X, dtype=dtype, device="meta"))
+    assert pick((256, 256, 256), torch.float32) == "cell8"                 # C1-C3: 512 MiB
+    assert pick((512, 512, 512), torch.float32) == "cell8"                 # C4: 4 GiB
+    assert pick((1024, 1024, 1024), torch.float16) == "cell8"              # C5: 16 GiB
+    assert pick((1024, 1024, 1024), torch.float32) == "cell8"              # 32 GiB
+    assert pick((1536, 1536, 1536), torch.float16) == "brick8"             # 54 GiB of cell-major data: over the limit
+    assert pick((512, 512, 512), torch.float32, bvol=16) == "brick8"       # 16 batched volumes: 64 GiB
+    assert pick((2100, 64, 64), torch.float32) == "linear"                 # generic taps: linear layout only
+    for forced in ("linear", "brick8", "cell8"):
+        assert pick((256, 256, 256), torch.float32, layout=forced) == forced
+    with pytest.raises(ValueError):
+        VolumeRaycaster((8, 8, 8), (8, 8), layout="morton")
