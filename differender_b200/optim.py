@@ -26,9 +26,15 @@ class MomentumSGD:
         g = self.param.grad if grad is None else grad
         if g is None:
             raise RuntimeError("no gradient to apply")
+        if not g.is_cuda or g.device != self.param.device or g.numel() != self.param.numel():
+            raise RuntimeError(f"MomentumSGD.step: gradient must be a CUDA tensor on {self.param.device} with {self.param.numel()} "
+                               f"elements (got {tuple(g.shape)} on {g.device}); the kernel reads one gradient element per parameter element")
         g = g.float().contiguous()
         with torch.cuda.device(self.param.device):
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(_lib.load().dr_momentum_step(_lib.ptr(self.param), _lib.ptr(g), _lib.ptr(self.state), self.param.numel(),
                                                     self.lr, self.gamma, self.max_grad, self.lo, self.hi, st), "dr_momentum_step")
+        # the kernel wrote the parameter through its raw pointer: tell PyTorch (autograd's in-place checks, and the caches of
+        # VolumeRaycaster, which are keyed on the version counter) that the tensor changed
+        torch.autograd.graph.increment_version(self.param)
         self.lr *= self.lr_decay

@@ -42,7 +42,7 @@ class VolumeRaycaster:
         self.layout = layout
         self.skip_empty = bool(skip_empty)   # exact empty-space skipping in the forward march (dr_build_skip_grid / dr_forward_ex)
         self._skip_ring, self._skip_pending, self._skip_use = None, [], True     # asynchronous read-back of the grids' empty counts
-        self._skip_calls, self._skip_minmax = 0, None
+        self._skip_calls, self._skip_minmax, self._copy_cache = 0, None, None
         self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
         self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
         self.max_samples = int(max_samples)
@@ -70,32 +70,71 @@ class VolumeRaycaster:
     # cell is one sector and two 16-byte loads instead of eight 4-byte loads spread over ~5 sectors each.  It costs 8x the
     # volume's bytes, so `auto` falls back to the 8x8x8-bricked copy (1x) above AUTO_CELL_BYTES of cell-major data.
     AUTO_CELL_BYTES = 48 << 30
+    AUTO_FREE_FRACTION = 0.8                     # of the memory that is free right now (driver-free + the allocator's idle blocks)
 
-    def resolve_layout(self, vol_lin):
+    @staticmethod
+    def _free_bytes(device):
+        """Bytes a new allocation can get on `device` without an out-of-memory error: what the driver reports free plus
+        the blocks the caching allocator holds but has not handed out."""
+        free, _ = torch.cuda.mem_get_info(device)
+        return free + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+
+    def resolve_layout(self, vol_lin, need_vol_grad=False):
+        """`auto`: the cell-major copy (8x the volume's bytes) when it is at most AUTO_CELL_BYTES AND it fits -- together with
+        the 32-byte-per-voxel cell-major gradient buffer when the volume gradient is wanted -- into AUTO_FREE_FRACTION of
+        the device memory that is free now; otherwise the 8x8x8-bricked copy (1x)."""
         if self.layout != "auto":
             return self.layout
         X, Y, Z = self.volume_resolution
         if max(X, Y, Z) > 2000:
             return "linear"                      # the generic tap path exists for the linear layout only
-        return "cell8" if X * Y * Z * 8 * vol_lin.element_size() * vol_lin.shape[0] <= self.AUTO_CELL_BYTES else "brick8"
+        cached = self._cached_copy(vol_lin)
+        if cached is not None:
+            return "cell8" if cached.ndim == 3 else "brick8"
+        copy = X * Y * Z * 8 * vol_lin.element_size() * vol_lin.shape[0]
+        if copy > self.AUTO_CELL_BYTES:
+            return "brick8"
+        need = copy + (X * Y * Z * 32 * vol_lin.shape[0] if need_vol_grad else 0)
+        if vol_lin.is_cuda and need > self.AUTO_FREE_FRACTION * self._free_bytes(vol_lin.device):
+            return "brick8"
+        return "cell8"
+
+    # -- caches keyed on a source tensor ------------------------------------------------------------------------------
+    # A key is (storage address, data pointer, version counter, shape, dtype).  Every cache entry also HOLDS the source's
+    # storage: while the entry lives the caching allocator cannot hand the same address to another tensor, so a fresh
+    # tensor (version 0) with different contents can never match a stale key.  In-place edits through PyTorch bump the
+    # version counter; kernels of this library that write a tensor behind PyTorch's back bump it themselves
+    # (torch.autograd.graph.increment_version).
+    @staticmethod
+    def _src_key(t):
+        return (t.untyped_storage().data_ptr(), t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+
+    def _cached_copy(self, vol_lin):
+        c = self._copy_cache
+        return c[2] if c is not None and c[0] == self._src_key(vol_lin) else None
 
     def _lflag(self, vol):
         """Layout flag for a tensor returned by brick(): a 2-D tensor is a bricked copy, a 3-D one [Bvol, cells, 8] the
         cell-major copy, a 4-D one the linear volume."""
         return F_LAYOUT_BRICK8 if vol.ndim == 2 else (F_LAYOUT_CELL8 if vol.ndim == 3 else 0)
 
-    def brick(self, vol_lin):
+    def brick(self, vol_lin, need_vol_grad=False):
         """[Bvol, Y, Z, X] contiguous fp32/fp16 CUDA tensor -> what the march kernels read: the tensor itself for the
         'linear' layout (zero copy), a bricked copy [Bvol, elems] for 'brick8', or the cell-major copy [Bvol, X*Y*Z, 8]
-        for 'cell8' (same dtype)."""
+        for 'cell8' (same dtype).  The copy is cached while the same tensor is unchanged (one entry; forget_volume()
+        drops it), so a loop that only changes the transfer function or the cameras re-lays the volume once."""
         X, Y, Z = self.volume_resolution
         if tuple(vol_lin.shape[1:]) != (Y, Z, X):
             raise ValueError(f"volume has spatial shape {tuple(vol_lin.shape[1:])}, raycaster was built for (D,H,W)={(Y, Z, X)}")
         if not vol_lin.is_contiguous():
             raise ValueError("volume must be contiguous")
-        layout = self.resolve_layout(vol_lin)
+        layout = self.resolve_layout(vol_lin, need_vol_grad)
         if layout == "linear":
             return vol_lin
+        cached = self._cached_copy(vol_lin)
+        if cached is not None and self._lflag(cached) == (F_LAYOUT_CELL8 if layout == "cell8" else F_LAYOUT_BRICK8):
+            return cached
+        self._copy_cache = None                  # release the previous copy before allocating the next one
         # (the copies below remember the linear tensor they were made from: the forward builds its skip grid from it)
         vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
         d = self.desc(1, 1, 1, vox, 0, 1.0)
@@ -104,17 +143,19 @@ class VolumeRaycaster:
         if layout == "cell8":
             out = torch.empty((vol_lin.shape[0], X * Y * Z, 8), dtype=vol_lin.dtype, device=vol_lin.device)
             _lib.check(lib.dr_expand_cells(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_expand_cells")
-            out.dr_source = vol_lin
-            return out
-        out = torch.empty((vol_lin.shape[0], lib.dr_bricked_elems(ctypes.byref(d))), dtype=vol_lin.dtype, device=vol_lin.device)
-        _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
+        else:
+            out = torch.empty((vol_lin.shape[0], lib.dr_bricked_elems(ctypes.byref(d))), dtype=vol_lin.dtype, device=vol_lin.device)
+            _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
         out.dr_source = vol_lin
+        self._copy_cache = (self._src_key(vol_lin), vol_lin.untyped_storage(), out)
         return out
 
     def forget_volume(self):
-        """Drops the cached per-macro-cell min / max (it is keyed on the volume tensor's pointer and version counter, so this is
-        only needed when the memory was changed behind PyTorch's back -- or by a benchmark that wants it rebuilt every step)."""
+        """Drops the cached volume copy and per-macro-cell min / max (and the references that keep their source volume alive).
+        The caches are keyed on the volume tensor's storage, pointer and version counter, so this is only needed when the memory
+        was changed behind PyTorch's back, to release the memory -- or by a benchmark that wants them rebuilt every step."""
         self._skip_minmax = None
+        self._copy_cache = None
 
     def skip_grid(self, d, bricked, tf_r4):
         """Macro-cell emptiness bytes for this call (exact empty-space skipping), or None when skipping is off, the volume's
@@ -127,14 +168,15 @@ class VolumeRaycaster:
             return None                          # not worth it lately: look again every SKIP_RETRY-th call
         lib = _lib.load()
         # the per-macro-cell min / max depends on the volume only: reused while the same tensor has not been written to
-        key = (src.data_ptr(), src._version, tuple(src.shape), src.dtype)
+        # (the entry holds the volume's storage, so its address cannot be recycled for another volume while the key lives)
+        key = self._src_key(src)
         mm_valid = self._skip_minmax is not None and self._skip_minmax[0] == key
-        mm = self._skip_minmax[1] if mm_valid else \
+        mm = self._skip_minmax[2] if mm_valid else \
             torch.empty(max(lib.dr_skip_minmax_bytes(ctypes.byref(d)) // 4, 2), dtype=torch.float32, device=src.device)
         grid = torch.empty(max(lib.dr_skip_grid_bytes(ctypes.byref(d)), 1), dtype=torch.uint8, device=src.device)
         _lib.check(lib.dr_build_skip_grid(ctypes.byref(d), _lib.ptr(src), _lib.ptr(tf_r4), _lib.ptr(mm), int(mm_valid), _lib.ptr(grid),
                                           _stream()), "dr_build_skip_grid")
-        self._skip_minmax = (key, mm)
+        self._skip_minmax = (key, src.untyped_storage(), mm)
         # Performance hint only (results are bit-identical either way): with (almost) no empty macro-cells the skip kernels'
         # bookkeeping costs ~5 % of the forward, so they are not used while the PREVIOUS call's grid -- its count is read back
         # asynchronously, never waited for -- had fewer than MIN_EMPTY_FRACTION of its macro-cells empty.
@@ -296,32 +338,34 @@ def _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor):
     return BS, vol_b, vol_lin, tf_r4, cam, jit
 
 
-def _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, image_layout):
+def _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, image_layout, target=None):
     vr.last_K = K
     ctx.vr, ctx.sampling_rate, ctx.image_layout = vr, sampling_rate, image_layout
     ctx.is_batched, ctx.vol_batched, ctx.tf_batched = batched[0], vol_b, tf.ndim == 3
     ctx.vol_shape, ctx.tf_shape = tuple(volume.shape), tuple(tf.shape)
-    # `out` is also the tensor the Function returns: keeping that very object on ctx would close a reference cycle
-    # (out.grad_fn -> ctx -> out) and leave every buffer of the step (the cell-major volume copy, K, Tprev ...) to Python's
-    # cyclic collector -- the caching allocator then cudaMallocs ~1 GiB of fresh blocks per step (measured: 50-300 ms
-    # stalls).  A detached alias shares the storage and has no grad_fn.
-    ctx.tf_r4, ctx.cam, ctx.jit, ctx.out, ctx.K, ctx.Tp = tf_r4, cam, jit, out.detach(), K, Tp
-    if bricked.data_ptr() == volume.data_ptr():
-        ctx.save_for_backward(volume)          # zero-copy layout: let autograd detect in-place edits before backward
-        ctx.bricked = None
-    else:
-        ctx.save_for_backward()
-        ctx.bricked = bricked                  # our own copy (bricked layout, or a cast/contiguous copy)
+    # Everything the backward re-marches with goes through save_for_backward: tf_r4 / cam / jit alias the caller's tensors
+    # when those are already fp32 and contiguous, and the zero-copy layout reads the caller's volume in place -- autograd's
+    # version check then turns an in-place edit between forward and backward (tf.clamp_(), an optimiser step ...) into an
+    # error instead of a backward that silently re-marches with other inputs than the forward's K / Tprev / image
+    # (the reference snapshots its inputs in Taichi fields, :419-421).  `out` is saved the same way: for an output of the
+    # Function save_for_backward keeps no reference cycle (a plain ctx attribute would: out.grad_fn -> ctx -> out left
+    # every buffer of the step to Python's cyclic collector and cost ~1 GiB of fresh cudaMalloc per step).
+    zero_copy = bricked.data_ptr() == volume.data_ptr()
+    ctx.save_for_backward(volume if zero_copy else None, tf_r4, cam, jit, out, K, Tp, target)
+    ctx.bricked = None if zero_copy else bricked       # our own copy (cell-major / bricked layout, or a cast / contiguous copy)
 
 
-def _saved_volume(ctx):
+def _saved(ctx):
+    """(volume as the march kernels read it, tf_r4, cam, jit, out, K, Tp, mse target or None) of the forward."""
+    volume, tf_r4, cam, jit, out, K, Tp, target = ctx.saved_tensors
     if ctx.bricked is not None:
-        return ctx.bricked
-    (volume,) = ctx.saved_tensors
-    v = volume if ctx.vol_batched else volume[None]
-    if ctx.vol_batched and v.shape[0] > 1 and v.stride(0) == 0:
-        v = v[:1]
-    return v.permute(0, 2, 3, 1).contiguous()              # the same zero-copy view the forward read
+        vol = ctx.bricked
+    else:
+        v = volume if ctx.vol_batched else volume[None]
+        if ctx.vol_batched and v.shape[0] > 1 and v.stride(0) == 0:
+            v = v[:1]
+        vol = v.permute(0, 2, 3, 1).contiguous()           # the same zero-copy view the forward read
+    return vol, tf_r4, cam, jit, out, K, Tp, target
 
 
 def _shape_grads(ctx, gvol, gtf, need_vol, need_tf):
@@ -351,7 +395,7 @@ class RaycastFunction(torch.autograd.Function):
         _require_cuda(volume, tf, look_from, jitter_tensor)
         with torch.cuda.device(volume.device):
             BS, vol_b, vol_lin, tf_r4, cam, jit = _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor)
-            bricked = vr.brick(vol_lin)
+            bricked = vr.brick(vol_lin, need_vol_grad=ctx.needs_input_grad[1])
             out, K, Tp = vr.march(bricked, tf_r4, cam, sampling_rate, jit, nondiff=False, image_layout=image_layout)
         _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, image_layout)
         return out if batched[0] else out[0]
@@ -365,8 +409,9 @@ class RaycastFunction(torch.autograd.Function):
         with torch.cuda.device(grad_output.device):
             go = grad_output if ctx.is_batched else grad_output[None]
             go = go.float().contiguous()
-            gvol, gtf = ctx.vr.march_backward(_saved_volume(ctx), ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, go, ctx.out,
-                                              ctx.K, ctx.Tp, need_vol, need_tf, image_layout=ctx.image_layout)
+            vol, tf_r4, cam, jit, out, K, Tp, _ = _saved(ctx)
+            gvol, gtf = ctx.vr.march_backward(vol, tf_r4, cam, ctx.sampling_rate, jit, go, out, K, Tp, need_vol, need_tf,
+                                              image_layout=ctx.image_layout)
         gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
         return None, gv, gt, None, None, None, None, None, None
 
@@ -385,10 +430,9 @@ class RaycastMSEFunction(torch.autograd.Function):
             BS, vol_b, vol_lin, tf_r4, cam, jit = _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor)
             w, h = vr.resolution
             tgt = target.float().reshape(BS, 4, h, w).contiguous()
-            bricked = vr.brick(vol_lin)
+            bricked = vr.brick(vol_lin, need_vol_grad=ctx.needs_input_grad[1])
             out, K, Tp, loss_sum = vr.march(bricked, tf_r4, cam, sampling_rate, jit, image_layout=True, mse_target=tgt)
-        _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, True)
-        ctx.tgt = tgt
+        _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, cam, jit, out, K, Tp, True, target=tgt)
         img = out if batched[0] else out[0]
         ctx.mark_non_differentiable(img)
         return loss_sum.sum() / out.numel(), img
@@ -400,9 +444,10 @@ class RaycastMSEFunction(torch.autograd.Function):
         if not (need_vol or need_tf):
             return (None,) * 9
         with torch.cuda.device(grad_loss.device):
-            scale = 2.0 * float(grad_loss) / ctx.out.numel()       # one scalar read; keeps the kernel argument a plain float
-            gvol, gtf = ctx.vr.march_backward(_saved_volume(ctx), ctx.tf_r4, ctx.cam, ctx.sampling_rate, ctx.jit, ctx.tgt,
-                                              ctx.out, ctx.K, ctx.Tp, need_vol, need_tf, image_layout=True, mse_scale=scale)
+            vol, tf_r4, cam, jit, out, K, Tp, tgt = _saved(ctx)
+            scale = 2.0 * float(grad_loss) / out.numel()           # one scalar read; keeps the kernel argument a plain float
+            gvol, gtf = ctx.vr.march_backward(vol, tf_r4, cam, ctx.sampling_rate, jit, tgt, out, K, Tp, need_vol, need_tf,
+                                              image_layout=True, mse_scale=scale)
         gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
         return None, gv, gt, None, None, None, None, None, None
 

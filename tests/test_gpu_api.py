@@ -112,3 +112,77 @@ def test_shape_errors_raise():
         rc(torch.rand(1, 16, 32, 32, device=DEV), tf.to(DEV), cams[0].to(DEV))
     with pytest.raises(ValueError, match="tf has shape"):
         rc(vol.to(DEV), torch.rand(4, 8, device=DEV), cams[0].to(DEV))
+
+
+def test_skip_caches_do_not_go_stale_when_the_allocator_recycles_an_address():
+    # the per-macro-cell min/max and the cached volume copy are keyed on pointer + version; a fresh tensor
+    # (version 0) at a recycled address must not match.  The caches hold the source's storage, so it cannot be recycled.
+    out_shape = (64, 48)
+    vol, tf, cams, jit = case_inputs((48, 48, 48), out_shape, 128, seed=41, tf_name="tf1", views=1)
+    rc_skip = _rc(vol, out_shape, 128, skip_empty=True)
+    rc_ref = _rc(vol, out_shape, 128, skip_empty=False)
+    t, c, j = tf.to(DEV), cams[0].to(DEV), jit[0].to(DEV)
+    a = vol.to(DEV)
+    ptr_a = a.data_ptr()
+    img_a = rc_skip(a, t, c, j)
+    assert torch.equal(img_a, rc_ref(a, t, c, j))
+    del a
+    b = torch.flip(vol, (1, 2, 3)).contiguous().to(DEV)      # a different volume, same shape/dtype; a fresh tensor has version 0
+    img_b = rc_skip(b, t, c, j)
+    assert torch.equal(img_b, rc_ref(b, t, c, j))
+    assert not torch.equal(img_a, img_b)
+    assert torch.equal(rc_skip.vr.last_K, rc_ref.vr.last_K)
+    # the cached keys kept the first volume's storage alive, so the allocator could not hand its address to `b`
+    assert b.data_ptr() != ptr_a
+
+
+def test_momentum_step_on_the_volume_invalidates_the_caches():
+    # dr_momentum_step writes through a raw pointer; MomentumSGD must bump the version counter
+    from differender_b200 import MomentumSGD
+    out_shape = (64, 48)
+    vol, tf, cams, jit = case_inputs((48, 48, 48), out_shape, 128, seed=42, tf_name="tf1", views=1)
+    rc_skip = _rc(vol, out_shape, 128, skip_empty=True)
+    rc_ref = _rc(vol, out_shape, 128, skip_empty=False)
+    t, c, j = tf.to(DEV), cams[0].to(DEV), jit[0].to(DEV)
+    v = vol.to(DEV).contiguous()
+    assert torch.equal(rc_skip(v, t, c, j), rc_ref(v, t, c, j))
+    ver = v._version
+    opt = MomentumSGD(v, lr=1.0, momentum=0.0, max_grad=1.0, lo=0.0, hi=1.0)
+    opt.step(torch.where(v > 0.3, -0.3, 0.3).to(v))          # moves many voxels across TF bumps
+    assert v._version > ver
+    assert torch.equal(rc_skip(v, t, c, j), rc_ref(v, t, c, j))
+    assert torch.equal(rc_skip.vr.last_K, rc_ref.vr.last_K)
+    with pytest.raises(RuntimeError, match="gradient must be a CUDA tensor"):
+        opt.step(torch.zeros(7, device=DEV))
+    with pytest.raises(RuntimeError, match="gradient must be a CUDA tensor"):
+        opt.step(torch.zeros(v.shape))
+
+
+def test_inplace_edit_between_forward_and_backward_is_detected():
+    # tf / look_from / jitter alias the caller's tensors when already fp32 + contiguous
+    from differender_b200 import RaycastFunction
+    out_shape = (32, 24)
+    vol, tf, cams, jit = case_inputs((32, 32, 32), out_shape, 16, seed=43, views=1)
+    rc = _rc(vol, out_shape, 16)
+    _, _, vol_in, _, lf_in = rc._determine_batch(vol.to(DEV), tf.to(DEV), cams[0].to(DEV))
+    tf_r4 = tf.to(DEV).t().contiguous().requires_grad_(True)                    # [R,4] fp32 contiguous: passed through as is
+    raw = RaycastFunction.apply(rc.vr, vol_in, tf_r4, lf_in, 1.0, (False, 0), True, jit[0].to(DEV))
+    with torch.no_grad():
+        tf_r4.clamp_(0.2, 0.8)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        raw.sum().backward()
+
+
+def test_cell_major_copy_is_cached_per_volume_version():
+    out_shape = (32, 24)
+    vol, tf, cams, jit = case_inputs((32, 32, 32), out_shape, 16, seed=44, views=1)
+    rc = _rc(vol, out_shape, 16, layout="cell8")
+    v = vol.to(DEV)
+    lin = v.reshape(1, 32, 32, 32)
+    a = rc.vr.brick(lin)
+    assert rc.vr.brick(v.reshape(1, 32, 32, 32)) is a        # another view of the same unchanged storage
+    v.mul_(0.5)
+    b = rc.vr.brick(lin)
+    assert b is not a and torch.equal(b[0, :, 0].reshape(32, 32, 32), lin[0])
+    rc.vr.forget_volume()
+    assert rc.vr.brick(lin) is not b
