@@ -25,17 +25,49 @@ class OraDesc(ctypes.Structure):
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile (building the checker is not using it)."""
     outs = [os.path.join(_HERE, "build", n) for n in ("liboracle.so", "liboracle_fp64.so", "liboracle_fast.so")]
-    if force or not all(os.path.exists(o) for o in outs):
-        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []),
-                              stdout=subprocess.DEVNULL)
+    # always through make: it compares the mtimes of cpu_ref.c and the libraries (a no-op when they are current)
+    subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return outs
 
 
-def _lib(fast=False, fp64=False):
-    key = "fp64" if fp64 else ("fast" if fast else "strict")
+# Rounding-envelope variants of the strict fp32 oracle (cpu_ref.c header): name -> -D switches.  Diagnostic only
+# (tools/rounding_envelope.py); no parity test uses them.
+VARIANTS = {
+    "mix_unfused": ["ORA_MIX_UNFUSED"],
+    "mix_fma_b": ["ORA_MIX_FMA_B"],
+    "div_true": ["ORA_DIV_TRUE"],
+    "div_approx": ["ORA_DIV_APPROX"],
+    "pow_fast": ["ORA_POW_FAST"],
+    "tan_f32": ["ORA_TAN_F32"],
+    "pos_unfused": ["ORA_POS_UNFUSED"],
+    "composite_unfused": ["ORA_COMPOSITE_UNFUSED"],
+    "normalize_div": ["ORA_NORMALIZE_DIV"],
+    # no contraction anywhere + true division: what a target without FMA contraction (or fast_math=False) computes
+    "strict_ieee": ["ORA_MIX_UNFUSED", "ORA_POS_UNFUSED", "ORA_COMPOSITE_UNFUSED", "ORA_DIV_TRUE", "ORA_NORMALIZE_DIV"],
+    # every fast-math liberty at once, the other way
+    "all_fast": ["ORA_MIX_FMA_B", "ORA_DIV_APPROX", "ORA_POW_FAST", "ORA_TAN_F32"],
+}
+
+
+def build_variant(name):
+    """Compile one rounding variant of the strict fp32 oracle into oracle/build/variants/ (same flags as liboracle.so)."""
+    out = os.path.join(_HERE, "build", "variants", f"liboracle_{name}.so")
+    src = os.path.join(_HERE, "cpu_ref.c")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
+                               "-O2", "-mfma"] + ["-D" + d for d in VARIANTS[name]] + ["-o", out, src, "-lm"])
+    return out
+
+
+def _lib(fast=False, fp64=False, variant=None):
+    key = ("variant:" + variant) if variant else ("fp64" if fp64 else ("fast" if fast else "strict"))
     if key not in _LIBS:
-        path = os.path.join(_HERE, "build", {"fp64": "liboracle_fp64.so", "fast": "liboracle_fast.so",
-                                             "strict": "liboracle.so"}[key])
+        if variant:
+            path = build_variant(variant)
+        else:
+            path = os.path.join(_HERE, "build", {"fp64": "liboracle_fp64.so", "fast": "liboracle_fast.so",
+                                                 "strict": "liboracle.so"}[key])
         if not os.path.exists(path):
             build()
         lib = ctypes.CDLL(path)
@@ -103,7 +135,7 @@ def _jitter_raw(jitter):
 
 
 def forward(volume, tf, look_from, output_shape, sampling_rate=1.0, max_samples=512, fov=30.0, near=0.1,
-            jitter=None, nondiff=False, fast=False, fp64=False, return_counts=False):
+            jitter=None, nondiff=False, fast=False, fp64=False, return_counts=False, variant=None):
     """One view.  volume (D,H,W) or (1,D,H,W); tf (4,R); look_from (3,).  Returns (4,H,W) float32
     (float64 with fp64=True) [and K (H,W), n (H,W) int32 in image orientation]."""
     vol = _real(volume, fp64).reshape(np.asarray(volume).shape[-3:])
@@ -116,7 +148,7 @@ def forward(volume, tf, look_from, output_shape, sampling_rate=1.0, max_samples=
     out = np.zeros((w, h, 4), vol.dtype)
     K = np.zeros((w, h), np.int32)
     n = np.zeros((w, h), np.int32)
-    _lib(fast, fp64).ora_forward(ctypes.byref(d), _ptr(vol), _ptr(tf_r4), _ptr(cam), _ptr(jr), _ptr(out),
+    _lib(fast, fp64, variant).ora_forward(ctypes.byref(d), _ptr(vol), _ptr(tf_r4), _ptr(cam), _ptr(jr), _ptr(out),
                            _ptr(K, ctypes.c_int32), _ptr(n, ctypes.c_int32))
     img = _raw_to_image(out)
     if return_counts:
@@ -125,7 +157,7 @@ def forward(volume, tf, look_from, output_shape, sampling_rate=1.0, max_samples=
 
 
 def backward(volume, tf, look_from, grad_image, output_shape, sampling_rate=1.0, max_samples=512, fov=30.0,
-             near=0.1, jitter=None, want_vol=True, want_tf=True, fast=False, fp64=False):
+             near=0.1, jitter=None, want_vol=True, want_tf=True, fast=False, fp64=False, variant=None):
     """One view.  grad_image (4,H,W).  Returns (grad_volume (D,H,W) float64 or None, grad_tf (4,R) float64 or None)."""
     vol = _real(volume, fp64).reshape(np.asarray(volume).shape[-3:])
     tfa = _real(tf, fp64)
@@ -137,6 +169,6 @@ def backward(volume, tf, look_from, grad_image, output_shape, sampling_rate=1.0,
     gvol = np.zeros(vol.shape, np.float64)
     gtf = np.zeros(tf_r4.shape, np.float64)
     flags = (1 if want_vol else 0) | (2 if want_tf else 0)
-    _lib(fast, fp64).ora_backward(ctypes.byref(d), _ptr(vol), _ptr(tf_r4), _ptr(cam), _ptr(jr), _ptr(go),
+    _lib(fast, fp64, variant).ora_backward(ctypes.byref(d), _ptr(vol), _ptr(tf_r4), _ptr(cam), _ptr(jr), _ptr(go),
                             _ptr(gvol, ctypes.c_double), _ptr(gtf, ctypes.c_double), flags)
     return (gvol if want_vol else None), (np.ascontiguousarray(gtf.T) if want_tf else None)

@@ -29,6 +29,20 @@
  * (-ffp-contract=off).  With -DORACLE_FP64 the same code runs in double (used to pin the adjoint
  * against torch.autograd in float64).
  *
+ * ROUNDING ENVELOPE.  Each choice above (and a few more that Taichi's fast_math leaves open) has a compile-time
+ * switch that selects another plausible rounding; tools/rounding_envelope.py builds every variant and measures how far
+ * it moves the image and the gradients from the default build (profiles/r02_rounding_envelope.txt):
+ *     -DORA_MIX_UNFUSED        mix := fl(fl(a*(1-t)) + fl(b*t))           (no contraction)
+ *     -DORA_MIX_FMA_B          mix := fma(b, t, fl(a*(1-t)))              (the other contraction)
+ *     -DORA_DIV_TRUE           float(s)/float(n-1) as one IEEE division   (:279-280)
+ *     -DORA_DIV_APPROX         s * r, r = reciprocal off by one ulp on odd n (div.approx-style, <= 2 ulp)
+ *     -DORA_POW_FAST           pow(x, y) := exp2f(y * log2f(x))           (libdevice fast pow, :284-285, :296)
+ *     -DORA_TAN_F32            near_h / near_w folded in fp32 with tanf   (:146-147)
+ *     -DORA_POS_UNFUSED        pos := cam + fl(t*dir), 0.5*p + 0.5 unfused (:163-165, :277)
+ *     -DORA_COMPOSITE_UNFUSED  A_s := fl(fl((1-A.w)*C) + A)               (:300-302)
+ *     -DORA_NORMALIZE_DIV      normalized() := v / |v| per component      (:203, :290)
+ * None of them is used by a parity test: the default build IS the oracle.
+ *
  * Every function cites the reference lines it follows
  * (paths relative to /root/reference/differender/volume_raycaster.py).
  *
@@ -96,6 +110,10 @@ static void fold_constants(const OraDesc *d, OraConst *c)
     c->near_ = (real)(float)d->near_;
     c->near_h = (real)(float)near_h;
     c->near_w = (real)(float)near_w;
+#if defined(ORA_TAN_F32) && !defined(ORACLE_FP64)
+    c->near_h = 2.0f * tanf((float)fov_rad) * (float)d->near_;  /* evaluated in the kernel's fp32 instead of folded in double */
+    c->near_w = c->near_h * (float)aspect;
+#endif
     c->dim[0] = d->X; c->dim[1] = d->Y; c->dim[2] = d->Z;
     for (int a = 0; a < 3; ++a)
         c->scale[a] = (real)(float)((double)c->dim[a] - 1.0 - 1e-4);  /* :165 */
@@ -110,7 +128,35 @@ typedef struct { real x, y, z; } v3;
 typedef struct { real x, y, z, w; } v4;
 
 /* taichi_glsl.mix(x, y, a) = x*(1-a) + y*a, contracted as LLVM does: fma(x, 1-a, y*a) (see header) */
-static inline real mixf(real a, real b, real t) { return R_FMA(a, RC(1.0) - t, b * t); }
+static inline real mixf(real a, real b, real t)
+{
+#if defined(ORA_MIX_UNFUSED)
+    real p = a * (RC(1.0) - t), q = b * t;
+    return p + q;
+#elif defined(ORA_MIX_FMA_B)
+    return R_FMA(b, t, a * (RC(1.0) - t));
+#else
+    return R_FMA(a, RC(1.0) - t, b * t);
+#endif
+}
+/* a*b + c as written at :163-165 (0.5*pos + 0.5), :277 (look_from + t*vd) */
+static inline real muladd_pos(real a, real b, real c)
+{
+#if defined(ORA_POS_UNFUSED)
+    real p = a * b;
+    return p + c;
+#else
+    return R_FMA(a, b, c);
+#endif
+}
+static inline real pow_r(real x, real y)
+{
+#if defined(ORA_POW_FAST) && !defined(ORACLE_FP64)
+    return exp2f(y * log2f(x));
+#else
+    return R_POW(x, y);
+#endif
+}
 static inline real dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline v3 cross3(v3 a, v3 b)
 {
@@ -120,8 +166,13 @@ static inline v3 cross3(v3 a, v3 b)
 /* Taichi Vector.normalized(eps=0): invlen = 1/(norm + eps); v * invlen */
 static inline v3 normalized3(v3 a)
 {
+#if defined(ORA_NORMALIZE_DIV)
+    real len = R_SQRT(dot3(a, a));
+    v3 r = { a.x / len, a.y / len, a.z / len };
+#else
     real inv = RC(1.0) / R_SQRT(dot3(a, a));
     v3 r = { a.x * inv, a.y * inv, a.z * inv };
+#endif
     return r;
 }
 
@@ -175,9 +226,9 @@ typedef struct { int x0, x1, y0, y1, z0, z1; real fx, fy, fz; } Cell;
 /* address part of sample_volume_trilinear  :163-172 */
 static inline void locate(const OraConst *c, v3 pos, Cell *k)
 {
-    real px = R_FMIN(RC(1.0), R_FMAX(RC(0.0), R_FMA(RC(0.5), pos.x, RC(0.5)))) * c->scale[0];
-    real py = R_FMIN(RC(1.0), R_FMAX(RC(0.0), R_FMA(RC(0.5), pos.y, RC(0.5)))) * c->scale[1];
-    real pz = R_FMIN(RC(1.0), R_FMAX(RC(0.0), R_FMA(RC(0.5), pos.z, RC(0.5)))) * c->scale[2];
+    real px = R_FMIN(RC(1.0), R_FMAX(RC(0.0), muladd_pos(RC(0.5), pos.x, RC(0.5)))) * c->scale[0];
+    real py = R_FMIN(RC(1.0), R_FMAX(RC(0.0), muladd_pos(RC(0.5), pos.y, RC(0.5)))) * c->scale[1];
+    real pz = R_FMIN(RC(1.0), R_FMAX(RC(0.0), muladd_pos(RC(0.5), pos.z, RC(0.5)))) * c->scale[2];
     low_high_frac(px, &k->x0, &k->x1, &k->fx);
     low_high_frac(py, &k->y0, &k->y1, &k->fy);
     low_high_frac(pz, &k->z0, &k->z1, &k->fz);
@@ -280,9 +331,19 @@ static inline v3 sample_pos(const Ray *r, int s)
     real ray_len = r->exit_ - r->entry;                              /* :272 */
     real t0 = r->entry + RC(0.5) * ray_len / (real)r->n;               /* :273-275 */
     real t;
-    if (r->n > 1) t = mixf(t0, r->exit_, (real)s * (RC(1.0) / (real)(r->n - 1)));   /* :277-280, see header */
-    else t = t0;
-    v3 p = { R_FMA(t, r->dir.x, r->cam.x), R_FMA(t, r->dir.y, r->cam.y), R_FMA(t, r->dir.z, r->cam.z) };
+    if (r->n > 1) {
+#if defined(ORA_DIV_TRUE)
+        real q = (real)s / (real)(r->n - 1);
+#elif defined(ORA_DIV_APPROX) && !defined(ORACLE_FP64)
+        float rcp = 1.0f / (float)(r->n - 1);
+        if (r->n & 1) rcp = nextafterf(rcp, 2.0f);                     /* an approximate reciprocal: off by one ulp on odd n */
+        real q = (real)s * rcp;
+#else
+        real q = (real)s * (RC(1.0) / (real)(r->n - 1));
+#endif
+        t = mixf(t0, r->exit_, q);                                    /* :277-280, see header */
+    } else t = t0;
+    v3 p = { muladd_pos(t, r->dir.x, r->cam.x), muladd_pos(t, r->dir.y, r->cam.y), muladd_pos(t, r->dir.z, r->cam.z) };
     return p;
 }
 
@@ -293,7 +354,7 @@ static inline void shade_sample(const OraDesc *d, const OraConst *c, const real 
     q->pos = sample_pos(r, s);
     q->I = trilinear(c, vol, q->pos, &q->cc);                          /* :282 */
     q->c = apply_tf(c, tf, d->R, q->I, &q->lo, &q->hi, &q->f, &q->x); /* :283 */
-    q->o = RC(1.0) - R_POW(RC(1.0) - q->c.w, c->inv_sr);                      /* :284-285 */
+    q->o = RC(1.0) - pow_r(RC(1.0) - q->c.w, c->inv_sr);                      /* :284-285 */
     if (!want_normal) return;
     /* get_volume_normal  :191-203 */
     const real delta = RC(1e-3);
@@ -317,7 +378,7 @@ static inline void shade_sample(const OraDesc *d, const OraConst *c, const real 
     v3 mv = { -r->dir.x, -r->dir.y, -r->dir.z };
     q->rv = dot3(rr, mv);
     q->rdv = R_FMAX(q->rv, RC(0.0));                                       /* :295 */
-    q->pw = R_POW(q->rdv, RC(32.0));                                       /* :296 */
+    q->pw = pow_r(q->rdv, RC(32.0));                                       /* :296 */
     q->kraw = RC(0.8) * q->ndl + RC(0.3) * q->pw + RC(0.4);                     /* diffuse + specular + ambient */
     q->k = d->nondiff ? q->kraw : R_FMIN(RC(1.0), q->kraw);                /* :298 vs :345 */
     q->C.x = q->k * q->c.x * q->o * RC(1.0);                              /* :297-299 */
@@ -329,7 +390,12 @@ static inline void shade_sample(const OraDesc *d, const OraConst *c, const real 
 static inline v4 composite(v4 A, v4 C)
 {
     real T = RC(1.0) - A.w;                                              /* :300-302 */
+#if defined(ORA_COMPOSITE_UNFUSED)
+    real px = T * C.x, py = T * C.y, pz = T * C.z, pw = T * C.w;
+    v4 r = { px + A.x, py + A.y, pz + A.z, pw + A.w };
+#else
     v4 r = { R_FMA(T, C.x, A.x), R_FMA(T, C.y, A.y), R_FMA(T, C.z, A.z), R_FMA(T, C.w, A.w) };
+#endif
     return r;
 }
 

@@ -169,7 +169,7 @@ def test_inplace_edit_between_forward_and_backward_is_detected():
     raw = RaycastFunction.apply(rc.vr, vol_in, tf_r4, lf_in, 1.0, (False, 0), True, jit[0].to(DEV))
     with torch.no_grad():
         tf_r4.clamp_(0.2, 0.8)
-    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+    with pytest.raises(RuntimeError, match="inplace"):       # autograd's saved-tensor version check (either of its messages)
         raw.sum().backward()
 
 

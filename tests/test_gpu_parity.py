@@ -9,15 +9,21 @@ from helpers import GRAD_TOL, RGBA_TOL, case_inputs, oracle_backward_views, orac
 pytestmark = pytest.mark.gpu
 
 
-def _vr(vol, out_shape, R, M, layout="linear"):
+# The product default is layout="auto" (the cell-major copy, `cell8`, at these sizes) with the exact empty-space skip grid; the
+# zero-copy `linear` layout is the variant.  Every oracle comparison below runs on the default unless it names a layout.
+DEFAULT_LAYOUT = "auto"
+
+
+def _vr(vol, out_shape, R, M, layout=DEFAULT_LAYOUT):
     from differender_b200 import VolumeRaycaster
     D, H, W = vol.shape[-3:]
     return VolumeRaycaster((W, D, H), out_shape, max_samples=M, tf_resolution=R, layout=layout)
 
 
 def _cuda_forward(vol, tf, cams, out_shape, jit, M=2048, sr=1.0, nondiff=False, dtype=torch.float32, image_layout=True,
-                  layout="linear"):
+                  layout=DEFAULT_LAYOUT):
     vr = _vr(vol, out_shape, tf.shape[-1], M, layout)
+    assert vr.skip_empty
     dev = "cuda:0"
     bricked = vr.brick(vol.to(dev, dtype).reshape(1, *vol.shape[-3:]).contiguous())
     tf_r4 = tf.to(dev).t().contiguous()[None]
@@ -40,25 +46,62 @@ CASES = [
 ]
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle_case(case, dtype=torch.float32, tf_name="rand"):
+    """Oracle image, counts and gradients of one CASES row (computed once, shared by the layout / dtype variants)."""
+    key = (case, dtype, tf_name)
+    if key not in _ORACLE_CACHE:
+        shape, out_shape, R, views, jitter, sr, M = case
+        vol, tf, cams, jit = case_inputs(shape, out_shape, R, seed=len(shape) + R, tf_name=tf_name, views=views, jitter=jitter)
+        if dtype == torch.float16:
+            vol = vol.half().float()                          # the oracle marches the fp16-rounded values in fp32
+        ref, Kr, nr = oracle_forward_views(vol, tf, cams, out_shape, jit, sampling_rate=sr, max_samples=M)
+        go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(7))
+        gv_ref, gt_ref = oracle_backward_views(vol, tf, cams, go.numpy(), out_shape, jit, sampling_rate=sr, max_samples=M)
+        _ORACLE_CACHE[key] = (vol, tf, cams, jit, ref, Kr, go, gv_ref, gt_ref)
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("layout", ["auto", "linear"])
 @pytest.mark.parametrize("case", CASES)
-def test_forward_backward_match_oracle(case):
+def test_forward_backward_match_oracle(case, layout):
     shape, out_shape, R, views, jitter, sr, M = case
-    vol, tf, cams, jit = case_inputs(shape, out_shape, R, seed=len(shape) + R, views=views, jitter=jitter)
-    ref, Kr, nr = oracle_forward_views(vol, tf, cams, out_shape, jit, sampling_rate=sr, max_samples=M)
-    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, out_shape, jit, M=M, sr=sr)
+    vol, tf, cams, jit, ref, Kr, go, gv_ref, gt_ref = _oracle_case(case)
+    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, out_shape, jit, M=M, sr=sr, layout=layout)
+    assert bricked.ndim == (4 if layout == "linear" else 3)               # auto = the cell-major copy at these sizes
     got = out.cpu().numpy()
     same = K.cpu().numpy() == Kr
     # H6: rays whose discrete sample count differs are reported and excluded; they must be (almost) absent
     assert (~same).mean() <= 1e-4, f"{(~same).sum()} rays differ in active sample count"
     diff = np.abs(got - ref)
     assert np.moveaxis(diff, 1, 0)[:, same].max() <= RGBA_TOL          # diff is (views,4,H,W), same is (views,H,W)
-    g = torch.Generator().manual_seed(7)
-    go = torch.randn(ref.shape, generator=g)
-    gv_ref, gt_ref = oracle_backward_views(vol, tf, cams, go.numpy(), out_shape, jit, sampling_rate=sr, max_samples=M)
     gvol, gtf = vr.march_backward(bricked, tf_r4, cams.cuda().contiguous(), sr, None if jit is None else jit.cuda().contiguous(),
                                   go.cuda().contiguous(), out, K, Tp, True, True)
     assert rel_l2(gvol[0].cpu().numpy(), gv_ref) <= GRAD_TOL
     assert rel_l2(gtf[0].cpu().numpy().T, gt_ref) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if max(c[0]) > 1000])
+@pytest.mark.parametrize("tf_name", ["rand", "tf1"])
+def test_fp16_cell8_two_neighbour_taps_match_oracle(case, tf_name):
+    # the kernel variant behind the C5 numbers: bwd_kernel<__half, cell8, TAPS_TWO, vol, tf, SR1> and the fp16 SKIP forward,
+    # against the oracle (not only against the linear layout), both gradients; tf1 has exactly-transparent bins (skip grid, transparent-sample paths)
+    shape, out_shape, R, views, jitter, sr, M = case
+    vol, tf, cams, jit, ref, Kr, go, gv_ref, gt_ref = _oracle_case(case, torch.float16, tf_name)
+    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, out_shape, jit, M=M, sr=sr, dtype=torch.float16, layout="cell8")
+    assert bricked.dtype == torch.float16 and bricked.ndim == 3
+    same = K.cpu().numpy() == Kr
+    assert (~same).mean() <= 1e-4
+    assert np.moveaxis(np.abs(out.cpu().numpy() - ref), 1, 0)[:, same].max() <= RGBA_TOL
+    gvol, gtf = vr.march_backward(bricked, tf_r4, cams.cuda().contiguous(), sr, jit.cuda().contiguous(), go.cuda().contiguous(),
+                                  out, K, Tp, True, True)
+    assert rel_l2(gvol[0].cpu().numpy(), gv_ref) <= GRAD_TOL
+    assert rel_l2(gtf[0].cpu().numpy().T, gt_ref) <= GRAD_TOL
+    # and bit-identical forward without the skip grid
+    out2, K2, Tp2 = vr.march(bricked, tf_r4, cams.cuda().contiguous(), sr, jit.cuda().contiguous(), skip=False)
+    assert torch.equal(out, out2) and torch.equal(K, K2) and torch.equal(Tp, Tp2)
 
 
 def test_tf_only_and_volume_only_backward():
@@ -104,7 +147,7 @@ def test_fp16_volume_matches_oracle_on_rounded_values():
 def test_generic_tap_path_equals_corner_reuse_path():
     from differender_b200 import _lib
     vol, tf, cams, jit = case_inputs((40, 40, 40), (48, 48), 64, seed=11, views=1)
-    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (48, 48), jit)
+    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (48, 48), jit, layout="linear")    # the generic path reads the linear tensor
     orig = vr.desc
 
     def desc_generic(*a, **k):
@@ -127,7 +170,7 @@ def test_generic_tap_path_equals_corner_reuse_path():
 @pytest.mark.parametrize("layout,dtype", [("brick8", torch.float32), ("cell8", torch.float32), ("cell8", torch.float16), ("brick8", torch.float16)])
 def test_copied_layouts_are_bit_identical_to_linear_layout(layout, dtype):
     vol, tf, cams, jit = case_inputs((37, 29, 45), (56, 40), 64, seed=13, views=2)
-    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (56, 40), jit, dtype=dtype)
+    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (56, 40), jit, dtype=dtype, layout="linear")
     vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (56, 40), jit, layout=layout, dtype=dtype)
     # zero-copy view vs bricked / cell-major copy
     assert vlin.shape == (1, 37, 29, 45) and bricked.dtype == dtype
@@ -145,10 +188,11 @@ def test_copied_layouts_are_bit_identical_to_linear_layout(layout, dtype):
 
 @pytest.mark.parametrize("shape", [(1100, 6, 6), (6, 1100, 6), (6, 6, 1100)])
 @pytest.mark.parametrize("layout", ["brick8", "cell8"])
-def test_copied_layouts_with_both_taps_crossing(shape, layout):
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_copied_layouts_with_both_taps_crossing(shape, layout, dtype):
     vol, tf, cams, jit = case_inputs(shape, (24, 20), 32, seed=5, views=1)
-    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096)
-    vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096, layout=layout)
+    vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096, dtype=dtype, layout="linear")
+    vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096, layout=layout, dtype=dtype)
     assert torch.equal(out, out_b) and torch.equal(K, K_b) and torch.equal(Tp, Tp_b)
     go = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).cuda()
     c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
