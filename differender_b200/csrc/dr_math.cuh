@@ -555,11 +555,11 @@ DR_HD void setup_ray(const DrDesc& d, F3 cam, int i, int j, float jit, Ray& r)
 
 // sample position :277-280.  float(s)/float(n-1) is evaluated as s * fl(1/(n-1)) (reciprocal-multiply, what a
 // fast-math compiler emits for the reference's division; the oracle defines it the same way).  H3: n == 1 -> t = t0.
-DR_HD F3 sample_pos(const Ray& r, F3 cam, int s)
+DR_HD F3 sample_pos(const Ray& r, F3 cam, int s, float& t)
 {
     // n <= 1: inv_nm1 = 0, so q = 0 and mix_e(t0, texit, 1, 0) = fma(t0, 1, texit*0) = t0 exactly (no branch)
     const float q = DR_MUL((float)s, r.inv_nm1);
-    const float t = mix_e(r.t0, r.texit, DR_SUB(1.0f, q), q);
+    t = mix_e(r.t0, r.texit, DR_SUB(1.0f, q), q);
     F3 p = { DR_FMA(t, r.dir.x, cam.x), DR_FMA(t, r.dir.y, cam.y), DR_FMA(t, r.dir.z, cam.z) };
     return p;
 }
@@ -1054,31 +1054,41 @@ DR_HD float opacity(const DrDesc& d, float alpha)
 // Phong factor :287-298.  Not on the exact path (only rgb depends on it).
 // ---------------------------------------------------------------------------------------------------------
 struct Shade {
-    F3 N, l;
     float inv_g;       // 1/|g| (0 when flat)
-    float nl, rv, p32, kraw, k;       // p32 = max(rv,0)^32
+    float inv_l;       // 1/|pos - light|
+    float nl, rv, p32, kraw, k;       // N.l, r.(-dir), max(rv,0)^32, un-clamped and clamped Phong factor
 };
 
-DR_HD void shade(const DrDesc& d, F3 cam, F3 dir, F3 pos, F3 g, bool clamp_k, Shade& s)
+// Only scalars are formed: with L = pos - (cam + (0,1,0)) = t*dir - (0,1,0) and |dir| = 1,
+//   L.dir = t - dir.y,  |L|^2 = t*(t - 2*dir.y) + 1,  g.L = t*(g.dir) - g.y,
+//   N.l = (g.L) / (|g| |L|),   r.(-dir) = (l - 2 (N.l) N).(-dir) = -(L.dir)/|L| + 2 (N.l) (g.dir)/|g|,
+// i.e. the normal N, the light direction l and the reflected vector r of :287-295 are never materialised (32 instead of 45
+// instructions per sample; every sample of the backward needs k, only the shaded ones need N and l -- shade_vectors()).
+DR_HD void shade(const DrDesc& d, F3 dir, float t, F3 g, bool clamp_k, Shade& s)
 {
-    float g2 = g.x * g.x + g.y * g.y + g.z * g.z;
-    bool flat = !(g2 > 0.0f);                     // H4: 0/0 normal -> ambient only
-    float ig = flat ? 0.0f : DR_RSQRT(g2);
+    const float g2 = g.x * g.x + g.y * g.y + g.z * g.z;
+    const bool flat = !(g2 > 0.0f);               // H4: 0/0 normal -> ambient only
+    const float ig = flat ? 0.0f : DR_RSQRT(g2);
     s.inv_g = ig;
-    s.N.x = g.x * ig; s.N.y = g.y * ig; s.N.z = g.z * ig;
-    float lx = pos.x - cam.x, ly = pos.y - (cam.y + 1.0f), lz = pos.z - cam.z;    // light at cam + (0,1,0) :281
-    float il = DR_RSQRT(lx * lx + ly * ly + lz * lz);
-    s.l.x = lx * il; s.l.y = ly * il; s.l.z = lz * il;
-    s.nl = s.N.x * s.l.x + s.N.y * s.l.y + s.N.z * s.l.z;
-    float ndl = fmaxf(s.nl, 0.0f);                                                 // :291
-    float t2 = 2.0f * s.nl;
-    float rx = s.l.x - t2 * s.N.x, ry = s.l.y - t2 * s.N.y, rz = s.l.z - t2 * s.N.z;   // reflect :293
-    s.rv = flat ? 0.0f : -(rx * dir.x + ry * dir.y + rz * dir.z);                 // NaN normal -> max(NaN,0) = 0
+    const float gd = g.x * dir.x + g.y * dir.y + g.z * dir.z;
+    const float u = t - dir.y;                                                     // L.dir
+    const float il = DR_RSQRT(t * (u - dir.y) + 1.0f);                             // light at cam + (0,1,0) :281
+    s.inv_l = il;
+    s.nl = (t * gd - g.y) * (ig * il);
+    const float ndl = fmaxf(s.nl, 0.0f);                                           // :291
+    s.rv = flat ? 0.0f : (2.0f * s.nl) * (ig * gd) - il * u;                       // :293-294; NaN normal -> max(NaN,0) = 0
     const float rdv = fmaxf(s.rv, 0.0f);                                           // :295
     float p2 = rdv * rdv, p4 = p2 * p2, p8 = p4 * p4, p16 = p8 * p8;
     s.p32 = p16 * p16;                                                             // shininess 32 :296
     s.kraw = d.diffuse * ndl + d.specular * s.p32 + d.ambient;
     s.k = clamp_k ? fminf(1.0f, s.kraw) : s.kraw;                                  // :298 vs :345
+}
+// the unit normal and light direction behind a Shade (the normal-path adjoint of a shaded sample needs them)
+DR_HD void shade_vectors(const Shade& s, F3 dir, float t, F3 g, F3& N, F3& l)
+{
+    N.x = g.x * s.inv_g; N.y = g.y * s.inv_g; N.z = g.z * s.inv_g;
+    const float ti = t * s.inv_l;
+    l.x = ti * dir.x; l.y = ti * dir.y - s.inv_l; l.z = ti * dir.z;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1090,7 +1100,7 @@ DR_HD void shade(const DrDesc& d, F3 cam, F3 dir, F3 pos, F3 g, bool clamp_k, Sh
 struct SampleAdj { F4 dc; float dI; F3 dg; bool has_dg; };
 
 template <bool SR1>
-DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, const Shade& s, float T, F4 g,
+DR_HD float sample_adjoint(const DrDesc& d, F3 dir, float t, F3 grad, const TfHit& h, float o, const Shade& s, float T, F4 g,
                            bool want_vol, SampleAdj& a)
 {
     const float ko = s.k * o;
@@ -1112,14 +1122,16 @@ DR_HD float sample_adjoint(const DrDesc& d, F3 dir, const TfHit& h, float o, con
             const float d_ndl = (s.nl > 0.0f) ? d.diffuse * dk : 0.0f;
             // d/d(rdv) rdv^32 = 32 rdv^31 = 32 p32 / rdv; below 1e-6 rdv^31 is exactly 0 in fp32 anyway
             const float d_rdv = (s.rv > 1e-6f) ? d.specular * 32.0f * (s.p32 * fast_rcp(s.rv)) * dk : 0.0f;
+            F3 N, l;
+            shade_vectors(s, dir, t, grad, N, l);
             const float drx = -dir.x * d_rdv, dry = -dir.y * d_rdv, drz = -dir.z * d_rdv;
-            const float drN = drx * s.N.x + dry * s.N.y + drz * s.N.z;
+            const float drN = drx * N.x + dry * N.y + drz * N.z;
             const float cN = d_ndl - 2.0f * drN, c2 = 2.0f * s.nl;
-            const float dNx = cN * s.l.x - c2 * drx, dNy = cN * s.l.y - c2 * dry, dNz = cN * s.l.z - c2 * drz;
-            const float NdN = s.N.x * dNx + s.N.y * dNy + s.N.z * dNz;
-            a.dg.x = (dNx - s.N.x * NdN) * s.inv_g;
-            a.dg.y = (dNy - s.N.y * NdN) * s.inv_g;
-            a.dg.z = (dNz - s.N.z * NdN) * s.inv_g;
+            const float dNx = cN * l.x - c2 * drx, dNy = cN * l.y - c2 * dry, dNz = cN * l.z - c2 * drz;
+            const float NdN = N.x * dNx + N.y * dNy + N.z * dNz;
+            a.dg.x = (dNx - N.x * NdN) * s.inv_g;
+            a.dg.y = (dNy - N.y * NdN) * s.inv_g;
+            a.dg.z = (dNz - N.z * NdN) * s.inv_g;
             a.has_dg = true;
         }
     }
@@ -1329,7 +1341,8 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
     bool in_empty = false;                              // ... and whether its macro-cell is empty
     for (int s = 0; s < nn; ++s) {
         if (!(A.w < d.ert)) break;                      // :267 / :318; later iterations only copy A forward :304-306
-        const F3 pos = sample_pos(r, cam, s);
+        float ts;
+        const F3 pos = sample_pos(r, cam, s, ts);
         Centre c;
         if (SKIP && TAPS != TAPS_GENERIC && skip_grid) {
             locate_centre(d, L, pos, c);
@@ -1371,7 +1384,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         Taps t;
         sample_normals<VT, LAYOUT, TAPS, false>(d, vol, L, pos, c, t);
         Shade sh;
-        shade(d, cam, r.dir, pos, t.g, !NONDIFF, sh);
+        shade(d, r.dir, ts, t.g, !NONDIFF, sh);
         const float ko = sh.k * o;
         Tprev = T;
         A.x = DR_FMA(T, ko * h.c.x, A.x);
@@ -1401,7 +1414,8 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
 {
     float Tafter = 1.0f - Afinal.w;                     // transmittance after sample K-1
     for (int s = K - 1; s >= 0; --s) {
-        const F3 pos = sample_pos(r, cam, s);
+        float ts;
+        const F3 pos = sample_pos(r, cam, s, ts);
         Centre c;
         sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
         TfHit h;
@@ -1414,7 +1428,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         Taps t;
         sample_normals<VT, LAYOUT, TAPS, TAPS == TAPS_ONE>(d, vol, L, pos, c, t);
         Shade sh;
-        shade(d, cam, r.dir, pos, t.g, true, sh);
+        shade(d, r.dir, ts, t.g, true, sh);
         if (o == 0.0f) {
             // Exactly transparent sample (78 % of the active samples under the tf1 preset): C = 0, so g.w and the
             // transmittance do not change (T_{s-1} = T_s; the forward saved Tprev = T for it too), dc.rgb = k*o*T*g = 0 and
@@ -1437,7 +1451,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         const float T = (s == K - 1) ? Tprev : Tafter * fast_rcp(1.0f - o);     // 1-o in (0.01, 1]: one MUFU.RCP, no fix-up code
         Tafter = T;
         SampleAdj a;
-        const float Cg = sample_adjoint<SR1>(d, r.dir, h, o, sh, T, g, WANT_VOL, a);
+        const float Cg = sample_adjoint<SR1>(d, r.dir, ts, t.g, h, o, sh, T, g, WANT_VOL, a);
         g.w -= Cg;
         if (WANT_TF) tsink.add(h.lo, h.f, a.dc);
         if (WANT_VOL && (a.has_dg || a.dI != 0.0f))          // exactly-zero contributions (transparent samples) are not scattered

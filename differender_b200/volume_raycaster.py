@@ -42,7 +42,7 @@ class VolumeRaycaster:
         self.layout = layout
         self.skip_empty = bool(skip_empty)   # exact empty-space skipping in the forward march (dr_build_skip_grid / dr_forward_ex)
         self._skip_ring, self._skip_pending, self._skip_use = None, [], True     # asynchronous read-back of the grids' empty counts
-        self._skip_calls, self._skip_minmax, self._copy_cache = 0, None, None
+        self._skip_calls, self._skip_minmax, self._copy_cache, self._auto_layout = 0, None, None, {}
         self.volume_resolution = tuple(int(v) for v in volume_resolution)     # Taichi order (X, Y, Z) = torch (W, D, H)
         self.resolution = tuple(int(v) for v in render_resolution)            # (w, h)
         self.max_samples = int(max_samples)
@@ -91,13 +91,15 @@ class VolumeRaycaster:
         cached = self._cached_copy(vol_lin)
         if cached is not None:
             return "cell8" if cached.ndim == 3 else "brick8"
-        copy = X * Y * Z * 8 * vol_lin.element_size() * vol_lin.shape[0]
-        if copy > self.AUTO_CELL_BYTES:
-            return "brick8"
-        need = copy + (X * Y * Z * 32 * vol_lin.shape[0] if need_vol_grad else 0)
-        if vol_lin.is_cuda and need > self.AUTO_FREE_FRACTION * self._free_bytes(vol_lin.device):
-            return "brick8"
-        return "cell8"
+        # decided once per (batch, dtype, gradient wanted): cudaMemGetInfo costs 0.2-4 ms of host time per call on B200
+        # (measured as a bubble in front of every forward), and a loop should not flip layouts from step to step
+        key = (vol_lin.shape[0], vol_lin.dtype, bool(need_vol_grad), str(vol_lin.device))
+        if key not in self._auto_layout:
+            copy = X * Y * Z * 8 * vol_lin.element_size() * vol_lin.shape[0]
+            need = copy + (X * Y * Z * 32 * vol_lin.shape[0] if need_vol_grad else 0)
+            fits = copy <= self.AUTO_CELL_BYTES and not (vol_lin.is_cuda and need > self.AUTO_FREE_FRACTION * self._free_bytes(vol_lin.device))
+            self._auto_layout[key] = "cell8" if fits else "brick8"
+        return self._auto_layout[key]
 
     # -- caches keyed on a source tensor ------------------------------------------------------------------------------
     # A key is (storage address, data pointer, version counter, shape, dtype).  Every cache entry also HOLDS the source's
