@@ -6,7 +6,9 @@
 //   bwd_kernel       tape-free reverse march, TF + volume gradient scatter   (raycast.grad, :460-461)   dr_bwd_f32.cu / dr_bwd_f16.cu
 //   tf_reduce_kernel sums the privatised TF-gradient copies                  (tf_tex.grad.to_torch, :464,475)
 //   gather_grad_kernel cell-major fp32 gradient -> linear, nan_to_num        (volume.grad.to_torch, :463,474)
+//   gather_step_kernel gather + momentum/projection step + cell-major volume refresh, fused   (examples :375-381, test_opt_tf.py:86-88)
 //   momentum_step_kernel, ingest_u8_kernel                                   (the caller's steps either side of the march)
+//   l2_read_probe_kernel L2 -> SM read bandwidth of the device (bench.py's L2 roof)
 //
 // The march kernels are instantiated in four other translation units so that the library builds in parallel; the
 // bounds-checking debug build (-DDR_BOUNDS_CHECK -DDR_UNITY_BUILD) compiles everything as one unit instead, because its
@@ -139,23 +141,170 @@ __global__ void __launch_bounds__(256) skip_classify_kernel(DrDesc d, const floa
     if (threadIdx.x == 0 && n) atomicAdd(reinterpret_cast<unsigned*>(grid), (unsigned)n);
 }
 
-// cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 (HBM-bound: reads 32 B per voxel once, L2 serves the 8x reuse)
-__global__ void __launch_bounds__(256) gather_grad_kernel(DrDesc d, const float* __restrict__ gcell, float* __restrict__ lin, int accumulate)
+// ---------------------------------------------------------------------------------------------------------
+// Gather of the cell-major gradient, and the fused optimiser step on top of it.
+//
+// The gradient of voxel (x,y,z) is the sum of the (up to) 8 slots that alias it: cell (x-a, y-b, z-c), slot a + 2b + 4c.
+// A CTA owns a GT_X x GT_Y x GT_Z tile of voxels.  It loads the records of the cells [origin - 1, origin + T) once, each as
+// two coalesced 16-byte streaming loads, into shared memory transposed to 8 slot planes (consecutive lanes -> consecutive
+// cells -> conflict-free), and every voxel then sums its 8 slots from shared memory in a fixed order.  Round 1's kernel read 8
+// scattered 4-byte words per voxel through L1 out of local index arrays (51 LDL/STL) and reached 36 % of the HBM roof; this
+// one moves 32 bytes per voxel once, plus the one-cell halo (1.45x, served by L2: the neighbouring tile runs next door).
+// Voxels on the last plane of an axis also receive the clamped slot of their own cell (:170-172); the march never writes
+// such cells, but dr_gather_grad defines it, so those voxels take gather_voxel()'s general path from global memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GT_X = 32, GT_Y = 4, GT_Z = 8, GT_THREADS = 512;
+constexpr int GR_X = GT_X + 1, GR_Y = GT_Y + 1, GR_Z = GT_Z + 1;       // records per axis: the tile and its -1 halo
+constexpr int GR_XP = GR_X | 1;                                          // odd row pitch
+constexpr int GR_PLANE = GR_Y * GR_Z * GR_XP;
+constexpr size_t kGatherSmem = (size_t)8 * GR_PLANE * sizeof(float);    // 47.5 KB
+
+__device__ __forceinline__ float nan_to_num(float v)           // torch.nan_to_num (:463, :474)
 {
+    if (v != v) return 0.0f;
+    return fminf(fmaxf(v, -3.4028234663852886e38f), 3.4028234663852886e38f);
+}
+
+__device__ __forceinline__ void gather_tile_origin(const DrDesc& d, int& ox, int& oy, int& oz)
+{
+    const int ntx = (d.X + GT_X - 1) / GT_X, ntz = (d.Z + GT_Z - 1) / GT_Z;
+    ox = (blockIdx.x % ntx) * GT_X; oz = ((blockIdx.x / ntx) % ntz) * GT_Z; oy = (blockIdx.x / (ntx * ntz)) * GT_Y;
+}
+
+// loads the tile's gradient records into shared memory (slot planes); cells outside the volume read as zero
+__device__ __forceinline__ void gather_load_tile(const DrDesc& d, const float* __restrict__ gcell, int ox, int oy, int oz, float* s)
+{
+    for (int r = threadIdx.x; r < GR_X * GR_Y * GR_Z; r += GT_THREADS) {
+        const int rx = r % GR_X, rz = (r / GR_X) % GR_Z, ry = r / (GR_X * GR_Z);
+        const int cx = ox - 1 + rx, cy = oy - 1 + ry, cz = oz - 1 + rz;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (cx >= 0 && cy >= 0 && cz >= 0 && cx < d.X && cy < d.Y && cz < d.Z) {
+            const float4* p = reinterpret_cast<const float4*>(gcell) + (((size_t)cy * d.Z + cz) * d.X + cx) * 2;
+            a = __ldcs(p); b = __ldcs(p + 1);                  // streaming: a record is needed once (plus the halo)
+        }
+        float* q = s + (ry * GR_Z + rz) * GR_XP + rx;
+        q[0 * GR_PLANE] = a.x; q[1 * GR_PLANE] = a.y; q[2 * GR_PLANE] = a.z; q[3 * GR_PLANE] = a.w;
+        q[4 * GR_PLANE] = b.x; q[5 * GR_PLANE] = b.y; q[6 * GR_PLANE] = b.z; q[7 * GR_PLANE] = b.w;
+    }
+}
+
+// gradient of the voxel at tile-local coordinates (vx, vy, vz) = global (x, y, z), summed in gather_voxel()'s order
+__device__ __forceinline__ float gather_from_tile(const DrDesc& d, const float* __restrict__ gcell, const float* s, int vx, int vy, int vz,
+                                                  int x, int y, int z)
+{
+    if (x == d.X - 1 || y == d.Y - 1 || z == d.Z - 1) return gather_voxel(d, gcell, x, y, z);     // clamped slots: general path
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)      // record local index = voxel local index + 1 - offset; cells outside the volume hold +0
+                sum += s[(a + 2 * b + 4 * c) * GR_PLANE + ((vy + 1 - b) * GR_Z + (vz + 1 - c)) * GR_XP + (vx + 1 - a)];
+    return sum;
+}
+
+// cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 with nan_to_num
+__global__ void __launch_bounds__(GT_THREADS) gather_grad_kernel(DrDesc d, const float* __restrict__ gcell, float* __restrict__ lin, int accumulate)
+{
+    extern __shared__ __align__(16) float s_rec[];
+    int ox, oy, oz;
+    gather_tile_origin(d, ox, oy, oz);
     const size_t n = (size_t)d.X * d.Y * d.Z;
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const int b = blockIdx.y;
-    const int x = (int)(e % d.X);
-    const size_t r = e / d.X;
-    const int z = (int)(r % d.Z), y = (int)(r / d.Z);
-    float v = gather_voxel(d, gcell + (size_t)b * n * 8, x, y, z);
-    // torch.nan_to_num (:463, :474)
-    if (v != v) v = 0.0f;
-    else if (v > 3.4028234663852886e38f) v = 3.4028234663852886e38f;
-    else if (v < -3.4028234663852886e38f) v = -3.4028234663852886e38f;
-    float* o = lin + (size_t)b * n + e;
-    *o = accumulate ? (*o + v) : v;
+    const float* gc = gcell + (size_t)blockIdx.y * n * 8;
+    gather_load_tile(d, gc, ox, oy, oz, s_rec);
+    __syncthreads();
+    for (int v = threadIdx.x; v < GT_X * GT_Y * GT_Z; v += GT_THREADS) {
+        const int vx = v % GT_X, vz = (v / GT_X) % GT_Z, vy = v / (GT_X * GT_Z);
+        const int x = ox + vx, y = oy + vy, z = oz + vz;
+        if (x >= d.X || y >= d.Y || z >= d.Z) continue;
+        const float g = nan_to_num(gather_from_tile(d, gc, s_rec, vx, vy, vz, x, y, z));
+        float* o = lin + (size_t)blockIdx.y * n + ((size_t)y * d.Z + z) * d.X + x;
+        *o = accumulate ? (*o + g) : g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dr_gather_step: [gather + nan_to_num] + momentum-SGD step with clipping and projection + refresh of the cell-major
+// VOLUME copy, in ONE kernel (replaces gather_grad_kernel + momentum_step_kernel + expand_cells_kernel).
+//   m = gamma*m + lr*clamp(g, -max_grad, max_grad);  p = clamp(p - m, lo, hi)    one rounding per operator (numpy float32)
+//   (examples/taichi_volume_raycaster.py:375-381 `apply_grad`; examples/test_opt_tf.py:86-88 vol.clamp_(0, 1))
+// Every (record, slot) of the volume copy has exactly one source voxel -- slot c + 2a + 4b of cell q is voxel min(q + (a,b,c),
+// dim - 1) -- so a CTA writes the slots fed by ITS OWN voxels and nothing else: no halo of parameters is read (the update is in
+// place and race-free), records inside the tile go out as whole 32-byte (fp16: 16-byte) stores, and the records on the tile's low
+// faces are completed by the neighbouring CTAs' partial stores (merged in L2).
+// ---------------------------------------------------------------------------------------------------------
+struct StepArgs { float lr, gamma, max_grad, lo, hi; };
+
+template <typename VT, bool FROM_CELLS>
+__global__ void __launch_bounds__(GT_THREADS) gather_step_kernel(DrDesc d, const float* __restrict__ gcell, const float* __restrict__ glin,
+                                                                  float* __restrict__ param, float* __restrict__ mom, VT* __restrict__ vcells,
+                                                                  float* __restrict__ gout, StepArgs sa)
+{
+    extern __shared__ __align__(16) float s_rec[];
+    float (*s_p)[GT_Z][GT_X] = reinterpret_cast<float (*)[GT_Z][GT_X]>(s_rec + (FROM_CELLS ? 8 * GR_PLANE : 0));   // the tile's new parameter values
+    int ox, oy, oz;
+    gather_tile_origin(d, ox, oy, oz);
+    if (FROM_CELLS) {
+        gather_load_tile(d, gcell, ox, oy, oz, s_rec);
+        __syncthreads();
+    }
+    for (int v = threadIdx.x; v < GT_X * GT_Y * GT_Z; v += GT_THREADS) {
+        const int vx = v % GT_X, vz = (v / GT_X) % GT_Z, vy = v / (GT_X * GT_Z);
+        const int x = ox + vx, y = oy + vy, z = oz + vz;
+        if (x >= d.X || y >= d.Y || z >= d.Z) continue;
+        const size_t e = ((size_t)y * d.Z + z) * d.X + x;
+        const float g = FROM_CELLS ? nan_to_num(gather_from_tile(d, gcell, s_rec, vx, vy, vz, x, y, z)) : __ldg(glin + e);
+        const float gc = fminf(fmaxf(g, -sa.max_grad), sa.max_grad);
+        const float m = __fadd_rn(__fmul_rn(sa.gamma, mom[e]), __fmul_rn(sa.lr, gc));
+        const float p = fminf(fmaxf(__fsub_rn(param[e], m), sa.lo), sa.hi);
+        mom[e] = m; param[e] = p;
+        if (gout) gout[e] = g;
+        s_p[vy][vz][vx] = p;
+    }
+    if (!vcells) return;
+    __syncthreads();
+    // records of the cells [origin - 1, origin + T): slot (a,b,c) comes from voxel min(cell + (a,b,c), dim - 1) if that voxel is ours
+    for (int r = threadIdx.x; r < GR_X * GR_Y * GR_Z; r += GT_THREADS) {
+        const int rx = r % GR_X, rz = (r / GR_X) % GR_Z, ry = r / (GR_X * GR_Z);
+        const int cx = ox - 1 + rx, cy = oy - 1 + ry, cz = oz - 1 + rz;
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= d.X || cy >= d.Y || cz >= d.Z) continue;
+        struct alignas(16) Rec { VT v[8]; } rec;
+        unsigned mine = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                                              // slot q = c + 2a + 4b
+            const int a = (q >> 1) & 1, b = q >> 2, c = q & 1;
+            const int lx = min(cx + a, d.X - 1) - ox, ly = min(cy + b, d.Y - 1) - oy, lz = min(cz + c, d.Z - 1) - oz;
+            const bool in = lx >= 0 && ly >= 0 && lz >= 0 && lx < GT_X && ly < GT_Y && lz < GT_Z;
+            rec.v[q] = VT(in ? s_p[in ? ly : 0][in ? lz : 0][in ? lx : 0] : 0.0f);
+            mine |= in ? (1u << q) : 0u;
+        }
+        VT* dst = vcells + (((size_t)cy * d.Z + cz) * d.X + cx) * 8;
+        if (mine == 0xFFu) *reinterpret_cast<Rec*>(dst) = rec;
+        else
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (mine & (1u << q)) dst[q] = rec.v[q];
+    }
+}
+
+// L2 -> SM read-bandwidth probe (bench.py's L2 roof; SURVEY 8(d): MEASURED_PEAKS.json has no L2 figure): every CTA reads the whole
+// buffer `reps` times with 16-byte ld.global.cg loads (L1 bypassed), CTA b starting at a different offset so that the CTAs do not
+// march through the same lines in lock-step.  With a buffer that fits L2 (<= 64 MiB of the 126 MB) all passes after the first are L2 hits.
+__global__ void __launch_bounds__(512) l2_read_probe_kernel(const uint4* __restrict__ buf, size_t n16, int reps, unsigned* __restrict__ sink)
+{
+    unsigned acc = 0;
+    const size_t start = ((size_t)blockIdx.x * 8191u * 512u) % n16;
+    for (int r = 0; r < reps; ++r) {
+        size_t i = start + threadIdx.x;
+#pragma unroll 8
+        for (size_t k = threadIdx.x; k < n16; k += 512) {
+            if (i >= n16) i -= n16;
+            const uint4 v = __ldcg(buf + i);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+            i += 512;
+        }
+    }
+    if (acc == 0x9E3779B9u) *sink = acc;          // keeps the loads alive; practically never taken
 }
 
 // sums the kTfSlots privatised copies; one thread per (tf, bin, channel); adds into grad_tf in the caller's layout
@@ -196,6 +345,11 @@ int check_desc(const DrDesc* d)
 }
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+unsigned gather_tiles(const DrDesc* d)
+{
+    return (unsigned)(((d->X + GT_X - 1) / GT_X) * ((d->Z + GT_Z - 1) / GT_Z) * ((d->Y + GT_Y - 1) / GT_Y));
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // caller-side steps either side of the march: optimiser update and raw-volume ingest.  Elementwise, HBM-bound.
@@ -455,11 +609,51 @@ int dr_gather_grad(const DrDesc* d, const float* grad_vol_cells, float* grad_lin
 {
     if (int rc = check_desc(d)) return rc;
     if (!grad_vol_cells || !grad_linear) return fail(DR_EINVAL, "dr_gather_grad: null pointer");
-    const size_t n = (size_t)d->X * d->Y * d->Z;
-    dim3 grid((unsigned)((n + 255) / 256), d->Bvol);
-    gather_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_cells, grad_linear, accumulate);
+    if (!aligned(grad_vol_cells, 16)) return fail(DR_EALIGN, "dr_gather_grad: grad_vol_cells must be 16-byte aligned");
+    dim3 grid(gather_tiles(d), d->Bvol);
+    gather_grad_kernel<<<grid, GT_THREADS, kGatherSmem, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_cells, grad_linear, accumulate);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "gather_grad_kernel launch");
+}
+
+int dr_gather_step(const DrDesc* d, const float* grad_vol_cells, const float* grad_linear, float* param, float* momentum, void* vol_cells,
+                   float* grad_out, float lr, float gamma, float max_grad, float lo, float hi, void* stream)
+{
+    if (int rc = check_desc(d)) return rc;
+    if (!param || !momentum) return fail(DR_EINVAL, "dr_gather_step: null pointer");
+    if ((grad_vol_cells == nullptr) == (grad_linear == nullptr))
+        return fail(DR_EINVAL, "dr_gather_step: give exactly one of grad_vol_cells (cell-major) and grad_linear (already gathered)");
+    if (d->Bvol != 1) return fail(DR_EINVAL, "dr_gather_step: one volume per call (Bvol == 1)");
+    if (grad_vol_cells && !aligned(grad_vol_cells, 16)) return fail(DR_EALIGN, "dr_gather_step: grad_vol_cells must be 16-byte aligned");
+    if (vol_cells && !aligned(vol_cells, 32)) return fail(DR_EALIGN, "dr_gather_step: vol_cells must be 32-byte aligned");
+    const StepArgs sa { lr, gamma, max_grad, lo, hi };
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid(gather_tiles(d));
+    constexpr size_t kTileSmem = (size_t)GT_X * GT_Y * GT_Z * sizeof(float);
+#define DR_GS(VT, FC) do { \
+        const size_t smem = (FC ? kGatherSmem : 0) + kTileSmem; \
+        cudaError_t ea = cudaFuncSetAttribute(gather_step_kernel<VT, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (ea != cudaSuccess) return fail_cuda(ea, "cudaFuncSetAttribute(gather_step_kernel)"); \
+        gather_step_kernel<VT, FC><<<grid, GT_THREADS, smem, st>>>(*d, grad_vol_cells, grad_linear, param, momentum, \
+                                                                   static_cast<VT*>(vol_cells), grad_out, sa); } while (0)
+    if (d->vox_dtype == DR_VOX_F32) { if (grad_vol_cells) DR_GS(float, true); else DR_GS(float, false); }
+    else { if (grad_vol_cells) DR_GS(__half, true); else DR_GS(__half, false); }
+#undef DR_GS
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DR_OK : fail_cuda(e, "gather_step_kernel launch");
+}
+
+long long dr_probe_l2_read(const void* buf, size_t bytes, int reps, void* sink, void* stream)
+{
+    if (!buf || !sink || bytes < 16 * 512 * 8 || reps < 1) return fail(DR_EINVAL, "dr_probe_l2_read: bad arguments");
+    if (!aligned(buf, 16) || !aligned(sink, 4)) return fail(DR_EALIGN, "dr_probe_l2_read: buffer must be 16-byte aligned");
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    l2_read_probe_kernel<<<sms * 2, 512, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(buf), bytes / 16, reps,
+                                                                                 static_cast<unsigned*>(sink));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? (long long)(sms * 2) * reps * (long long)(bytes / 16 * 16) : fail_cuda(e, "l2_read_probe_kernel launch");
 }
 
 }  // extern "C"

@@ -51,6 +51,10 @@ class VolumeRaycaster:
         self.near, self.far = float(nearfar[0]), float(nearfar[1])
         self.ambient, self.diffuse, self.specular, self.shininess = 0.4, 0.8, 0.3, 32.0    # :91-94
         self.last_K = None           # per-ray active sample counts of the most recent forward ([BS,H,W] int32)
+        # FusedVolumeSGD (optim.py): the autograd backward leaves the volume gradient un-gathered in `pending_grad_cells`
+        # (cell-major, accumulated over backward calls) and returns None for the volume; dr_gather_step consumes it
+        self.defer_volume_gather = False
+        self.pending_grad_cells = None
 
     @property
     def max_valid_sample_step_count(self):
@@ -244,6 +248,10 @@ class VolumeRaycaster:
         dev = bricked.device
         lib = _lib.load()
         keep_cells = grad_cells is not None
+        if need_vol and grad_cells is None and self.defer_volume_gather and bricked.shape[0] == 1:
+            if self.pending_grad_cells is None:
+                self.pending_grad_cells = torch.zeros((1, lib.dr_grad_cells_elems(ctypes.byref(d))), dtype=torch.float32, device=dev)
+            grad_cells, keep_cells = self.pending_grad_cells, True
         if need_vol and grad_cells is None:
             grad_cells = torch.zeros((bricked.shape[0], lib.dr_grad_cells_elems(ctypes.byref(d))), dtype=torch.float32, device=dev)
         gtf = torch.zeros(tf_r4.t.shape if isinstance(tf_r4, _Tf4R) else tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
@@ -372,6 +380,8 @@ def _saved(ctx):
 
 def _shape_grads(ctx, gvol, gtf, need_vol, need_tf):
     gv = gt = None
+    if need_vol and gvol is ctx.vr.pending_grad_cells:
+        need_vol = False                                       # deferred: FusedVolumeSGD gathers and applies it (volume.grad stays None)
     if need_vol:
         gv = gvol.permute(0, 3, 1, 2)                          # [Bvol, X, Y, Z] view (Taichi order, :447)
         if not ctx.vol_batched:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DR_VERSION 100
+#define DR_VERSION 101
 
 /* error codes */
 #define DR_OK 0
@@ -214,6 +214,30 @@ int dr_backward_mse(const DrDesc* d, const void* vol, const float* tf, const flo
  */
 int dr_momentum_step(float* param, const float* grad, float* momentum, size_t n, float lr, float gamma, float max_grad,
                      float lo, float hi, void* stream);
+
+/*
+ * The whole parameter update of a volume-optimisation step in ONE kernel: gather of the cell-major
+ * gradient with nan_to_num (what dr_gather_grad does; volume.grad.to_torch + torch.nan_to_num, :463, :474), the momentum-SGD
+ * step with clipping and projection of dr_momentum_step (examples/taichi_volume_raycaster.py:375-381; vol.clamp_(0, 1) of
+ * examples/test_opt_tf.py:86-88), and the refresh of the cell-major VOLUME copy that the next forward reads (so the next
+ * step needs no dr_expand_cells; replaces set_volume's from_torch, :118-119).
+ *   grad_vol_cells  [X*Y*Z][8] fp32 cell-major gradient as scattered by dr_backward          } exactly one of the two;
+ *   grad_linear     [Y][Z][X] fp32, already gathered (e.g. all-reduced across GPUs)          } the other is NULL
+ *   param, momentum [Y][Z][X] fp32, updated in place
+ *   vol_cells       cell-major volume copy [X*Y*Z][8] of d->vox_dtype (fp32 / fp16) to refresh from the new param, or NULL
+ *   grad_out        optional [Y][Z][X] fp32: receives the gathered gradient (for logging), or NULL
+ * Results are bit-identical to dr_gather_grad followed by dr_momentum_step followed by dr_expand_cells.  d->Bvol must be 1.
+ */
+int dr_gather_step(const DrDesc* d, const float* grad_vol_cells, const float* grad_linear, float* param, float* momentum,
+                   void* vol_cells, float* grad_out, float lr, float gamma, float max_grad, float lo, float hi, void* stream);
+
+/*
+ * Diagnostic for the benchmark's L2 roofline (the L2 -> SM bandwidth is not in MEASURED_PEAKS.json and has to
+ * be measured on the box): 2 CTAs per SM each read the whole buffer `reps` times with 16-byte ld.global.cg loads.  With a
+ * buffer that stays L2-resident (32-64 MiB) the bytes moved / elapsed time is the L2 read bandwidth.  Returns the number of
+ * bytes the launch reads (>= 0) or a negative DR_E* code; `sink` is 4 bytes of scratch.  Time it with events on `stream`.
+ */
+long long dr_probe_l2_read(const void* buf, size_t bytes, int reps, void* sink, void* stream);
 
 /*
  * Raw uint8 volume -> linear voxel volume [Y][Z][X] of d->vox_dtype with value = u8 / 255, as the reference ingests

@@ -123,3 +123,21 @@ def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_s
     gv = np.zeros_like(vol)
     L.sim_gather(ctypes.byref(d), _p(gbr), _p(gv))
     return gv, np.ascontiguousarray(gtf.T)
+
+
+def gather(cells, vol_shape_dhw):
+    """gather_voxel() over a cell-major gradient [D*H*W*8] -> [D,H,W] (host build of the device function; no nan_to_num)."""
+    d = make_desc(vol_shape_dhw, (8, 8), 2, 1, 0)
+    ce = np.ascontiguousarray(cells, np.float32).reshape(-1)
+    out = np.zeros(vol_shape_dhw, np.float32)
+    lib().sim_gather(ctypes.byref(d), _p(ce), _p(out))
+    return out
+
+
+def expand(volume):
+    """dr_expand_cells on the host: [D,H,W] -> [D*H*W, 8] cell-major records."""
+    vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
+    d = make_desc(vol.shape, (8, 8), 2, 1, 0)
+    ce = np.zeros(vol.size * 8, np.float32)
+    lib().sim_expand(ctypes.byref(d), _p(vol), _p(ce))
+    return ce.reshape(-1, 8)
