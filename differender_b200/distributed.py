@@ -4,6 +4,9 @@ The reference is single-GPU and walks a batch of views in a Python loop (volume_
 independent, so the batch shards across ranks with the volume and the transfer function replicated; the only exchange is
 the gradient sum: ONE all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) of a flat buffer
 [volume gradient | TF gradient].  One process per GPU (torchrun); nothing here spawns processes.
+
+The flat buffer is allocated once and the gather of the cell-major volume gradient writes into it directly, so the volume
+gradient (64 MiB - 4 GiB) is neither concatenated nor copied before the collective; the 2 KiB TF gradient is copied into its slot.
 """
 import torch
 import torch.distributed as dist
@@ -12,68 +15,100 @@ __all__ = ["shard_views", "SyncGradients", "DistributedRaycaster"]
 
 
 def shard_views(n_views, rank, world_size):
-    """Indices of the views rendered by `rank`: contiguous blocks, sizes differ by at most one."""
-    base, rem = divmod(n_views, world_size)
-    start = rank * base + min(rank, rem)
-    return list(range(start, start + base + (1 if rank < rem else 0)))
+    """Indices of the views rendered by `rank`: round-robin, view v -> rank v mod world_size.  Neighbouring
+    cameras of an orbit cost about the same, so dealing them out one by one spreads the expensive poses over all ranks
+    (contiguous blocks left the ranks 1.3 % apart in samples at 8 GPUs); sizes differ by at most one."""
+    return list(range(rank, n_views, world_size))
+
+
+class _FlatGrads:
+    """One preallocated fp32 buffer [g_0 | g_1 | ...] for the gradients of a fixed list of parameter shapes."""
+
+    def __init__(self):
+        self.buf, self.sizes = None, None
+
+    def views(self, tensors):
+        sizes = tuple(int(t.numel()) for t in tensors)
+        dev = tensors[0].device
+        if self.buf is None or self.sizes != sizes or self.buf.device != dev:
+            self.buf, self.sizes = torch.empty(sum(sizes), dtype=torch.float32, device=dev), sizes
+        out, off = [], 0
+        for n in sizes:
+            out.append(self.buf[off:off + n])
+            off += n
+        return out
 
 
 class SyncGradients(torch.autograd.Function):
-    """Identity in the forward; in the backward the gradients of all inputs are packed into one flat fp32 buffer and
-    all-reduced (SUM) with a single collective, then unpacked.  Replicated parameters (volume, TF) pass through this
-    before the per-rank render so that every rank ends up with the gradient of the whole view batch."""
+    """Identity in the forward; in the backward the gradients of all inputs are summed over the ranks with a single
+    all-reduce of one preallocated flat fp32 buffer.  A gradient that already lives at its place in that buffer (the
+    raycaster's backward writes there, see DistributedRaycaster) is not copied; anything else is copied in once.
+    Replicated parameters (volume, TF) pass through this before the per-rank render so that every rank ends up with the
+    gradient of the whole view batch."""
 
     @staticmethod
-    def forward(ctx, group, *tensors):
-        ctx.group = group
+    def forward(ctx, group, flat, *tensors):
+        ctx.group, ctx.flat = group, flat
         return tuple(t.view_as(t) for t in tensors)
 
     @staticmethod
     def backward(ctx, *grads):
+        if all(g is None for g in grads):
+            return (None, None) + tuple(grads)
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1):
+            return (None, None) + tuple(grads)
+        flat = ctx.flat if ctx.flat is not None else _FlatGrads()
         present = [g for g in grads if g is not None]
-        if not present:
-            return (None,) + tuple(grads)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
-            flat = torch.cat([g.reshape(-1).float() for g in present])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=ctx.group)
-            out, off = [], 0
-            for g in grads:
-                if g is None:
-                    out.append(None)
-                    continue
-                n = g.numel()
-                out.append(flat[off:off + n].view(g.shape).to(g.dtype))
-                off += n
-            return (None,) + tuple(out)
-        return (None,) + tuple(grads)
+        slots = flat.views(present)
+        for g, s in zip(present, slots):
+            if not (g.dtype == torch.float32 and g.is_contiguous() and g.data_ptr() == s.data_ptr()):
+                s.copy_(g.reshape(-1))                      # not written in place by the backward kernels: one copy, no concatenation
+        dist.all_reduce(flat.buf, op=dist.ReduceOp.SUM, group=ctx.group)
+        out, it = [], iter(slots)
+        for g in grads:
+            out.append(None if g is None else next(it).view(g.shape).to(g.dtype))
+        return (None, None) + tuple(out)
 
 
 class DistributedRaycaster(torch.nn.Module):
     """Wraps a `Raycaster`: each rank renders its shard of the cameras; volume/TF gradients are summed over ranks.
 
-    forward(volume, tf, look_from_all[, jitter_all]) -> this rank's images ([n_local, 4, H, W]) and the view indices.
+    forward(volume, tf, look_from_all[, jitter]) -> this rank's images ([n_local, 4, H, W]) and the view indices.
+    `jitter` holds either every view's jitter ([n_views, H, W]) or only this rank's ([n_local, H, W], in shard order).
     """
 
     def __init__(self, raycaster, group=None):
         super().__init__()
         self.raycaster = raycaster
         self.group = group
+        self._flat = _FlatGrads()
 
     def _rank_world(self):
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(self.group), dist.get_world_size(self.group)
         return 0, 1
 
-    def forward(self, volume, tf, look_from_all, jitter_all=None):
+    def forward(self, volume, tf, look_from_all, jitter=None):
         rank, world = self._rank_world()
         idx = shard_views(look_from_all.shape[0], rank, world)
-        volume, tf = SyncGradients.apply(self.group, volume, tf)
+        need = [t for t in (volume, tf) if t.requires_grad]
+        vr = getattr(self.raycaster, "vr", None)
+        if vr is not None:
+            vr.grad_sink = None
+            if world > 1 and volume.requires_grad and volume.ndim == 4 and not getattr(vr, "defer_volume_gather", False):
+                # a shared volume: the backward gathers its gradient straight into the flat buffer that is all-reduced
+                # (the TF gradient, 2 KiB, comes back through a permute and is copied into its slot)
+                X, Y, Z = vr.volume_resolution
+                vr.grad_sink = {"vol": self._flat.views(need)[0].view(1, Y, Z, X)}
+        volume, tf = SyncGradients.apply(self.group, self._flat, volume, tf)
         if not idx:
             h, w = self.raycaster.output_shape[1], self.raycaster.output_shape[0]
             # keep the graph connected so the collective in the backward still runs on this rank
             empty = volume.new_zeros((0, 4, h, w), dtype=torch.float32) + 0.0 * (volume.sum() + tf.sum()).float()
             return empty, idx
         sel = torch.as_tensor(idx, device=look_from_all.device)
-        jit = None if jitter_all is None else jitter_all.index_select(0, sel.to(jitter_all.device))
+        jit = jitter
+        if jitter is not None and jitter.shape[0] != len(idx):
+            jit = jitter.index_select(0, sel.to(jitter.device))
         img = self.raycaster(volume, tf, look_from_all.index_select(0, sel), jit)
         return img, idx

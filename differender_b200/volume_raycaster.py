@@ -55,6 +55,8 @@ class VolumeRaycaster:
         # (cell-major, accumulated over backward calls) and returns None for the volume; dr_gather_step consumes it
         self.defer_volume_gather = False
         self.pending_grad_cells = None
+        # DistributedRaycaster: {"vol": [1,Y,Z,X] fp32 view of its flat all-reduce buffer}; the gather writes there directly
+        self.grad_sink = None
 
     @property
     def max_valid_sample_step_count(self):
@@ -271,7 +273,10 @@ class VolumeRaycaster:
             return None, gtf
         if keep_cells:
             return grad_cells, gtf
-        return self.gather(grad_cells), gtf
+        sink = self.grad_sink.get("vol") if self.grad_sink else None
+        if sink is not None and (grad_cells.shape[0] != 1 or sink.device != grad_cells.device):
+            sink = None
+        return self.gather(grad_cells, out=sink), gtf
 
     def gather(self, grad_cells, out=None):
         """Cell-major gradient [Bvol, X*Y*Z*8] -> linear [Bvol, Y, Z, X] fp32 with nan_to_num (into `out` if given, e.g. a
