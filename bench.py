@@ -9,15 +9,22 @@ min/max + TF classification), forward march, backward march (TF + volume gradien
 for N > 1, all-reduce [volume grad | TF grad]).  A "sample" is one ACTIVE ray-march step; the count is the sum
 of the forward kernel's per-ray K -- identical with and without the exact empty-space skipping (--no-skip).
 
-Prints ONE JSON line on rank 0.  `value` = device-resident throughput through the C ABI; `e2e` = the same metric through
-the public `Raycaster` autograd API with all inputs copied from pinned host memory every step (double-buffered: step i+1's
-copies run on a second stream under step i's compute).
+Prints ONE JSON line on rank 0:
+  value        device-resident throughput of the default workload (C3) through the C ABI
+  e2e          the same metric through the public `Raycaster` autograd API with every input copied from pinned host memory
+               and the results (loss, TF gradient, volume gradient) copied back every step
+  roofline     BASELINE.md 5: three roof times of the dominant kernel (HBM, L2, instruction issue), `bound` = the largest,
+               `frac` = that time / measured time
+  configs_other  the other BASELINE.json configurations (C1, C2, C4, C5) and C3 with a dense TF, a few seconds each
+  strong_scaling (N > 1) C4 and C5 at their TOTAL view counts divided over the N GPUs, with their 512 MiB / 4 GiB all-reduce
+  cpu_baseline   the CPU oracle on a bounded sample of the workload (rank 0, N = 1)
 `--impl reference` times the CPU oracle (oracle/cpu_ref.c, kind "port": the real reference needs Taichi, which is not
 installable here) on the host cores on a bounded sample of the same workload.
 """
 import argparse
+import ctypes
+import hashlib
 import json
-import math
 import os
 import subprocess
 import sys
@@ -28,20 +35,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: volume N^3, dtype, image (w,h), views per GPU, mode
-    "c1": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="nondiff", sr=16.0, M=1, jitter=False,
+    # name: volume N^3, dtype, image (w,h), views per GPU (total views over 8 GPUs for the strong-scaling block), mode
+    "c1": dict(n=256, dtype="f32", res=(512, 512), views=1, total_views=1, mode="nondiff", sr=16.0, M=1, jitter=False,
                desc="C1 forward-only nondiff render, 256^3 fp32, 512x512, 1 view, sr 16"),
-    "c2": dict(n=256, dtype="f32", res=(512, 512), views=1, mode="tf", sr=1.0, M=2048, jitter=True, tf="black",
-               desc="C2 TF optimisation step: fwd+bwd w.r.t. TF only + momentum update, 256^3 fp32, 512x512, 1 view"),
-    "c3": dict(n=256, dtype="f32", res=(1024, 1024), views=16, mode="full", sr=1.0, M=2048, jitter=True,
+    "c2": dict(n=256, dtype="f32", res=(512, 512), views=1, total_views=1, mode="tf", sr=1.0, M=2048, jitter=True, tf="black",
+               desc="C2 TF optimisation loop: fwd+bwd w.r.t. TF only + momentum-SGD step per iteration, 256^3 fp32, 512x512, 1 view, TF init `black`"),
+    "c3": dict(n=256, dtype="f32", res=(1024, 1024), views=16, total_views=16, mode="full", sr=1.0, M=2048, jitter=True,
                desc="C3 volume-gradient backprop: fwd+bwd (TF+volume grad), 256^3 fp32, 1024x1024, 16 views per GPU"),
-    "c4": dict(n=512, dtype="f32", res=(1024, 1024), views=8, mode="full", sr=1.0, M=4096, jitter=True,
+    "c4": dict(n=512, dtype="f32", res=(1024, 1024), views=8, total_views=64, mode="full", sr=1.0, M=4096, jitter=True,
                desc="C4 multi-view batch: fwd+bwd, 512^3 fp32, 1024x1024, 8 views per GPU (64 over 8 GPUs)"),
-    "c5": dict(n=1024, dtype="f16", res=(2048, 2048), views=32, mode="full", sr=1.0, M=8192, jitter=True,
+    "c5": dict(n=1024, dtype="f16", res=(2048, 2048), views=32, total_views=256, mode="full", sr=1.0, M=8192, jitter=True,
                desc="C5 large volume: fwd+bwd, 1024^3 fp16-stored, 2048x2048, jittered, 32 views per GPU (256 over 8 GPUs)"),
 }
 L2_FLUSH_BYTES = 256 << 20
 METRIC = {"full": "Gsamples/s fwd+bwd (TF+volume grad)", "tf": "Gsamples/s fwd+bwd (TF grad)", "nondiff": "Gsamples/s fwd"}
+NVLINK_PEAK_GBS = 900.0
 
 
 def parse():
@@ -54,6 +62,9 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-others", action="store_true", help="skip the configs_other / strong_scaling blocks (A/B runs, profiler runs)")
+    p.add_argument("--others", default=None, help="comma list for configs_other (default: c1,c2,c3gray,c4,c5 at N=1; none for N>1)")
+    p.add_argument("--strong", default=None, help="comma list for the N>1 strong_scaling block (default: c4,c5)")
     p.add_argument("--tf", default=None, help="transfer-function preset (reference utils.get_tf): tf1..tf5, gray, black, rand; "
                                               "default tf1 (C2: its optimisation start `black`)")
     p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8", "cell8"], help="volume layout read by the march kernels")
@@ -103,6 +114,29 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parity basis: what the numbers' correctness rests on
+# ------------------------------------------------------------------------------------------------------------------
+def parity_basis():
+    """One string for the JSON line: the oracle is unpinned against real Taichi; the committed rounding envelope says how far
+    the plausible alternative roundings of the reference's arithmetic move an image / a gradient (profiles/r02_rounding_envelope.txt)."""
+    env = "envelope not measured"
+    try:
+        last = open(os.path.join(ROOT, "profiles", "r02_rounding_envelope.txt")).read().strip().splitlines()[-1]
+        if last.startswith("ENVELOPE"):
+            env = last[last.index(":") + 2:]
+    except OSError:
+        pass
+    taichi = "Taichi probe not run"
+    try:
+        from oracle import taichi_probe
+        st = taichi_probe.status()
+        taichi = st["note"]
+    except Exception as e:  # the probe is optional test infrastructure
+        taichi = f"Taichi probe unavailable ({type(e).__name__})"
+    return f"oracle (oracle/cpu_ref.c; unpinned against the real Taichi reference); rounding envelope of the oracle's open choices: {env}; {taichi}"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -163,19 +197,316 @@ def run_reference(args, cfg):
         "config": {"workload": cfg["desc"], "note": "CPU restatement of the reference (oracle/cpu_ref.c); Taichi ti.cpu is not installable here"},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "parity_basis": parity_basis(),
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# our arm
+# our arm: one workload = device-resident inputs of a config + its step
 # ------------------------------------------------------------------------------------------------------------------
+def csrc_digest():
+    """Identifies the kernel sources a committed ncu capture belongs to."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "differender_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+class Workload:
+    """Inputs of one config resident in HBM and the step that is timed (C ABI through VolumeRaycaster's thin wrappers)."""
+
+    def __init__(self, cfg, args, dev, rank, world, views, tf_name=None, total_views=None):
+        import torch
+        from differender_b200 import MomentumSGD, VolumeRaycaster
+        from differender_b200.distributed import shard_views
+        from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
+        self.cfg, self.dev, self.rank, self.world, self.args = cfg, dev, rank, world, args
+        n, (w, h), R, M = cfg["n"], cfg["res"], 128, cfg["M"]
+        self.n, self.w, self.h, self.R, self.sr, self.mode = n, w, h, R, cfg["sr"], cfg["mode"]
+        vdtype = torch.float16 if cfg["dtype"] == "f16" else torch.float32
+        self.vol = make_volume(n, device=dev, dtype=vdtype)                              # (1, D, H, W), replicated on every rank
+        self.tf_name = tf_name or cfg.get("tf", "tf1")
+        self.tf = make_tf(self.tf_name, R, device=dev)                                   # (4, R)
+        # weak scaling: `views` per GPU; strong scaling: `total_views` dealt round-robin (view v -> rank v mod world)
+        n_all = total_views if total_views is not None else views * world
+        ids = shard_views(n_all, rank, world)
+        self.views = len(ids)
+        all_cams = make_cameras(n_all, device=dev)
+        self.cams = all_cams[ids].contiguous() if ids else all_cams[:0]
+        self.jit = make_jitter(max(self.views, 1), h, w, seed=4321 + rank, device=dev)[:self.views] if cfg["jitter"] else None
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        self.target = torch.rand((self.views, 4, h, w), generator=g, device=dev)
+        self.vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=args.layout, skip_empty=not args.no_skip)
+        self.vol_lin = self.vol.reshape(1, n, n, n)
+        self.tf_r4 = self.tf.t().contiguous()[None]
+        self.need_vol, self.need_tf = self.mode == "full", self.mode in ("full", "tf")
+        self.flat_grad = torch.empty(n ** 3 + R * 4, dtype=torch.float32, device=dev) if world > 1 else None
+        self.cells = None                                                                # cell-major gradient buffer, allocated once
+        self.tf_opt = MomentumSGD(self.tf_r4[0], lr=0.1, momentum=0.9, max_grad=0.1, lr_decay=0.99) if self.mode == "tf" else None
+        self.ar_bytes = int((n ** 3 + R * 4) * 4 if self.need_vol else R * 16)
+
+    def ev(self):
+        import torch
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(self, timed, flush):
+        import torch
+        import torch.distributed as dist
+        vr, n, R = self.vr, self.n, self.R
+        self._k0 = vr.kernel_launches
+        e = [self.ev() for _ in range(5)] if timed else None
+        flush.zero_()                                                                # L2 flush between steps
+        if timed: e[0].record()
+        if self.need_vol:
+            vr.forget_volume()         # a volume-gradient loop changes the volume every step: re-lay the volume and rebuild the skip grid's min/max too
+        bricked = vr.brick(self.vol_lin, need_vol_grad=self.need_vol)
+        if timed: e[1].record()
+        out, K, Tp = vr.march(bricked, self.tf_r4, self.cams, self.sr, self.jit, nondiff=self.mode == "nondiff")
+        if timed: e[2].record()
+        if self.mode != "nondiff":
+            go = (2.0 / out.numel()) * (out - self.target)                           # MSE gradient (SURVEY 8(d))
+            if self.need_vol:
+                if self.cells is None:
+                    self.cells = torch.zeros((1, n ** 3 * 8), dtype=torch.float32, device=self.dev)
+                else:
+                    self.cells.zero_()
+                _, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, True, self.need_tf, grad_cells=self.cells)
+                # the gather writes straight into the flat [volume grad | TF grad] buffer that is all-reduced (no concatenation copy)
+                gvol = vr.gather(self.cells, out=self.flat_grad[:n ** 3].view(1, n, n, n) if self.world > 1 else None)
+                if self.world > 1:
+                    self.flat_grad[n ** 3:].copy_(gtf.reshape(-1))
+            else:
+                gvol, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, False, self.need_tf)
+            if timed: e[3].record()
+            if self.world > 1:
+                if not self.need_vol:
+                    self.flat_grad[:gtf.numel()].copy_(gtf.reshape(-1))
+                dist.all_reduce(self.flat_grad if self.need_vol else self.flat_grad[:gtf.numel()])      # ONE collective: NCCL over NVLink
+            if self.mode == "tf":                                                    # C2: momentum-SGD step on the TF (reference example :375-381), one kernel
+                self.tf_opt.step(gtf[0])
+                vr.kernel_launches += 1                                              # momentum_step_kernel
+        elif timed:
+            e[3].record()
+        if timed:
+            e[4].record()
+        n_k = vr.kernel_launches - self._k0
+        self._k0 = vr.kernel_launches
+        return e, K, n_k
+
+
+def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
+    """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    dev, world = wl.dev, wl.world
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    K = None
+    for _ in range(max(warmup, 1)):
+        _, K, _ = wl.step(False, flush)
+    samples = int(K.sum().item()) if wl.views else 0
+    shaded_fraction = None
+    if wl.views:
+        # diagnostic (untimed): how many of the active samples have non-zero opacity, i.e. are actually shaded
+        _, Ksh, _ = wl.vr.march(wl.vr.brick(wl.vol_lin), wl.tf_r4, wl.cams, wl.sr, wl.jit, nondiff=wl.mode == "nondiff", extra_flags=512)
+        shaded_fraction = float(Ksh.sum().item()) / max(samples, 1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        time.sleep(0.25)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    if profiler_range:
+        torch.cuda.profiler.start()
+    t0, t1 = wl.ev(), wl.ev()
+    t0.record()
+    evs, launches = [], 0
+    for _ in range(steps):
+        e, K, n_k = wl.step(True, flush)
+        evs.append(e)
+        launches += n_k
+    t1.record()
+    torch.cuda.synchronize()
+    if profiler_range:
+        torch.cuda.profiler.stop()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    total_ms = t0.elapsed_time(t1)
+    phase_ms = {"brick": 0.0, "fwd": 0.0, "bwd": 0.0, "post": 0.0}
+    for e in evs:
+        for name, a, b in (("brick", 0, 1), ("fwd", 1, 2), ("bwd", 2, 3), ("post", 3, 4)):
+            phase_ms[name] += e[a].elapsed_time(e[b])
+    tot = torch.tensor([total_ms, float(samples)], dtype=torch.float64, device=dev)
+    per_rank = [samples]
+    if world > 1:
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        mn = tot.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        total_ms, all_samples = float(mx[0]), float(sm[1])
+        per_rank = [float(mn[1]), float(mx[1])]
+    else:
+        all_samples = float(samples)
+    del flush
+    fwd_ms, bwd_ms = phase_ms["fwd"] / steps, phase_ms["bwd"] / steps
+    return dict(value=all_samples * steps / (total_ms * 1e-3) / 1e9, ms_per_step=total_ms / steps, samples=samples, all_samples=all_samples,
+                samples_min_max_over_ranks=per_rank, shaded_fraction=shaded_fraction, launches=launches, clocks=clocks,
+                phase_ms={k: v / steps for k, v in phase_ms.items()}, fwd_ms=fwd_ms, bwd_ms=bwd_ms,
+                fwd=samples / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 and samples else None,
+                bwd=samples / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 and samples else None)
+
+
+def time_allreduce(wl, reps=5):
+    """The collective alone: barrier first (no straggler wait inside), CUDA events around `reps` all-reduces of the step's flat buffer."""
+    import torch
+    import torch.distributed as dist
+    buf = wl.flat_grad if wl.need_vol else wl.flat_grad[:wl.R * 4]
+    buf.zero_()
+    for _ in range(2):
+        dist.all_reduce(buf)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = wl.ev(), wl.ev()
+    a.record()
+    for _ in range(reps):
+        dist.all_reduce(buf)
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=wl.dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    nbytes = buf.numel() * 4
+    return {"bytes": nbytes, "ms_isolated": ms, "busbw_gbs": nbytes * 2 * (wl.world - 1) / wl.world / (ms * 1e-3) / 1e9,
+            "nvlink_peak_gbs": NVLINK_PEAK_GBS, "frac_of_nvlink_peak": nbytes * 2 * (wl.world - 1) / wl.world / (ms * 1e-3) / 1e9 / NVLINK_PEAK_GBS,
+            "how": f"barrier, then CUDA events around {reps} back-to-back all_reduce(SUM) of the flat [volume grad | TF grad] fp32 buffer, max over ranks"}
+
+
+def small_line(name, cfg, r, extra=None):
+    d = {"config": name, "workload": cfg["desc"], "metric": METRIC[cfg["mode"]], "value": r["value"], "unit": "Gsamples/s", "ms": r["ms_per_step"],
+         "fwd": r["fwd"], "fwd_ms": r["fwd_ms"], "bwd": r["bwd"], "bwd_ms": r["bwd_ms"], "active_samples_per_step_per_gpu": r["samples"],
+         "shaded_fraction": None if r["shaded_fraction"] is None else round(r["shaded_fraction"], 4)}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def measure_l2_peak(dev, rank):
+    """L2 -> SM read bandwidth of this box with the library's own probe kernel (16-byte ld.global.cg over a 48 MiB buffer that
+    stays L2-resident; 2 CTAs per SM each read the whole buffer `reps` times)."""
+    import torch
+    from differender_b200 import _lib
+    lib = _lib.load()
+    buf = torch.empty(48 << 18, dtype=torch.float32, device=dev).normal_()
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nbytes = buf.numel() * 4
+    lib.dr_probe_l2_read(_lib.ptr(buf), nbytes, 1, _lib.ptr(sink), st)                # warm: brings the buffer into L2
+    best = 0.0
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        moved = lib.dr_probe_l2_read(_lib.ptr(buf), nbytes, 2, _lib.ptr(sink), st)
+        b.record()
+        torch.cuda.synchronize()
+        if moved < 0:
+            return None
+        best = max(best, moved / (a.elapsed_time(b) * 1e-3) / 1e9)
+    return best
+
+
+def roofline_block(args, cfg, wl, r, clocks, l2_gbs, peaks):
+    """roofline time = max(HBM bytes / HBM peak, L2 bytes / measured L2 peak, warp instructions / issue rate) of the
+    DOMINANT kernel, fraction = roofline time / measured time.  HBM and L2 bytes and the instruction count per sample come from the
+    committed ncu capture of this very workload (profiles/traffic_r02.json), labelled stale when the kernel sources changed since."""
+    import torch
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    vox_b = 2 if cfg["dtype"] == "f16" else 4
+    s = r["samples"]
+    mode = cfg["mode"]
+    dominant = "bwd_kernel" if (mode != "nondiff" and r["bwd_ms"] >= r["fwd_ms"]) else "fwd_kernel"
+    dom_ms = r["bwd_ms"] if dominant == "bwd_kernel" else r["fwd_ms"]
+    alg_l2 = 8 * vox_b + (64 if (dominant == "bwd_kernel" and wl.need_vol) else 0)     # SURVEY 8(d): corner reads (+ 8 fp32 atomic RMWs)
+    n3, rays = cfg["n"] ** 3, cfg["res"][0] * cfg["res"][1]
+    # compulsory HBM bytes per launch (BASELINE.md 5, per view: |V| sizeof(voxel) + 24 rays forward; + 8 |V| + 40 rays backward), for
+    # the layout actually marched: the cell-major copy is 8 |V| sizeof(voxel), the cell-major gradient 32 |V| read-modify-written
+    layout = wl.vr.resolve_layout(wl.vol_lin, wl.need_vol)
+    vol_bytes = n3 * vox_b * (8 if layout == "cell8" else 1)
+    comp = wl.views * (vol_bytes + 24 * rays) if dominant == "fwd_kernel" else wl.views * (vol_bytes + 40 * rays) + (2 * 32 * n3 if wl.need_vol else 0)
+    cap, cap_note = None, "no committed ncu capture for this workload"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+        k = tj["kernels"][dominant]
+        if tj["config"] == args.config and tj["layout"] == layout and tj["tf"] == wl.tf_name:
+            cap = k
+            stale = tj.get("csrc_digest") != csrc_digest()
+            cap_note = tj["source"] + (" [STALE: kernel sources changed since the capture]" if stale else "")
+    except (OSError, KeyError, ValueError):
+        pass
+    sm_count = torch.cuda.get_device_properties(wl.dev).multi_processor_count
+    sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    issue_rate = sm_count * 4 * sm_hz                         # warp-instructions per second: one per scheduler (4 per SM) per cycle
+    t_meas = dom_ms * 1e-3
+    roofs = {"hbm_compulsory": {"bytes": comp, "ms": 1e3 * comp / (hbm * 1e9)}}
+    if cap:
+        dram = cap["dram_bytes_per_sample"] * s
+        roofs["hbm_measured_traffic"] = {"bytes": dram, "ms": 1e3 * dram / (hbm * 1e9), "from": "committed capture, scaled by this run's sample count"}
+    if l2_gbs:
+        roofs["l2_algorithmic"] = {"bytes": alg_l2 * s, "ms": 1e3 * alg_l2 * s / (l2_gbs * 1e9), "bytes_per_sample": alg_l2}
+        if cap:
+            l2b = cap["lts_bytes_per_sample"] * s
+            roofs["l2_measured_traffic"] = {"bytes": l2b, "ms": 1e3 * l2b / (l2_gbs * 1e9), "from": "committed capture (lts__t_bytes), scaled"}
+    if cap:
+        wi = cap["warp_inst_per_sample"] * s
+        roofs["issue"] = {"warp_instructions": wi, "ms": 1e3 * wi / issue_rate, "warp_inst_per_32_samples": 32 * cap["warp_inst_per_sample"],
+                          "thread_inst_per_sample": cap["thread_inst_per_sample"], "issue_rate_per_s": issue_rate,
+                          "from": "smsp__inst_executed of the committed capture, scaled; SMs x 4 schedulers x the SM clock sampled in this run"}
+    # the binding roof: measured traffic where a capture exists (the algorithmic L2 figure is served mostly by L1, see `note`)
+    cands = {"hbm": roofs.get("hbm_measured_traffic", roofs["hbm_compulsory"])["ms"]}
+    if "l2_measured_traffic" in roofs:
+        cands["l2"] = roofs["l2_measured_traffic"]["ms"]
+    elif "l2_algorithmic" in roofs:
+        cands["l2"] = roofs["l2_algorithmic"]["ms"]
+    if "issue" in roofs:
+        cands["issue"] = roofs["issue"]["ms"]
+    bound = max(cands, key=cands.get)
+    roof_ms = cands[bound]
+    if bound == "issue":
+        achieved, peak, unit = roofs["issue"]["warp_instructions"] / t_meas / 1e9, issue_rate / 1e9, "Gwarp-inst/s"
+    elif bound == "l2":
+        b = roofs.get("l2_measured_traffic", roofs.get("l2_algorithmic"))["bytes"]
+        achieved, peak, unit = b / t_meas / 1e9, l2_gbs, "GB/s"
+    else:
+        b = roofs.get("hbm_measured_traffic", roofs["hbm_compulsory"])["bytes"]
+        achieved, peak, unit = b / t_meas / 1e9, hbm, "GB/s"
+    return {
+        "bound": bound, "kernel": dominant, "achieved": achieved, "peak": peak, "unit": unit, "frac": roof_ms / dom_ms if dom_ms > 0 else None,
+        "traffic": cap["dram_bytes_per_sample"] * s if cap else None,
+        "traffic_source": (cap_note + " -- NOT measured in this run (ncu is not attached); dram bytes per sample of the capture x this run's samples") if cap else None,
+        "kernel_ms": dom_ms, "roof_ms": roof_ms, "roof_times_ms": {k: v for k, v in cands.items()}, "roofs": roofs,
+        "algorithmic_l2_bytes_per_sample": alg_l2,
+        "peaks": {"hbm_gbs": hbm, "hbm_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                  "l2_read_gbs": l2_gbs, "l2_source": "measured in this run: dr_probe_l2_read, 16-byte ld.global.cg over an L2-resident 48 MiB buffer, best of 3",
+                  "issue_gwarp_inst_per_s": issue_rate / 1e9, "sm_count": sm_count, "sm_mhz_used": sm_hz / 1e6},
+        "ncu": None if not cap else {"source": cap_note, "issue_active_pct": cap.get("issue_active_pct"), "l1tex_throughput_pct": cap.get("l1tex_throughput_pct"),
+                                     "lts_throughput_pct": cap.get("lts_throughput_pct"), "dram_throughput_pct": cap.get("dram_throughput_pct")},
+        "note": "the path is instruction-issue-bound, not memory-bound: DRAM traffic is 1-2 % and L2 traffic < 20 % of their peaks (most corner fetches hit "
+                "L1), so the north_star's '>= 60 % of the L2/HBM roofline' cannot be met by these kernels by construction -- the binding roof is issue, "
+                "and `frac` is reported against it.  `algorithmic_l2_bytes_per_sample` (SURVEY 8(d)) is kept as a per-sample work measure only.",
+    }
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
-    from differender_b200 import Raycaster, VolumeRaycaster
-    from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
+    from differender_b200 import Raycaster
+    from differender_b200.distributed import DistributedRaycaster
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,133 +519,51 @@ def run_ours(args, cfg):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    n, (w, h), R, M, sr = cfg["n"], cfg["res"], 128, cfg["M"], cfg["sr"]
     views = args.views or cfg["views"]
-    mode = cfg["mode"]
-    vdtype = torch.float16 if cfg["dtype"] == "f16" else torch.float32
-    vol = make_volume(n, device=dev, dtype=vdtype)                                   # (1, D, H, W), replicated on every rank
-    tf_name = args.tf or cfg.get("tf", "tf1")
-    tf = make_tf(tf_name, R, device=dev)                                             # (4, R)
-    all_cams = make_cameras(views * world, device=dev)
-    cams = all_cams[rank * views:(rank + 1) * views].contiguous()                   # this rank's shard of the view batch
-    jit = make_jitter(views, h, w, seed=4321 + rank, device=dev) if cfg["jitter"] else None
-    g = torch.Generator(device=dev).manual_seed(99 + rank)
-    target = torch.rand((views, 4, h, w), generator=g, device=dev)
-
-    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=args.layout, skip_empty=not args.no_skip)
-    vol_lin = vol.reshape(1, n, n, n)
-    tf_r4 = tf.t().contiguous()[None]
-    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
-    need_vol, need_tf = mode == "full", mode in ("full", "tf")
-    momentum = torch.zeros_like(tf)
-    flat_grad = torch.empty(n ** 3 + R * 4, dtype=torch.float32, device=dev) if world > 1 else None
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    phase_ms = {"brick": 0.0, "fwd": 0.0, "bwd": 0.0, "post": 0.0}
-    samples_per_step = [0]
-    launches = [0]
-
-    def step(timed):
-        e = [ev() for _ in range(5)] if timed else None
-        flush.zero_()                                                                # L2 flush between steps
-        if timed: e[0].record()
-        if need_vol:
-            vr.forget_volume()                                                       # a volume-gradient loop changes the volume every step: rebuild the skip grid's min/max too
-        bricked = vr.brick(vol_lin)
-        if timed: e[1].record()
-        out, K, Tp = vr.march(bricked, tf_r4, cams, sr, jit, nondiff=mode == "nondiff")
-        if timed: e[2].record()
-        n_k = (2 if bricked.ndim in (2, 3) else 1) + (0 if args.no_skip else 2)      # (brick_kernel / expand_cells_kernel +) (skip_minmax + skip_classify +) fwd_kernel
-        if mode != "nondiff":
-            go = (2.0 / out.numel()) * (out - target)                                # MSE gradient
-            xf = 0
-            if world > 1 and need_vol:
-                # the gather writes straight into the flat [volume grad | TF grad] buffer that is all-reduced (no concatenation copy)
-                cells = torch.zeros((1, n ** 3 * 8), dtype=torch.float32, device=dev)
-                _, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf, grad_cells=cells, extra_flags=xf)
-                gvol = vr.gather(cells, out=flat_grad[:n ** 3].view(1, n, n, n))
-                flat_grad[n ** 3:].copy_(gtf.reshape(-1))
-            else:
-                gvol, gtf = vr.march_backward(bricked, tf_r4, cams, sr, jit, go, out, K, Tp, need_vol, need_tf, extra_flags=xf)
-            if timed: e[3].record()
-            n_k += 1 + (1 if need_tf else 0) + (1 if need_vol else 0)                 # bwd_kernel (+ tf_reduce_kernel) (+ gather_grad_kernel)
-            if world > 1:
-                if not need_vol:
-                    flat_grad[:gtf.numel()].copy_(gtf.reshape(-1))
-                dist.all_reduce(flat_grad if need_vol else flat_grad[:gtf.numel()])      # ONE collective: NCCL over NVLink
-            if mode == "tf":                                                         # C2: momentum update (reference example :375-381)
-                gt = gtf[0].t().clamp(-0.1, 0.1)
-                momentum.mul_(0.9).add_(gt, alpha=0.1)
-        elif timed:
-            e[3].record()
-        if timed:
-            e[4].record()
-        return e, K, n_k
-
-    for _ in range(max(args.warmup, 3)):
-        _, K, n_k = step(False)
-    samples_per_step[0] = int(K.sum().item())
-    # diagnostic (untimed): how many of the active samples have non-zero opacity, i.e. are actually shaded
-    _, Ksh, _ = vr.march(vr.brick(vol_lin), tf_r4, cams, sr, jit, nondiff=mode == "nondiff", extra_flags=512)
-    shaded_fraction = float(Ksh.sum().item()) / max(samples_per_step[0], 1)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
-    torch.cuda.synchronize()
-    t_wall0 = time.time()
-    if args.cuda_profiler_range:
-        torch.cuda.profiler.start()
-    t0, t1 = ev(), ev()
-    t0.record()
-    evs = []
-    for _ in range(args.steps):
-        e, K, n_k = step(True)
-        evs.append(e)
-        launches[0] += n_k
-    t1.record()
-    torch.cuda.synchronize()
-    if args.cuda_profiler_range:
-        torch.cuda.profiler.stop()
-    if world > 1:
-        dist.barrier()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1)
-    total_ms = t0.elapsed_time(t1)
-    for e in evs:
-        for name, a, b in (("brick", 0, 1), ("fwd", 1, 2), ("bwd", 2, 3), ("post", 3, 4)):
-            phase_ms[name] += e[a].elapsed_time(e[b])
-    tot = torch.tensor([total_ms, float(samples_per_step[0])], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, all_samples = float(mx[0]), float(sm[1])
-    else:
-        all_samples = float(tot[1])
-    value = all_samples * args.steps / (total_ms * 1e-3) / 1e9
+    wl = Workload(cfg, args, dev, rank, world, views, tf_name=args.tf)
+    n, (w, h), R, M, sr, mode = wl.n, cfg["res"], wl.R, cfg["M"], wl.sr, wl.mode
+    need_vol, need_tf = wl.need_vol, wl.need_tf
+    r = time_workload(wl, args.steps, max(args.warmup, 3), profiler_range=args.cuda_profiler_range, sample_clocks=True)
+    clocks = r["clocks"]
+    allreduce = None
+    if world > 1 and mode != "nondiff":
+        allreduce = time_allreduce(wl)
+        allreduce["in_step_ms"] = r["phase_ms"]["post"]
+        allreduce["in_step_note"] = "rank-0 CUDA-event time of the step's `post` phase: the collective plus the wait for the slowest rank"
 
     # ---- end-to-end through the public autograd API, inputs from pinned host memory every step ---------------------
     e2e = None
     if not args.no_e2e:
+        vol, tf, cams, jit, target = wl.vol, wl.tf, wl.cams, wl.jit, wl.target
+        flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+        ev = wl.ev
         rc = Raycaster((n, n, n), (w, h), R, sampling_rate=sr, jitter=cfg["jitter"], max_samples=M, layout=args.layout, skip_empty=not args.no_skip)
+        drc = DistributedRaycaster(rc) if world > 1 else None
         pin = lambda t: t.detach().cpu().pin_memory()
         h_vol, h_tf, h_cams, h_target = pin(vol), pin(tf), pin(cams), pin(target)
         h_jit = pin(jit) if jit is not None else None
         h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
         h_gtf = torch.empty((4, R), dtype=torch.float32).pin_memory()
+        h_gvol = [torch.empty(vol.shape, dtype=torch.float32).pin_memory() for _ in range(2)] if need_vol else None
         h2d = sum(t.numel() * t.element_size() for t in (h_vol, h_tf, h_cams, h_target) + ((h_jit,) if h_jit is not None else ()))
-        d2h = 4 + (h_gtf.numel() * 4 if need_tf else 0)
+        d2h = 4 + (h_gtf.numel() * 4 if need_tf else 0) + (h_gvol[0].numel() * 4 if need_vol else 0)
 
         e2e_phase = {"wait_for_inputs": 0.0, "forward": 0.0, "loss+backward": 0.0, "d2h+sync": 0.0}
         # Inputs are double-buffered like a data loader would: while step i computes, the copy engine brings step i+1's inputs
         # (volume, TF, cameras, jitter, target: every step copies all of them from pinned host memory) into the other buffer set
-        # on a second stream.  Every timed step issues exactly one such set of copies inside the timed region.
+        # on a second stream.  Every timed step issues exactly one such set of copies inside the timed region.  The volume
+        # gradient goes home on a third stream (its own pinned buffer per parity of the step) under the next step's compute;
+        # loss and TF gradient are read synchronously, as a training loop reads them.
         copy_stream = torch.cuda.Stream(device=dev)
+        out_stream = torch.cuda.Stream(device=dev)
         bufs = [dict(v=torch.empty_like(vol), t=torch.empty_like(tf), c=torch.empty_like(cams), tg=torch.empty_like(target),
                      j=torch.empty_like(jit) if jit is not None else None) for _ in range(2)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         step_no = [0]
+        all_cams_dev = None
+        if world > 1:
+            from differender_b200.synthetic import make_cameras
+            all_cams_dev = make_cameras(views * world, device=dev)
 
         def prefetch(k):
             copy_stream.wait_stream(torch.cuda.current_stream())      # the set's previous consumer (two steps back) is done
@@ -346,19 +595,26 @@ def run_ours(args, cfg):
                 loss = ((img - tg) ** 2).mean()
             else:
                 v.requires_grad_(need_vol); t.requires_grad_(need_tf)
-                img = rc(v, t, c, j)
+                if world > 1:                                         # the product's multi-GPU API: views dealt round-robin, ONE all-reduce in the backward
+                    all_c = all_cams_dev.clone(); all_c[rank::world] = c
+                    img, _ = drc(v, t, all_c, j)
+                else:
+                    img = rc(v, t, c, j)
                 if timed: e[2].record()
                 loss = ((img - tg) ** 2).mean()
+                main.wait_stream(out_stream)          # the previous step's volume gradient has left its buffer (copied under this step's forward)
                 loss.backward()
-                if world > 1:
-                    flat = torch.cat([x.grad.reshape(-1).float() for x in (v, t) if x.grad is not None])
-                    dist.all_reduce(flat)
                 if need_tf:
                     h_gtf.copy_(t.grad, non_blocking=True)
+                if need_vol:
+                    out_stream.wait_stream(main)
+                    with torch.cuda.stream(out_stream):
+                        h_gvol[k].copy_(v.grad, non_blocking=True)
+                    v.grad.record_stream(out_stream)
             if timed: e[3].record()
             h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
             if timed: e[4].record()
-            torch.cuda.synchronize()                                                  # the user reads the loss every step
+            main.synchronize()                                                        # the user reads the loss every step
             if timed:
                 for name, x, y in (("wait_for_inputs", 0, 1), ("forward", 1, 2), ("loss+backward", 2, 3), ("d2h+sync", 3, 4)):
                     e2e_phase[name] += e[x].elapsed_time(e[y])
@@ -376,96 +632,99 @@ def run_ours(args, cfg):
             t_s = time.perf_counter()
             e2e_step(True)
             step_ms.append(round(1e3 * (time.perf_counter() - t_s), 2))
+        torch.cuda.current_stream().wait_stream(out_stream)                            # the last volume gradient has arrived on the host
         b.record()
         torch.cuda.synchronize()
         ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        e2e = {"value": all_samples * args.steps / (float(ms[0]) * 1e-3) / 1e9, "unit": "Gsamples/s",
+        e2e = {"value": r["all_samples"] * args.steps / (float(ms[0]) * 1e-3) / 1e9, "unit": "Gsamples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ms[0]) / args.steps,
                "phase_ms_per_step": {k: v / args.steps for k, v in e2e_phase.items()}, "wall_ms_each_step": step_ms,
-               "api": "differender_b200.Raycaster.forward + loss.backward()" if mode != "nondiff" else "Raycaster.raycast_nondiff",
+               "api": ("differender_b200.DistributedRaycaster.forward + loss.backward() (ONE all-reduce inside the backward)" if world > 1 else
+                       "differender_b200.Raycaster.forward + loss.backward()") if mode != "nondiff" else "Raycaster.raycast_nondiff",
+               "results_read_back": "loss (4 B) + TF gradient (2 KiB) synchronously; the volume gradient (all of it) to pinned host memory on a side stream, "
+                                    "double-buffered under the next step's compute, the last one awaited before the clock stops" if need_vol else
+                                    "loss + TF gradient" if need_tf else "loss",
                "overlap": "inputs are double-buffered: step i+1's H2D copies (all inputs, every step) run on a second stream under step i's compute; "
                           "`wait_for_inputs` is what a step still waits for them"}
+        del bufs, flush, rc, drc
 
-    # L2 -> SM read bandwidth of this box (not in MEASURED_PEAKS.json, so measured here): repeated reduction
-    # of a 48 MiB buffer that stays L2-resident (126 MB L2); a library reduction, so a lower bound of the hardware figure
-    l2_gbs = None
-    if rank == 0:
-        lb = torch.empty(48 << 18, dtype=torch.float32, device=dev).normal_()
-        for _ in range(5):
-            lb.sum()
-        a, b = ev(), ev()
-        a.record()
-        for _ in range(20):
-            lb.sum()
-        b.record()
-        torch.cuda.synchronize()
-        l2_gbs = 20 * lb.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9
-        del lb
+    # ---- the other configurations, a few seconds each -----------------------------------------------
+    others, strong = [], []
+    if not args.no_others:
+        names = args.others.split(",") if args.others is not None else (["c1", "c2", "c3gray", "c4", "c5"] if world == 1 else [])
+        for name in [x for x in names if x]:
+            try:
+                base = "c3" if name == "c3gray" else name
+                c2 = CONFIGS[base]
+                tfn = "gray" if name == "c3gray" else None
+                steps = {"c1": 5, "c2": 100, "c3gray": 3, "c4": 3, "c5": 2}.get(name, 3)
+                torch.cuda.empty_cache()
+                w2 = Workload(c2, args, dev, rank, world, c2["views"], tf_name=tfn)
+                r2 = time_workload(w2, steps, 2 if name != "c2" else 5)
+                extra = {"tf": w2.tf_name, "steps": steps, "views_per_gpu": w2.views}
+                if name == "c2":
+                    extra["note"] = "100 iterations of fwd + TF-only bwd + dr_momentum_step (lr .1, gamma .9, clip .1, decay .99), TF starting from `black`; the volume copy and its min/max are cached across iterations"
+                if name == "c3gray":
+                    extra["note"] = "C3 with the dense `gray` TF: no exactly-transparent bin, every active sample is shaded, nothing to skip (the worst case for the transparent-sample shortcuts)"
+                others.append(small_line(name, c2, r2, extra))
+                del w2
+            except Exception as e:  # a side measurement must not take the headline down
+                others.append({"config": name, "error": f"{type(e).__name__}: {e}"})
+        if world > 1:
+            names = args.strong.split(",") if args.strong is not None else ["c4", "c5"]
+            for name in [x for x in names if x]:
+                try:
+                    c2 = CONFIGS[name]
+                    torch.cuda.empty_cache()
+                    w2 = Workload(c2, args, dev, rank, world, None, total_views=c2["total_views"])
+                    steps = 2 if name == "c4" else 1
+                    r2 = time_workload(w2, steps, 1)
+                    ar = time_allreduce(w2, reps=3)
+                    ar["in_step_ms"] = r2["phase_ms"]["post"]
+                    strong.append(small_line(name, c2, r2, {"scaling": "strong", "total_views": c2["total_views"], "views_on_rank0": w2.views, "steps": steps,
+                                                            "samples_min_max_over_ranks": r2["samples_min_max_over_ranks"], "allreduce": ar}))
+                    del w2
+                except Exception as e:
+                    strong.append({"config": name, "error": f"{type(e).__name__}: {e}"})
+
+    l2_gbs = measure_l2_peak(dev, rank) if rank == 0 else None
     if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        vox_b = 2 if cfg["dtype"] == "f16" else 4
-        s = samples_per_step[0]
-        fwd_ms, bwd_ms = phase_ms["fwd"] / args.steps, phase_ms["bwd"] / args.steps
-        # algorithmic bytes per sample (SURVEY 8(d) / BASELINE.md 5): forward 8 corner voxels; backward 8 corner reads +
-        # 8 fp32 atomic read-modify-writes (TF-only backward = forward figure)
-        fwd_bytes = 8 * vox_b
-        bwd_bytes = 8 * vox_b + (64 if need_vol else 0)
-        dominant = "bwd_kernel" if (mode != "nondiff" and bwd_ms >= fwd_ms) else "fwd_kernel"
-        dom_bytes, dom_ms = (bwd_bytes, bwd_ms) if dominant == "bwd_kernel" else (fwd_bytes, fwd_ms)
-        achieved = dom_bytes * s / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        # DRAM bytes of the dominant kernel per launch, from the committed `ncu --set full` capture of this very workload
-        traffic = None
-        ncu_note = {"source": None}
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-            if tj["config"] == args.config and tj["views_per_gpu"] == views and tj["layout"] == vr.resolve_layout(vol_lin):
-                traffic = tj["kernels"][dominant]["traffic_bytes_per_launch"]
-                ncu_note = {"source": tj["source"],
-                            "issue_active_pct": {k: round(v["issue_active_pct"], 1) for k, v in tj["kernels"].items()},
-                            "l1tex_throughput_pct": {k: round(v["l1tex_throughput_pct"], 1) for k, v in tj["kernels"].items()},
-                            "lts_throughput_pct": {k: round(v["lts_throughput_pct"], 1) for k, v in tj["kernels"].items()}}
-        except (OSError, KeyError, ValueError):
-            pass
+        s = r["samples"]
         line = {
             "metric": METRIC[mode],
-            "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": r["value"], "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "volume": f"{n}^3 {cfg['dtype']}", "image": f"{w}x{h}", "views_per_gpu": views,
-                       "volume_layout": vr.resolve_layout(vol_lin), "tf": tf_name, "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
-                       "parallelism": f"views sharded over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
+                       "volume_layout": wl.vr.resolve_layout(wl.vol_lin, need_vol), "tf": wl.tf_name, "tf_resolution": R, "sampling_rate": sr, "max_samples": M, "jitter": cfg["jitter"],
+                       "parallelism": f"views dealt round-robin over {world} GPU(s), volume+TF replicated" + (", grads all-reduced (NCCL)" if world > 1 else ""),
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset); per-step working set also exceeds L2",
-                       "active_samples_per_step_per_gpu": s, "shaded_fraction_of_active_samples": round(shaded_fraction, 4),
+                       "active_samples_per_step_per_gpu": s, "samples_min_max_over_ranks": r["samples_min_max_over_ranks"],
+                       "shaded_fraction_of_active_samples": round(r["shaded_fraction"], 4),
                        "empty_space_skipping": not args.no_skip,
                        "note": "samples whose TF alpha is exactly 0 are composited exactly without evaluating their normal, and runs of them inside "
                                "macro-cells that are transparent under the TF are counted without being marched (exact; DESIGN.md 4)"},
-            "fwd": {"value": s / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "unit": "Gsamples/s", "ms": fwd_ms},
-            "bwd": {"value": s / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "unit": "Gsamples/s", "ms": bwd_ms},
-            "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes * s, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_sample": dom_bytes,
-                         "note": "algorithmic bytes are the L2-level figure of SURVEY 8(d) (8 corner reads [+ 8 fp32 atomic RMWs] per sample); the kernels are instruction-issue-bound and most accesses hit L1/L2, so measured DRAM traffic (`traffic`) is far BELOW the algorithmic bytes"},
-            "rooflines_other": {"l2_read_gbs_measured": l2_gbs, "l2_how": "torch.sum over a 48 MiB L2-resident buffer, 20 reps",
-                                "achieved_over_l2": (achieved / l2_gbs) if l2_gbs else None,
-                                "ncu": ncu_note,
-                                "binding": "instruction issue (backward 75 % issue-active, FMA pipe 56 %, ALU 41 %; forward 69 % issue-active and "
-                                           "latency-exposed, L1TEX 43 %); DRAM < 2 % of peak"},
-            "allreduce": None if world == 1 else {
-                "bytes": int((n ** 3 + R * 4) * 4 if need_vol else R * 16), "ms": phase_ms["post"] / args.steps,
-                "busbw_gbs": ((n ** 3 + R * 4) * 4 if need_vol else R * 16) * 2 * (world - 1) / world / (phase_ms["post"] / args.steps * 1e-3) / 1e9,
-                "nvlink_peak_gbs": 900.0, "note": "one all_reduce(SUM) of the flat [volume grad | TF grad] fp32 buffer, rank-0 CUDA-event time of the `post` phase"},
-            "clocks": clocks, "gpu_launches": launches[0],
+            "fwd": {"value": r["fwd"], "unit": "Gsamples/s", "ms": r["fwd_ms"]},
+            "bwd": {"value": r["bwd"], "unit": "Gsamples/s", "ms": r["bwd_ms"]},
+            "phase_ms_per_step": r["phase_ms"],
+            "roofline": roofline_block(args, cfg, wl, r, clocks, l2_gbs, peaks),
+            "allreduce": allreduce,
+            "clocks": clocks, "gpu_launches": r["launches"],
+            "parity_basis": parity_basis(),
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if others:
+            line["configs_other"] = others
+        if strong:
+            line["strong_scaling"] = strong
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sample(cfg)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}

@@ -49,6 +49,7 @@ class SyncGradients(torch.autograd.Function):
     @staticmethod
     def forward(ctx, group, flat, *tensors):
         ctx.group, ctx.flat = group, flat
+        ctx.set_materialize_grads(False)     # an input without a gradient (e.g. a volume whose gradient FusedVolumeSGD keeps cell-major) stays None
         return tuple(t.view_as(t) for t in tensors)
 
     @staticmethod

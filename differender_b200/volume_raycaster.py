@@ -57,6 +57,7 @@ class VolumeRaycaster:
         self.pending_grad_cells = None
         # DistributedRaycaster: {"vol": [1,Y,Z,X] fp32 view of its flat all-reduce buffer}; the gather writes there directly
         self.grad_sink = None
+        self.kernel_launches = 0     # this object's kernel launches so far (the library's own kernels only; bench.py reports the count)
 
     @property
     def max_valid_sample_step_count(self):
@@ -151,9 +152,11 @@ class VolumeRaycaster:
         if layout == "cell8":
             out = torch.empty((vol_lin.shape[0], X * Y * Z, 8), dtype=vol_lin.dtype, device=vol_lin.device)
             _lib.check(lib.dr_expand_cells(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_expand_cells")
+            self.kernel_launches += 1
         else:
             out = torch.empty((vol_lin.shape[0], lib.dr_bricked_elems(ctypes.byref(d))), dtype=vol_lin.dtype, device=vol_lin.device)
             _lib.check(lib.dr_brick_volume(ctypes.byref(d), _lib.ptr(vol_lin), _lib.ptr(out), _stream()), "dr_brick_volume")
+            self.kernel_launches += 1
         out.dr_source = vol_lin
         self._copy_cache = (self._src_key(vol_lin), vol_lin.untyped_storage(), out)
         return out
@@ -184,6 +187,7 @@ class VolumeRaycaster:
         grid = torch.empty(max(lib.dr_skip_grid_bytes(ctypes.byref(d)), 1), dtype=torch.uint8, device=src.device)
         _lib.check(lib.dr_build_skip_grid(ctypes.byref(d), _lib.ptr(src), _lib.ptr(tf_r4), _lib.ptr(mm), int(mm_valid), _lib.ptr(grid),
                                           _stream()), "dr_build_skip_grid")
+        self.kernel_launches += 1 if mm_valid else 2             # skip_classify_kernel (+ skip_minmax_kernel)
         self._skip_minmax = (key, src.untyped_storage(), mm)
         # Performance hint only (results are bit-identical either way): with (almost) no empty macro-cells the skip kernels'
         # bookkeeping costs ~5 % of the forward, so they are not used while the PREVIOUS call's grid -- its count is read back
@@ -229,6 +233,7 @@ class VolumeRaycaster:
         _lib.check(_lib.load().dr_forward_ex(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
                                              _lib.ptr(mse_target), _lib.ptr(grid), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp),
                                              _lib.ptr(loss_sum), _stream()), "dr_forward_ex")
+        self.kernel_launches += 1
         if mse_target is not None:
             return out, K, Tp, loss_sum
         return out, K, Tp
@@ -269,6 +274,7 @@ class VolumeRaycaster:
                                        _lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
                                        _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
                                        _stream()), "dr_backward")
+        self.kernel_launches += 1 + (1 if need_tf else 0)           # bwd_kernel (+ tf_reduce_kernel)
         if not need_vol:
             return None, gtf
         if keep_cells:
@@ -288,6 +294,7 @@ class VolumeRaycaster:
         if tuple(gl.shape) != (grad_cells.shape[0], Y, Z, X) or gl.dtype != torch.float32 or not gl.is_contiguous():
             raise ValueError("gather: `out` must be a contiguous fp32 tensor of shape [Bvol, Y, Z, X]")
         _lib.check(_lib.load().dr_gather_grad(ctypes.byref(d), _lib.ptr(grad_cells), _lib.ptr(gl), 0, _stream()), "dr_gather_grad")
+        self.kernel_launches += 1
         return gl
 
 

@@ -26,5 +26,20 @@ v2 = vol.clone().requires_grad_(True); t2 = tf.clone().requires_grad_(True)
 ev = float((v.grad - v2.grad).norm() / v2.grad.norm()); et = float((t.grad - t2.grad).norm() / t2.grad.norm())
 print(f"rank {rank}: views {idx}, rel-L2 vs single process: volume {ev:.2e}, tf {et:.2e}", flush=True)
 assert ev < 1e-5 and et < 1e-5
+# the same batch through FusedVolumeSGD: the gradient stays cell-major, is gathered into a flat buffer, all-reduced and applied by
+# dr_gather_step from the reduced linear gradient; every rank must end up with the volume a single process computes
+from differender_b200 import FusedVolumeSGD, MomentumSGD
+rc_f = Raycaster((N, N, N), (w, h), R, max_samples=1024)
+vf = vol.clone().requires_grad_(True)
+opt = FusedVolumeSGD(rc_f, vf, lr=2.0, momentum=0.5, max_grad=0.05, hi=1.0)
+imgf, _ = DistributedRaycaster(rc_f)(vf, tf, cams, jit)
+(imgf * go[idx]).sum().backward()
+assert vf.grad is None
+opt.step()
+vs = vol.clone()
+MomentumSGD(vs, lr=2.0, momentum=0.5, max_grad=0.05, lo=0.0, hi=1.0).step(v2.grad)
+ef = float((vf.detach() - vs).norm() / vs.norm())
+print(f"rank {rank}: fused distributed volume step vs single process: rel-L2 {ef:.2e}", flush=True)
+assert ef < 1e-5
 dist.barrier()
 dist.destroy_process_group()
