@@ -264,22 +264,24 @@ class Workload:
             vr.forget_volume()         # a volume-gradient loop changes the volume every step: re-lay the volume and rebuild the skip grid's min/max too
         bricked = vr.brick(self.vol_lin, need_vol_grad=self.need_vol)
         if timed: e[1].record()
-        out, K, Tp = vr.march(bricked, self.tf_r4, self.cams, self.sr, self.jit, nondiff=self.mode == "nondiff")
+        fused = self.mode != "nondiff"          # MSE loss fused into the forward epilogue, its gradient formed inside the backward
+        res = vr.march(bricked, self.tf_r4, self.cams, self.sr, self.jit, nondiff=self.mode == "nondiff", mse_target=self.target if fused else None)
+        out, K, Tp = res[:3]
         if timed: e[2].record()
         if self.mode != "nondiff":
-            go = (2.0 / out.numel()) * (out - self.target)                           # MSE gradient
+            go, ms = self.target, 2.0 / out.numel()                                  # dL/d(out) = 2 (out - target) / numel   
             if self.need_vol:
                 if self.cells is None:
                     self.cells = torch.zeros((1, n ** 3 * 8), dtype=torch.float32, device=self.dev)
                 else:
                     self.cells.zero_()
-                _, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, True, self.need_tf, grad_cells=self.cells)
+                _, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, True, self.need_tf, grad_cells=self.cells, mse_scale=ms)
                 # the gather writes straight into the flat [volume grad | TF grad] buffer that is all-reduced (no concatenation copy)
                 gvol = vr.gather(self.cells, out=self.flat_grad[:n ** 3].view(1, n, n, n) if self.world > 1 else None)
                 if self.world > 1:
                     self.flat_grad[n ** 3:].copy_(gtf.reshape(-1))
             else:
-                gvol, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, False, self.need_tf)
+                gvol, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, False, self.need_tf, mse_scale=ms)
             if timed: e[3].record()
             if self.world > 1:
                 if not self.need_vol:
@@ -542,13 +544,14 @@ def run_ours(args, cfg):
         pin = lambda t: t.detach().cpu().pin_memory()
         h_vol, h_tf, h_cams, h_target = pin(vol), pin(tf), pin(cams), pin(target)
         h_jit = pin(jit) if jit is not None else None
-        h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        h_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_done, losses, pending = [torch.cuda.Event(), torch.cuda.Event()], [], []
         h_gtf = torch.empty((4, R), dtype=torch.float32).pin_memory()
         h_gvol = [torch.empty(vol.shape, dtype=torch.float32).pin_memory() for _ in range(2)] if need_vol else None
         h2d = sum(t.numel() * t.element_size() for t in (h_vol, h_tf, h_cams, h_target) + ((h_jit,) if h_jit is not None else ()))
         d2h = 4 + (h_gtf.numel() * 4 if need_tf else 0) + (h_gvol[0].numel() * 4 if need_vol else 0)
 
-        e2e_phase = {"wait_for_inputs": 0.0, "forward": 0.0, "loss+backward": 0.0, "d2h+sync": 0.0}
+        e2e_phase = {"wait_for_inputs": 0.0, "forward": 0.0, "loss+backward": 0.0, "d2h": 0.0}
         # Inputs are double-buffered like a data loader would: while step i computes, the copy engine brings step i+1's inputs
         # (volume, TF, cameras, jitter, target: every step copies all of them from pinned host memory) into the other buffer set
         # on a second stream.  Every timed step issues exactly one such set of copies inside the timed region.  The volume
@@ -597,11 +600,10 @@ def run_ours(args, cfg):
                 v.requires_grad_(need_vol); t.requires_grad_(need_tf)
                 if world > 1:                                         # the product's multi-GPU API: views dealt round-robin, ONE all-reduce in the backward
                     all_c = all_cams_dev.clone(); all_c[rank::world] = c
-                    img, _ = drc(v, t, all_c, j)
+                    loss, img, _ = drc.mse_loss(v, t, all_c, tg, j)
                 else:
-                    img = rc(v, t, c, j)
+                    loss, img = rc.mse_loss(v, t, c, tg, j)           # render + MSE fused (loss in the forward epilogue, its gradient inside the backward kernel)
                 if timed: e[2].record()
-                loss = ((img - tg) ** 2).mean()
                 main.wait_stream(out_stream)          # the previous step's volume gradient has left its buffer (copied under this step's forward)
                 loss.backward()
                 if need_tf:
@@ -612,13 +614,16 @@ def run_ours(args, cfg):
                         h_gvol[k].copy_(v.grad, non_blocking=True)
                     v.grad.record_stream(out_stream)
             if timed: e[3].record()
-            h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            h_loss[k].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_done[k].record(main)
             if timed: e[4].record()
-            main.synchronize()                                                        # the user reads the loss every step
+            # the loop reads every step's loss, one step late: the previous step's value is on the host by now, so the read does not
+            # drain the GPU (a training loop that logs its loss does not have to stall the device for it)
+            if step_no[0] > 1:
+                loss_done[k ^ 1].synchronize()
+                losses.append(float(h_loss[k ^ 1][0]))
             if timed:
-                for name, x, y in (("wait_for_inputs", 0, 1), ("forward", 1, 2), ("loss+backward", 2, 3), ("d2h+sync", 3, 4)):
-                    e2e_phase[name] += e[x].elapsed_time(e[y])
-            return float(h_loss[0])
+                pending.append(e)
 
         for _ in range(max(args.warmup, 3)):
             e2e_step()
@@ -635,17 +640,22 @@ def run_ours(args, cfg):
         torch.cuda.current_stream().wait_stream(out_stream)                            # the last volume gradient has arrived on the host
         b.record()
         torch.cuda.synchronize()
+        losses.append(float(h_loss[(step_no[0] - 1) & 1][0]))                          # ... and so has the last loss
+        for e in pending:
+            for name, x, y in (("wait_for_inputs", 0, 1), ("forward", 1, 2), ("loss+backward", 2, 3), ("d2h", 3, 4)):
+                e2e_phase[name] += e[x].elapsed_time(e[y])
         ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         e2e = {"value": r["all_samples"] * args.steps / (float(ms[0]) * 1e-3) / 1e9, "unit": "Gsamples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ms[0]) / args.steps,
                "phase_ms_per_step": {k: v / args.steps for k, v in e2e_phase.items()}, "wall_ms_each_step": step_ms,
-               "api": ("differender_b200.DistributedRaycaster.forward + loss.backward() (ONE all-reduce inside the backward)" if world > 1 else
-                       "differender_b200.Raycaster.forward + loss.backward()") if mode != "nondiff" else "Raycaster.raycast_nondiff",
-               "results_read_back": "loss (4 B) + TF gradient (2 KiB) synchronously; the volume gradient (all of it) to pinned host memory on a side stream, "
-                                    "double-buffered under the next step's compute, the last one awaited before the clock stops" if need_vol else
-                                    "loss + TF gradient" if need_tf else "loss",
+               "api": ("differender_b200.DistributedRaycaster.mse_loss + loss.backward() (ONE all-reduce inside the backward)" if world > 1 else
+                       "differender_b200.Raycaster.mse_loss + loss.backward() (render + MSE fused)") if mode != "nondiff" else "Raycaster.raycast_nondiff",
+               "results_read_back": "every step: loss (4 B, read by the host one step late so the device is never drained for it) + TF gradient (2 KiB) + "
+                                    "the WHOLE volume gradient to pinned host memory on a side stream, double-buffered under the next step's compute; the last "
+                                    "step's loss and gradients are awaited before the clock stops" if need_vol else "loss + TF gradient" if need_tf else "loss",
+               "last_loss": losses[-1] if losses else None,
                "overlap": "inputs are double-buffered: step i+1's H2D copies (all inputs, every step) run on a second stream under step i's compute; "
                           "`wait_for_inputs` is what a step still waits for them"}
         del bufs, flush, rc, drc

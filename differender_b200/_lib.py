@@ -8,8 +8,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIFFRENDER_LIB") or os.path.join(_PKG, "libdiffrender.so")
 
 # include/diffrender.h
-DR_VERSION = 101
-VOX_F32, VOX_F16 = 0, 1
+DR_VERSION = 102
+VOX_F32, VOX_F16, VOX_U8 = 0, 1, 2
 F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_LAYOUT_BRICK8, F_COUNT_SHADED, F_LAYOUT_CELL8 = 1, 2, 4, 8, 16, 32, 64, 256, 512, 2048
 
 EXPORTS = ("dr_version", "dr_debug_oob_count", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_expand_cells", "dr_forward",

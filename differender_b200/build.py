@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libdiffrender.so")
 DEBUG_LIB_PATH = os.path.join(_PKG, "libdiffrender_dbg.so")      # -DDR_BOUNDS_CHECK build used by tests/test_gpu_bounds.py
-UNITS = ["diffrender.cu", "dr_fwd_f32.cu", "dr_fwd_f16.cu", "dr_bwd_f32.cu", "dr_bwd_f16.cu"]
+UNITS = ["diffrender.cu", "dr_fwd_f32.cu", "dr_fwd_f16.cu", "dr_fwd_u8.cu", "dr_bwd_f32.cu", "dr_bwd_f16.cu", "dr_bwd_u8.cu"]
 SOURCES = [os.path.join(_CSRC, u) for u in UNITS]
 HEADERS = [os.path.join(_CSRC, h) for h in ("dr_math.cuh", "dr_kernels.cuh", "dr_host.h", "dr_desc.h")] + \
           [os.path.join(_ROOT, "include", "diffrender.h")]

@@ -30,8 +30,10 @@ __device__ unsigned long long dr_oob_counter = 0ULL;
 #if defined(DR_UNITY_BUILD)
 #include "dr_fwd_f32.cu"
 #include "dr_fwd_f16.cu"
+#include "dr_fwd_u8.cu"
 #include "dr_bwd_f32.cu"
 #include "dr_bwd_f16.cu"
+#include "dr_bwd_u8.cu"
 #endif
 
 using namespace dr;
@@ -52,6 +54,11 @@ int fail_cuda(cudaError_t e, const char* where)
 }  // namespace dr
 
 namespace {
+
+// the fp32 value of a stored voxel
+__device__ __forceinline__ float vox_value(float v) { return v; }
+__device__ __forceinline__ float vox_value(__half v) { return __half2float(v); }
+__device__ __forceinline__ float vox_value(u8vox v) { return u8_unit(v); }
 
 // ---------------------------------------------------------------------------------------------------------
 // bricking / un-bricking  (HBM-bound: 2 * sizeof(voxel) bytes per voxel)
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(256) expand_cells_kernel(DrDesc d, const VT* _
     const int z = (int)(r % d.Z), y = (int)(r / d.Z);
     const size_t dx = x + 1 < d.X ? 1 : 0, dz = z + 1 < d.Z ? (size_t)d.X : 0, dy = y + 1 < d.Y ? (size_t)d.X * d.Z : 0;
     const VT* p = lin + (size_t)b * n + e;
-    struct alignas(16) Rec { VT v[8]; } rec;
+    struct alignas(sizeof(VT) * 8 < 16 ? sizeof(VT) * 8 : 16) Rec { VT v[8]; } rec;      // 32 / 16 / 8 bytes
     rec.v[0] = p[0]; rec.v[1] = p[dz]; rec.v[2] = p[dx]; rec.v[3] = p[dx + dz];
     rec.v[4] = p[dy]; rec.v[5] = p[dy + dz]; rec.v[6] = p[dy + dx]; rec.v[7] = p[dy + dx + dz];
     reinterpret_cast<Rec*>(cells)[(size_t)b * n + e] = rec;
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(256) skip_minmax_kernel(DrDesc d, const VT* __
     bool bad = false;
     for (int e = lane; e < 729; e += 32) {
         const int x = min(mx_ * 8 + e % 9, d.X - 1), z = min(mz_ * 8 + (e / 9) % 9, d.Z - 1), y = min(my_ * 8 + e / 81, d.Y - 1);
-        const float f = (float)v[((size_t)y * d.Z + z) * d.X + x];
+        const float f = vox_value(v[((size_t)y * d.Z + z) * d.X + x]);
         bad |= (f != f);
         mn = fminf(mn, f); mx = fmaxf(mx, f);
     }
@@ -336,7 +343,7 @@ int check_desc(const DrDesc* d)
         return fail(DR_EINVAL, "descriptor not initialised (use dr_desc_init)");
     if (d->nbx != (d->X + 7) / 8 || d->nby != (d->Y + 7) / 8 || d->nbz != (d->Z + 7) / 8)
         return fail(DR_EINVAL, "descriptor brick counts inconsistent (use dr_desc_init)");
-    if (d->vox_dtype != DR_VOX_F32 && d->vox_dtype != DR_VOX_F16) return fail(DR_EDTYPE, "unsupported voxel dtype");
+    if (d->vox_dtype != DR_VOX_F32 && d->vox_dtype != DR_VOX_F16 && d->vox_dtype != DR_VOX_U8) return fail(DR_EDTYPE, "unsupported voxel dtype");
     if (d->BS > 65535) return fail(DR_EINVAL, "more than 65535 views in one call");
     if (d->tap_generic && (d->flags & (DR_F_LAYOUT_BRICK8 | DR_F_LAYOUT_CELL8)))
         return fail(DR_EINVAL, "the generic tap path (volumes > ~2000 voxels per axis) needs the linear layout");
@@ -395,6 +402,10 @@ int forward_impl(const DrDesc* d, const void* vol, const float* tf, const float*
     if ((size_t)d->R * 32 > kMaxTfSmem) return fail(DR_EINVAL, "tf resolution too large for shared memory staging (R <= 6400)");
     if (skip_grid && d->tap_generic) skip_grid = nullptr;          // the generic tap path marches every sample
     const FwdArgs a { d, vol, tf, cam, jitter, out_rgba, out_K, out_Tprev, static_cast<cudaStream_t>(stream), target, loss_sum, skip_grid };
+    if (d->vox_dtype == DR_VOX_U8) {
+        if (!(d->flags & DR_F_LAYOUT_CELL8)) return fail(DR_EDTYPE, "uint8 volumes are marched from their cell-major copy only (dr_expand_cells, DR_F_LAYOUT_CELL8)");
+        return launch_forward_u8(a);
+    }
     return d->vox_dtype == DR_VOX_F32 ? launch_forward_f32(a) : launch_forward_f16(a);
 }
 
@@ -426,7 +437,9 @@ int backward_impl(const DrDesc* d, const void* vol, const float* tf, const float
     if ((size_t)d->R * 32 > kMaxTfSmem) return fail(DR_EINVAL, "tf resolution too large for shared memory staging (R <= 6400)");
     const BwdArgs a { d, vol, tf, cam, jitter, grad_out, out_rgba, K, Tprev, reinterpret_cast<float4*>(grad_vol_cells),
                       static_cast<float4*>(workspace), st, mse_scale };
-    const int rc = d->vox_dtype == DR_VOX_F32 ? launch_backward_f32(a) : launch_backward_f16(a);
+    if (d->vox_dtype == DR_VOX_U8 && !(d->flags & DR_F_LAYOUT_CELL8))
+        return fail(DR_EDTYPE, "uint8 volumes are marched from their cell-major copy only (dr_expand_cells, DR_F_LAYOUT_CELL8)");
+    const int rc = d->vox_dtype == DR_VOX_U8 ? launch_backward_u8(a) : d->vox_dtype == DR_VOX_F32 ? launch_backward_f32(a) : launch_backward_f16(a);
     if (rc) return rc;
     if (wt) {
         dim3 grid((d->R * 4 + 255) / 256, d->Btf);
@@ -482,6 +495,7 @@ int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, 
 {
     if (int rc = check_desc(d)) return rc;
     if (!vol_linear || !vol_bricked) return fail(DR_EINVAL, "dr_brick_volume: null pointer");
+    if (d->vox_dtype == DR_VOX_U8) return fail(DR_EDTYPE, "dr_brick_volume: uint8 volumes use the cell-major copy (dr_expand_cells)");
     const size_t elems = dr_bricked_elems(d);
     dim3 grid((unsigned)((elems + 255) / 256), d->Bvol);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -503,8 +517,10 @@ int dr_expand_cells(const DrDesc* d, const void* vol_linear, void* vol_cells, vo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->vox_dtype == DR_VOX_F32)
         expand_cells_kernel<float><<<grid, 256, 0, st>>>(*d, static_cast<const float*>(vol_linear), static_cast<float*>(vol_cells));
-    else
+    else if (d->vox_dtype == DR_VOX_F16)
         expand_cells_kernel<__half><<<grid, 256, 0, st>>>(*d, static_cast<const __half*>(vol_linear), static_cast<__half*>(vol_cells));
+    else
+        expand_cells_kernel<u8vox><<<grid, 256, 0, st>>>(*d, static_cast<const u8vox*>(vol_linear), static_cast<u8vox*>(vol_cells));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "expand_cells_kernel launch");
 }
@@ -545,8 +561,10 @@ int dr_build_skip_grid(const DrDesc* d, const void* vol_linear, const float* tf,
         dim3 grid((unsigned)((cells * 32 + 255) / 256), d->Bvol);
         if (d->vox_dtype == DR_VOX_F32)
             skip_minmax_kernel<float><<<grid, 256, 0, st>>>(*d, static_cast<const float*>(vol_linear), static_cast<float2*>(minmax));
-        else
+        else if (d->vox_dtype == DR_VOX_F16)
             skip_minmax_kernel<__half><<<grid, 256, 0, st>>>(*d, static_cast<const __half*>(vol_linear), static_cast<float2*>(minmax));
+        else
+            skip_minmax_kernel<u8vox><<<grid, 256, 0, st>>>(*d, static_cast<const u8vox*>(vol_linear), static_cast<float2*>(minmax));
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail_cuda(e, "skip_minmax_kernel launch");
     }
@@ -594,6 +612,7 @@ int dr_ingest_u8(const DrDesc* d, const uint8_t* src, void* vol_linear, int swap
 {
     if (int rc = check_desc(d)) return rc;
     if (!src || !vol_linear) return fail(DR_EINVAL, "dr_ingest_u8: null pointer");
+    if (d->vox_dtype == DR_VOX_U8) return fail(DR_EDTYPE, "dr_ingest_u8 converts TO fp32 / fp16; a uint8 volume is marched as it is (DR_VOX_U8)");
     const size_t n = (size_t)d->X * d->Y * d->Z;
     const unsigned grid = (unsigned)((n + 255) / 256);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -624,6 +643,7 @@ int dr_gather_step(const DrDesc* d, const float* grad_vol_cells, const float* gr
     if ((grad_vol_cells == nullptr) == (grad_linear == nullptr))
         return fail(DR_EINVAL, "dr_gather_step: give exactly one of grad_vol_cells (cell-major) and grad_linear (already gathered)");
     if (d->Bvol != 1) return fail(DR_EINVAL, "dr_gather_step: one volume per call (Bvol == 1)");
+    if (d->vox_dtype == DR_VOX_U8) return fail(DR_EDTYPE, "dr_gather_step: the refreshed volume copy is fp32 or fp16 (a uint8 volume is not a parameter)");
     if (grad_vol_cells && !aligned(grad_vol_cells, 16)) return fail(DR_EALIGN, "dr_gather_step: grad_vol_cells must be 16-byte aligned");
     if (vol_cells && !aligned(vol_cells, 32)) return fail(DR_EALIGN, "dr_gather_step: vol_cells must be 32-byte aligned");
     const StepArgs sa { lr, gamma, max_grad, lo, hi };

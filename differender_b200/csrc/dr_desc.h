@@ -23,7 +23,7 @@ inline const char* desc_init(DrDesc* d, int X, int Y, int Z, int W, int H, int R
     if (!(Bvol == 1 || Bvol == BS)) return "Bvol must be 1 or BS";
     if (!(Btf == 1 || Btf == BS)) return "Btf must be 1 or BS";
     if (!(sr > 0.0)) return "sampling_rate must be > 0";
-    if (vox_dtype != DR_VOX_F32 && vox_dtype != DR_VOX_F16) return "unsupported voxel dtype";
+    if (vox_dtype != DR_VOX_F32 && vox_dtype != DR_VOX_F16 && vox_dtype != DR_VOX_U8) return "unsupported voxel dtype";
     const long long nbx = (X + 7) / 8, nby = (Y + 7) / 8, nbz = (Z + 7) / 8;
     if (nbx * nby * nbz * 512LL >= (1LL << 31)) return "volume too large (>= 2^31 bricked elements)";
     if ((long long)W * H >= (1LL << 30)) return "image too large";

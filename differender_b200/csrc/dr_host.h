@@ -34,5 +34,7 @@ DR_INTERNAL int launch_forward_f32(const FwdArgs& a);      // dr_fwd_f32.cu
 DR_INTERNAL int launch_forward_f16(const FwdArgs& a);      // dr_fwd_f16.cu
 DR_INTERNAL int launch_backward_f32(const BwdArgs& a);     // dr_bwd_f32.cu
 DR_INTERNAL int launch_backward_f16(const BwdArgs& a);     // dr_bwd_f16.cu
+DR_INTERNAL int launch_forward_u8(const FwdArgs& a);       // dr_fwd_u8.cu   (cell-major copy only)
+DR_INTERNAL int launch_backward_u8(const BwdArgs& a);      // dr_bwd_u8.cu
 
 }  // namespace dr

@@ -349,6 +349,13 @@ int dispatch_bwd(const BwdArgs& a)
 #undef DR_BWD
 }
 
+// uint8 volumes are marched from their cell-major copy only (8-byte records)
+template <typename VT>
+int dispatch_bwd_cell8(const BwdArgs& a)
+{
+    return tap_mode(*a.d) == TAPS_ONE ? dispatch_bwd<VT, LAYOUT_CELL8, TAPS_ONE>(a) : dispatch_bwd<VT, LAYOUT_CELL8, TAPS_TWO>(a);
+}
+
 template <typename VT>
 int dispatch_bwd_layout(const BwdArgs& a)
 {
@@ -373,6 +380,18 @@ int forward_vt(const FwdArgs& a)
     if (d->flags & DR_F_LAYOUT_BRICK8) return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_BRICK8, TAPS_ONE) : DR_FWD_SR(LAYOUT_BRICK8, TAPS_TWO);
     if (taps == TAPS_GENERIC) return DR_FWD_ND(LAYOUT_LINEAR, TAPS_GENERIC, false);
     return taps == TAPS_ONE ? DR_FWD_SR(LAYOUT_LINEAR, TAPS_ONE) : DR_FWD_SR(LAYOUT_LINEAR, TAPS_TWO);
+#undef DR_FWD_SR
+#undef DR_FWD_ND
+}
+
+template <typename VT>
+int forward_cell8(const FwdArgs& a)
+{
+    const DrDesc* d = a.d;
+    const bool nd = d->flags & DR_F_NONDIFF, sr1 = d->inv_sr == 1.0f;
+#define DR_FWD_ND(TAPS, SR1) (nd ? launch_fwd<VT, LAYOUT_CELL8, true, TAPS, SR1>(a) : launch_fwd<VT, LAYOUT_CELL8, false, TAPS, SR1>(a))
+#define DR_FWD_SR(TAPS) (sr1 ? DR_FWD_ND(TAPS, true) : DR_FWD_ND(TAPS, false))
+    return tap_mode(*d) == TAPS_ONE ? DR_FWD_SR(TAPS_ONE) : DR_FWD_SR(TAPS_TWO);
 #undef DR_FWD_SR
 #undef DR_FWD_ND
 }

@@ -243,7 +243,7 @@ DR_HD uoff offz(int z, int sZ) { return (uoff)((z >> 3) * sZ + ((z & 7) << 6)); 
 // type becomes four 64-bit IADD3/IADD3.X per address (base + off + off), which made integer adds 25 % of the fp16 kernels.
 // The element size comes from constant memory so that ptxas cannot strength-reduce the multiply back into LEA + LEA.HI.X.
 #if defined(__CUDACC__)
-static __constant__ unsigned dr_elem_size[3] = { 0u, 2u, 4u };     // indexed by sizeof(VT) / 2
+static __constant__ unsigned dr_elem_size[3] = { 1u, 2u, 4u };     // indexed by sizeof(VT) / 2
 #endif
 template <typename VT>
 DR_HD const VT* ptr_add(const VT* p, uoff off)
@@ -303,7 +303,7 @@ DR_HD float load_vox_if(const __half* p, bool pred)
 #endif
 // ---- cell-major records (LAYOUT_CELL8): 8 consecutive elements per cell ---------------------------------
 #if defined(__CUDACC__)
-static __constant__ unsigned dr_rec_size[3] = { 0u, 16u, 32u };    // bytes per record, indexed by sizeof(VT) / 2
+static __constant__ unsigned dr_rec_size[3] = { 8u, 16u, 32u };    // bytes per record, indexed by sizeof(VT) / 2
 #endif
 template <typename VT>
 DR_HD const VT* rec_add(const VT* p, uoff cell)                     // p + 8*cell as ONE IMAD.WIDE.U32 (64-bit result)
@@ -499,6 +499,124 @@ DR_HD void cell_plane_z(const __half* rp, const __half* rm, int bp, int bm, int 
 #endif
 }
 #endif
+// ---- uint8-stored volumes (DR_VOX_U8; the reference's skull.raw, examples/taichi_volume_raycaster.py:548-550) -----------
+// A voxel is u8 / 255 in fp32, exactly as dr_ingest_u8 (and numpy's float32 division) rounds it:
+//   fl(x / 255) == fma(x, r, fl(x * r_lo))   for every x in 0..255, with r = fl(1/255), r_lo = fl(1/255 - r)
+// (checked exhaustively: tests/test_host_logic.py; a plain multiply by r is off by one ulp for 126 of the 256 values).
+// Two FMA-pipe instructions per voxel (one FMUL2 + one FFMA2 per pair) instead of a division.  A cell record is 8 bytes:
+// ONE 8-byte load per cell, an eighth of the fp32 record.
+typedef unsigned char u8vox;
+constexpr float kU8r = 1.0f / 255.0f;
+constexpr float kU8rlo = (float)(1.0 / 255.0 - (double)kU8r);
+DR_HD float u8_unit(unsigned b)
+{
+    const float x = (float)b;
+    return DR_FMA(x, kU8r, DR_MUL(x, kU8rlo));
+}
+DR_HD F2 u8_unit2(unsigned b0, unsigned b1)
+{
+    const F2 x = f2((float)b0, (float)b1);
+    return fma2(x, splat(kU8r), mul2(x, splat(kU8rlo)));
+}
+DR_HD void u8_unpack4(unsigned w, float n[4])       // bytes 0..3 of w -> n[0..3]
+{
+    const F2 a = u8_unit2(w & 0xffu, (w >> 8) & 0xffu), b = u8_unit2((w >> 16) & 0xffu, w >> 24);
+    n[0] = a.x; n[1] = a.y; n[2] = b.x; n[3] = b.y;
+}
+DR_HD float load_vox(const u8vox* p, int off)
+{
+#if defined(__CUDA_ARCH__)
+    return u8_unit(__ldg(p + off));
+#else
+    return u8_unit(p[off]);
+#endif
+}
+DR_HD float load_vox(const u8vox* p, uoff off) { return load_vox(ptr_add(p, off), 0); }
+DR_HD float load_vox_if(const u8vox* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned b;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.u8 %0, [%1];\n\t}" : "=r"(b) : "l"(p), "r"((int)pred));
+    return u8_unit(b & 0xffu);
+#else
+    return pred ? u8_unit(*p) : 0.0f;
+#endif
+}
+DR_HD void load_vox8(const u8vox* r, float v[8])
+{
+#if defined(__CUDA_ARCH__)
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(r));
+    u8_unpack4(a.x, v); u8_unpack4(a.y, v + 4);
+#else
+    for (int q = 0; q < 8; ++q) v[q] = u8_unit(r[q]);
+#endif
+}
+DR_HD void load_vox4_if(const u8vox* r, bool pred, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned w;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(w) : "l"(r), "r"((int)pred));
+    u8_unpack4(w, n);
+#else
+    for (int q = 0; q < 4; ++q) n[q] = pred ? u8_unit(r[q]) : 0.0f;
+#endif
+}
+DR_HD void load_vox2_if(const u8vox* r, bool pred, float n[2])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned short h;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.b16 %0, [%1];\n\t}" : "=h"(h) : "l"(r), "r"((int)pred));
+    const F2 a = u8_unit2((unsigned)h & 0xffu, ((unsigned)h >> 8) & 0xffu);
+    n[0] = a.x; n[1] = a.y;
+#else
+    for (int q = 0; q < 2; ++q) n[q] = pred ? u8_unit(r[q]) : 0.0f;
+#endif
+}
+// DUAL plane fetches (one predicated load per neighbour, see the fp32 versions above); records are 8 bytes
+DR_HD void cell_plane_y(const u8vox* rp, const u8vox* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned w;
+    asm("{\n\t.reg .pred p, m;\n\tsetp.ne.s32 p, %3, %5;\n\tsetp.ne.s32 m, %4, %5;\n\t"
+        "@m ld.global.nc.b32 %0, [%2];\n\t@p ld.global.nc.b32 %0, [%1+4];\n\t}" : "=r"(w) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    u8_unpack4(w, n);
+#else
+    const u8vox* r = bp != bc ? rp + 4 : rm;
+    for (int q = 0; q < 4; ++q) n[q] = (bp != bc || bm != bc) ? u8_unit(r[q]) : 0.0f;
+#endif
+}
+DR_HD void cell_plane_x(const u8vox* rc, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned short lo, hi;
+    asm("{\n\t.reg .pred p, m;\n\tsetp.ne.s32 p, %3, %5;\n\tsetp.ne.s32 m, %4, %5;\n\t"
+        "@m ld.global.nc.b16 %0, [%2+-8];\n\t@m ld.global.nc.b16 %1, [%2+-4];\n\t"
+        "@p ld.global.nc.b16 %0, [%2+10];\n\t@p ld.global.nc.b16 %1, [%2+14];\n\t}"
+        : "=h"(lo), "=h"(hi) : "l"(rc), "r"(bp), "r"(bm), "r"(bc));
+    const F2 a = u8_unit2((unsigned)lo & 0xffu, ((unsigned)lo >> 8) & 0xffu), b = u8_unit2((unsigned)hi & 0xffu, ((unsigned)hi >> 8) & 0xffu);
+    n[0] = a.x; n[1] = a.y; n[2] = b.x; n[3] = b.y;
+#else
+    const u8vox* r = bp != bc ? rc + 8 + 2 : rc - 8;
+    const bool any = bp != bc || bm != bc;
+    n[0] = any ? u8_unit(r[0]) : 0.0f; n[1] = any ? u8_unit(r[1]) : 0.0f; n[2] = any ? u8_unit(r[4]) : 0.0f; n[3] = any ? u8_unit(r[5]) : 0.0f;
+#endif
+}
+DR_HD void cell_plane_z(const u8vox* rp, const u8vox* rm, int bp, int bm, int bc, float n[4])
+{
+#if defined(__CUDA_ARCH__)
+    unsigned b0, b1, b2, b3;
+    asm(DR_PM_PRED4 "@m ld.global.nc.u8 %0, [%5];\n\t@m ld.global.nc.u8 %1, [%5+4];\n\t@m ld.global.nc.u8 %2, [%5+2];\n\t"
+        "@m ld.global.nc.u8 %3, [%5+6];\n\t@p ld.global.nc.u8 %0, [%4+1];\n\t@p ld.global.nc.u8 %1, [%4+5];\n\t"
+        "@p ld.global.nc.u8 %2, [%4+3];\n\t@p ld.global.nc.u8 %3, [%4+7];\n\t}"
+        : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(rp), "l"(rm), "r"(bp), "r"(bm), "r"(bc));
+    const F2 a = u8_unit2(b0 & 0xffu, b1 & 0xffu), b = u8_unit2(b2 & 0xffu, b3 & 0xffu);
+    n[0] = a.x; n[1] = a.y; n[2] = b.x; n[3] = b.y;
+#else
+    const u8vox* r = bp != bc ? rp + 1 : rm;
+    const bool any = bp != bc || bm != bc;
+    n[0] = any ? u8_unit(r[0]) : 0.0f; n[1] = any ? u8_unit(r[4]) : 0.0f; n[2] = any ? u8_unit(r[2]) : 0.0f; n[3] = any ? u8_unit(r[6]) : 0.0f;
+#endif
+}
 template <typename VT> struct VolView {
     const VT* p;
     DR_HD float ld(uoff off) const { return load_vox(p, off); }

@@ -90,6 +90,15 @@ class DistributedRaycaster(torch.nn.Module):
         return 0, 1
 
     def forward(self, volume, tf, look_from_all, jitter=None):
+        return self._render(volume, tf, look_from_all, jitter, None)
+
+    def mse_loss(self, volume, tf, look_from_all, target, jitter=None):
+        """Fused render + MSE of this rank's views against `target` ([n_local, 4, H, W]): returns (sum of squared errors over
+        this rank's views / (n_views_total * 4 * H * W), images, view indices) -- the per-rank terms add up to the batch's mean-squared
+        error, so after loss.backward() every rank holds the gradient of the whole batch's MSE (all-reduced inside the backward)."""
+        return self._render(volume, tf, look_from_all, jitter, target)
+
+    def _render(self, volume, tf, look_from_all, jitter, target):
         rank, world = self._rank_world()
         idx = shard_views(look_from_all.shape[0], rank, world)
         need = [t for t in (volume, tf) if t.requires_grad]
@@ -106,10 +115,14 @@ class DistributedRaycaster(torch.nn.Module):
             h, w = self.raycaster.output_shape[1], self.raycaster.output_shape[0]
             # keep the graph connected so the collective in the backward still runs on this rank
             empty = volume.new_zeros((0, 4, h, w), dtype=torch.float32) + 0.0 * (volume.sum() + tf.sum()).float()
-            return empty, idx
+            return (empty.sum(), empty, idx) if target is not None else (empty, idx)
         sel = torch.as_tensor(idx, device=look_from_all.device)
         jit = jitter
         if jitter is not None and jitter.shape[0] != len(idx):
             jit = jitter.index_select(0, sel.to(jitter.device))
-        img = self.raycaster(volume, tf, look_from_all.index_select(0, sel), jit)
+        cams = look_from_all.index_select(0, sel)
+        if target is not None:
+            loss, img = self.raycaster.mse_loss(volume, tf, cams, target, jit)
+            return loss * (len(idx) / look_from_all.shape[0]), img, idx      # mean over this rank's views -> this rank's share of the batch mean
+        img = self.raycaster(volume, tf, cams, jit)
         return img, idx

@@ -13,7 +13,9 @@ __all__ = ["volume_from_raw_u8"]
 
 def volume_from_raw_u8(raw, shape=None, swap_axes01=True, dtype=torch.float32, device="cuda"):
     """raw: path to a .raw file, a numpy uint8 array or a uint8 tensor with `shape` (A, B, C) (default: the array's own).
-    Returns the (1, D, H, W) volume tensor the Raycaster takes, with D,H = (B, A) if swap_axes01 else (A, B), values u8/255."""
+    Returns the (1, D, H, W) volume tensor the Raycaster takes, with D,H = (B, A) if swap_axes01 else (A, B), values u8/255.
+    dtype=torch.uint8 keeps the bytes as they are (only the axis swap is applied): the Raycaster marches a uint8 volume
+    directly (DR_VOX_U8: value u8/255 formed in registers, 8-byte cell records), bit-identical to the fp32 conversion."""
     if isinstance(raw, str):
         raw = np.fromfile(raw, dtype=np.uint8)
     t = torch.as_tensor(raw)
@@ -28,6 +30,8 @@ def volume_from_raw_u8(raw, shape=None, swap_axes01=True, dtype=torch.float32, d
         raise RuntimeError("volume_from_raw_u8 runs on CUDA only (no CPU fallback)")
     A, B, C = t.shape
     D, H = (B, A) if swap_axes01 else (A, B)
+    if dtype == torch.uint8:
+        return (t.swapaxes(0, 1) if swap_axes01 else t).contiguous()[None]
     vox = _lib.VOX_F16 if dtype == torch.float16 else _lib.VOX_F32
     d = _lib.make_desc(C, D, H, 8, 8, 2, 1, 1, 1, 1, vox, 0, 1.0, 30.0, 0.1)       # X = W, Y = D, Z = H
     out = torch.empty((1, D, H, C), dtype=dtype, device=t.device)

@@ -18,13 +18,22 @@ import torch
 
 from . import _lib
 from ._lib import (F_HAS_JITTER, F_LAYOUT_BRICK8, F_LAYOUT_CELL8, F_NEEDS_TF_GRAD, F_NEEDS_VOL_GRAD, F_NONDIFF, F_OUT_IMAGE, F_TF_4R, VOX_F16,
-                   VOX_F32)
+                   VOX_F32, VOX_U8)
 
 __all__ = ["VolumeRaycaster", "RaycastFunction", "RaycastMSEFunction", "Raycaster"]
 
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+VOLUME_DTYPES = (torch.float32, torch.float16, torch.uint8)      # how a volume may be STORED; arithmetic is always fp32
+
+
+def _vox(dtype):
+    """DR_VOX_* of a stored volume dtype.  uint8 voxels mean u8 / 255 (the reference's skull.raw ingest,
+    examples/taichi_volume_raycaster.py:548-550) and are marched from an 8-byte-per-cell copy without ever being widened in HBM."""
+    return VOX_F16 if dtype == torch.float16 else (VOX_U8 if dtype == torch.uint8 else VOX_F32)
 
 
 class VolumeRaycaster:
@@ -90,9 +99,14 @@ class VolumeRaycaster:
         """`auto`: the cell-major copy (8x the volume's bytes) when it is at most AUTO_CELL_BYTES AND it fits -- together with
         the 32-byte-per-voxel cell-major gradient buffer when the volume gradient is wanted -- into AUTO_FREE_FRACTION of
         the device memory that is free now; otherwise the 8x8x8-bricked copy (1x)."""
+        X, Y, Z = self.volume_resolution
+        if vol_lin.dtype == torch.uint8:
+            if self.layout not in ("auto", "cell8") or max(X, Y, Z) > 2000:
+                raise ValueError("uint8 volumes are marched from the cell-major copy (layout 'auto' or 'cell8', axes <= 2000 voxels); "
+                                 "convert with volume_from_raw_u8(dtype=torch.float16 / float32) for the other layouts")
+            return "cell8"
         if self.layout != "auto":
             return self.layout
-        X, Y, Z = self.volume_resolution
         if max(X, Y, Z) > 2000:
             return "linear"                      # the generic tap path exists for the linear layout only
         cached = self._cached_copy(vol_lin)
@@ -145,7 +159,7 @@ class VolumeRaycaster:
             return cached
         self._copy_cache = None                  # release the previous copy before allocating the next one
         # (the copies below remember the linear tensor they were made from: the forward builds its skip grid from it)
-        vox = VOX_F16 if vol_lin.dtype == torch.float16 else VOX_F32
+        vox = _vox(vol_lin.dtype)
         d = self.desc(1, 1, 1, vox, 0, 1.0)
         d.Bvol = vol_lin.shape[0]
         lib = _lib.load()
@@ -220,7 +234,7 @@ class VolumeRaycaster:
         if extra_flags & F_TF_4R:
             tf_r4 = _Tf4R(tf_r4)
         w, h = self.resolution
-        vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
+        vox = _vox(bricked.dtype)
         flags = (F_NONDIFF if nondiff else 0) | (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
                 self._lflag(bricked) | extra_flags
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
@@ -248,7 +262,7 @@ class VolumeRaycaster:
         BS = cam.shape[0]
         if extra_flags & F_TF_4R:
             tf_r4 = _Tf4R(tf_r4)
-        vox = VOX_F16 if bricked.dtype == torch.float16 else VOX_F32
+        vox = _vox(bricked.dtype)
         flags = (F_HAS_JITTER if jitter is not None else 0) | (F_OUT_IMAGE if image_layout else 0) | \
                 (F_NEEDS_VOL_GRAD if need_vol else 0) | (F_NEEDS_TF_GRAD if need_tf else 0) | extra_flags | self._lflag(bricked)
         d = self.desc(BS, bricked.shape[0], tf_r4.shape[0], vox, flags, sampling_rate)
@@ -327,8 +341,8 @@ def _prepare(vr, volume, tf, look_from, batched, jitter, jitter_tensor):
     v = volume if vol_b else volume[None]
     if vol_b and v.shape[0] > 1 and v.stride(0) == 0:
         v = v[:1]                                          # an .expand()ed shared volume: do not clone it (:566)
-    if v.dtype not in (torch.float16, torch.float32):
-        v = v.float()                                      # set_volume's .float() (:119); fp16 is kept
+    if v.dtype not in VOLUME_DTYPES:
+        v = v.float()                                      # set_volume's .float() (:119); fp16 and uint8 (= u8 / 255) are kept as stored
     vol_lin = v.permute(0, 2, 3, 1).contiguous()           # [Bvol, Y, Z, X] == torch (D, H, W); no-op for our views
     if vol_lin.shape[0] not in (1, BS):
         raise ValueError(f"volume batch {vol_lin.shape[0]} does not match batch size {BS}")
@@ -502,7 +516,7 @@ class Raycaster(torch.nn.Module):
             BS = bs if batched else 1
             with torch.cuda.device(volume.device):
                 v = vol_in if vol_in.ndim == 4 else vol_in[None]
-                if v.dtype not in (torch.float16, torch.float32):
+                if v.dtype not in VOLUME_DTYPES:
                     v = v.float()
                 vol_lin = v.permute(0, 2, 3, 1).contiguous()
                 t = (tf_in if tf_in.ndim == 3 else tf_in[None]).float().contiguous()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DR_VERSION 101
+#define DR_VERSION 102
 
 /* error codes */
 #define DR_OK 0
@@ -44,6 +44,8 @@ extern "C" {
 /* voxel storage types */
 #define DR_VOX_F32 0
 #define DR_VOX_F16 1
+#define DR_VOX_U8 2       /* uint8-stored volume, voxel value = u8 / 255 in fp32 exactly as dr_ingest_u8 rounds it (the reference's skull.raw,
+                             examples/taichi_volume_raycaster.py:548-550); marched from the cell-major copy only (DR_F_LAYOUT_CELL8: 8-byte records) */
 
 /* DrDesc.flags */
 #define DR_F_NONDIFF 1u        /* raycast_nondiff + get_final_image_nondiff (:308-361) instead of raycast (:261-306) */

@@ -174,3 +174,13 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
 }
 
 }  // extern "C"
+
+// the fp32 value the kernels give the 256 possible uint8 voxels (DR_VOX_U8): must equal fl(b / 255) for every b
+extern "C" void sim_u8_values(float* out256)
+{
+    for (int b = 0; b < 256; ++b) {
+        out256[b] = u8_unit((unsigned)b);
+        const F2 p = u8_unit2((unsigned)b, (unsigned)(255 - b));
+        if (p.x != out256[b] || p.y != u8_unit((unsigned)(255 - b))) out256[b] = -1.0f;     // the packed form must agree with the scalar one
+    }
+}

@@ -31,9 +31,10 @@ def test_no_out_of_range_access_in_debug_build():
     cams = torch.tensor([[1.2, 0.7, 2.2], [0.3, 0.2, 0.4], [-2.0, 1.5, 0.1], [0.0, 0.7, 2.5]], device=dev)   # incl. a camera inside the box
     for layout in ("linear", "brick8", "cell8"):
         for (D, H, W) in ((2, 2, 2), (5, 9, 3), (16, 16, 16), (21, 18, 27)):
-            for dtype in (torch.float32, torch.float16):
-                vol = torch.rand((1, D, H, W), generator=g).to(dev, dtype)
+            for dtype in (torch.float32, torch.float16) + ((torch.uint8,) if layout == "cell8" else ()):
+                vol = torch.rand((1, D, H, W), generator=g).to(dev)
                 vol[0, 0] = 1.0; vol[0, -1] = 0.0                                  # extreme intensities: TF index clamps
+                vol = (vol * 255.0).to(torch.uint8) if dtype == torch.uint8 else vol.to(dtype)
                 tf = make_tf("tf1", 32, device=dev).t().contiguous()[None]
                 vr = VolumeRaycaster((W, D, H), (19, 13), max_samples=256, tf_resolution=32, layout=layout)
                 v = vr.brick(vol.reshape(1, D, H, W).contiguous())

@@ -109,3 +109,15 @@ def test_auto_layout_policy():
         assert pick((256, 256, 256), torch.float32, layout=forced) == forced
     with pytest.raises(ValueError):
         VolumeRaycaster((8, 8, 8), (8, 8), layout="morton")
+
+
+def test_uint8_voxel_value_is_exactly_the_fp32_quotient():
+    # DR_VOX_U8: the kernels form u8 / 255 as fma(x, r, x * r_lo) (two FMA-pipe instructions, no division); it must round
+    # exactly like numpy's float32 division (= dr_ingest_u8, reference examples/taichi_volume_raycaster.py:548-550) for all 256 values
+    import ctypes
+    import numpy as np
+    import hostsim_lib as hs
+    out = np.zeros(256, np.float32)
+    hs.lib().sim_u8_values(out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    ref = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
+    assert np.array_equal(out, ref)
