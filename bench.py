@@ -48,7 +48,8 @@ CONFIGS = {
                desc="C5 large volume: fwd+bwd, 1024^3 fp16-stored, 2048x2048, jittered, 32 views per GPU (256 over 8 GPUs)"),
 }
 L2_FLUSH_BYTES = 256 << 20
-METRIC = {"full": "Gsamples/s fwd+bwd (TF+volume grad)", "tf": "Gsamples/s fwd+bwd (TF grad)", "nondiff": "Gsamples/s fwd"}
+METRIC = {"full": "Gsamples/s fwd+bwd (TF+volume grad)", "tf": "Gsamples/s fwd+bwd (TF grad)", "vol": "Gsamples/s fwd+bwd (volume grad)",
+          "nondiff": "Gsamples/s fwd"}
 NVLINK_PEAK_GBS = 900.0
 
 
@@ -242,7 +243,7 @@ class Workload:
         self.vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=args.layout, skip_empty=not args.no_skip)
         self.vol_lin = self.vol.reshape(1, n, n, n)
         self.tf_r4 = self.tf.t().contiguous()[None]
-        self.need_vol, self.need_tf = self.mode == "full", self.mode in ("full", "tf")
+        self.need_vol, self.need_tf = self.mode in ("full", "vol"), self.mode in ("full", "tf")
         self.flat_grad = torch.empty(n ** 3 + R * 4, dtype=torch.float32, device=dev) if world > 1 else None
         self.cells = None                                                                # cell-major gradient buffer, allocated once
         self.tf_opt = MomentumSGD(self.tf_r4[0], lr=0.1, momentum=0.9, max_grad=0.1, lr_decay=0.99) if self.mode == "tf" else None
@@ -275,10 +276,11 @@ class Workload:
                     self.cells = torch.zeros((1, n ** 3 * 8), dtype=torch.float32, device=self.dev)
                 else:
                     self.cells.zero_()
-                _, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, True, self.need_tf, grad_cells=self.cells, mse_scale=ms)
+                _, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, True, self.need_tf, grad_cells=self.cells, mse_scale=ms,
+                                           skip_grid=vr.last_skip_grid)
                 # the gather writes straight into the flat [volume grad | TF grad] buffer that is all-reduced (no concatenation copy)
                 gvol = vr.gather(self.cells, out=self.flat_grad[:n ** 3].view(1, n, n, n) if self.world > 1 else None)
-                if self.world > 1:
+                if self.world > 1 and gtf is not None:
                     self.flat_grad[n ** 3:].copy_(gtf.reshape(-1))
             else:
                 gvol, gtf = vr.march_backward(bricked, self.tf_r4, self.cams, self.sr, self.jit, go, out, K, Tp, False, self.need_tf, mse_scale=ms)
@@ -663,19 +665,24 @@ def run_ours(args, cfg):
     # ---- the other configurations, a few seconds each -----------------------------------------------
     others, strong = [], []
     if not args.no_others:
-        names = args.others.split(",") if args.others is not None else (["c1", "c2", "c3gray", "c4", "c5"] if world == 1 else [])
+        names = args.others.split(",") if args.others is not None else (["c1", "c2", "c3gray", "c3vol", "c4", "c5"] if world == 1 else [])
         for name in [x for x in names if x]:
             try:
-                base = "c3" if name == "c3gray" else name
-                c2 = CONFIGS[base]
+                base = "c3" if name in ("c3gray", "c3vol") else name
+                c2 = dict(CONFIGS[base])
+                if name == "c3vol":
+                    c2.update(mode="vol", desc="C3 with the volume gradient only (the reference's own optimisation case, examples/test_opt_tf.py:49-55): "
+                                               "fwd+bwd, 256^3 fp32, 1024x1024, 16 views")
                 tfn = "gray" if name == "c3gray" else None
-                steps = {"c1": 5, "c2": 100, "c3gray": 3, "c4": 3, "c5": 2}.get(name, 3)
+                steps = {"c1": 5, "c2": 100, "c3gray": 3, "c3vol": 3, "c4": 3, "c5": 2}.get(name, 3)
                 torch.cuda.empty_cache()
                 w2 = Workload(c2, args, dev, rank, world, c2["views"], tf_name=tfn)
                 r2 = time_workload(w2, steps, 2 if name != "c2" else 5)
                 extra = {"tf": w2.tf_name, "steps": steps, "views_per_gpu": w2.views}
                 if name == "c2":
                     extra["note"] = "100 iterations of fwd + TF-only bwd + dr_momentum_step (lr .1, gamma .9, clip .1, decay .99), TF starting from `black`; the volume copy and its min/max are cached across iterations"
+                if name == "c3vol":
+                    extra["note"] = "no TF gradient: exactly transparent samples contribute nothing, so the backward jumps over the forward's empty macro-cells too (dr_backward_ex)"
                 if name == "c3gray":
                     extra["note"] = "C3 with the dense `gray` TF: no exactly-transparent bin, every active sample is shaded, nothing to skip (the worst case for the transparent-sample shortcuts)"
                 others.append(small_line(name, c2, r2, extra))

@@ -8,14 +8,14 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIFFRENDER_LIB") or os.path.join(_PKG, "libdiffrender.so")
 
 # include/diffrender.h
-DR_VERSION = 102
+DR_VERSION = 103
 VOX_F32, VOX_F16, VOX_U8 = 0, 1, 2
 F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_LAYOUT_BRICK8, F_COUNT_SHADED, F_LAYOUT_CELL8 = 1, 2, 4, 8, 16, 32, 64, 256, 512, 2048
 
 EXPORTS = ("dr_version", "dr_debug_oob_count", "dr_last_error", "dr_desc_init", "dr_bricked_elems", "dr_brick_volume", "dr_expand_cells", "dr_forward",
            "dr_workspace_bytes", "dr_grad_cells_elems", "dr_backward", "dr_gather_grad", "dr_forward_mse", "dr_backward_mse",
            "dr_skip_minmax_bytes", "dr_skip_grid_bytes", "dr_build_skip_grid", "dr_forward_ex",
-           "dr_momentum_step", "dr_ingest_u8", "dr_gather_step", "dr_probe_l2_read")
+           "dr_momentum_step", "dr_ingest_u8", "dr_gather_step", "dr_probe_l2_read", "dr_backward_ex")
 
 
 class DrDesc(ctypes.Structure):
@@ -63,6 +63,8 @@ def load():
     lib.dr_build_skip_grid.argtypes = [dp, vp, vp, vp, ctypes.c_int, vp, vp]; lib.dr_build_skip_grid.restype = ctypes.c_int
     lib.dr_backward_mse.argtypes = [dp] + [vp] * 5 + [ctypes.c_float] + [vp] * 6 + [ctypes.c_size_t, vp]
     lib.dr_backward_mse.restype = ctypes.c_int
+    lib.dr_backward_ex.argtypes = [dp] + [vp] * 6 + [ctypes.c_float] + [vp] * 7 + [ctypes.c_size_t, vp]
+    lib.dr_backward_ex.restype = ctypes.c_int
     lib.dr_momentum_step.argtypes = [vp, vp, vp, ctypes.c_size_t] + [ctypes.c_float] * 5 + [vp]
     lib.dr_momentum_step.restype = ctypes.c_int
     lib.dr_ingest_u8.argtypes = [dp, vp, vp, ctypes.c_int, vp]; lib.dr_ingest_u8.restype = ctypes.c_int

@@ -37,6 +37,12 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 #ifndef DR_BWD_MIN_BLOCKS_BRICK
 #define DR_BWD_MIN_BLOCKS_BRICK 4
 #endif
+#ifndef DR_BWD_MIN_BLOCKS_TFONLY    // TF-only backward (C2): 80 registers without the volume sink
+#define DR_BWD_MIN_BLOCKS_TFONLY 5
+#endif
+#ifndef DR_BWD_MIN_BLOCKS_SR        // sampling rate != 1 with both gradients (the powf path): spills 72 / 96 bytes at 96 registers
+#define DR_BWD_MIN_BLOCKS_SR 4
+#endif
 #ifndef DR_BWD_MIN_BLOCKS_TWO       // two-neighbour taps (an axis of 1001..2000 voxels) with both gradients: 114 registers, spills at 96 (C5 backward +7.5 % at 4)
 #define DR_BWD_MIN_BLOCKS_TWO 4
 #endif
@@ -222,13 +228,16 @@ struct RedTfSink {
     }
 };
 
-template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1>
+template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1, bool SKIP>
 __global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN_BLOCKS_BRICK
-                                              : (TAPS == TAPS_TWO && WANT_VOL && WANT_TF) ? DR_BWD_MIN_BLOCKS_TWO : DR_BWD_MIN_BLOCKS_LINEAR)
+                                              : (TAPS == TAPS_TWO && WANT_VOL && WANT_TF) ? DR_BWD_MIN_BLOCKS_TWO
+                                              : (!SR1 && WANT_VOL && WANT_TF) ? DR_BWD_MIN_BLOCKS_SR
+                                              : (SR1 && !WANT_VOL && LAYOUT == LAYOUT_CELL8 && TAPS == TAPS_ONE) ? DR_BWD_MIN_BLOCKS_TFONLY : DR_BWD_MIN_BLOCKS_LINEAR)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
-           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale, unsigned cbias)
+           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale, unsigned cbias,
+           const unsigned char* __restrict__ skip_grid, size_t skip_stride)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.z;
@@ -275,7 +284,9 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
     ts.cur = -1; ts.Rm1 = d.R - 1; ts.rgb = false;
     ts.s = make_float4(0.f, 0.f, 0.f, 0.f); ts.s1 = ts.s;
-    march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts);
+    const unsigned char* grid = nullptr;
+    if (SKIP && __ldg(reinterpret_cast<const unsigned*>(skip_grid)) != 0u) grid = skip_grid + kSkipHeader + (size_t)b * skip_stride;
+    march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1, SKIP>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts, grid);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -311,18 +322,26 @@ int launch_fwd_skip(const FwdArgs& a)
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
 
-template <typename VT, int LAYOUT, int TAPS, bool WV, bool WT, bool SR1>
-int launch_bwd(const BwdArgs& a)
+template <typename VT, int LAYOUT, int TAPS, bool WV, bool WT, bool SR1, bool SKIP>
+int launch_bwd_skip(const BwdArgs& a)
 {
     const DrDesc* d = a.d;
     const size_t smem = (size_t)d->R * sizeof(TfBin);
-    auto kern = bwd_kernel<VT, LAYOUT, TAPS, WV, WT, SR1>;
+    auto kern = bwd_kernel<VT, LAYOUT, TAPS, WV, WT, SR1, SKIP>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
-                                         a.slots, vol_stride(d), a.mse_scale, cell_bias(*d));
+                                         a.slots, vol_stride(d), a.mse_scale, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
+}
+// the skip grid only serves the volume-only backward (no TF gradient) of the corner-reuse tap paths
+template <typename VT, int LAYOUT, int TAPS, bool WV, bool WT, bool SR1>
+int launch_bwd(const BwdArgs& a)
+{
+    constexpr bool kCanSkip = WV && !WT && TAPS != TAPS_GENERIC;
+    if (kCanSkip && a.skip_grid) return launch_bwd_skip<VT, LAYOUT, TAPS, WV, WT, SR1, kCanSkip>(a);
+    return launch_bwd_skip<VT, LAYOUT, TAPS, WV, WT, SR1, false>(a);
 }
 
 // with or without the skip grid (the kernels without it carry none of the skip code); the generic tap path never skips

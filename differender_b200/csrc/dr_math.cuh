@@ -1423,6 +1423,28 @@ DR_HD int skip_run(const DrDesc& d, const Ray& r, F3 cam, int s, int nn, int cx,
     return m < 1 ? 1 : m;
 }
 
+// the same for the backward march, which walks s, s-1, ...: number of consecutive samples (at least 1) down from s whose cells
+// stay in the macro-cell of sample s's cell; never more than s + 1.  The ray ENTERS the macro-cell at the latest of the per-axis
+// entry faces (shrunk by the margin); one more sample than necessary is left to the normal path.
+DR_HD int skip_run_back(const DrDesc& d, const Ray& r, F3 cam, int s, int cx, int cy, int cz)
+{
+    if (r.n < 2) return 1;
+    const float Px = (0.5f * cam.x + 0.5f) * d.scale[0], Dx = 0.5f * r.dir.x * d.scale[0];
+    const float Py = (0.5f * cam.y + 0.5f) * d.scale[1], Dy = 0.5f * r.dir.y * d.scale[1];
+    const float Pz = (0.5f * cam.z + 0.5f) * d.scale[2], Dz = 0.5f * r.dir.z * d.scale[2];
+    const float bx = (float)(cx & ~7), by = (float)(cy & ~7), bz = (float)(cz & ~7);
+    float tin = -3.0e38f;
+    if (fabsf(Dx) > 1e-20f) tin = fmaxf(tin, ((Dx > 0.0f ? bx + kSkipMargin : bx + (8.0f - kSkipMargin)) - Px) * fast_rcp(Dx));
+    if (fabsf(Dy) > 1e-20f) tin = fmaxf(tin, ((Dy > 0.0f ? by + kSkipMargin : by + (8.0f - kSkipMargin)) - Py) * fast_rcp(Dy));
+    if (fabsf(Dz) > 1e-20f) tin = fmaxf(tin, ((Dz > 0.0f ? bz + kSkipMargin : bz + (8.0f - kSkipMargin)) - Pz) * fast_rcp(Dz));
+    const float dt = (r.texit - r.t0) * r.inv_nm1;
+    if (!(dt > 1e-20f)) return 1;
+    // samples sit at t(s') = t0 + dt * s': the first one strictly after tin, plus one for safety
+    const float first = fmaxf(ceilf((tin - r.t0) * fast_rcp(dt)) + 1.0f, 0.0f);
+    if (!(first <= (float)s)) return 1;                       // (also NaN)
+    return s - (int)first + 1;
+}
+
 // 1 when every TF bin reachable from voxel values in [mn, mx] has alpha 0 (tf is the staged bin table's source: alpha of bin
 // r is tf_alpha[r * tf_stride]).  The range is widened by the rounding slack of three fp32 mix levels and of the bin scale.
 DR_HD unsigned char skip_classify(const DrDesc& d, float mn, float mx, const float* tf_alpha, int tf_stride)
@@ -1526,16 +1548,40 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
 // VolSink::open/close/direct the volume gradient; both may hold a partial sum in registers and are flushed at the end
 // of the ray.
 // ---------------------------------------------------------------------------------------------------------
-template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1, typename VolSink, typename TfSink>
+template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1, bool SKIP, typename VolSink, typename TfSink>
 DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout& L, const TfTable& tf, F3 cam,
-                          const Ray& r, F4 Afinal, int K, float Tprev, F4 g, VolSink& vsink, TfSink& tsink)
+                          const Ray& r, F4 Afinal, int K, float Tprev, F4 g, VolSink& vsink, TfSink& tsink,
+                          const unsigned char* skip_grid = nullptr)
 {
     float Tafter = 1.0f - Afinal.w;                     // transmittance after sample K-1
+    // SKIP (volume gradient only): a sample in a macro-cell that is exactly transparent under the TF has o = 0 and both TF bins
+    // transparent, so it contributes nothing and changes neither g.w nor the transmittance -- runs of them are jumped over with
+    // the forward's skip grid (the TF gradient, in contrast, receives d(alpha) from every transparent sample)
+    int pbx = -1, pby = -1, pbz = -1;
+    bool in_empty = false;
     for (int s = K - 1; s >= 0; --s) {
         float ts;
         const F3 pos = sample_pos(r, cam, s, ts);
         Centre c;
-        sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
+        if (SKIP && !WANT_TF && TAPS != TAPS_GENERIC && skip_grid) {
+            locate_centre(d, L, pos, c);
+            if ((((c.cx.b ^ pbx) | (c.cy.b ^ pby) | (c.cz.b ^ pbz)) & ~7) != 0) {
+                pbx = c.cx.b; pby = c.cy.b; pbz = c.cz.b;
+                const int cx = lo_of(c.cx), cy = lo_of(c.cy), cz = lo_of(c.cz);
+                in_empty = load_u8(skip_grid + macro_index(d, cx, cy, cz)) != 0;
+                if (in_empty) {
+                    s -= skip_run_back(d, r, cam, s, cx, cy, cz) - 1;
+                    continue;
+                }
+            } else if (in_empty) {
+                continue;
+            }
+            typename AddrOf<VT, LAYOUT, false>::type ad;
+            ad.init(d, vol.p, L, c);
+            eval_centre(ad, c);
+        } else {
+            sample_centre<VT, LAYOUT, TAPS>(d, vol, L, pos, c);
+        }
         TfHit h;
         apply_tf(d, tf, c.I, h);
         tf_colour(h, WANT_VOL);

@@ -66,6 +66,7 @@ class VolumeRaycaster:
         self.pending_grad_cells = None
         # DistributedRaycaster: {"vol": [1,Y,Z,X] fp32 view of its flat all-reduce buffer}; the gather writes there directly
         self.grad_sink = None
+        self.last_skip_grid = None
         self.kernel_launches = 0     # this object's kernel launches so far (the library's own kernels only; bench.py reports the count)
 
     @property
@@ -243,6 +244,7 @@ class VolumeRaycaster:
         K = torch.empty((BS, h, w), dtype=torch.int32, device=dev) if want_aux else None
         Tp = torch.empty((BS, h, w), dtype=torch.float32, device=dev) if (want_aux and not nondiff) else None
         grid = self.skip_grid(d, bricked, tf_r4) if skip is None or skip else None
+        self.last_skip_grid = grid           # the volume-only backward of the same call can jump over the same empty runs
         loss_sum = torch.zeros((BS,), dtype=torch.float32, device=dev) if mse_target is not None else None
         _lib.check(_lib.load().dr_forward_ex(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
                                              _lib.ptr(mse_target), _lib.ptr(grid), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tp),
@@ -253,12 +255,14 @@ class VolumeRaycaster:
         return out, K, Tp
 
     def march_backward(self, bricked, tf_r4, cam, sampling_rate, jitter, grad_out, out, K, Tprev, need_vol, need_tf,
-                       image_layout=True, grad_cells=None, extra_flags=0, mse_scale=None):
+                       image_layout=True, grad_cells=None, extra_flags=0, mse_scale=None, skip_grid=None):
         """Backward of cam.shape[0] views.  Returns (grad_vol_linear [Bvol,Y,Z,X] fp32 or None, grad_tf [Btf,R,4] or None).
         The volume gradient is scattered into a cell-major buffer [Bvol, X*Y*Z*8] (zeroed here) and gathered once.
         If `grad_cells` is given it is accumulated into and NOT gathered (it is returned instead), so that several calls
         (e.g. chunks of a large view batch) share one buffer and one gather.
-        With `mse_scale`, `grad_out` is the TARGET image and dL/d(out) = mse_scale*(out - target) is formed in the kernel."""
+        With `mse_scale`, `grad_out` is the TARGET image and dL/d(out) = mse_scale*(out - target) is formed in the kernel.
+        `skip_grid`: the grid the forward of the same (volume, TF) built (march() leaves it in `last_skip_grid`); only the
+        volume-only backward (need_tf False) uses it, to jump over runs of samples in exactly transparent macro-cells."""
         BS = cam.shape[0]
         if extra_flags & F_TF_4R:
             tf_r4 = _Tf4R(tf_r4)
@@ -278,16 +282,12 @@ class VolumeRaycaster:
         gtf = torch.zeros(tf_r4.t.shape if isinstance(tf_r4, _Tf4R) else tf_r4.shape, dtype=torch.float32, device=dev) if need_tf else None
         ws_bytes = lib.dr_workspace_bytes(ctypes.byref(d))
         ws = torch.empty((max(ws_bytes, 16) + 3) // 4, dtype=torch.float32, device=dev)
-        if mse_scale is not None:
-            _lib.check(lib.dr_backward_mse(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
-                                           _lib.ptr(grad_out), ctypes.c_float(mse_scale), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
-                                           _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
-                                           _stream()), "dr_backward_mse")
-        else:
-            _lib.check(lib.dr_backward(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
-                                       _lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev),
-                                       _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf), _lib.ptr(ws), ws_bytes,
-                                       _stream()), "dr_backward")
+        fused = mse_scale is not None
+        _lib.check(lib.dr_backward_ex(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
+                                      None if fused else _lib.ptr(grad_out), _lib.ptr(grad_out) if fused else None,
+                                      ctypes.c_float(mse_scale if fused else 0.0), _lib.ptr(skip_grid) if (need_vol and not need_tf) else None,
+                                      _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev), _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf),
+                                      _lib.ptr(ws), ws_bytes, _stream()), "dr_backward_ex")
         self.kernel_launches += 1 + (1 if need_tf else 0)           # bwd_kernel (+ tf_reduce_kernel)
         if not need_vol:
             return None, gtf
@@ -387,13 +387,13 @@ def _save(ctx, vr, volume, tf, sampling_rate, batched, vol_b, bricked, tf_r4, ca
     # Function save_for_backward keeps no reference cycle (a plain ctx attribute would: out.grad_fn -> ctx -> out left
     # every buffer of the step to Python's cyclic collector and cost ~1 GiB of fresh cudaMalloc per step).
     zero_copy = bricked.data_ptr() == volume.data_ptr()
-    ctx.save_for_backward(volume if zero_copy else None, tf_r4, cam, jit, out, K, Tp, target)
+    ctx.save_for_backward(volume if zero_copy else None, tf_r4, cam, jit, out, K, Tp, target, vr.last_skip_grid)
     ctx.bricked = None if zero_copy else bricked       # our own copy (cell-major / bricked layout, or a cast / contiguous copy)
 
 
 def _saved(ctx):
     """(volume as the march kernels read it, tf_r4, cam, jit, out, K, Tp, mse target or None) of the forward."""
-    volume, tf_r4, cam, jit, out, K, Tp, target = ctx.saved_tensors
+    volume, tf_r4, cam, jit, out, K, Tp, target, ctx.skip_grid = ctx.saved_tensors
     if ctx.bricked is not None:
         vol = ctx.bricked
     else:
@@ -449,7 +449,7 @@ class RaycastFunction(torch.autograd.Function):
             go = go.float().contiguous()
             vol, tf_r4, cam, jit, out, K, Tp, _ = _saved(ctx)
             gvol, gtf = ctx.vr.march_backward(vol, tf_r4, cam, ctx.sampling_rate, jit, go, out, K, Tp, need_vol, need_tf,
-                                              image_layout=ctx.image_layout)
+                                              image_layout=ctx.image_layout, skip_grid=ctx.skip_grid)
         gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
         return None, gv, gt, None, None, None, None, None, None
 
@@ -485,7 +485,7 @@ class RaycastMSEFunction(torch.autograd.Function):
             vol, tf_r4, cam, jit, out, K, Tp, tgt = _saved(ctx)
             scale = 2.0 * float(grad_loss) / out.numel()           # one scalar read; keeps the kernel argument a plain float
             gvol, gtf = ctx.vr.march_backward(vol, tf_r4, cam, ctx.sampling_rate, jit, tgt, out, K, Tp, need_vol, need_tf,
-                                              image_layout=True, mse_scale=scale)
+                                              image_layout=True, mse_scale=scale, skip_grid=ctx.skip_grid)
         gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
         return None, gv, gt, None, None, None, None, None, None
 

@@ -138,7 +138,7 @@ void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const 
 
 void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
                   const float* grad_out, const float* out, const int* Kin, const float* Tprev,
-                  float* gvol_cells, float* gtf)
+                  float* gvol_cells, float* gtf, const unsigned char* skip_grid)
 {
     Layout L = make_layout(*d, cell_bias(*d));
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
@@ -159,8 +159,8 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
         F4 g = { grad_out[pix], grad_out[plane + pix], grad_out[2 * plane + pix], grad_out[3 * plane + pix] };
         const int K = Kin[pix];
         const float Tp = Tprev[pix];
-#define CALL(LAY, TAPS, WV, WT) do { if (sr1 && TAPS != TAPS_GENERIC) march_backward<float, LAY, TAPS, WV, WT, TAPS != TAPS_GENERIC>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); \
-                                     else march_backward<float, LAY, TAPS, WV, WT, false>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts); } while (0)
+#define CALL(LAY, TAPS, WV, WT) do { if (sr1 && TAPS != TAPS_GENERIC) march_backward<float, LAY, TAPS, WV, WT, TAPS != TAPS_GENERIC, true>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts, skip_grid); \
+                                     else march_backward<float, LAY, TAPS, WV, WT, false, true>(*d, vol, L, tf4, cam, r, A, K, Tp, g, vs, ts, skip_grid); } while (0)
 #define CALL3(LAY, TAPS) do { if (wv && wt) CALL(LAY, TAPS, true, true); else if (wv) CALL(LAY, TAPS, true, false); else if (wt) CALL(LAY, TAPS, false, true); } while (0)
         if (d->flags & DR_F_LAYOUT_CELL8) { if (taps == TAPS_ONE) CALL3(LAYOUT_CELL8, TAPS_ONE); else CALL3(LAYOUT_CELL8, TAPS_TWO); }
         else if (d->flags & DR_F_LAYOUT_BRICK8) { if (taps == TAPS_ONE) CALL3(LAYOUT_BRICK8, TAPS_ONE); else CALL3(LAYOUT_BRICK8, TAPS_TWO); }

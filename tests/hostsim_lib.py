@@ -105,7 +105,7 @@ def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, j
 
 
 def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_samples=512, jitter=None,
-             want_vol=True, want_tf=True, generic=False, brick=False, cell=False):
+             want_vol=True, want_tf=True, generic=False, brick=False, cell=False, skip=False):
     vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
     tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
     out, K, Tp, _ = forward(volume, tf, cam, output_shape, sampling_rate, max_samples, jitter, False, generic, brick, cell)
@@ -118,8 +118,12 @@ def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_s
     cam = np.ascontiguousarray(cam, np.float32)
     jit = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
     go = np.ascontiguousarray(grad_image, np.float32)
+    grid = None
+    if skip:                                               # the forward's skip grid: only the volume-only backward uses it
+        grid = np.zeros((d.nby, d.nbz, d.nbx), np.uint8)
+        L.sim_skip_grid(ctypes.byref(d), _p(vol), _p(tf_r4), _p(grid, ctypes.c_ubyte))
     L.sim_backward(ctypes.byref(d), _p(br), _p(tf_r4), _p(cam), _p(jit), _p(go), _p(out), _p(K, ctypes.c_int32),
-                   _p(Tp), _p(gbr), _p(gtf))
+                   _p(Tp), _p(gbr), _p(gtf), _p(grid, ctypes.c_ubyte))
     gv = np.zeros_like(vol)
     L.sim_gather(ctypes.byref(d), _p(gbr), _p(gv))
     return gv, np.ascontiguousarray(gtf.T)

@@ -75,3 +75,49 @@ def test_device_grid_equals_host_grid():
     assert g.size == 16 + ref.size and ref.size == 5 * 7 * 9
     assert np.array_equal(g[16:].reshape(ref.shape), ref) and 0 < ref.mean() < 1
     assert int(g[:4].view(np.uint32)[0]) == int(ref.sum())          # header: number of empty macro-cells
+
+
+@pytest.mark.parametrize("layout,dtype,shape", [("cell8", torch.float32, (72, 64, 80)), ("linear", torch.float32, (72, 64, 80)),
+                                                ("cell8", torch.float16, (9, 1100, 9)), ("brick8", torch.float32, (40, 56, 72))])
+def test_volume_only_backward_skips_exactly(layout, dtype, shape):
+    # dr_backward_ex with the forward's grid: the volume-only backward jumps over empty macro-cells; the gradient must equal the
+    # full march's (to the rounding of the atomics' order) and the oracle's
+    from differender_b200 import VolumeRaycaster
+    from helpers import GRAD_TOL, oracle_backward_views, oracle_forward_views
+    out_shape = (64, 48)
+    vol, tf, cams, jit = case_inputs(shape, out_shape, 128, seed=33, tf_name="tf1", views=2)
+    D, H, W = shape
+    vr = VolumeRaycaster((W, D, H), out_shape, max_samples=4096, tf_resolution=128, layout=layout)
+    b = vr.brick(vol.to(DEV, dtype).reshape(1, D, H, W).contiguous())
+    tf_r4 = tf.to(DEV).t().contiguous()[None]
+    c, j = cams.to(DEV).contiguous(), jit.to(DEV).contiguous()
+    out, K, Tp = vr.march(b, tf_r4, c, 1.0, j)
+    grid = vr.last_skip_grid
+    assert grid is not None and int(grid[:4].view(torch.int32)[0]) > 0
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).to(DEV)
+    gv0, _ = vr.march_backward(b, tf_r4, c, 1.0, j, go, out, K, Tp, True, False)
+    gv1, gt1 = vr.march_backward(b, tf_r4, c, 1.0, j, go, out, K, Tp, True, False, skip_grid=grid)
+    assert gt1 is None and gv0.abs().max().item() > 0
+    assert rel_l2(gv1.cpu().numpy(), gv0.cpu().numpy()) <= 1e-5
+    # with a TF gradient the grid is ignored
+    gv2, gt2 = vr.march_backward(b, tf_r4, c, 1.0, j, go, out, K, Tp, True, True, skip_grid=grid)
+    gv3, gt3 = vr.march_backward(b, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
+    assert rel_l2(gv2.cpu().numpy(), gv3.cpu().numpy()) <= 1e-5 and rel_l2(gt2.cpu().numpy(), gt3.cpu().numpy()) <= 1e-5
+    if dtype == torch.float32 and max(shape) < 1000:
+        ref, _, _ = oracle_forward_views(vol, tf, cams, out_shape, jit, max_samples=4096)
+        gvr, _ = oracle_backward_views(vol, tf, cams, go.cpu().numpy(), out_shape, jit, max_samples=4096, want_tf=False)
+        assert rel_l2(gv1[0].cpu().numpy(), gvr) <= GRAD_TOL
+
+
+def test_volume_only_autograd_uses_the_grid_and_matches():
+    from differender_b200 import Raycaster
+    vol, tf, cams, jit = case_inputs((64, 64, 64), (48, 40), 128, seed=35, tf_name="tf1", views=2)
+    res = []
+    for skip in (False, True):
+        rc = Raycaster((64, 64, 64), (48, 40), 128, max_samples=2048, skip_empty=skip)
+        v = vol.to(DEV).requires_grad_(True)
+        img = rc(v, tf.to(DEV), cams.to(DEV), jit.to(DEV))                    # the TF does not require grad: volume-only backward
+        (img * torch.linspace(0, 1, img.numel(), device=DEV).reshape(img.shape)).sum().backward()
+        res.append((img.detach(), v.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert rel_l2(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) <= 1e-5

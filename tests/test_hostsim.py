@@ -123,3 +123,24 @@ def test_empty_space_skipping_respects_max_samples_and_views_without_hits():
     a = hs.forward(vol.numpy(), tf.numpy(), cam, (40, 32), max_samples=2048, jitter=J)
     b = hs.forward(vol.numpy(), tf.numpy(), cam, (40, 32), max_samples=2048, jitter=J, skip=True)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("shape,tf_name,sr", [((64, 64, 64), "tf1", 1.0), ((40, 56, 72), "tf5", 1.0), ((64, 64, 64), "tf1", 0.7), ((1100, 9, 9), "tf1", 1.0)])
+@pytest.mark.parametrize("layout", ["linear", "cell8"])
+def test_volume_only_backward_with_skip_grid_is_exact(shape, tf_name, sr, layout):
+    # the volume-only backward jumps over runs of samples in macro-cells that are transparent under the TF: they contribute
+    # nothing, so the cell-major gradient must be IDENTICAL (same additions in the same order on the host) with and without the grid
+    out_shape = (40, 32)
+    vol, tf, cams, jit = case_inputs(shape, out_shape, 128, seed=21, tf_name=tf_name, jitter=True)
+    J = jit[0].numpy()
+    go = np.random.default_rng(3).normal(size=(4, 32, 40)).astype(np.float32)
+    kw = dict(sampling_rate=sr, max_samples=4096, jitter=J, want_vol=True, want_tf=False, cell=layout == "cell8")
+    gv, gt = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, **kw)
+    gv2, gt2 = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, skip=True, **kw)
+    assert np.abs(gv).max() > 0 and np.array_equal(gv, gv2) and not gt2.any()
+    ref, _ = co.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, max_samples=4096, jitter=J, want_tf=False)
+    assert rel_l2(gv2, ref) <= 1e-4
+    # with a TF gradient the grid must be ignored (transparent samples feed d(alpha))
+    a = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, max_samples=4096, jitter=J, cell=layout == "cell8")
+    b = hs.backward(vol.numpy(), tf.numpy(), cams[0].numpy(), go, out_shape, sampling_rate=sr, max_samples=4096, jitter=J, cell=layout == "cell8", skip=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
