@@ -79,11 +79,16 @@ __device__ __forceinline__ TfTable stage_tf(const DrDesc& d, const float* __rest
     return t;
 }
 
+// Tile rows are handed out from the image centre outwards (mid, mid-1, mid+1, ...): the hardware dispatches CTAs in blockIdx
+// order, the rays through the middle of the volume are the longest, and a launch of only a few waves (C1, C2: one 512^2 view)
+// ends when its last long ray does -- so the long ones start first.
 __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
 {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int k = blockIdx.y, mid = gridDim.y >> 1;
+    const int ty = (k & 1) ? mid - ((k + 1) >> 1) : mid + (k >> 1);
     i = blockIdx.x * kTileW + (w % kWarpsX) * 8 + (l & 7);
-    j = blockIdx.y * kTileH + (w / kWarpsX) * 4 + (l >> 3);
+    j = ty * kTileH + (w / kWarpsX) * 4 + (l >> 3);
     return i < d.W && j < d.H;
 }
 
@@ -226,6 +231,7 @@ struct RedTfSink {
         if (lo != cur) next(lo);
         s.w += dcw; s1.w += f * dcw;
     }
+    __device__ __forceinline__ void init() { cur = -1; rgb = false; s = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s; }
 };
 
 template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1, bool SKIP>
@@ -282,8 +288,8 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
     RedTfSink ts;
     ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
-    ts.cur = -1; ts.Rm1 = d.R - 1; ts.rgb = false;
-    ts.s = make_float4(0.f, 0.f, 0.f, 0.f); ts.s1 = ts.s;
+    ts.Rm1 = d.R - 1;
+    ts.init();
     const unsigned char* grid = nullptr;
     if (SKIP && __ldg(reinterpret_cast<const unsigned*>(skip_grid)) != 0u) grid = skip_grid + kSkipHeader + (size_t)b * skip_stride;
     march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1, SKIP>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts, grid);
