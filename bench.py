@@ -244,7 +244,11 @@ class Workload:
         self.vol_lin = self.vol.reshape(1, n, n, n)
         self.tf_r4 = self.tf.t().contiguous()[None]
         self.need_vol, self.need_tf = self.mode in ("full", "vol"), self.mode in ("full", "tf")
-        self.flat_grad = torch.empty(n ** 3 + R * 4, dtype=torch.float32, device=dev) if world > 1 else None
+        self.grad_buffer = None
+        if world > 1:                                   # collective allocation: NVLS multimem all-reduce for the C3-sized buffer, NCCL above 256 MiB
+            from differender_b200.distributed import GradBuffer
+            self.grad_buffer = GradBuffer(n ** 3 + R * 4, dev)
+        self.flat_grad = self.grad_buffer.buf if world > 1 else None
         self.cells = None                                                                # cell-major gradient buffer, allocated once
         self.tf_opt = MomentumSGD(self.tf_r4[0], lr=0.1, momentum=0.9, max_grad=0.1, lr_decay=0.99) if self.mode == "tf" else None
         self.ar_bytes = int((n ** 3 + R * 4) * 4 if self.need_vol else R * 16)
@@ -288,7 +292,7 @@ class Workload:
             if self.world > 1:
                 if not self.need_vol:
                     self.flat_grad[:gtf.numel()].copy_(gtf.reshape(-1))
-                dist.all_reduce(self.flat_grad if self.need_vol else self.flat_grad[:gtf.numel()])      # ONE collective: NCCL over NVLink
+                self.grad_buffer.all_reduce(None if self.need_vol else self.flat_grad[:gtf.numel()])     # ONE collective over NVLink / NVSwitch
             if self.mode == "tf":                                                    # C2: momentum-SGD step on the TF (reference example :375-381), one kernel
                 self.tf_opt.step(gtf[0])
                 vr.kernel_launches += 1                                              # momentum_step_kernel
@@ -372,15 +376,16 @@ def time_allreduce(wl, reps=5):
     import torch
     import torch.distributed as dist
     buf = wl.flat_grad if wl.need_vol else wl.flat_grad[:wl.R * 4]
+    part = None if wl.need_vol else buf
     buf.zero_()
     for _ in range(2):
-        dist.all_reduce(buf)
+        wl.grad_buffer.all_reduce(part)
     torch.cuda.synchronize()
     dist.barrier()
     a, b = wl.ev(), wl.ev()
     a.record()
     for _ in range(reps):
-        dist.all_reduce(buf)
+        wl.grad_buffer.all_reduce(part)
     b.record()
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=wl.dev)
@@ -389,7 +394,8 @@ def time_allreduce(wl, reps=5):
     nbytes = buf.numel() * 4
     return {"bytes": nbytes, "ms_isolated": ms, "busbw_gbs": nbytes * 2 * (wl.world - 1) / wl.world / (ms * 1e-3) / 1e9,
             "nvlink_peak_gbs": NVLINK_PEAK_GBS, "frac_of_nvlink_peak": nbytes * 2 * (wl.world - 1) / wl.world / (ms * 1e-3) / 1e9 / NVLINK_PEAK_GBS,
-            "how": f"barrier, then CUDA events around {reps} back-to-back all_reduce(SUM) of the flat [volume grad | TF grad] fp32 buffer, max over ranks"}
+            "algorithm": wl.grad_buffer.how if part is None else "all_reduce",
+            "how": f"barrier, then CUDA events around {reps} back-to-back all-reduces (SUM) of the flat [volume grad | TF grad] fp32 buffer, max over ranks"}
 
 
 def small_line(name, cfg, r, extra=None):

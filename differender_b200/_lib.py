@@ -8,7 +8,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIFFRENDER_LIB") or os.path.join(_PKG, "libdiffrender.so")
 
 # include/diffrender.h
-DR_VERSION = 103
+DR_VERSION = 104
 VOX_F32, VOX_F16, VOX_U8 = 0, 1, 2
 F_NONDIFF, F_NEEDS_VOL_GRAD, F_NEEDS_TF_GRAD, F_HAS_JITTER, F_OUT_IMAGE, F_TF_4R, F_GENERIC_TAPS, F_LAYOUT_BRICK8, F_COUNT_SHADED, F_LAYOUT_CELL8 = 1, 2, 4, 8, 16, 32, 64, 256, 512, 2048
 
@@ -63,7 +63,7 @@ def load():
     lib.dr_build_skip_grid.argtypes = [dp, vp, vp, vp, ctypes.c_int, vp, vp]; lib.dr_build_skip_grid.restype = ctypes.c_int
     lib.dr_backward_mse.argtypes = [dp] + [vp] * 5 + [ctypes.c_float] + [vp] * 6 + [ctypes.c_size_t, vp]
     lib.dr_backward_mse.restype = ctypes.c_int
-    lib.dr_backward_ex.argtypes = [dp] + [vp] * 6 + [ctypes.c_float] + [vp] * 7 + [ctypes.c_size_t, vp]
+    lib.dr_backward_ex.argtypes = [dp] + [vp] * 6 + [ctypes.c_float] + [vp] * 8 + [ctypes.c_size_t, vp]
     lib.dr_backward_ex.restype = ctypes.c_int
     lib.dr_momentum_step.argtypes = [vp, vp, vp, ctypes.c_size_t] + [ctypes.c_float] * 5 + [vp]
     lib.dr_momentum_step.restype = ctypes.c_int

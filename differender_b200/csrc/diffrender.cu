@@ -412,7 +412,7 @@ int forward_impl(const DrDesc* d, const void* vol, const float* tf, const float*
 int backward_impl(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter,
                   const float* grad_out, const float* out_rgba, const int32_t* K, const float* Tprev, float* grad_vol_cells,
                   float* grad_tf, void* workspace, size_t workspace_bytes, float mse_scale, void* stream,
-                  const unsigned char* skip_grid = nullptr)
+                  const unsigned char* skip_grid = nullptr, const float* scale_dev = nullptr)
 {
     if (int rc = check_desc(d)) return rc;
     if (d->flags & DR_F_NONDIFF) return fail(DR_EINVAL, "dr_backward: the non-differentiable march has no backward");
@@ -439,7 +439,7 @@ int backward_impl(const DrDesc* d, const void* vol, const float* tf, const float
     if (skip_grid && (wt || d->tap_generic)) skip_grid = nullptr;         // transparent samples feed the TF gradient: nothing to skip then
     if (skip_grid && !aligned(skip_grid, 4)) return fail(DR_EALIGN, "dr_backward_ex: skip_grid must be 4-byte aligned");
     const BwdArgs a { d, vol, tf, cam, jitter, grad_out, out_rgba, K, Tprev, reinterpret_cast<float4*>(grad_vol_cells),
-                      static_cast<float4*>(workspace), st, mse_scale, skip_grid };
+                      static_cast<float4*>(workspace), st, mse_scale, skip_grid, scale_dev };
     if (d->vox_dtype == DR_VOX_U8 && !(d->flags & DR_F_LAYOUT_CELL8))
         return fail(DR_EDTYPE, "uint8 volumes are marched from their cell-major copy only (dr_expand_cells, DR_F_LAYOUT_CELL8)");
     const int rc = d->vox_dtype == DR_VOX_U8 ? launch_backward_u8(a) : d->vox_dtype == DR_VOX_F32 ? launch_backward_f32(a) : launch_backward_f16(a);
@@ -601,8 +601,8 @@ int dr_backward_mse(const DrDesc* d, const void* vol, const float* tf, const flo
 }
 
 int dr_backward_ex(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, const float* grad_out,
-                   const float* target, float scale, const uint8_t* skip_grid, const float* out_rgba, const int32_t* K, const float* Tprev,
-                   float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
+                   const float* target, float scale, const float* scale_dev, const uint8_t* skip_grid, const float* out_rgba, const int32_t* K,
+                   const float* Tprev, float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (!d) return fail(DR_EINVAL, "null descriptor");
     if ((grad_out == nullptr) == (target == nullptr)) return fail(DR_EINVAL, "dr_backward_ex: give exactly one of grad_out and target");
@@ -610,7 +610,7 @@ int dr_backward_ex(const DrDesc* d, const void* vol, const float* tf, const floa
     DrDesc dd = *d;
     if (target) dd.flags |= DR_F_FUSED_MSE;
     return backward_impl(&dd, vol, tf, cam, jitter, target ? target : grad_out, out_rgba, K, Tprev, grad_vol_cells, grad_tf, workspace,
-                         workspace_bytes, target ? scale : 0.0f, stream, skip_grid);
+                         workspace_bytes, target ? scale : 0.0f, stream, skip_grid, target ? scale_dev : nullptr);
 }
 
 int dr_momentum_step(float* param, const float* grad, float* momentum, size_t n, float lr, float gamma, float max_grad,

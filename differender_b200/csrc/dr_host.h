@@ -29,6 +29,7 @@ struct BwdArgs {
     const float* gout; const float* out; const int32_t* K; const float* T; float4* gvol; float4* slots;
     cudaStream_t st; float mse_scale;
     const unsigned char* skip_grid;      // from dr_build_skip_grid (the forward's), or null; used by the volume-only backward
+    const float* scale_dev;              // optional device scalar multiplied into mse_scale (the upstream gradient of the fused loss)
 };
 
 DR_INTERNAL int launch_forward_f32(const FwdArgs& a);      // dr_fwd_f32.cu

@@ -243,7 +243,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
            float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale, unsigned cbias,
-           const unsigned char* __restrict__ skip_grid, size_t skip_stride)
+           const unsigned char* __restrict__ skip_grid, size_t skip_stride, const float* __restrict__ scale_dev)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.z;
@@ -272,7 +272,9 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
         g = F4 { g4.x, g4.y, g4.z, g4.w };
     }
     if (d.flags & DR_F_FUSED_MSE) {
-        // `gout` holds the TARGET image: dL/dA = mse_scale * (A - target), never materialised in HBM
+        // `gout` holds the TARGET image: dL/dA = mse_scale * (A - target), never materialised in HBM.  The upstream gradient of the
+        // loss may stay on the device (scale_dev): reading it on the host would stall the host on the whole forward
+        if (scale_dev) mse_scale *= __ldg(scale_dev);
         g.x = mse_scale * (A.x - g.x); g.y = mse_scale * (A.y - g.y); g.z = mse_scale * (A.z - g.z); g.w = mse_scale * (A.w - g.w);
     }
     if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;       // this ray's gradient is exactly zero
@@ -337,7 +339,8 @@ int launch_bwd_skip(const BwdArgs& a)
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
-                                         a.slots, vol_stride(d), a.mse_scale, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d));
+                                         a.slots, vol_stride(d), a.mse_scale, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d),
+                                         a.scale_dev);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");
 }

@@ -1049,6 +1049,48 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
     }
 }
 
+// Direct taps (cell-major records in the two-neighbour regime, 1000 < dim <= 2000: C5).  With the tap offset above half a voxel
+// a tap leaves the centre cell about every other time, on every axis, so the corner-reuse path above spends its time on
+// predicated plane fetches, operand selects and the divergent "both taps crossed" branches.  Here each of the six taps simply
+// evaluates the trilinear polynomial of ITS OWN cell -- the record at cell + (lo_tap - lo_centre) * stride: one 16-byte (fp16) or
+// two 16-byte (fp32) loads that mostly hit L1 -- with the same seven mixes in the same order on the same eight corners, so the
+// values are bit-identical to the other paths; there is no branch, no select and no second-plane case.
+template <typename VT>
+DR_HD F2 tap_rows(const VT* vp, uoff cell, float fx, float fy)      // x then y mixes of one cell record: the pair (value at z0, at z1)
+{
+    float v[8];
+    load_vox8(rec_add(vp, cell), v);
+    const F2 fx2 = splat(fx), ox2 = splat(DR_SUB(1.0f, fx));
+    const F2 m0 = mix2(f2(v[0], v[1]), f2(v[2], v[3]), ox2, fx2), m1 = mix2(f2(v[4], v[5]), f2(v[6], v[7]), ox2, fx2);
+    return mix2(m0, m1, splat(DR_SUB(1.0f, fy)), splat(fy));
+}
+template <typename VT>
+DR_HD void eval_normals_direct(const DrDesc& d, const VT* vp, F3 pos, const Centre& c, Taps& t)
+{
+    t.cx = c.cx; t.cy = c.cy; t.cz = c.cz; t.cidx = c.cidx; t.I = c.I;
+    locate_pair(pos.x, d.delta, d.scale[0], t.xp, t.xm);
+    locate_pair(pos.y, d.delta, d.scale[1], t.yp, t.ym);
+    locate_pair(pos.z, d.delta, d.scale[2], t.zp, t.zm);
+    const uoff cell = (uoff)c.cidx, sz = (uoff)d.X, sy = (uoff)(d.X * d.Z);
+    const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f, oz = DR_SUB(1.0f, fz);
+    {   // x taps: cells cell + (b_tap - b_centre), x fraction of the tap
+        const F2 p = tap_rows(vp, cell + (uoff)(t.xp.b - c.cx.b), t.xp.f, fy), m = tap_rows(vp, cell + (uoff)(t.xm.b - c.cx.b), t.xm.f, fy);
+        const F2 v = mix2(f2(p.x, m.x), f2(p.y, m.y), splat(oz), splat(fz));
+        t.g.x = DR_SUB(v.x, v.y);
+    }
+    {   // y taps
+        const F2 p = tap_rows(vp, cell + (uoff)(t.yp.b - c.cy.b) * sy, fx, t.yp.f), m = tap_rows(vp, cell + (uoff)(t.ym.b - c.cy.b) * sy, fx, t.ym.f);
+        const F2 v = mix2(f2(p.x, m.x), f2(p.y, m.y), splat(oz), splat(fz));
+        t.g.y = DR_SUB(v.x, v.y);
+    }
+    {   // z taps: z fraction of the tap
+        const F2 p = tap_rows(vp, cell + (uoff)(t.zp.b - c.cz.b) * sz, fx, fy), m = tap_rows(vp, cell + (uoff)(t.zm.b - c.cz.b) * sz, fx, fy);
+        const F2 f = f2(t.zp.f, t.zm.f);
+        const F2 v = mix2(f2(p.x, m.x), f2(p.y, m.y), sub2(splat(1.0f), f), f);
+        t.g.z = DR_SUB(v.x, v.y);
+    }
+}
+
 // Generic path (a normal tap can skip a whole cell: dims > ~2000; linear layout only): every tap is a full 8-load
 // trilinear evaluation with the reference's clamps hi = min(lo+1, dim-1)                    :170-172
 template <typename VT>
@@ -1094,6 +1136,7 @@ template <typename VT, int LAYOUT, int TAPS, bool DUAL>
 DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, const Centre& c, Taps& t)
 {
     if (TAPS == TAPS_GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
+    if (TAPS == TAPS_TWO && LAYOUT == LAYOUT_CELL8) { eval_normals_direct(d, vol.p, pos, c, t); return; }     // C5: fwd +6.6 %, bwd +3.3 %
     typename AddrOf<VT, LAYOUT, DUAL>::type ad;
     ad.init(d, vol.p, L, c);
     eval_normals<TAPS>(d, ad, pos, c, t);

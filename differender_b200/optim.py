@@ -92,12 +92,12 @@ class FusedVolumeSGD:
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             g_cells, g_lin = cells, None
             if self._world() > 1:
-                import torch.distributed as dist
+                from .distributed import GradBuffer
                 if self._flat is None:
-                    self._flat = torch.empty(p.numel(), dtype=torch.float32, device=p.device)
-                vr.gather(cells, out=self._flat.view(1, Y, Z, X))
-                dist.all_reduce(self._flat, group=self.group)
-                g_cells, g_lin = None, self._flat
+                    self._flat = GradBuffer(p.numel(), p.device, self.group)       # NVLS multimem up to 256 MiB, NCCL above
+                vr.gather(cells, out=self._flat.buf.view(1, Y, Z, X))
+                self._flat.all_reduce()
+                g_cells, g_lin = None, self._flat.buf
             if grad_out is not None and (grad_out.dtype != torch.float32 or not grad_out.is_contiguous() or grad_out.numel() != p.numel()):
                 raise ValueError("grad_out must be a contiguous fp32 tensor of the volume's size")
             _lib.check(_lib.load().dr_gather_step(ctypes.byref(d), _lib.ptr(g_cells), _lib.ptr(g_lin), _lib.ptr(p), _lib.ptr(self.state),

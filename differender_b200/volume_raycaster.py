@@ -255,12 +255,13 @@ class VolumeRaycaster:
         return out, K, Tp
 
     def march_backward(self, bricked, tf_r4, cam, sampling_rate, jitter, grad_out, out, K, Tprev, need_vol, need_tf,
-                       image_layout=True, grad_cells=None, extra_flags=0, mse_scale=None, skip_grid=None):
+                       image_layout=True, grad_cells=None, extra_flags=0, mse_scale=None, skip_grid=None, mse_scale_dev=None):
         """Backward of cam.shape[0] views.  Returns (grad_vol_linear [Bvol,Y,Z,X] fp32 or None, grad_tf [Btf,R,4] or None).
         The volume gradient is scattered into a cell-major buffer [Bvol, X*Y*Z*8] (zeroed here) and gathered once.
         If `grad_cells` is given it is accumulated into and NOT gathered (it is returned instead), so that several calls
         (e.g. chunks of a large view batch) share one buffer and one gather.
-        With `mse_scale`, `grad_out` is the TARGET image and dL/d(out) = mse_scale*(out - target) is formed in the kernel.
+        With `mse_scale`, `grad_out` is the TARGET image and dL/d(out) = mse_scale*(out - target) is formed in the kernel
+        (times the fp32 device scalar `mse_scale_dev` when given: an upstream gradient that never has to visit the host).
         `skip_grid`: the grid the forward of the same (volume, TF) built (march() leaves it in `last_skip_grid`); only the
         volume-only backward (need_tf False) uses it, to jump over runs of samples in exactly transparent macro-cells."""
         BS = cam.shape[0]
@@ -285,7 +286,8 @@ class VolumeRaycaster:
         fused = mse_scale is not None
         _lib.check(lib.dr_backward_ex(ctypes.byref(d), _lib.ptr(bricked), _lib.ptr(tf_r4), _lib.ptr(cam), _lib.ptr(jitter),
                                       None if fused else _lib.ptr(grad_out), _lib.ptr(grad_out) if fused else None,
-                                      ctypes.c_float(mse_scale if fused else 0.0), _lib.ptr(skip_grid) if (need_vol and not need_tf) else None,
+                                      ctypes.c_float(mse_scale if fused else 0.0), _lib.ptr(mse_scale_dev) if fused else None,
+                                      _lib.ptr(skip_grid) if (need_vol and not need_tf) else None,
                                       _lib.ptr(out), _lib.ptr(K), _lib.ptr(Tprev), _lib.ptr(grad_cells) if need_vol else None, _lib.ptr(gtf),
                                       _lib.ptr(ws), ws_bytes, _stream()), "dr_backward_ex")
         self.kernel_launches += 1 + (1 if need_tf else 0)           # bwd_kernel (+ tf_reduce_kernel)
@@ -483,9 +485,11 @@ class RaycastMSEFunction(torch.autograd.Function):
             return (None,) * 9
         with torch.cuda.device(grad_loss.device):
             vol, tf_r4, cam, jit, out, K, Tp, tgt = _saved(ctx)
-            scale = 2.0 * float(grad_loss) / out.numel()           # one scalar read; keeps the kernel argument a plain float
+            # the upstream gradient of the loss stays on the device (the kernel multiplies it in): float(grad_loss) would make the
+            # host wait for the whole forward and leave the device idle while the backward is being launched
+            up = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
             gvol, gtf = ctx.vr.march_backward(vol, tf_r4, cam, ctx.sampling_rate, jit, tgt, out, K, Tp, need_vol, need_tf,
-                                              image_layout=True, mse_scale=scale, skip_grid=ctx.skip_grid)
+                                              image_layout=True, mse_scale=2.0 / out.numel(), skip_grid=ctx.skip_grid, mse_scale_dev=up)
         gv, gt = _shape_grads(ctx, gvol, gtf, need_vol, need_tf)
         return None, gv, gt, None, None, None, None, None, None
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DR_VERSION 103
+#define DR_VERSION 104
 
 /* error codes */
 #define DR_OK 0
@@ -208,16 +208,17 @@ int dr_backward_mse(const DrDesc* d, const void* vol, const float* tf, const flo
                     float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * dr_backward (grad_out != NULL, target == NULL) or dr_backward_mse (target != NULL, grad_out == NULL, `scale` as there) with the
- * forward's skip grid (dr_build_skip_grid; NULL = march every sample).  The grid is used by the VOLUME-ONLY backward (flags without
+ * dr_backward (grad_out != NULL, target == NULL) or dr_backward_mse (target != NULL, grad_out == NULL, `scale` as there; an optional
+ * DEVICE scalar `scale_dev` is multiplied into it inside the kernel -- the upstream gradient of the loss, which the host then never
+ * has to read back) with the forward's skip grid (dr_build_skip_grid; NULL = march every sample).  The grid is used by the VOLUME-ONLY backward (flags without
  * DR_F_NEEDS_TF_GRAD): a sample in a macro-cell that is exactly transparent under the transfer function has zero opacity and two
  * transparent TF bins, so it contributes nothing to the volume gradient and leaves the transmittance and dL/dA unchanged; runs of
  * such samples are jumped over.  With a TF gradient every transparent sample contributes d(alpha) and the grid is ignored.
  * This is the reference's own optimisation case (examples/test_opt_tf.py optimises the VOLUME, :49-55, :86-88).
  */
 int dr_backward_ex(const DrDesc* d, const void* vol, const float* tf, const float* cam, const float* jitter, const float* grad_out,
-                   const float* target, float scale, const uint8_t* skip_grid, const float* out_rgba, const int32_t* K, const float* Tprev,
-                   float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
+                   const float* target, float scale, const float* scale_dev, const uint8_t* skip_grid, const float* out_rgba, const int32_t* K,
+                   const float* Tprev, float* grad_vol_cells, float* grad_tf, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Momentum-SGD step with gradient clipping and projection, the reference's `apply_grad`

@@ -7,7 +7,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_SO = os.path.join(_HERE, "hostsim", "build", "libhostsim.so")
+# HOSTSIM_DEFINES="NAME ..." builds (into its own .so) a variant of the device math with tuning macros set, e.g. DR_DIRECT_TAPS
+_DEFS = os.environ.get("HOSTSIM_DEFINES", "").split()
+_SO = os.path.join(_HERE, "hostsim", "build", "libhostsim" + "".join("_" + d for d in _DEFS) + ".so")
 
 # flag values of include/diffrender.h
 F_NONDIFF, F_VOL, F_TF, F_JIT, F_IMG, F_TF4R, F_GENERIC, F_BRICK8, F_CELL8 = 1, 2, 4, 8, 16, 32, 64, 256, 2048
@@ -30,7 +32,7 @@ def build(force=False):
     if force or not os.path.exists(_SO) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-fno-fast-math",
-                               "-fPIC", "-shared", "-x", "c++", "-I" + os.path.join(_ROOT, "include"),
+                               "-fPIC", "-shared", "-x", "c++"] + ["-D" + d for d in _DEFS] + ["-I" + os.path.join(_ROOT, "include"),
                                "-I" + os.path.join(_ROOT, "differender_b200", "csrc"), "-o", _SO, src])
     return _SO
 

@@ -193,7 +193,12 @@ def test_copied_layouts_with_both_taps_crossing(shape, layout, dtype):
     vol, tf, cams, jit = case_inputs(shape, (24, 20), 32, seed=5, views=1)
     vr, vlin, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096, dtype=dtype, layout="linear")
     vb, bricked, _, out_b, K_b, Tp_b = _cuda_forward(vol, tf, cams, (24, 20), jit, M=4096, layout=layout, dtype=dtype)
-    assert torch.equal(out, out_b) and torch.equal(K, K_b) and torch.equal(Tp, Tp_b)
+    # the exact path (alpha, K, Tprev) is bit-identical in every layout.  In this two-neighbour regime the cell-major layout
+    # evaluates each normal tap from the tap's own cell record (eval_normals_direct): the same mixes on the same values, but a
+    # differently shaped kernel in which the compiler fuses the (not exactly rounded) shading arithmetic differently -- RGB may
+    # differ in the last bit (measured: <= 6e-8 in a few dozen pixels)
+    assert torch.equal(out[:, 3], out_b[:, 3]) and torch.equal(K, K_b) and torch.equal(Tp, Tp_b)
+    assert (out - out_b).abs().max().item() <= (2e-7 if layout == "cell8" else 0.0)
     go = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).cuda()
     c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
     gv, gt = vr.march_backward(vlin, tf_r4, c, 1.0, j, go, out, K, Tp, True, True)
