@@ -43,7 +43,8 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 #ifndef DR_BWD_MIN_BLOCKS_SR        // sampling rate != 1 with both gradients (the powf path): spills 72 / 96 bytes at 96 registers
 #define DR_BWD_MIN_BLOCKS_SR 4
 #endif
-#ifndef DR_BWD_MIN_BLOCKS_TWO       // two-neighbour taps (an axis of 1001..2000 voxels) with both gradients: 114 registers, spills at 96 (C5 backward +7.5 % at 4)
+#ifndef DR_BWD_MIN_BLOCKS_TWO       // two-neighbour taps (an axis of 1001..2000 voxels) with both gradients, corner-reuse path (linear layout): 114 registers, spills at 96.
+                                    // (The cell-major layout uses direct taps there -- 94 registers, no spills at 5 CTAs/SM: C5 backward 60.2 -> 62.6.)
 #define DR_BWD_MIN_BLOCKS_TWO 4
 #endif
 
@@ -236,7 +237,7 @@ struct RedTfSink {
 
 template <typename VT, int LAYOUT, int TAPS, bool WANT_VOL, bool WANT_TF, bool SR1, bool SKIP>
 __global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN_BLOCKS_BRICK
-                                              : (TAPS == TAPS_TWO && WANT_VOL && WANT_TF) ? DR_BWD_MIN_BLOCKS_TWO
+                                              : (TAPS == TAPS_TWO && WANT_VOL && WANT_TF && LAYOUT != LAYOUT_CELL8) ? DR_BWD_MIN_BLOCKS_TWO
                                               : (!SR1 && WANT_VOL && WANT_TF) ? DR_BWD_MIN_BLOCKS_SR
                                               : (SR1 && !WANT_VOL && LAYOUT == LAYOUT_CELL8 && TAPS == TAPS_ONE) ? DR_BWD_MIN_BLOCKS_TFONLY : DR_BWD_MIN_BLOCKS_LINEAR)
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
