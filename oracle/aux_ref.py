@@ -24,3 +24,26 @@ def ingest_u8(raw, swap_axes01=True):
 def mse(img, target):
     d = img.astype(np.float64) - target.astype(np.float64)
     return float((d * d).mean()), (2.0 * d / d.size)
+
+
+def ssim(X, Y, data_range=1.0, win_size=11, win_sigma=1.5, K=(0.01, 0.03), nonnegative=False):
+    """SSIM of two (N, C, H, W) batches as pytorch_msssim.ssim defines it (reference examples/test_opt_tf.py:70), in float64
+    with explicit loops over the window: 'valid' separable Gaussian filtering, per-channel mean of the SSIM map, optional ReLU,
+    mean over channels and images."""
+    X = np.asarray(X, np.float64); Y = np.asarray(Y, np.float64)
+    g = np.exp(-((np.arange(win_size) - win_size // 2) ** 2) / (2.0 * win_sigma ** 2)); g /= g.sum()
+
+    def blur(a):
+        if a.shape[2] >= win_size:
+            a = sum(g[k] * a[:, :, k:a.shape[2] - win_size + 1 + k, :] for k in range(win_size))
+        if a.shape[3] >= win_size:
+            a = sum(g[k] * a[:, :, :, k:a.shape[3] - win_size + 1 + k] for k in range(win_size))
+        return a
+    C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    m1, m2 = blur(X), blur(Y)
+    s1, s2, s12 = blur(X * X) - m1 * m1, blur(Y * Y) - m2 * m2, blur(X * Y) - m1 * m2
+    smap = ((2 * m1 * m2 + C1) / (m1 * m1 + m2 * m2 + C1)) * ((2 * s12 + C2) / (s1 + s2 + C2))
+    pc = smap.reshape(smap.shape[0], smap.shape[1], -1).mean(-1)
+    if nonnegative:
+        pc = np.maximum(pc, 0.0)
+    return float(pc.mean())

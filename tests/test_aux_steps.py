@@ -82,3 +82,23 @@ def test_fused_mse_matches_unfused_and_oracle():
     v3 = vol.to(dev).requires_grad_(True)
     (3.0 * rc.mse_loss(v3, tf.to(dev), cams.to(dev), target.to(dev), jit.to(dev))[0]).backward()
     assert rel_l2(v3.grad.cpu().numpy(), 3.0 * v2.grad.cpu().numpy()) <= 1e-5
+
+
+def test_ssim_and_the_reference_training_loss():
+    # reference examples/test_opt_tf.py:70-72: nan_to_num(1 - ssim(res, gt, data_range=1, nonnegative_ssim=True)) + mse_loss(res, gt)
+    from differender_b200.losses import dssim_loss, mse_dssim_loss, ssim
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(2, 4, 40, 48, generator=g, dtype=torch.float64)
+    b = (a + 0.1 * torch.randn(2, 4, 40, 48, generator=g, dtype=torch.float64)).clamp(0, 1)
+    assert abs(ssim(a, a).item() - 1.0) < 1e-12
+    ref = aux_ref.ssim(a.numpy(), b.numpy(), nonnegative=True)
+    assert abs(ssim(a, b, nonnegative_ssim=True).item() - ref) < 1e-10 and 0.0 < ref < 1.0
+    assert abs(dssim_loss(a, b).item() - (1.0 - ref)) < 1e-10
+    mref, _ = aux_ref.mse(a.numpy(), b.numpy())
+    assert abs(mse_dssim_loss(a, b).item() - (1.0 - ref + mref)) < 1e-10
+    # differentiable (the gradient reaches the march through Raycaster.forward's ordinary backward)
+    x = a.clone().requires_grad_(True)
+    mse_dssim_loss(x, b).backward()
+    assert torch.isfinite(x.grad).all() and x.grad.abs().max() > 0
+    with pytest.raises(ValueError):
+        ssim(a[0], b[0])

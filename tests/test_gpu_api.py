@@ -186,3 +186,28 @@ def test_cell_major_copy_is_cached_per_volume_version():
     assert b is not a and torch.equal(b[0, :, 0].reshape(32, 32, 32), lin[0])
     rc.vr.forget_volume()
     assert rc.vr.brick(lin) is not b
+
+
+def test_reference_style_volume_optimisation_loop():
+    # examples/test_opt_tf.py:63-88 in miniature: targets from raycast_nondiff of a ground-truth volume, DSSIM + MSE loss, AdamW on
+    # the volume, clamp_(0, 1) -- the loss must go down and everything must stay finite
+    from differender_b200.losses import mse_dssim_loss
+    out_shape = (64, 48)
+    vol, tf, cams, jit = case_inputs((32, 32, 32), out_shape, 64, seed=61, tf_name="tf1", views=3)
+    rc = _rc(vol, out_shape, 64, sampling_rate=1.0)
+    t, c = tf.to(DEV), cams.to(DEV)
+    with torch.no_grad():
+        gt = rc.raycast_nondiff(vol.to(DEV), t, c, sampling_rate=8.0)
+    v = (0.5 * vol + 0.25).to(DEV).requires_grad_(True)
+    opt = torch.optim.AdamW([v], lr=2e-2, weight_decay=0)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = mse_dssim_loss(rc(v, t, c), gt)
+        loss.backward()
+        assert torch.isfinite(v.grad).all()
+        opt.step()
+        with torch.no_grad():
+            v.clamp_(0.0, 1.0)
+        losses.append(loss.item())
+    assert losses[-1] < losses[0] and all(np.isfinite(losses))
