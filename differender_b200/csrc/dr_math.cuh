@@ -1403,16 +1403,21 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
 // with min(c + a, dim-1) == v: (v,0), (v-1,1) and, on the last plane only, the clamped (dim-1,1)  (:170-172).
 DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int z)
 {
-    int cx[3], ax[3], cy[3], ay[3], cz[3], az[3];
-    int nx = 0, ny = 0, nz = 0;
-    cx[nx] = x; ax[nx++] = 0; if (x > 0) { cx[nx] = x - 1; ax[nx++] = 1; } if (x == d.X - 1) { cx[nx] = x; ax[nx++] = 1; }
-    cy[ny] = y; ay[ny++] = 0; if (y > 0) { cy[ny] = y - 1; ay[ny++] = 1; } if (y == d.Y - 1) { cy[ny] = y; ay[ny++] = 1; }
-    cz[nz] = z; az[nz++] = 0; if (z > 0) { cz[nz] = z - 1; az[nz++] = 1; } if (z == d.Z - 1) { cz[nz] = z; az[nz++] = 1; }
+    // per axis the candidates are, in this order: (cell v, slot 0), (cell v-1, slot 1) if v > 0, (cell v, slot 1) if v is the last plane
     float s = 0.0f;
-    for (int k = 0; k < nz; ++k)
-        for (int j = 0; j < ny; ++j)
-            for (int i = 0; i < nx; ++i)
-                s += gcell[(size_t)cell_index(d, cx[i], cy[j], cz[k]) * 8 + (ax[i] + 2 * ay[j] + 4 * az[k])];
+    for (int k = 0; k < 3; ++k) {
+        const int cz = k == 1 ? z - 1 : z, az = k == 0 ? 0 : 1;
+        if (k == 1 ? z == 0 : (k == 2 && z != d.Z - 1)) continue;
+        for (int j = 0; j < 3; ++j) {
+            const int cy = j == 1 ? y - 1 : y, ay = j == 0 ? 0 : 1;
+            if (j == 1 ? y == 0 : (j == 2 && y != d.Y - 1)) continue;
+            for (int i = 0; i < 3; ++i) {
+                const int cx = i == 1 ? x - 1 : x, ax = i == 0 ? 0 : 1;
+                if (i == 1 ? x == 0 : (i == 2 && x != d.X - 1)) continue;
+                s += gcell[(size_t)cell_index(d, cx, cy, cz) * 8 + (ax + 2 * ay + 4 * az)];
+            }
+        }
+    }
     return s;
 }
 
