@@ -363,12 +363,12 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
     else:
         all_samples = float(samples)
     del flush
-    fwd_ms, bwd_ms = phase_ms["fwd"] / steps, phase_ms["bwd"] / steps
+    fwd_ms, bwd_ms = phase_ms["fwd"] / steps, (phase_ms["bwd"] / steps if wl.mode != "nondiff" else 0.0)
     return dict(value=all_samples * steps / (total_ms * 1e-3) / 1e9, ms_per_step=total_ms / steps, samples=samples, all_samples=all_samples,
                 samples_min_max_over_ranks=per_rank, shaded_fraction=shaded_fraction, launches=launches, clocks=clocks,
                 phase_ms={k: v / steps for k, v in phase_ms.items()}, fwd_ms=fwd_ms, bwd_ms=bwd_ms,
                 fwd=samples / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 and samples else None,
-                bwd=samples / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 and samples else None)
+                bwd=samples / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 and samples and wl.mode != "nondiff" else None)
 
 
 def time_allreduce(wl, reps=5):
