@@ -22,17 +22,24 @@ CASES = [
     ("256^3 fp32 (C3 volume), 256x256, tf1, sr 1, jitter", 256, (256, 256), "tf1", 128, 1.0, True, torch.float32, "auto"),
     ("256^3 fp32 (C3 volume), 256x256, tf5, sr 1, no jitter", 256, (256, 256), "tf5", 128, 1.0, False, torch.float32, "auto"),
     ("256^3 fp32, 192x192, 'gray' TF (no transparent bins), sr 1", 256, (192, 192), "gray", 128, 1.0, True, torch.float32, "auto"),
+    ("128^3 uint8 (DR_VOX_U8, 8-byte records), 128x128, tf1, sr 1", 128, (128, 128), "tf1", 128, 1.0, True, torch.uint8, "auto"),
+    ("1100x24x24 fp16 (two-neighbour regime, direct taps), 64x48, tf1", (1100, 24, 24), (64, 48), "tf1", 128, 1.0, True, torch.float16, "auto"),
+    ("24x24x1100 fp32 (two-neighbour regime, direct taps), 64x48, rand", (24, 24, 1100), (64, 48), "rand", 64, 1.0, True, torch.float32, "auto"),
 ]
 for name, n, (w, h), tfn, R, sr, jitter, dt, layout in CASES:
     vol = make_volume(n)
+    D, Hh, Ww = (n, n, n) if isinstance(n, int) else n
     if dt == torch.float16:
         vol = vol.half().float()
+    if dt == torch.uint8:                                     # the oracle marches u8 / 255 in fp32 (numpy's float32 division)
+        q = (vol * 255.0 + 0.5).to(torch.uint8)
+        vol = torch.from_numpy((q.numpy().astype(np.float32) / np.float32(255.0)).astype(np.float32))
     tf = make_tf(tfn, R) if tfn != "rand" else torch.rand(4, R, generator=torch.Generator().manual_seed(1)) * torch.tensor([1, 1, 1, 0.15]).view(4, 1)
     cam = make_cameras(16)[3:4]
     jit = make_jitter(1, h, w) if jitter else None
     M = 8192
-    vr = VolumeRaycaster((n, n, n), (w, h), max_samples=M, tf_resolution=R, layout=layout)
-    v = vr.brick(vol.to(dev, dt).reshape(1, n, n, n).contiguous())
+    vr = VolumeRaycaster((Ww, D, Hh), (w, h), max_samples=M, tf_resolution=R, layout=layout)
+    v = vr.brick((q if dt == torch.uint8 else vol.to(dt)).to(dev).reshape(1, D, Hh, Ww).contiguous())
     tf_r4 = tf.to(dev).t().contiguous()[None]
     j = None if jit is None else jit.to(dev)
     out, K, Tp = vr.march(v, tf_r4, cam.to(dev), sr, j)
