@@ -576,7 +576,12 @@ def run_ours(args, cfg):
             from differender_b200.synthetic import make_cameras
             all_cams_dev = make_cameras(views * world, device=dev)
 
+        diag = os.environ.get("BENCH_E2E_DIAG", "")                   # diagnostics only: "noh2d" / "nod2h" drop the copies after warm-up
+
         def prefetch(k):
+            if "noh2d" in diag and step_no[0] > 2:
+                ready[k].record(copy_stream)
+                return
             copy_stream.wait_stream(torch.cuda.current_stream())      # the set's previous consumer (two steps back) is done
             with torch.cuda.stream(copy_stream):
                 bb = bufs[k]
@@ -612,18 +617,21 @@ def run_ours(args, cfg):
                 else:
                     loss, img = rc.mse_loss(v, t, c, tg, j)           # render + MSE fused (loss in the forward epilogue, its gradient inside the backward kernel)
                 if timed: e[2].record()
-                main.wait_stream(out_stream)          # the previous step's volume gradient has left its buffer (copied under this step's forward)
+                main.wait_stream(out_stream)          # the previous step's results have left their buffers (copied under this step's forward)
                 loss.backward()
-                if need_tf:
-                    h_gtf.copy_(t.grad, non_blocking=True)
-                if need_vol:
-                    out_stream.wait_stream(main)
-                    with torch.cuda.stream(out_stream):
-                        h_gvol[k].copy_(v.grad, non_blocking=True)
-                    v.grad.record_stream(out_stream)
             if timed: e[3].record()
-            h_loss[k].copy_(loss.detach().reshape(1), non_blocking=True)
-            loss_done[k].record(main)
+            # every device-to-host copy runs on the side stream: on the compute stream even a 4-byte copy queues behind whatever
+            # occupies the copy engine and would hold the next kernels back
+            out_stream.wait_stream(main)
+            with torch.cuda.stream(out_stream):
+                h_loss[k].copy_(loss.detach().reshape(1), non_blocking=True)
+                if mode != "nondiff" and need_tf:
+                    h_gtf.copy_(t.grad, non_blocking=True)
+                loss_done[k].record(out_stream)
+                if mode != "nondiff" and need_vol and "nod2h" not in diag:
+                    h_gvol[k].copy_(v.grad, non_blocking=True)
+            for x in ((loss,) + ((t.grad,) if (mode != "nondiff" and need_tf) else ()) + ((v.grad,) if (mode != "nondiff" and need_vol) else ())):
+                x.record_stream(out_stream)
             if timed: e[4].record()
             # the loop reads every step's loss, one step late: the previous step's value is on the host by now, so the read does not
             # drain the GPU (a training loop that logs its loss does not have to stall the device for it)
