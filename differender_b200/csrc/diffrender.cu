@@ -108,16 +108,18 @@ __global__ void __launch_bounds__(256) expand_cells_kernel(DrDesc d, const VT* _
 template <typename VT>
 __global__ void __launch_bounds__(256) skip_minmax_kernel(DrDesc d, const VT* __restrict__ lin, float2* __restrict__ mm)
 {
-    const size_t cells = (size_t)d.nbx * d.nby * d.nbz;
+    const int nx = macro_nx(d), nz = macro_nz(d);
+    const size_t cells = (size_t)nx * macro_ny(d) * nz;
     const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= cells) return;
     const int lane = threadIdx.x & 31, b = blockIdx.y;
-    const int mx_ = (int)(w % d.nbx), mz_ = (int)((w / d.nbx) % d.nbz), my_ = (int)(w / ((size_t)d.nbx * d.nbz));
+    const int mx_ = (int)(w % nx), mz_ = (int)((w / nx) % nz), my_ = (int)(w / ((size_t)nx * nz));
+    constexpr int E = kMacro + 1;                                  // the (kMacro + 1)^3 voxels the macro-cell's cells touch
     const VT* v = lin + (size_t)b * d.X * d.Y * d.Z;
     float mn = 3.4e38f, mx = -3.4e38f;
     bool bad = false;
-    for (int e = lane; e < 729; e += 32) {
-        const int x = min(mx_ * 8 + e % 9, d.X - 1), z = min(mz_ * 8 + (e / 9) % 9, d.Z - 1), y = min(my_ * 8 + e / 81, d.Y - 1);
+    for (int e = lane; e < E * E * E; e += 32) {
+        const int x = min(mx_ * kMacro + e % E, d.X - 1), z = min(mz_ * kMacro + (e / E) % E, d.Z - 1), y = min(my_ * kMacro + e / (E * E), d.Y - 1);
         const float f = vox_value(v[((size_t)y * d.Z + z) * d.X + x]);
         bad |= (f != f);
         mn = fminf(mn, f); mx = fmaxf(mx, f);
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) skip_minmax_kernel(DrDesc d, const VT* __
 __global__ void __launch_bounds__(256) skip_classify_kernel(DrDesc d, const float2* __restrict__ mm, const float* __restrict__ tf,
                                                             unsigned char* __restrict__ grid, int views)
 {
-    const size_t cells = (size_t)d.nbx * d.nby * d.nbz;
+    const size_t cells = skip_cells(&d);
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const bool live = e < cells;

@@ -50,7 +50,7 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 
 // skip grid: one byte per macro-cell; shared by all views when the volume and the TF are, else one grid per view
 constexpr size_t kSkipHeader = 16;      // bytes before the grid: uint32 number of empty macro-cells (+ padding)
-inline size_t skip_cells(const DrDesc* d) { return (size_t)d->nbx * d->nby * d->nbz; }
+__host__ __device__ inline size_t skip_cells(const DrDesc* d) { return (size_t)macro_nx(*d) * macro_ny(*d) * macro_nz(*d); }
 inline int skip_views(const DrDesc* d) { return (d->Bvol == 1 && d->Btf == 1) ? 1 : d->BS; }
 
 // ---------------------------------------------------------------------------------------------------------

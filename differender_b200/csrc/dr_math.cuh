@@ -1432,6 +1432,13 @@ DR_HD float gather_voxel(const DrDesc& d, const float* gcell, int x, int y, int 
 // one more sample is left to the normal path.  Images, K and Tprev are bit-identical with and without the grid.
 // ---------------------------------------------------------------------------------------------------------
 constexpr float kSkipMargin = 0.02f;
+#ifndef DR_MACRO_SHIFT
+#define DR_MACRO_SHIFT 3            // macro-cells of 8 x 8 x 8 cells
+#endif
+constexpr int kMacroShift = DR_MACRO_SHIFT, kMacro = 1 << kMacroShift;
+DR_HD int macro_nx(const DrDesc& d) { return (d.X + kMacro - 1) >> kMacroShift; }
+DR_HD int macro_ny(const DrDesc& d) { return (d.Y + kMacro - 1) >> kMacroShift; }
+DR_HD int macro_nz(const DrDesc& d) { return (d.Z + kMacro - 1) >> kMacroShift; }
 
 DR_HD unsigned char load_u8(const unsigned char* p)
 {
@@ -1444,7 +1451,7 @@ DR_HD unsigned char load_u8(const unsigned char* p)
 
 DR_HD size_t macro_index(const DrDesc& d, int cx, int cy, int cz)       // cell low corner -> macro-cell, [y][z][x] order
 {
-    return ((size_t)(cy >> 3) * d.nbz + (cz >> 3)) * d.nbx + (cx >> 3);
+    return ((size_t)(cy >> kMacroShift) * macro_nz(d) + (cz >> kMacroShift)) * macro_nx(d) + (cx >> kMacroShift);
 }
 
 // number of consecutive samples s, s+1, ... (at least 1: sample s itself is known to be inside) whose cells stay in the
@@ -1456,13 +1463,13 @@ DR_HD int skip_run(const DrDesc& d, const Ray& r, F3 cam, int s, int nn, int cx,
     const float Px = (0.5f * cam.x + 0.5f) * d.scale[0], Dx = 0.5f * r.dir.x * d.scale[0];
     const float Py = (0.5f * cam.y + 0.5f) * d.scale[1], Dy = 0.5f * r.dir.y * d.scale[1];
     const float Pz = (0.5f * cam.z + 0.5f) * d.scale[2], Dz = 0.5f * r.dir.z * d.scale[2];
-    const float bx = (float)(cx & ~7), by = (float)(cy & ~7), bz = (float)(cz & ~7);
+    const float bx = (float)(cx & ~(kMacro - 1)), by = (float)(cy & ~(kMacro - 1)), bz = (float)(cz & ~(kMacro - 1));
     // exit parameter per axis (the face the ray moves towards, shrunk by the margin); an axis the ray does not move along never exits
     float tout = 3.0e38f;
     // (approximate reciprocals: their 1e-7 relative error moves a position by far less than the margin)
-    if (fabsf(Dx) > 1e-20f) tout = fminf(tout, ((Dx > 0.0f ? bx + (8.0f - kSkipMargin) : bx + kSkipMargin) - Px) * fast_rcp(Dx));
-    if (fabsf(Dy) > 1e-20f) tout = fminf(tout, ((Dy > 0.0f ? by + (8.0f - kSkipMargin) : by + kSkipMargin) - Py) * fast_rcp(Dy));
-    if (fabsf(Dz) > 1e-20f) tout = fminf(tout, ((Dz > 0.0f ? bz + (8.0f - kSkipMargin) : bz + kSkipMargin) - Pz) * fast_rcp(Dz));
+    if (fabsf(Dx) > 1e-20f) tout = fminf(tout, ((Dx > 0.0f ? bx + ((float)kMacro - kSkipMargin) : bx + kSkipMargin) - Px) * fast_rcp(Dx));
+    if (fabsf(Dy) > 1e-20f) tout = fminf(tout, ((Dy > 0.0f ? by + ((float)kMacro - kSkipMargin) : by + kSkipMargin) - Py) * fast_rcp(Dy));
+    if (fabsf(Dz) > 1e-20f) tout = fminf(tout, ((Dz > 0.0f ? bz + ((float)kMacro - kSkipMargin) : bz + kSkipMargin) - Pz) * fast_rcp(Dz));
     // samples sit at t(s') = t0 + (texit - t0) * s'/(n-1): the last one strictly before tout, minus one for safety
     const float dt = (r.texit - r.t0) * r.inv_nm1;
     if (!(dt > 1e-20f)) return 1;
@@ -1480,11 +1487,11 @@ DR_HD int skip_run_back(const DrDesc& d, const Ray& r, F3 cam, int s, int cx, in
     const float Px = (0.5f * cam.x + 0.5f) * d.scale[0], Dx = 0.5f * r.dir.x * d.scale[0];
     const float Py = (0.5f * cam.y + 0.5f) * d.scale[1], Dy = 0.5f * r.dir.y * d.scale[1];
     const float Pz = (0.5f * cam.z + 0.5f) * d.scale[2], Dz = 0.5f * r.dir.z * d.scale[2];
-    const float bx = (float)(cx & ~7), by = (float)(cy & ~7), bz = (float)(cz & ~7);
+    const float bx = (float)(cx & ~(kMacro - 1)), by = (float)(cy & ~(kMacro - 1)), bz = (float)(cz & ~(kMacro - 1));
     float tin = -3.0e38f;
-    if (fabsf(Dx) > 1e-20f) tin = fmaxf(tin, ((Dx > 0.0f ? bx + kSkipMargin : bx + (8.0f - kSkipMargin)) - Px) * fast_rcp(Dx));
-    if (fabsf(Dy) > 1e-20f) tin = fmaxf(tin, ((Dy > 0.0f ? by + kSkipMargin : by + (8.0f - kSkipMargin)) - Py) * fast_rcp(Dy));
-    if (fabsf(Dz) > 1e-20f) tin = fmaxf(tin, ((Dz > 0.0f ? bz + kSkipMargin : bz + (8.0f - kSkipMargin)) - Pz) * fast_rcp(Dz));
+    if (fabsf(Dx) > 1e-20f) tin = fmaxf(tin, ((Dx > 0.0f ? bx + kSkipMargin : bx + ((float)kMacro - kSkipMargin)) - Px) * fast_rcp(Dx));
+    if (fabsf(Dy) > 1e-20f) tin = fmaxf(tin, ((Dy > 0.0f ? by + kSkipMargin : by + ((float)kMacro - kSkipMargin)) - Py) * fast_rcp(Dy));
+    if (fabsf(Dz) > 1e-20f) tin = fmaxf(tin, ((Dz > 0.0f ? bz + kSkipMargin : bz + ((float)kMacro - kSkipMargin)) - Pz) * fast_rcp(Dz));
     const float dt = (r.texit - r.t0) * r.inv_nm1;
     if (!(dt > 1e-20f)) return 1;
     // samples sit at t(s') = t0 + dt * s': the first one strictly after tin, plus one for safety
@@ -1534,7 +1541,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         Centre c;
         if (SKIP && TAPS != TAPS_GENERIC && skip_grid) {
             locate_centre(d, L, pos, c);
-            if ((((c.cx.b ^ pbx) | (c.cy.b ^ pby) | (c.cz.b ^ pbz)) & ~7) != 0) {
+            if ((((c.cx.b ^ pbx) | (c.cy.b ^ pby) | (c.cz.b ^ pbz)) & ~(kMacro - 1)) != 0) {
                 pbx = c.cx.b; pby = c.cy.b; pbz = c.cz.b;
                 const int cx = lo_of(c.cx), cy = lo_of(c.cy), cz = lo_of(c.cz);
                 in_empty = load_u8(skip_grid + macro_index(d, cx, cy, cz)) != 0;
@@ -1613,7 +1620,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         Centre c;
         if (SKIP && !WANT_TF && TAPS != TAPS_GENERIC && skip_grid) {
             locate_centre(d, L, pos, c);
-            if ((((c.cx.b ^ pbx) | (c.cy.b ^ pby) | (c.cz.b ^ pbz)) & ~7) != 0) {
+            if ((((c.cx.b ^ pbx) | (c.cy.b ^ pby) | (c.cz.b ^ pbz)) & ~(kMacro - 1)) != 0) {
                 pbx = c.cx.b; pby = c.cy.b; pbz = c.cz.b;
                 const int cx = lo_of(c.cx), cy = lo_of(c.cy), cz = lo_of(c.cz);
                 in_empty = load_u8(skip_grid + macro_index(d, cx, cy, cz)) != 0;

@@ -52,6 +52,8 @@ int sim_desc_init(DrDesc* d, int X, int Y, int Z, int W, int H, int R, int M, un
 }
 
 size_t sim_bricked_elems(const DrDesc* d) { return (size_t)d->nbx * d->nby * d->nbz * 512; }
+// macro-cells of the skip grid per axis (y, z, x) and their edge length in cells
+void sim_macro_dims(const DrDesc* d, int* out4) { out4[0] = macro_ny(*d); out4[1] = macro_nz(*d); out4[2] = macro_nx(*d); out4[3] = kMacro; }
 
 // linear [Y][Z][X] -> bricked
 void sim_brick(const DrDesc* d, const float* lin, float* bricked)
@@ -76,17 +78,18 @@ void sim_expand(const DrDesc* d, const float* lin, float* cells)
 // skip grid (what dr_build_skip_grid builds): per-macro-cell voxel min / max, then skip_classify; tf is [R][4]
 void sim_skip_grid(const DrDesc* d, const float* lin, const float* tf, unsigned char* grid)
 {
-    for (int my = 0; my < d->nby; ++my) for (int mz = 0; mz < d->nbz; ++mz) for (int mx = 0; mx < d->nbx; ++mx) {
+    const int E = kMacro + 1;
+    for (int my = 0; my < macro_ny(*d); ++my) for (int mz = 0; mz < macro_nz(*d); ++mz) for (int mx = 0; mx < macro_nx(*d); ++mx) {
         float mn = 3.4e38f, mxv = -3.4e38f;
         bool bad = false;
-        for (int e = 0; e < 729; ++e) {
-            const int x = mx * 8 + e % 9 < d->X ? mx * 8 + e % 9 : d->X - 1, z = mz * 8 + (e / 9) % 9 < d->Z ? mz * 8 + (e / 9) % 9 : d->Z - 1;
-            const int y = my * 8 + e / 81 < d->Y ? my * 8 + e / 81 : d->Y - 1;
+        for (int e = 0; e < E * E * E; ++e) {
+            const int x = mx * kMacro + e % E < d->X ? mx * kMacro + e % E : d->X - 1, z = mz * kMacro + (e / E) % E < d->Z ? mz * kMacro + (e / E) % E : d->Z - 1;
+            const int y = my * kMacro + e / (E * E) < d->Y ? my * kMacro + e / (E * E) : d->Y - 1;
             const float f = lin[((size_t)y * d->Z + z) * d->X + x];
             bad |= (f != f);
             mn = f < mn ? f : mn; mxv = f > mxv ? f : mxv;
         }
-        grid[((size_t)my * d->nbz + mz) * d->nbx + mx] = bad ? 0 : skip_classify(*d, mn, mxv, tf + 3, 4);
+        grid[((size_t)my * macro_nz(*d) + mz) * macro_nx(*d) + mx] = bad ? 0 : skip_classify(*d, mn, mxv, tf + 3, 4);
     }
 }
 // cell-major gradient [Y*Z*X][8] -> linear [Y][Z][X]

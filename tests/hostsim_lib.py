@@ -73,12 +73,19 @@ def _layout_data(L, d, vol, brick, cell):
     return vol
 
 
+def macro_dims(d):
+    """(ny, nz, nx, edge): macro-cells of the skip grid per axis and their edge length in cells."""
+    out = (ctypes.c_int * 4)()
+    lib().sim_macro_dims(ctypes.byref(d), out)
+    return tuple(out)
+
+
 def skip_grid(volume, tf, output_shape, sampling_rate=1.0, max_samples=512):
     """The macro-cell emptiness bytes dr_build_skip_grid would produce for (volume, tf): array [nby][nbz][nbx] of 0/1."""
     vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
     tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
     d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, 0, sampling_rate)
-    g = np.zeros((d.nby, d.nbz, d.nbx), np.uint8)
+    g = np.zeros(macro_dims(d)[:3], np.uint8)
     lib().sim_skip_grid(ctypes.byref(d), _p(vol), _p(tf_r4), _p(g, ctypes.c_ubyte))
     return g
 
@@ -99,7 +106,7 @@ def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, j
     jit = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
     grid = None
     if skip:
-        grid = np.zeros((d.nby, d.nbz, d.nbx), np.uint8)
+        grid = np.zeros(macro_dims(d)[:3], np.uint8)
         L.sim_skip_grid(ctypes.byref(d), _p(vol), _p(tf_r4), _p(grid, ctypes.c_ubyte))
     L.sim_forward(ctypes.byref(d), _p(br), _p(tf_r4), _p(cam), _p(jit), _p(out), _p(K, ctypes.c_int32), _p(Tp),
                   _p(n, ctypes.c_int32), _p(grid, ctypes.c_ubyte))
@@ -122,7 +129,7 @@ def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_s
     go = np.ascontiguousarray(grad_image, np.float32)
     grid = None
     if skip:                                               # the forward's skip grid: only the volume-only backward uses it
-        grid = np.zeros((d.nby, d.nbz, d.nbx), np.uint8)
+        grid = np.zeros(macro_dims(d)[:3], np.uint8)
         L.sim_skip_grid(ctypes.byref(d), _p(vol), _p(tf_r4), _p(grid, ctypes.c_ubyte))
     L.sim_backward(ctypes.byref(d), _p(br), _p(tf_r4), _p(cam), _p(jit), _p(go), _p(out), _p(K, ctypes.c_int32),
                    _p(Tp), _p(gbr), _p(gtf), _p(grid, ctypes.c_ubyte))

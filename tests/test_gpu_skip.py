@@ -72,7 +72,7 @@ def test_device_grid_equals_host_grid():
     grid = vr.skip_grid(d, lin, tf_r4)
     ref = hs.skip_grid(vol.numpy(), tf.numpy(), (8, 8), max_samples=64)
     g = grid.cpu().numpy()
-    assert g.size == 16 + ref.size and ref.size == 5 * 7 * 9
+    assert g.size == 16 + ref.size and ref.size in (5 * 7 * 9, 10 * 14 * 18)          # 8^3- or 4^3-cell macro-cells of a 40 x 56 x 72 volume
     assert np.array_equal(g[16:].reshape(ref.shape), ref) and 0 < ref.mean() < 1
     assert int(g[:4].view(np.uint32)[0]) == int(ref.sum())          # header: number of empty macro-cells
 

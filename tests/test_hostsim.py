@@ -105,10 +105,11 @@ def test_skip_grid_never_marks_a_cell_that_can_be_opaque():
     lo = np.minimum(np.floor(np.maximum(v, 0) * 63).astype(int), 63)
     opaque = (a[lo] != 0) | (a[np.minimum(lo + 1, 63)] != 0)
     ys, zs, xs = np.nonzero(opaque)
+    E = 40 // g.shape[0] if 40 % g.shape[0] == 0 else 8     # macro-cell edge (8 cells; 4 in the DR_MACRO_SHIFT=2 variant)
     for dy in (0, -1):                                     # a voxel is a corner of cells in its own and the previous macro-cell row
         for dz in (0, -1):
             for dx in (0, -1):
-                assert not g[np.maximum(ys + dy, 0) // 8, np.maximum(zs + dz, 0) // 8, np.maximum(xs + dx, 0) // 8].any()
+                assert not g[np.maximum(ys + dy, 0) // E, np.maximum(zs + dz, 0) // E, np.maximum(xs + dx, 0) // E].any()
 
 
 def test_empty_space_skipping_respects_max_samples_and_views_without_hits():
