@@ -69,6 +69,7 @@ def parse():
     p.add_argument("--tf", default=None, help="transfer-function preset (reference utils.get_tf): tf1..tf5, gray, black, rand; "
                                               "default tf1 (C2: its optimisation start `black`)")
     p.add_argument("--layout", default="auto", choices=["auto", "linear", "brick8", "cell8"], help="volume layout read by the march kernels")
+    p.add_argument("--sr", type=float, default=None, help="sampling rate (default: the config's); != 1 exercises the powf kernels")
     p.add_argument("--no-skip", action="store_true", help="march every sample (no exact empty-space skip grid in the forward)")
     p.add_argument("--cuda-profiler-range", action="store_true",
                    help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
@@ -226,7 +227,7 @@ class Workload:
         from differender_b200.synthetic import make_cameras, make_jitter, make_tf, make_volume
         self.cfg, self.dev, self.rank, self.world, self.args = cfg, dev, rank, world, args
         n, (w, h), R, M = cfg["n"], cfg["res"], 128, cfg["M"]
-        self.n, self.w, self.h, self.R, self.sr, self.mode = n, w, h, R, cfg["sr"], cfg["mode"]
+        self.n, self.w, self.h, self.R, self.sr, self.mode = n, w, h, R, (args.sr or cfg["sr"]), cfg["mode"]
         vdtype = torch.float16 if cfg["dtype"] == "f16" else torch.float32
         self.vol = make_volume(n, device=dev, dtype=vdtype)                              # (1, D, H, W), replicated on every rank
         self.tf_name = tf_name or cfg.get("tf", "tf1")
