@@ -93,6 +93,38 @@ __device__ __forceinline__ bool pixel_of_thread(const DrDesc& d, int& i, int& j)
     return i < d.W && j < d.H;
 }
 
+#if defined(DR_PERSIST)
+// EXPERIMENT: persistent warps and a Morton-ordered tile queue.  One counter per translation unit, zeroed by the
+// launcher before every launch (single-stream use only: this is a measurement variant, not the product path).
+static __device__ unsigned dr_tile_counter;
+__device__ __forceinline__ unsigned compact1by1(unsigned x)
+{
+    x &= 0x55555555u; x = (x | (x >> 1)) & 0x33333333u; x = (x | (x >> 2)) & 0x0f0f0f0fu; x = (x | (x >> 4)) & 0x00ff00ffu;
+    return (x | (x >> 8)) & 0x0000ffffu;
+}
+__device__ __forceinline__ bool next_tile(const DrDesc& d, unsigned* counter, int& b, int& i, int& j, bool& valid)
+{
+    const int twx = (d.W + 7) >> 3, twy = (d.H + 3) >> 2;
+    unsigned P = 1;
+    while ((int)P < max(twx, twy)) P <<= 1;
+    const unsigned per_view = P * P, total = per_view * (unsigned)d.BS;
+    const int l = threadIdx.x & 31;
+    for (;;) {
+        unsigned t = 0;
+        if (l == 0) t = atomicAdd(counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= total) return false;
+        const unsigned m = t % per_view;
+        const int wx = (int)compact1by1(m), wy = (int)compact1by1(m >> 1);
+        if (wx >= twx || wy >= twy) continue;
+        b = (int)(t / per_view);
+        i = wx * 8 + (l & 7); j = wy * 4 + (l >> 3);
+        valid = i < d.W && j < d.H;
+        return true;
+    }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
@@ -104,11 +136,21 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
            const unsigned char* __restrict__ skip_grid, size_t skip_stride)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
+#if defined(DR_PERSIST)
+    // EXPERIMENT (profiles/r02_experiments.md): persistent warps pulling 8x4-pixel tiles of all views from a Morton-ordered queue
+    const TfTable s_tf = stage_tf(d, tf, 0, reinterpret_cast<TfBin*>(s_raw));       // the launcher guarantees Btf == 1
+    for (;;) {
+    int b, i, j;
+    bool valid;
+    if (!next_tile(d, &dr_tile_counter, b, i, j, valid)) break;
+    if (!valid && !target) continue;
+#else
     const int b = blockIdx.z;
     const TfTable s_tf = stage_tf(d, tf, d.Btf == 1 ? 0 : b, reinterpret_cast<TfBin*>(s_raw));
     int i, j;
     const bool valid = pixel_of_thread(d, i, j);
     if (!valid && !target) return;
+#endif
     float sq = 0.0f;
     if (valid) {
     const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;      // image orientation
@@ -151,6 +193,9 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, o);
         if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum + b, sq);
     }
+#if defined(DR_PERSIST)
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -247,6 +292,19 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
            const unsigned char* __restrict__ skip_grid, size_t skip_stride, const float* __restrict__ scale_dev)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
+#if defined(DR_PERSIST)
+    const int tb = 0;
+    const TfTable s_tf = stage_tf(d, tf, 0, reinterpret_cast<TfBin*>(s_raw));
+    for (;;) {
+    int b, i, j;
+    bool valid;
+    if (!next_tile(d, &dr_tile_counter, b, i, j, valid)) break;
+    if (!valid) continue;
+    const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;
+    const int K = __ldg(Kp + pix);
+    if (K <= 0) continue;
+#define DR_RAY_DONE continue
+#else
     const int b = blockIdx.z;
     const int tb = d.Btf == 1 ? 0 : b;
     const TfTable s_tf = stage_tf(d, tf, tb, reinterpret_cast<TfBin*>(s_raw));
@@ -255,6 +313,8 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const size_t pix = (size_t)b * d.W * d.H + (size_t)(d.H - 1 - j) * d.W + i;
     const int K = __ldg(Kp + pix);
     if (K <= 0) return;
+#define DR_RAY_DONE return
+#endif
     const F3 cam = { __ldg(camp + 3 * b), __ldg(camp + 3 * b + 1), __ldg(camp + 3 * b + 2) };
     const float jit = (d.flags & DR_F_HAS_JITTER) ? __ldg(jitter + pix) : 0.0f;
     Ray r;
@@ -275,10 +335,10 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     if (d.flags & DR_F_FUSED_MSE) {
         // `gout` holds the TARGET image: dL/dA = mse_scale * (A - target), never materialised in HBM.  The upstream gradient of the
         // loss may stay on the device (scale_dev): reading it on the host would stall the host on the whole forward
-        if (scale_dev) mse_scale *= __ldg(scale_dev);
-        g.x = mse_scale * (A.x - g.x); g.y = mse_scale * (A.y - g.y); g.z = mse_scale * (A.z - g.z); g.w = mse_scale * (A.w - g.w);
+        const float ms = scale_dev ? mse_scale * __ldg(scale_dev) : mse_scale;
+        g.x = ms * (A.x - g.x); g.y = ms * (A.y - g.y); g.z = ms * (A.z - g.z); g.w = ms * (A.w - g.w);
     }
-    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;       // this ray's gradient is exactly zero
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) DR_RAY_DONE;       // this ray's gradient is exactly zero
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
     const VolView<VT> vol { volp + voff };
     const Layout L = make_layout(d, cbias);
@@ -288,7 +348,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
 #if defined(DR_BOUNDS_CHECK)
     vs.n_cells = (long long)d.X * d.Y * d.Z;
 #endif
-    const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);
+    const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);      // (persistent launch: blockIdx.y == 0)
     RedTfSink ts;
     ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
     ts.Rm1 = d.R - 1;
@@ -296,6 +356,10 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     const unsigned char* grid = nullptr;
     if (SKIP && __ldg(reinterpret_cast<const unsigned*>(skip_grid)) != 0u) grid = skip_grid + kSkipHeader + (size_t)b * skip_stride;
     march_backward<VT, LAYOUT, TAPS, WANT_VOL, WANT_TF, SR1, SKIP>(d, vol, L, s_tf, cam, r, A, K, __ldg(Tp + pix), g, vs, ts, grid);
+#if defined(DR_PERSIST)
+    }
+#endif
+#undef DR_RAY_DONE
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -311,6 +375,23 @@ template <typename K> int set_smem(K kernel, size_t bytes)
     return DR_OK;
 }
 
+#if defined(DR_PERSIST)
+template <typename K> int persistent_grid(K kernel, size_t smem, const DrDesc* d, dim3& grid, cudaStream_t st)
+{
+    if (d->Btf != 1) return fail(DR_EINVAL, "DR_PERSIST experiment: shared transfer function only");
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+    void* ctr = nullptr;
+    cudaGetSymbolAddress(&ctr, dr_tile_counter);
+    cudaMemsetAsync(ctr, 0, sizeof(unsigned), st);
+    const unsigned tiles = grid.x * grid.y * grid.z;
+    grid = dim3(min((unsigned)(sms * max(per_sm, 1)), tiles), 1, 1);
+    return DR_OK;
+}
+#endif
+
 inline size_t vol_stride(const DrDesc* d)
 {
     if (d->flags & DR_F_LAYOUT_CELL8) return (size_t)d->X * d->Y * d->Z * 8;
@@ -325,6 +406,9 @@ int launch_fwd_skip(const FwdArgs& a)
     auto kern = fwd_kernel<VT, LAYOUT, NONDIFF, TAPS, SR1, SKIP>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
+#if defined(DR_PERSIST)
+    if (int rc = persistent_grid(kern, smem, d, grid, a.st)) return rc;
+#endif
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.out, a.K, a.T, vol_stride(d),
                                          a.target, a.loss_sum, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d));
     cudaError_t e = cudaGetLastError();
@@ -339,6 +423,9 @@ int launch_bwd_skip(const BwdArgs& a)
     auto kern = bwd_kernel<VT, LAYOUT, TAPS, WV, WT, SR1, SKIP>;
     if (int rc = set_smem(kern, smem)) return rc;
     dim3 grid((d->W + kTileW - 1) / kTileW, (d->H + kTileH - 1) / kTileH, d->BS);
+#if defined(DR_PERSIST)
+    if (int rc = persistent_grid(kern, smem, d, grid, a.st)) return rc;
+#endif
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
                                          a.slots, vol_stride(d), a.mse_scale, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d),
                                          a.scale_dev);
