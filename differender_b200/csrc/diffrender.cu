@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(256) skip_classify_kernel(DrDesc d, const floa
 // Gather of the cell-major gradient, and the fused optimiser step on top of it.
 //
 // The gradient of voxel (x,y,z) is the sum of the (up to) 8 slots that alias it: cell (x-a, y-b, z-c), slot a + 2b + 4c.
-// A CTA owns a GT_X x GT_Y x GT_Z tile of voxels.  It loads the records of the cells [origin - 1, origin + T) once, each as
-// two coalesced 16-byte streaming loads, into shared memory transposed to 8 slot planes (consecutive lanes -> consecutive
-// cells -> conflict-free), and every voxel then sums its 8 slots from shared memory in a fixed order.  Round 1's kernel read 8
-// scattered 4-byte words per voxel through L1 out of local index arrays (51 LDL/STL) and reached 36 % of the HBM roof; this
-// one moves 32 bytes per voxel once, plus the one-cell halo (1.45x, served by L2: the neighbouring tile runs next door).
+// Both kernels below load whole records, each as two coalesced 16-byte loads, into shared memory transposed to 8 slot planes
+// (consecutive lanes -> consecutive cells -> conflict-free), and every voxel then sums its 8 slots from shared memory in a fixed
+// order.  Round 1's kernel read 8 scattered 4-byte words per voxel through L1 out of local index arrays (51 LDL/STL) and reached
+// 36 % of the HBM roof.  gather_step_kernel works on GT_X x GT_Y x GT_Z tiles (records of the cells [origin - 1, origin + T): the
+// tile plus a one-cell halo, 1.45x, served by L2); gather_grad_kernel marches along y instead (below).
 // Voxels on the last plane of an axis also receive the clamped slot of their own cell (:170-172); the march never writes
 // such cells, but dr_gather_grad defines it, so those voxels take gather_voxel()'s general path from global memory.
 // ---------------------------------------------------------------------------------------------------------
@@ -230,23 +230,76 @@ __device__ __forceinline__ float gather_from_tile(const DrDesc& d, const float* 
     return sum;
 }
 
-// cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 with nan_to_num
-__global__ void __launch_bounds__(GT_THREADS, 4) gather_grad_kernel(DrDesc d, const float* __restrict__ gcell, float* __restrict__ lin, int accumulate)
+// dr_gather_grad: cell-major gradient [cell][8] -> linear [Y][Z][X] fp32 with nan_to_num, marching along y.  A CTA owns a 32 (x) x
+// GM_Z (z) column of voxels and walks GM_CH planes of y.  Per step it loads ONE plane of records (33 x (GM_Z + 1)) into shared-memory
+// slot planes and keeps the previous plane, so there is no y halo (the re-read factor of the 32x4x8 tile above, 1.45, falls to
+// 33/32 * (GM_Z+1)/GM_Z * (GM_CH+1)/GM_CH = 1.19), and the records of plane y + 1 are already in flight in registers while plane y
+// is summed and written (software pipelining across the loop).  Measured: 60 % (256^3) / 74 % (512^3) of the HBM copy peak on
+// compulsory bytes, against 53 / 59 % for the tile version and 36 % for round 1's scattered loads (profiles/r02_experiments.md).
+constexpr int GM_X = 32, GM_Z = 8, GM_CH = 32, GM_THREADS = GM_X * GM_Z;
+constexpr int GM_RX = GM_X + 1, GM_RZ = GM_Z + 1, GM_RXP = GM_RX | 1, GM_PLANE = GM_RZ * GM_RXP;      // one slot plane of one y plane
+constexpr int GM_RECS = GM_RX * GM_RZ, GM_ITER = (GM_RECS + GM_THREADS - 1) / GM_THREADS;
+
+__global__ void __launch_bounds__(GM_THREADS) gather_grad_kernel(DrDesc d, const float* __restrict__ gcell, float* __restrict__ lin, int accumulate)
 {
-    extern __shared__ __align__(16) float s_rec[];
-    int ox, oy, oz;
-    gather_tile_origin(d, ox, oy, oz);
+    __shared__ float s[2][8][GM_PLANE];
+    const int ntx = (d.X + GM_X - 1) / GM_X, ntz = (d.Z + GM_Z - 1) / GM_Z;
+    const int ox = (blockIdx.x % ntx) * GM_X, oz = ((blockIdx.x / ntx) % ntz) * GM_Z, y0 = (blockIdx.x / (ntx * ntz)) * GM_CH;
     const size_t n = (size_t)d.X * d.Y * d.Z;
     const float* gc = gcell + (size_t)blockIdx.y * n * 8;
-    gather_load_tile(d, gc, ox, oy, oz, s_rec);
-    __syncthreads();
-    for (int v = threadIdx.x; v < GT_X * GT_Y * GT_Z; v += GT_THREADS) {
-        const int vx = v % GT_X, vz = (v / GT_X) % GT_Z, vy = v / (GT_X * GT_Z);
-        const int x = ox + vx, y = oy + vy, z = oz + vz;
-        if (x >= d.X || y >= d.Y || z >= d.Z) continue;
-        const float g = nan_to_num(gather_from_tile(d, gc, s_rec, vx, vy, vz, x, y, z));
-        float* o = lin + (size_t)blockIdx.y * n + ((size_t)y * d.Z + z) * d.X + x;
-        *o = accumulate ? (*o + g) : g;
+    float* out = lin + (size_t)blockIdx.y * n;
+    const int tx = threadIdx.x % GM_X, tz = threadIdx.x / GM_X;
+    const int y1 = min(y0 + GM_CH, d.Y);
+    float4 a[GM_ITER], b[GM_ITER];
+    auto fetch = [&](int cy) {                  // the records of cell plane cy -> registers (zeros outside the volume)
+#pragma unroll
+        for (int k = 0; k < GM_ITER; ++k) {
+            const int r = threadIdx.x + k * GM_THREADS;
+            const int cx = ox - 1 + r % GM_RX, cz = oz - 1 + r / GM_RX;
+            a[k] = make_float4(0.f, 0.f, 0.f, 0.f); b[k] = a[k];
+            if (r < GM_RECS && cy >= 0 && cy < d.Y && cx >= 0 && cz >= 0 && cx < d.X && cz < d.Z) {
+                const float4* p = reinterpret_cast<const float4*>(gc) + (((size_t)cy * d.Z + cz) * d.X + cx) * 2;
+                a[k] = __ldg(p); b[k] = __ldg(p + 1);
+            }
+        }
+    };
+    auto stash = [&](int buf) {                 // registers -> slot planes of buffer `buf`
+#pragma unroll
+        for (int k = 0; k < GM_ITER; ++k) {
+            const int r = threadIdx.x + k * GM_THREADS;
+            if (r >= GM_RECS) break;
+            float* q = &s[buf][0][(r / GM_RX) * GM_RXP + r % GM_RX];
+            q[0 * GM_PLANE] = a[k].x; q[1 * GM_PLANE] = a[k].y; q[2 * GM_PLANE] = a[k].z; q[3 * GM_PLANE] = a[k].w;
+            q[4 * GM_PLANE] = b[k].x; q[5 * GM_PLANE] = b[k].y; q[6 * GM_PLANE] = b[k].z; q[7 * GM_PLANE] = b[k].w;
+        }
+    };
+    fetch(y0 - 1);
+    stash(1);                                   // plane y0 - 1 plays "previous" for the first step
+    fetch(y0);
+    for (int y = y0; y < y1; ++y) {
+        const int cur = (y - y0) & 1;
+        __syncthreads();                        // everyone is done reading buffer `cur` (it held plane y - 2)
+        stash(cur);
+        if (y + 1 < y1) fetch(y + 1);           // in flight while this plane is summed
+        __syncthreads();
+        const int x = ox + tx, z = oz + tz;
+        if (x < d.X && z < d.Z) {
+            float g;
+            if (x == d.X - 1 || y == d.Y - 1 || z == d.Z - 1) g = gather_voxel(d, gc, x, y, z);       // clamped slots: general path
+            else {
+                g = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+                        for (int aa = 0; aa < 2; ++aa)      // cell (x - aa, y - bb, z - c), slot aa + 2 bb + 4 c; bb = 1 reads the previous plane
+                            g += s[bb ? cur ^ 1 : cur][aa + 2 * bb + 4 * c][(tz + 1 - c) * GM_RXP + (tx + 1 - aa)];
+            }
+            g = nan_to_num(g);
+            float* o = out + ((size_t)y * d.Z + z) * d.X + x;
+            *o = accumulate ? (*o + g) : g;
+        }
     }
 }
 
@@ -667,12 +720,8 @@ int dr_gather_grad(const DrDesc* d, const float* grad_vol_cells, float* grad_lin
     if (int rc = check_desc(d)) return rc;
     if (!grad_vol_cells || !grad_linear) return fail(DR_EINVAL, "dr_gather_grad: null pointer");
     if (!aligned(grad_vol_cells, 16)) return fail(DR_EALIGN, "dr_gather_grad: grad_vol_cells must be 16-byte aligned");
-    dim3 grid(gather_tiles(d), d->Bvol);
-    if (kGatherSmem > 48 * 1024) {
-        cudaError_t ea = cudaFuncSetAttribute(gather_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem);
-        if (ea != cudaSuccess) return fail_cuda(ea, "cudaFuncSetAttribute(gather_grad_kernel)");
-    }
-    gather_grad_kernel<<<grid, GT_THREADS, kGatherSmem, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_cells, grad_linear, accumulate);
+    const unsigned tiles = (unsigned)(((d->X + GM_X - 1) / GM_X) * ((d->Z + GM_Z - 1) / GM_Z) * ((d->Y + GM_CH - 1) / GM_CH));
+    gather_grad_kernel<<<dim3(tiles, d->Bvol), GM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*d, grad_vol_cells, grad_linear, accumulate);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "gather_grad_kernel launch");
 }
