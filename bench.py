@@ -350,6 +350,7 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     total_ms = t0.elapsed_time(t1)
     phase_ms = {"brick": 0.0, "fwd": 0.0, "bwd": 0.0, "post": 0.0}
+    each_ms = [round(e[0].elapsed_time(e[4]), 3) for e in evs]                     # device time of every timed step (outliers show here)
     for e in evs:
         for name, a, b in (("brick", 0, 1), ("fwd", 1, 2), ("bwd", 2, 3), ("post", 3, 4)):
             phase_ms[name] += e[a].elapsed_time(e[b])
@@ -366,7 +367,7 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
     del flush
     fwd_ms, bwd_ms = phase_ms["fwd"] / steps, (phase_ms["bwd"] / steps if wl.mode != "nondiff" else 0.0)
     return dict(value=all_samples * steps / (total_ms * 1e-3) / 1e9, ms_per_step=total_ms / steps, samples=samples, all_samples=all_samples,
-                samples_min_max_over_ranks=per_rank, shaded_fraction=shaded_fraction, launches=launches, clocks=clocks,
+                samples_min_max_over_ranks=per_rank, shaded_fraction=shaded_fraction, launches=launches, clocks=clocks, each_ms=each_ms,
                 phase_ms={k: v / steps for k, v in phase_ms.items()}, fwd_ms=fwd_ms, bwd_ms=bwd_ms,
                 fwd=samples / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 and samples else None,
                 bwd=samples / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 and samples and wl.mode != "nondiff" else None)
@@ -745,7 +746,7 @@ def run_ours(args, cfg):
                                "macro-cells that are transparent under the TF are counted without being marched (exact; DESIGN.md 4)"},
             "fwd": {"value": r["fwd"], "unit": "Gsamples/s", "ms": r["fwd_ms"]},
             "bwd": {"value": r["bwd"], "unit": "Gsamples/s", "ms": r["bwd_ms"]},
-            "phase_ms_per_step": r["phase_ms"],
+            "phase_ms_per_step": r["phase_ms"], "ms_each_step_rank0": r["each_ms"],
             "roofline": roofline_block(args, cfg, wl, r, clocks, l2_gbs, peaks),
             "allreduce": allreduce,
             "clocks": clocks, "gpu_launches": r["launches"],
