@@ -31,6 +31,9 @@ constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY, kThreads = 32 * DR_CTA
 #ifndef DR_FWD_MIN_BLOCKS
 #define DR_FWD_MIN_BLOCKS 5
 #endif
+#ifndef DR_FWD_MIN_BLOCKS_SKIP      // cell-major differentiable forward WITH the skip grid (it is only used while the TF leaves >= 5 % of the macro-cells
+#define DR_FWD_MIN_BLOCKS_SKIP 6    // empty): mostly short centre-only samples, latency-bound -- 6 CTAs/SM (80 registers, a few spilled bytes in the shaded
+#endif                              // path) gives C3 +2 %, C4 +6 %, C5 +4.5 % forward; the every-sample-shaded kernels (no grid, nondiff, sr != 1) lose 1-5 % at 6 and stay at 5
 #ifndef DR_BWD_MIN_BLOCKS_LINEAR
 #define DR_BWD_MIN_BLOCKS_LINEAR 5
 #endif
@@ -129,7 +132,7 @@ __device__ __forceinline__ bool next_tile(const DrDesc& d, unsigned* counter, in
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1, bool SKIP>
-__global__ void __launch_bounds__(kThreads, DR_FWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (LAYOUT == LAYOUT_CELL8 && SKIP && SR1 && !NONDIFF) ? DR_FWD_MIN_BLOCKS_SKIP : DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
            float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum, unsigned cbias,
