@@ -122,7 +122,8 @@ class ClockSampler:
 # parity basis: what the numbers' correctness rests on
 # ------------------------------------------------------------------------------------------------------------------
 def parity_basis():
-    """One string for the JSON line: the oracle is unpinned against real Taichi; the committed rounding envelope says how far
+    """One string for the JSON line: the oracle is pinned against the reference's source on the fp32 interpreter (tests/test_shim_pin.py)
+    and unpinned against the real Taichi compiler; the committed rounding envelope says how far
     the plausible alternative roundings of the reference's arithmetic move an image / a gradient (profiles/r02_rounding_envelope.txt)."""
     env = "envelope not measured"
     try:
@@ -138,7 +139,11 @@ def parity_basis():
         taichi = st["note"]
     except Exception as e:  # the probe is optional test infrastructure
         taichi = f"Taichi probe unavailable ({type(e).__name__})"
-    return f"oracle (oracle/cpu_ref.c; unpinned against the real Taichi reference); rounding envelope of the oracle's open choices: {env}; {taichi}"
+    n_fix = len([f for f in os.listdir(os.path.join(ROOT, "tests", "golden", "shim")) if f.endswith(".npz")]) if os.path.isdir(os.path.join(ROOT, "tests", "golden", "shim")) else 0
+    return (f"oracle (oracle/cpu_ref.c): its un-contracted `source_order` build is bit-identical (image, n, K; gradients <= 2e-6) to the reference's "
+            f"own source executed on a strict-IEEE-fp32 interpreter of its Taichi subset (oracle/ti_shim.py, {n_fix} committed fixtures, "
+            f"profiles/r02_shim_pin_report.txt); unpinned against the real Taichi COMPILER's rounding, for which the envelope of the open "
+            f"choices is: {env}; {taichi}")
 
 
 # ------------------------------------------------------------------------------------------------------------------

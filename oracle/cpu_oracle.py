@@ -42,6 +42,9 @@ VARIANTS = {
     "pos_unfused": ["ORA_POS_UNFUSED"],
     "composite_unfused": ["ORA_COMPOSITE_UNFUSED"],
     "normalize_div": ["ORA_NORMALIZE_DIV"],
+    # one IEEE-rounded operation per SOURCE operator, in source order: what oracle/ti_shim.py computes when it interprets the
+    # reference's own source -- this build must agree with it bit for bit (tests/test_shim_pin.py)
+    "source_order": ["ORA_MIX_UNFUSED", "ORA_POS_UNFUSED", "ORA_COMPOSITE_UNFUSED", "ORA_DIV_TRUE"],
     # no contraction anywhere + true division: what a target without FMA contraction (or fast_math=False) computes
     "strict_ieee": ["ORA_MIX_UNFUSED", "ORA_POS_UNFUSED", "ORA_COMPOSITE_UNFUSED", "ORA_DIV_TRUE", "ORA_NORMALIZE_DIV"],
     # every fast-math liberty at once, the other way

@@ -1,0 +1,212 @@
+"""The oracle pinned against the REFERENCE'S OWN SOURCE.
+
+tests/golden/shim/*.npz hold what differender/volume_raycaster.py computes when its source is executed on oracle/ti_shim.py (a
+strict-IEEE-fp32 interpreter of the Taichi subset it uses; tests/golden/make_shim_golden.py).  The oracle build without any
+contraction (`source_order`) must reproduce them BIT FOR BIT (image, sample counts, early-termination counts) and to float64
+accumulation accuracy on both gradients; the default oracle build (the contractions it defines, oracle/cpu_ref.c header) and the CUDA
+path must stay inside the north_star tolerances.  What this does not cover -- the real Taichi compiler's rounding -- is what
+tools/rounding_envelope.py bounds."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GRAD_TOL, RGBA_TOL
+from oracle import cpu_oracle as co
+from oracle import taichi_probe as tp
+from oracle import ti_shim
+
+FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "shim", "*.npz")))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _rel(a, b, nan):
+    a, b = np.where(nan, 0, np.asarray(a, np.float64)), np.where(nan, 0, np.asarray(b, np.float64))
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _kw(z, variant):
+    kw = dict(sampling_rate=float(z["sampling_rate"]), max_samples=int(z["max_samples"]), variant=variant)
+    if "jitter" in z.files:
+        kw["jitter"] = z["jitter"]
+    return kw
+
+
+def test_fixtures_are_committed():
+    assert len(FIXTURES) >= 5
+    kinds = [bool(np.load(f)["nondiff"]) for f in FIXTURES]
+    assert any(kinds) and not all(kinds)
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
+def test_source_order_oracle_is_bit_identical_to_the_reference_source(path):
+    z = np.load(path)
+    res = tuple(int(v) for v in z["output_shape"])
+    live = z["n"] > 1                                         # n == 1 rays are 0/0 in the reference
+    if bool(z["nondiff"]):
+        img, _, n = co.forward(z["volume"], z["tf"], z["cam"], res, return_counts=True, nondiff=True, **_kw(z, "source_order"))
+        assert np.array_equal(n, z["n"])
+        assert np.array_equal(_bits(img)[:, live], _bits(z["image"])[:, live])
+        return
+    img, K, n = co.forward(z["volume"], z["tf"], z["cam"], res, return_counts=True, **_kw(z, "source_order"))
+    assert np.array_equal(n, z["n"]) and np.array_equal(K[live], z["K"][live])
+    assert np.array_equal(_bits(img)[:, live], _bits(z["image"])[:, live])
+    gv, gt = co.backward(z["volume"], z["tf"], z["cam"], z["grad_image"], res, **_kw(z, "source_order"))
+    # the interpreter accumulates adjoints in float64, the oracle forms each sample's adjoint in fp32
+    assert _rel(gv, z["grad_volume"], z["gvol_nan"]) <= 5e-6 and _rel(gt, z["grad_tf"], z["gtf_nan"]) <= 5e-7
+    # H4: where the reference poisons a voxel's gradient with NaN (and then zeroes it), the oracle keeps the finite contributions
+    assert np.isfinite(gv).all() and np.isfinite(gt).all()
+    assert (z["grad_volume"][z["gvol_nan"]] == 0).all()
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
+def test_default_oracle_is_within_tolerance_of_the_reference_source(path):
+    z = np.load(path)
+    res = tuple(int(v) for v in z["output_shape"])
+    live = z["n"] > 1
+    nd = bool(z["nondiff"])
+    img, K, n = co.forward(z["volume"], z["tf"], z["cam"], res, return_counts=True, nondiff=nd, **_kw(z, None))
+    assert np.array_equal(n, z["n"])
+    assert np.abs(img - z["image"])[:, live].max() <= RGBA_TOL
+    if nd:
+        return
+    assert np.array_equal(K[live], z["K"][live])
+    gv, gt = co.backward(z["volume"], z["tf"], z["cam"], z["grad_image"], res, **_kw(z, None))
+    assert _rel(gv, z["grad_volume"], z["gvol_nan"]) <= GRAD_TOL and _rel(gt, z["grad_tf"], z["gtf_nan"]) <= GRAD_TOL
+
+
+def test_shim_regenerates_a_fixture_from_the_mounted_reference():
+    """Only where the reference tree is mounted (the development container): the committed fixture IS what the reference source
+    computes on the interpreter."""
+    if tp.find_reference() is None:
+        pytest.skip("reference source not mounted (GPU box)")
+    z = np.load(FIXTURES[0])
+    c = tp.SHIM_CASES[0]
+    assert str(z["name"]) == c["name"]
+    mod = tp._load_reference_module("shim")
+    vol, tf, cam, jit, go = tp.case_inputs(c)
+    assert np.array_equal(vol, z["volume"]) and np.array_equal(tf, z["tf"]) and np.array_equal(jit, z["jitter"])
+    ti_shim.reset()
+    r = tp.run_reference(mod, vol, tf, cam, jit, go, c["res"], c["M"], c["sr"])
+    assert np.array_equal(_bits(r["image"]), _bits(z["image"])) and np.array_equal(r["K"], z["K"]) and np.array_equal(r["n"], z["n"])
+    assert np.array_equal(r["gvol"], z["grad_volume"]) and np.array_equal(r["gtf"], z["grad_tf"])
+    assert np.array_equal(r["gvol_nan"], z["gvol_nan"])
+
+
+# ------------------------------------------------------------------------------------------------ the interpreter itself
+def test_shim_scalars_round_once_to_fp32_per_operator():
+    F, f32 = ti_shim.F, np.float32
+    a, b, c = 0.1, 0.7, 1e-3
+    x = F(f32(a)) * b + c                                     # Python constants become fp32 when they meet an fp32 value
+    assert x.v == f32(f32(f32(a) * f32(b)) + f32(c)) and x.v.dtype == np.float32
+    assert (F(f32(1)) / 3).v == f32(1) / f32(3)
+    assert ti_shim.tan(0.5) == np.tan(0.5) and isinstance(ti_shim.tan(0.5), float)      # Python scope: stays a double
+    assert ti_shim.ti_int(F(f32(-2.7))) == -2 and ti_shim.ti_int(F(f32(2.7))) == 2    # casts truncate
+    nan = F(f32(np.nan))
+    assert ti_shim.ti_max(nan, 0.0).v == 0 and np.isnan(ti_shim.ti_max(0.0, nan).v)     # a > b ? a : b
+    assert ti_shim.ti_min(nan, 1.0).v == 1 and np.isnan(ti_shim.ti_min(1.0, nan).v)
+    v = ti_shim.Vec([F(f32(3)), F(f32(4)), F(f32(0))])
+    assert v.norm().v == 5 and [e.v for e in v.normalized().e] == [f32(f32(1) / f32(5)) * f32(3), f32(f32(1) / f32(5)) * f32(4), 0]
+    assert np.isnan(ti_shim.Vec([F(f32(0))] * 3).normalized().x.v)                     # 0 * inf
+
+
+def _kernel_fixture():
+    ti, tl = ti_shim.make_modules()
+    ti_shim.reset()
+
+    class K:
+        def __init__(self):
+            self.x = ti.field(ti.f32, shape=4, needs_grad=True)
+            self.t = ti.Vector.field(4, dtype=ti.f32, shape=2, needs_grad=True)
+            self.y = ti.field(ti.f32, shape=(), needs_grad=True)
+
+        @ti.kernel
+        def f(self, p: ti_shim.ti_float):
+            a = tl.mix(self.x[0], self.x[1], 0.3) * ti.sqrt(self.x[2]) / self.x[3]
+            c = tl.mix(self.t[0], self.t[1], a)
+            n = tl.vec3(c.x, c.y, c.z).normalized()
+            self.y[None] = ti.pow(ti.max(n.dot(tl.vec3(0.2, -0.5, 0.7)), 0.0), p) + ti.min(1.0, c.w * a) + ti.floor(a)
+    return K()
+
+
+def test_shim_reverse_sweep_matches_finite_differences():
+    k = _kernel_fixture()
+    x0 = np.array([0.3, 0.9, 0.8, 1.7], np.float32)
+    t0 = np.array([[0.2, 0.5, 0.1, 0.4], [0.9, 0.3, 0.6, 0.8]], np.float32)
+
+    def run(x, t):
+        k.x.from_torch(torch.tensor(x)); k.t.from_torch(torch.tensor(t))
+        k.f(1.7)
+        return float(k.y.to_torch())
+    run(x0, t0)
+    k.x.grad.fill(0); k.t.grad.fill(0); k.y.grad.fill(0)
+    k.y.grad.from_torch(torch.tensor(1.0))
+    k.f.grad(1.7)
+    gx, gt = k.x.grad.to_numpy64(), k.t.grad.to_numpy64()
+    assert np.abs(gx).min() > 0 and np.abs(gt).min() > 0
+    h = 2e-3                                                  # fp32 forward: central differences are good to ~1e-3 relative
+    for i in range(4):
+        d = np.zeros(4, np.float32); d[i] = h
+        fd = (run(x0 + d, t0) - run(x0 - d, t0)) / (float((x0 + d)[i]) - float((x0 - d)[i]))
+        assert abs(fd - gx[i]) <= 5e-3 * max(1.0, abs(gx[i])), (i, fd, gx[i])
+    for i in range(2):
+        for c in range(4):
+            d = np.zeros((2, 4), np.float32); d[i, c] = h
+            fd = (run(x0, t0 + d) - run(x0, t0 - d)) / (float((t0 + d)[i, c]) - float((t0 - d)[i, c]))
+            assert abs(fd - gt[i, c]) <= 5e-3 * max(1.0, abs(gt[i, c])), (i, c, fd, gt[i, c])
+
+
+def test_shim_adjoint_conventions_of_the_reference_autodiff():
+    """max/min route the whole adjoint to the selected operand (a tie goes to the right-hand one); a zero adjoint still multiplies an
+    infinite partial (the NaN poisoning of SURVEY 7.3 H4)."""
+    ti, tl = ti_shim.make_modules()
+    ti_shim.reset()
+
+    class K:
+        def __init__(self):
+            self.x = ti.field(ti.f32, shape=3, needs_grad=True)
+            self.y = ti.field(ti.f32, shape=2, needs_grad=True)
+
+        @ti.kernel
+        def f(self):
+            self.y[0] = ti.max(self.x[0], 0.0) + ti.max(self.x[1], self.x[1] * 1.0)
+            v = tl.vec3(self.x[2], self.x[2], self.x[2]).normalized()          # x[2] = 0: 0/0
+            self.y[1] = ti.max(v.x, 0.0) + self.x[0]
+    k = K()
+    k.x.from_torch(torch.tensor([0.0, 2.0, 0.0]))
+    k.f()
+    assert k.y.to_torch().tolist() == [2.0, 0.0]              # max(NaN, 0) = 0 launders the forward
+    k.y.grad.from_torch(torch.tensor([1.0, 1.0]))
+    k.f.grad()
+    g = k.x.grad.to_numpy64()
+    assert g[0] == 1.0                                        # tie max(0, 0.0): the constant takes it; + the direct use in y[1]
+    assert g[1] == 1.0                                        # tie max(a, a*1): the right-hand operand, which is a*1
+    assert np.isnan(g[2])                                     # adjoint 0 x partial inf
+
+
+# ------------------------------------------------------------------------------------------------------- the CUDA path
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
+def test_cuda_path_against_the_reference_source(path):
+    from test_gpu_parity import _cuda_forward
+    z = np.load(path)
+    res = tuple(int(v) for v in z["output_shape"])
+    sr, M, nd = float(z["sampling_rate"]), int(z["max_samples"]), bool(z["nondiff"])
+    vol, tf, cams = torch.tensor(z["volume"])[None], torch.tensor(z["tf"]), torch.tensor(z["cam"])[None]
+    jit = torch.tensor(z["jitter"])[None] if "jitter" in z.files else None
+    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, res, jit, M=M, sr=sr, nondiff=nd)
+    live = z["n"] > 1
+    assert np.abs(out[0].cpu().numpy() - z["image"])[:, live].max() <= RGBA_TOL
+    if nd:
+        return
+    assert np.array_equal(K[0].cpu().numpy()[live], z["K"][live])
+    go = torch.tensor(z["grad_image"])[None].cuda().contiguous()
+    gv, gt = vr.march_backward(bricked, tf_r4, cams.cuda().contiguous(), sr, None if jit is None else jit.cuda().contiguous(),
+                               go, out, K, Tp, True, True)
+    assert _rel(gv[0].cpu().numpy(), z["grad_volume"], z["gvol_nan"]) <= GRAD_TOL
+    assert _rel(gt[0].cpu().numpy().T, z["grad_tf"], z["gtf_nan"]) <= GRAD_TOL
