@@ -8,7 +8,12 @@ the Taichi subset it uses.  Run in the development container (the reference tree
 Each file holds the inputs (volume (D,H,W), tf (4,R), cam (3,), jitter (H,W) if any, grad_image (4,H,W) with the seeds of n <= 1 rays
 zeroed), the parameters, and what the reference source computed: image (4,H,W), K, n (H,W), grad_volume (D,H,W) / grad_tf (4,R) in
 float64 after its nan_to_num, and the masks of the entries it had NaN-poisoned before that.  Forward-only
-(`nondiff`) cases hold image and n."""
+(`nondiff`) cases hold image and n.
+
+tests/golden/shim_api/*.npz: the same, one level up -- the reference's PUBLIC API (`Raycaster(...)(volume, tf, look_from)`, its
+`_determine_batch`, `RaycastFunction` through torch.autograd, the flips and permutes of :525-548, and `raycast_nondiff`) executed on
+the interpreter, non-batched and batched, with the user-level tensors: volume ([BS,] 1, D, H, W), tf ([BS,] 4, R), look_from
+([BS,] 3), image ([BS,] 4, H, W) and the gradients autograd returns for them."""
 import os
 import re
 import sys
@@ -46,5 +51,69 @@ def main():
         print(f"{path}: {os.path.getsize(path)} bytes, rays with samples {int((r['n'] > 0).sum())}, longest {int(r['n'].max())}")
 
 
+API_CASES = [
+    dict(name="single 12x16x8 tf1 16x8", shape=(12, 16, 8), tf="tf1", R=32, res=(16, 8), M=64, sr=1.0, jitter=True, cams=[2]),
+    dict(name="batched cameras 12^3 rand 8x16 sr 0.7", shape=(12, 12, 12), tf="rand", R=16, res=(8, 16), M=64, sr=0.7, jitter=True, cams=[1, 6, 12]),
+    dict(name="batched volumes and tfs 8x12x12 tf3 8x8 no jitter", shape=(8, 12, 12), tf="tf3", R=24, res=(8, 8), M=64, sr=1.0, jitter=False,
+         cams=[4, 9], batch_all=True),
+]
+
+
+def main_api():
+    import warnings
+    import torch
+    from differender_b200.synthetic import make_cameras
+    from oracle import cpu_oracle as co
+    mod = tp._load_reference_module("shim")
+    out_dir = os.path.join(HERE, "shim_api")
+    os.makedirs(out_dir, exist_ok=True)
+    for k, c in enumerate(API_CASES):
+        vol, tf, _, jit, _ = tp.case_inputs(c)
+        D, H, W = vol.shape
+        w, h = c["res"]
+        cams = make_cameras(16)[c["cams"]].numpy()
+        bs = len(c["cams"])
+        ti_shim.reset()
+        rc = mod.Raycaster((D, H, W), c["res"], tf.shape[1], sampling_rate=c["sr"], jitter=c["jitter"], max_samples=c["M"])
+        if jit is not None:
+            rc.vr.jitter_field.from_torch(torch.tensor(co._jitter_raw(jit)))                   # the probe's jitter field (PATCH): every item marches it
+        if c.get("batch_all"):                                                                 # every input batched, items differ
+            volume = torch.tensor(np.stack([vol, np.clip(vol[::-1].copy() * 0.9 + 0.05, 0, 1)]))[:, None]
+            tft = torch.tensor(np.stack([tf, tf[:, ::-1].copy()]))
+            look = torch.tensor(cams)
+        else:
+            volume, tft = torch.tensor(vol)[None], torch.tensor(tf)
+            look = torch.tensor(cams[0]) if bs == 1 else torch.tensor(cams)
+        volume.requires_grad_(True); tft.requires_grad_(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            image = rc(volume, tft, look)
+        # rays with n <= 1 (0/0 sample position in the reference) get no gradient seed; n from the bit-identical oracle build
+        go = np.random.default_rng(11).standard_normal(tuple(image.shape)).astype(np.float32)
+        for b in range(bs):
+            v = volume[b, 0] if volume.ndim == 5 else volume[0]
+            t = tft[b] if tft.ndim == 3 else tft
+            _, _, n = co.forward(v.detach().numpy(), t.detach().numpy(), cams[b], c["res"], return_counts=True, sampling_rate=c["sr"],
+                                 max_samples=c["M"], jitter=jit, variant="source_order")
+            if image.ndim == 4:
+                go[b][:, n <= 1] = 0
+            else:
+                go[:, n <= 1] = 0
+        (image * torch.tensor(go)).sum().backward()
+        with torch.no_grad():
+            nd = rc.raycast_nondiff(volume.detach(), tft.detach(), look)
+        z = dict(name=c["name"], volume=volume.detach().numpy(), tf=tft.detach().numpy(), look_from=look.numpy(), output_shape=np.array(c["res"]),
+                 volume_shape=np.array((D, H, W)), sampling_rate=c["sr"], max_samples=c["M"], image=image.detach().numpy(), grad_output=go,
+                 grad_volume=volume.grad.numpy(), grad_tf=tft.grad.numpy(), image_nondiff=nd.numpy())
+        if jit is not None:
+            z["jitter"] = jit
+        slug = re.sub(r"[^a-z0-9]+", "_", c["name"].lower()).strip("_")
+        path = os.path.join(out_dir, f"a{k}_{slug}.npz")
+        np.savez_compressed(path, **z)
+        print(f"{path}: {os.path.getsize(path)} bytes, image {tuple(image.shape)}, grad_volume {tuple(volume.grad.shape)}, grad_tf {tuple(tft.grad.shape)}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--api-only" not in sys.argv:
+        main()
+    main_api()
