@@ -196,6 +196,8 @@ SHIM_CASES = [
     dict(name="12^3 tf1 R=32 16x8", shape=(12, 12, 12), tf="tf1", R=32, res=(16, 8), M=64, sr=1.0, jitter=True, cam=1),
     dict(name="16x12x20 rand R=16 16x16 sr=0.7", shape=(16, 12, 20), tf="rand", R=16, res=(16, 16), M=64, sr=0.7, jitter=True, cam=5),
     dict(name="12x16x8 tf3 R=24 8x16 sr=2 no jitter", shape=(12, 16, 8), tf="tf3", R=24, res=(8, 16), M=128, sr=2.0, jitter=False, cam=11),
+    # the TF resolution of the benchmark configs, more rays (about a minute and ~1 GB of tape on the interpreter)
+    dict(name="24^3 tf1 R=128 32x24", shape=(24, 24, 24), tf="tf1", R=128, res=(32, 24), M=128, sr=1.0, jitter=True, cam=7),
     # a block of exactly constant voxels: zero local gradient, normalized() = 0/0
     dict(name="12^3 gray R=8 8x8 with a flat block", shape=(12, 12, 12), tf="gray", R=8, res=(8, 8), M=64, sr=1.0, jitter=True, cam=3, flat=True),
     # Raycaster.raycast_nondiff (:490-523): forward only, alpha gate 1e-3, no shading clamp, min(1, rgba) at the end, sr = 4

@@ -54,3 +54,31 @@ for name, n, (w, h), tfn, R, sr, jitter, dt, layout in CASES:
     print(f"{name:58s} {w*h:8d} {int(Kr.sum()):10d} {d[:, same].max():12.2e} {d[3][same].max():12.2e} {int((~same).sum()):4d} "
           f"{rel(gv[0].cpu().numpy(), gvr):11.2e} {rel(gt[0].cpu().numpy().T, gtr):10.2e}", flush=True)
 print("tolerances (BASELINE.json north_star): RGBA <= 1e-4 max-abs, gradients <= 1e-3 relative L2")
+
+# --- the same CUDA path against what the REFERENCE'S OWN SOURCE computes on the fp32 interpreter (oracle/ti_shim.py; fixtures made by
+#     tests/golden/make_shim_golden.py in the development container, where the reference tree is mounted)
+import glob
+print()
+print("CUDA path vs the reference source executed on oracle/ti_shim.py (strict IEEE fp32, source order; tests/golden/shim/*.npz):")
+print(f"{'case':58s} {'rays':>8s} {'samples':>10s} {'rgba max|d|':>12s} {'alpha max|d|':>12s} {'K!=':>4s} {'gvol relL2':>11s} {'gtf relL2':>10s}")
+for f in sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "shim", "*.npz"))):
+    z = np.load(f)
+    w, h = (int(v) for v in z["output_shape"])
+    sr, M, nd = float(z["sampling_rate"]), int(z["max_samples"]), bool(z["nondiff"])
+    D, Hh, Ww = z["volume"].shape
+    vr = VolumeRaycaster((Ww, D, Hh), (w, h), max_samples=M, tf_resolution=z["tf"].shape[1], layout="auto")
+    v = vr.brick(torch.tensor(z["volume"]).to(dev).reshape(1, D, Hh, Ww).contiguous())
+    tf_r4 = torch.tensor(z["tf"]).to(dev).t().contiguous()[None]
+    cam = torch.tensor(z["cam"])[None].to(dev)
+    j = torch.tensor(z["jitter"])[None].to(dev) if "jitter" in z.files else None
+    out, K, Tp = vr.march(v, tf_r4, cam, sr, j, nondiff=nd)
+    live = z["n"] > 1
+    d = np.abs(out[0].cpu().numpy() - z["image"])[:, live]
+    if nd:
+        print(f"{str(z['name']):58s} {w*h:8d} {'':>10s} {d.max():12.2e} {d[3].max():12.2e}")
+        continue
+    go = torch.tensor(z["grad_image"])[None].to(dev)
+    gv, gt = vr.march_backward(v, tf_r4, cam, sr, j, go, out, K, Tp, True, True)
+    m = lambda a, b, nan: rel(np.where(nan, 0, a), np.where(nan, 0, b))
+    print(f"{str(z['name']):58s} {w*h:8d} {int(z['K'].sum()):10d} {d.max():12.2e} {d[3].max():12.2e} {int((K[0].cpu().numpy() != z['K'])[live].sum()):4d} "
+          f"{m(gv[0].cpu().numpy(), z['grad_volume'], z['gvol_nan']):11.2e} {m(gt[0].cpu().numpy().T, z['grad_tf'], z['gtf_nan']):10.2e}", flush=True)
