@@ -57,7 +57,7 @@ _PRESETS = {   # control points of utils.py:9-65
 def get_tf(id, res):
     """Preset transfer functions as (4, res) tensors (utils.py:7-79)."""
     if id in _PRESETS:
-        return tex_from_pts(_PRESETS[id], res)
+        return tex_from_pts(torch.tensor(_PRESETS[id]), res)          # fp32 control points, as the reference passes them (utils.py:9)
     elif id == 'black':
         return torch.zeros((4, res)) + 1e-2
     elif id == 'gray':

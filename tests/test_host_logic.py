@@ -121,3 +121,45 @@ def test_uint8_voxel_value_is_exactly_the_fp32_quotient():
     hs.lib().sim_u8_values(out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
     ref = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
     assert np.array_equal(out, ref)
+
+
+def test_helpers_equal_the_reference_utils_where_it_is_mounted():
+    """differender/utils/utils.py of the reference, executed as it is with `torchvtk` (un-vendored, not installed) stubbed by this
+    package's tex_from_pts: the preset control points, `in_circles` and `get_rand_pos` must be the reference's, value for value."""
+    import os, sys, types
+    path = os.path.join(os.environ.get("DIFFERENDER_REFERENCE", "/root/reference"), "differender", "utils", "utils.py")
+    if not os.path.isfile(path):
+        pytest.skip("reference source not mounted (GPU box)")
+    stub, stub_utils = types.ModuleType("torchvtk"), types.ModuleType("torchvtk.utils")
+    stub_utils.tex_from_pts, stub_utils.TFGenerator = tex_from_pts, None
+    stub.utils = stub_utils
+    saved = {k: sys.modules.get(k) for k in ("torchvtk", "torchvtk.utils")}
+    sys.modules["torchvtk"], sys.modules["torchvtk.utils"] = stub, stub_utils
+    try:
+        ref = types.ModuleType("differender_reference_utils")
+        exec(compile(open(path).read(), path, "exec"), ref.__dict__)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for name in ("tf1", "tf2", "tf3", "tf4", "tf5", "black", "gray"):
+        for res in (16, 128, 257):
+            assert torch.equal(ref.get_tf(name, res), get_tf(name, res)), (name, res)
+    torch.manual_seed(5); a = ref.get_tf("rand", 64)
+    torch.manual_seed(5); b = get_tf("rand", 64)
+    assert torch.equal(a, b)
+    with pytest.raises(Exception):
+        ref.get_tf("nope", 8)
+    with pytest.raises(Exception):
+        get_tf("nope", 8)
+    for i in (0.0, 0.3, math.pi / 2, 4.0):
+        assert torch.equal(ref.in_circles(i), in_circles(i)) and torch.equal(ref.in_circles(i, y=0.2, dist=3.0), in_circles(i, y=0.2, dist=3.0))
+    for bs in (None, 1, 7):
+        torch.manual_seed(9); a = ref.get_rand_pos(bs)
+        torch.manual_seed(9); b = get_rand_pos(bs)
+        assert torch.equal(a, b)
+        torch.manual_seed(9); a = ref.get_rand_pos(bs, dist=1.5)
+        torch.manual_seed(9); b = get_rand_pos(bs, dist=1.5)
+        assert torch.equal(a, b)
