@@ -14,7 +14,8 @@
  *       the reference's OWN SOURCE (read from /root/reference, never copied) runs in this container.  The build of
  *       this file with every contraction switched off (`source_order`, oracle/cpu_oracle.py VARIANTS) agrees with it
  *       BIT FOR BIT on image, sample counts and early-termination counts, and to <= 2e-6 relative L2 on both gradients
- *       (forward + backward at three sampling rates, jittered and not, non-cubic volume, flat block, nondiff path):
+ *       (forward + backward at three sampling rates, jittered and not, non-cubic volume, camera inside the box, another
+ *       frustum, flat block, nondiff path; and through the reference's public Raycaster API, batched and not):
  *       tests/test_shim_pin.py, tests/golden/shim/ (+ make_shim_golden.py), profiles/r02_shim_pin_report.txt.  The two
  *       deliberate deviations are SURVEY 7.3 H3 (n == 1 rays: 0/0 sample position in the reference, t = 0 here) and H4
  *       (the reference NaN-poisons and then zeroes the gradient of voxels under an exactly flat sample; kept finite here).

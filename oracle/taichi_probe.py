@@ -125,7 +125,7 @@ def _load_reference_module(engine="taichi"):
     return mod
 
 
-def run_reference(mod, vol, tf, cam, jit, grad_img, res, M, sr, nondiff=False):
+def run_reference(mod, vol, tf, cam, jit, grad_img, res, M, sr, nondiff=False, fov=30.0, near=0.1):
     """One item through the reference's VolumeRaycaster (real Taichi or the shim), following RaycastFunction.forward/backward
     (:431-438, :467-476) or Raycaster.raycast_nondiff (:514-520).  vol (D,H,W) fp32; tf (4,R); cam (3,); jit (H,W) or None and
     grad_img (4,H,W) in image orientation.  The gradient seed of rays with n <= 1 is zeroed (their sample position
@@ -134,7 +134,7 @@ def run_reference(mod, vol, tf, cam, jit, grad_img, res, M, sr, nondiff=False):
     import torch
     from oracle.cpu_oracle import _image_to_raw, _jitter_raw, _raw_to_image
     D, Hv, Wv = vol.shape
-    vr = mod.VolumeRaycaster((Wv, D, Hv), res, max_samples=M, tf_resolution=tf.shape[1])       # Taichi order (X,Y,Z) = torch (W,D,H) :481
+    vr = mod.VolumeRaycaster((Wv, D, Hv), res, max_samples=M, tf_resolution=tf.shape[1], fov=fov, nearfar=(near, 100.0))   # Taichi order (X,Y,Z) = torch (W,D,H) :481
     vr.set_cam_pos(torch.tensor(cam))
     vr.set_volume(torch.tensor(vol).permute(2, 0, 1).contiguous())                              # _determine_batch :571
     vr.set_tf_tex(torch.tensor(tf).permute(1, 0).contiguous())
@@ -198,6 +198,9 @@ SHIM_CASES = [
     dict(name="12x16x8 tf3 R=24 8x16 sr=2 no jitter", shape=(12, 16, 8), tf="tf3", R=24, res=(8, 16), M=128, sr=2.0, jitter=False, cam=11),
     # the TF resolution of the benchmark configs, more rays (about a minute and ~1 GB of tape on the interpreter)
     dict(name="24^3 tf1 R=128 32x24", shape=(24, 24, 24), tf="tf1", R=128, res=(32, 24), M=128, sr=1.0, jitter=True, cam=7),
+    # the camera INSIDE the box (entry distance negative: the reference marches from behind the eye) and another frustum
+    dict(name="12^3 tf2 R=32 16x8 camera inside fov 45 near 0.5", shape=(12, 12, 12), tf="tf2", R=32, res=(16, 8), M=128, sr=1.0, jitter=True,
+         cam_pos=(0.3, 0.2, -0.55), fov=45.0, near=0.5),
     # a block of exactly constant voxels: zero local gradient, normalized() = 0/0
     dict(name="12^3 gray R=8 8x8 with a flat block", shape=(12, 12, 12), tf="gray", R=8, res=(8, 8), M=64, sr=1.0, jitter=True, cam=3, flat=True),
     # Raycaster.raycast_nondiff (:490-523): forward only, alpha gate 1e-3, no shading clamp, min(1, rgba) at the end, sr = 4
@@ -222,7 +225,7 @@ def case_inputs(c):
         tf = tf.numpy()
     else:
         tf = make_tf(c["tf"], R).numpy()
-    cam = make_cameras(16)[c.get("cam", 1)].numpy()
+    cam = np.asarray(c["cam_pos"], np.float32) if "cam_pos" in c else make_cameras(16)[c.get("cam", 1)].numpy()
     h, w = c["res"][1], c["res"][0]
     jit = make_jitter(1, h, w)[0].numpy() if c.get("jitter", True) else None
     go = np.random.default_rng(7).standard_normal((4, h, w)).astype(np.float32)
@@ -247,16 +250,17 @@ def probe(cases=None, out=None, engine="taichi"):
     worst_default = dict(max_abs=0.0, gvol=0.0, gtf=0.0)
     for c in (cases or (CASES if engine == "taichi" else SHIM_CASES)):
         vol, tf, cam, jit, go = case_inputs(c)
+        fk = dict(fov=c.get("fov", 30.0), near=c.get("near", 0.1))
         if engine == "shim":
             from oracle import ti_shim
             ti_shim.reset()
         if c.get("nondiff"):
-            ref = run_reference(mod, vol, tf, cam, None, None, c["res"], c["M"], c["sr"], nondiff=True)
+            ref = run_reference(mod, vol, tf, cam, None, None, c["res"], c["M"], c["sr"], nondiff=True, **fk)
             lines.append(f"## {c['name']}  ({what} vs oracle builds, forward only)")
             lines.append(f"{'oracle build':<20}{'n_diff':>8}{'px bits!=':>10}{'max_abs':>11}")
             rows[c["name"]] = {}
             for name in [None] + list(co.VARIANTS):
-                img, K, n = co.forward(vol, tf, cam, c["res"], return_counts=True, sampling_rate=c["sr"], max_samples=c["M"], nondiff=True, variant=name)
+                img, K, n = co.forward(vol, tf, cam, c["res"], return_counts=True, sampling_rate=c["sr"], max_samples=c["M"], nondiff=True, variant=name, **fk)
                 ok = ref["n"] > 1
                 bits = (np.ascontiguousarray(img, np.float32).view(np.uint32) != ref["image"].view(np.uint32)).any(axis=0)
                 r = dict(n_diff=int((n != ref["n"]).sum()), bit_diff=int(bits[ok].sum()), max_abs=float(np.abs(img - ref["image"]).max(axis=0)[ok].max()))
@@ -265,13 +269,13 @@ def probe(cases=None, out=None, engine="taichi"):
                 lines.append(f"{name or 'default':<20}{r['n_diff']:>8}{r['bit_diff']:>10}{r['max_abs']:>11.2e}")
             lines.append("")
             continue
-        ref = run_reference(mod, vol, tf, cam, jit, go, c["res"], c["M"], c["sr"])
+        ref = run_reference(mod, vol, tf, cam, jit, go, c["res"], c["M"], c["sr"], **fk)
         lines.append(f"## {c['name']}  ({what} vs oracle builds; rays with n <= 1 masked, SURVEY H3: {int((ref['n'] == 1).sum())} here; "
                      f"{int(ref['gvol_nan'].sum())} voxels / {int(ref['gtf_nan'].sum())} TF entries NaN-poisoned in the reference, H4)")
         lines.append(f"{'oracle build':<20}{'n_diff':>8}{'K_diff':>8}{'px bits!=':>10}{'max_abs':>11}{'within 1e-4':>13}{'gvol relL2':>12}{'gtf relL2':>12}")
         rows[c["name"]] = {}
         for name in [None] + list(co.VARIANTS):
-            kw = dict(sampling_rate=c["sr"], max_samples=c["M"], jitter=jit, variant=name)
+            kw = dict(sampling_rate=c["sr"], max_samples=c["M"], jitter=jit, variant=name, **fk)
             img, K, n = co.forward(vol, tf, cam, c["res"], return_counts=True, **kw)
             gv, gt = co.backward(vol, tf, cam, ref["grad_image"], c["res"], **kw)
             r = _cmp(ref, (img, K, n, gv, gt))

@@ -38,9 +38,11 @@ def main():
         vol, tf, cam, jit, go = tp.case_inputs(c)
         ti_shim.reset()
         nondiff = bool(c.get("nondiff"))
-        r = tp.run_reference(mod, vol, tf, cam, None if nondiff else jit, None if nondiff else go, c["res"], c["M"], c["sr"], nondiff=nondiff)
+        fov, near = c.get("fov", 30.0), c.get("near", 0.1)
+        r = tp.run_reference(mod, vol, tf, cam, None if nondiff else jit, None if nondiff else go, c["res"], c["M"], c["sr"], nondiff=nondiff,
+                             fov=fov, near=near)
         z = dict(name=c["name"], volume=vol, tf=tf, cam=cam, output_shape=np.array(c["res"]), sampling_rate=c["sr"], max_samples=c["M"],
-                 nondiff=nondiff, image=r["image"], n=r["n"])
+                 fov=fov, near=near, nondiff=nondiff, image=r["image"], n=r["n"])
         if not nondiff:
             if jit is not None:
                 z["jitter"] = jit

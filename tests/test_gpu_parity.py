@@ -14,15 +14,15 @@ pytestmark = pytest.mark.gpu
 DEFAULT_LAYOUT = "auto"
 
 
-def _vr(vol, out_shape, R, M, layout=DEFAULT_LAYOUT):
+def _vr(vol, out_shape, R, M, layout=DEFAULT_LAYOUT, fov=30.0, near=0.1):
     from differender_b200 import VolumeRaycaster
     D, H, W = vol.shape[-3:]
-    return VolumeRaycaster((W, D, H), out_shape, max_samples=M, tf_resolution=R, layout=layout)
+    return VolumeRaycaster((W, D, H), out_shape, max_samples=M, tf_resolution=R, layout=layout, fov=fov, nearfar=(near, 100.0))
 
 
 def _cuda_forward(vol, tf, cams, out_shape, jit, M=2048, sr=1.0, nondiff=False, dtype=torch.float32, image_layout=True,
-                  layout=DEFAULT_LAYOUT):
-    vr = _vr(vol, out_shape, tf.shape[-1], M, layout)
+                  layout=DEFAULT_LAYOUT, fov=30.0, near=0.1):
+    vr = _vr(vol, out_shape, tf.shape[-1], M, layout, fov, near)
     assert vr.skip_empty
     dev = "cuda:0"
     bricked = vr.brick(vol.to(dev, dtype).reshape(1, *vol.shape[-3:]).contiguous())

@@ -31,14 +31,14 @@ def _rel(a, b, nan):
 
 
 def _kw(z, variant):
-    kw = dict(sampling_rate=float(z["sampling_rate"]), max_samples=int(z["max_samples"]), variant=variant)
+    kw = dict(sampling_rate=float(z["sampling_rate"]), max_samples=int(z["max_samples"]), fov=float(z["fov"]), near=float(z["near"]), variant=variant)
     if "jitter" in z.files:
         kw["jitter"] = z["jitter"]
     return kw
 
 
 def test_fixtures_are_committed():
-    assert len(FIXTURES) >= 5
+    assert len(FIXTURES) >= 7
     kinds = [bool(np.load(f)["nondiff"]) for f in FIXTURES]
     assert any(kinds) and not all(kinds)
 
@@ -199,7 +199,7 @@ def test_cuda_path_against_the_reference_source(path):
     sr, M, nd = float(z["sampling_rate"]), int(z["max_samples"]), bool(z["nondiff"])
     vol, tf, cams = torch.tensor(z["volume"])[None], torch.tensor(z["tf"]), torch.tensor(z["cam"])[None]
     jit = torch.tensor(z["jitter"])[None] if "jitter" in z.files else None
-    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, res, jit, M=M, sr=sr, nondiff=nd)
+    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, res, jit, M=M, sr=sr, nondiff=nd, fov=float(z["fov"]), near=float(z["near"]))
     live = z["n"] > 1
     assert np.abs(out[0].cpu().numpy() - z["image"])[:, live].max() <= RGBA_TOL
     if nd:

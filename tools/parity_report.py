@@ -66,7 +66,7 @@ for f in sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.a
     w, h = (int(v) for v in z["output_shape"])
     sr, M, nd = float(z["sampling_rate"]), int(z["max_samples"]), bool(z["nondiff"])
     D, Hh, Ww = z["volume"].shape
-    vr = VolumeRaycaster((Ww, D, Hh), (w, h), max_samples=M, tf_resolution=z["tf"].shape[1], layout="auto")
+    vr = VolumeRaycaster((Ww, D, Hh), (w, h), max_samples=M, tf_resolution=z["tf"].shape[1], layout="auto", fov=float(z["fov"]), nearfar=(float(z["near"]), 100.0))
     v = vr.brick(torch.tensor(z["volume"]).to(dev).reshape(1, D, Hh, Ww).contiguous())
     tf_r4 = torch.tensor(z["tf"]).to(dev).t().contiguous()[None]
     cam = torch.tensor(z["cam"])[None].to(dev)
