@@ -91,12 +91,12 @@ def skip_grid(volume, tf, output_shape, sampling_rate=1.0, max_samples=512):
 
 
 def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, jitter=None, nondiff=False, generic=False,
-            brick=False, cell=False, skip=False):
+            brick=False, cell=False, skip=False, fov=30.0, near=0.1):
     vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
     tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
     flags = (F_NONDIFF if nondiff else 0) | (F_JIT if jitter is not None else 0) | (F_GENERIC if generic else 0) | F_IMG | \
             (F_BRICK8 if brick else 0) | (F_CELL8 if cell else 0)
-    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate)
+    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate, fov, near)
     L = lib()
     br = _layout_data(L, d, vol, brick, cell)
     w, h = output_shape
@@ -114,13 +114,13 @@ def forward(volume, tf, cam, output_shape, sampling_rate=1.0, max_samples=512, j
 
 
 def backward(volume, tf, cam, grad_image, output_shape, sampling_rate=1.0, max_samples=512, jitter=None,
-             want_vol=True, want_tf=True, generic=False, brick=False, cell=False, skip=False):
+             want_vol=True, want_tf=True, generic=False, brick=False, cell=False, skip=False, fov=30.0, near=0.1):
     vol = np.ascontiguousarray(volume, np.float32).reshape(np.asarray(volume).shape[-3:])
     tf_r4 = np.ascontiguousarray(np.asarray(tf, np.float32).T)
-    out, K, Tp, _ = forward(volume, tf, cam, output_shape, sampling_rate, max_samples, jitter, False, generic, brick, cell)
+    out, K, Tp, _ = forward(volume, tf, cam, output_shape, sampling_rate, max_samples, jitter, False, generic, brick, cell, fov=fov, near=near)
     flags = (F_JIT if jitter is not None else 0) | (F_GENERIC if generic else 0) | F_IMG | (F_BRICK8 if brick else 0) | \
             (F_CELL8 if cell else 0) | (F_VOL if want_vol else 0) | (F_TF if want_tf else 0)
-    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate)
+    d = make_desc(vol.shape, output_shape, tf_r4.shape[0], max_samples, flags, sampling_rate, fov, near)
     L = lib()
     br = _layout_data(L, d, vol, brick, cell)
     gbr = np.zeros(vol.size * 8, np.float32); gtf = np.zeros_like(tf_r4)

@@ -293,3 +293,25 @@ def test_drop_in_raycaster_against_the_reference_public_api(path):
     nd = rc.raycast_nondiff(vol.detach(), tf.detach(), look)
     assert tuple(nd.shape) == z["image_nondiff"].shape
     assert np.abs(nd.cpu().numpy() - z["image_nondiff"])[live].max() <= RGBA_TOL
+
+
+# ----------------------------------------------------- the device arithmetic (csrc/dr_math.cuh compiled for the host) on the CPU
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
+@pytest.mark.parametrize("layout", ["linear", "cell8"])
+def test_device_math_against_the_reference_source(path, layout):
+    """The kernels' per-ray code, run on the host by tests/hostsim, against what the reference source computes: the same bar the
+    GPU test applies, checkable where there is no GPU."""
+    import hostsim_lib as hs
+    z = np.load(path)
+    res = tuple(int(v) for v in z["output_shape"])
+    kw = dict(sampling_rate=float(z["sampling_rate"]), max_samples=int(z["max_samples"]), fov=float(z["fov"]), near=float(z["near"]),
+              jitter=z["jitter"] if "jitter" in z.files else None, cell=layout == "cell8")
+    live = z["n"] > 1
+    out, K, _, n = hs.forward(z["volume"], z["tf"], z["cam"], res, nondiff=bool(z["nondiff"]), **kw)
+    assert np.array_equal(n, z["n"])
+    assert np.abs(out - z["image"])[:, live].max() <= RGBA_TOL
+    if bool(z["nondiff"]):
+        return
+    assert np.array_equal(K[live], z["K"][live])
+    gv, gt = hs.backward(z["volume"], z["tf"], z["cam"], z["grad_image"], res, **kw)
+    assert _rel(gv, z["grad_volume"], z["gvol_nan"]) <= GRAD_TOL and _rel(gt, z["grad_tf"], z["gtf_nan"]) <= GRAD_TOL
