@@ -99,6 +99,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
+    def wait_ready(self, timeout=10.0):
+        """Blocks until the first sample has arrived, i.e. until nvidia-smi has finished attaching to the driver.  Measured on B200
+        (profiles/r02_experiments.md): when the timed region began 0.25 s after the launch, 2 of 9 processes caught that attach inside their
+        FIRST timed step, which then took 73-90 ms instead of 41.5 ms; every later step was unaffected by the 100 ms polling."""
+        t = time.time()
+        while self.proc is not None and not self.rows and self.proc.poll() is None and time.time() - t < timeout:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -333,7 +341,8 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
     if sample_clocks:
         sampler = ClockSampler(dev.index)
         sampler.start()
-        time.sleep(0.25)
+        sampler.wait_ready()
+        time.sleep(0.1)
     torch.cuda.synchronize()
     t_wall0 = time.time()
     if profiler_range:

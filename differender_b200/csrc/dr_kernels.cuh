@@ -135,7 +135,7 @@ template <typename VT, int LAYOUT, bool NONDIFF, int TAPS, bool SR1, bool SKIP>
 __global__ void __launch_bounds__(kThreads, (LAYOUT == LAYOUT_CELL8 && SKIP && SR1 && !NONDIFF) ? DR_FWD_MIN_BLOCKS_SKIP : DR_FWD_MIN_BLOCKS)
 fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, float* __restrict__ out, int32_t* __restrict__ outK,
-           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum, unsigned cbias,
+           float* __restrict__ outT, size_t vol_elems, const float* __restrict__ target, float* __restrict__ loss_sum, LayoutConsts lc,
            const unsigned char* __restrict__ skip_grid, size_t skip_stride)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -162,7 +162,7 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     Ray r;
     setup_ray(d, cam, i, j, jit, r);
     const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
-    const Layout L = make_layout(d, cbias);
+    const Layout L = make_layout(d, lc, SKIP);
     F4 A; int K; float Tp;
     // skip grid: a 16-byte header (the number of empty macro-cells: nothing to skip -> march as if there were no grid) + the bytes
     const unsigned char* grid = nullptr;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, LAYOUT == LAYOUT_BRICK8 ? DR_BWD_MIN
 bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, const float* __restrict__ camp,
            const float* __restrict__ jitter, const float* __restrict__ gout, const float* __restrict__ outp,
            const int32_t* __restrict__ Kp, const float* __restrict__ Tp, float4* __restrict__ gcell,
-           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale, unsigned cbias,
+           float4* __restrict__ tf_slots, size_t vol_elems, float mse_scale, LayoutConsts lc,
            const unsigned char* __restrict__ skip_grid, size_t skip_stride, const float* __restrict__ scale_dev)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -344,7 +344,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) DR_RAY_DONE;       // this ray's gradient is exactly zero
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
     const VolView<VT> vol { volp + voff };
-    const Layout L = make_layout(d, cbias);
+    const Layout L = make_layout(d, lc);
     CellVolSink vs;
     vs.g = WANT_VOL ? gcell + (d.Bvol == 1 ? 0 : (size_t)b * d.X * d.Y * d.Z * 2) : nullptr;
     vs.cur = -1;
@@ -413,7 +413,7 @@ int launch_fwd_skip(const FwdArgs& a)
     if (int rc = persistent_grid(kern, smem, d, grid, a.st)) return rc;
 #endif
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.out, a.K, a.T, vol_stride(d),
-                                         a.target, a.loss_sum, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d));
+                                         a.target, a.loss_sum, layout_consts(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "fwd_kernel launch");
 }
@@ -430,7 +430,7 @@ int launch_bwd_skip(const BwdArgs& a)
     if (int rc = persistent_grid(kern, smem, d, grid, a.st)) return rc;
 #endif
     kern<<<grid, kThreads, smem, a.st>>>(*d, static_cast<const VT*>(a.vol), a.tf, a.cam, a.jitter, a.gout, a.out, a.K, a.T, a.gvol,
-                                         a.slots, vol_stride(d), a.mse_scale, cell_bias(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d),
+                                         a.slots, vol_stride(d), a.mse_scale, layout_consts(*d), a.skip_grid, skip_views(d) == 1 ? 0 : skip_cells(d),
                                          a.scale_dev);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DR_OK : fail_cuda(e, "bwd_kernel launch");

@@ -232,7 +232,11 @@ struct Layout {
     int sY, sZ;           // element strides between bricks along y and z: nbx*512, nbx*nby*512
     int mx, my, mz;       // dim - 1 (index clamps)
     unsigned cbias;       // (kFloorBias*Z + kFloorBias)*X + kFloorBias mod 2^32: turns biased floor indices into a cell index
+    unsigned ycells;      // X*Z: cells (= voxels) between y-neighbours
 };
+// the two layout constants the kernels take as an ARGUMENT (constant-bank operands; derived on the device from d.X / d.Z the
+// compiler re-computed them inside the march loop with vector-register multiplies)
+struct LayoutConsts { unsigned cbias, ycells; };
 // Offsets are UNSIGNED so that `pointer + offset` is one IMAD.WIDE.U32 (a signed int needs LEA + LEA.HI.X.SX32).
 typedef unsigned int uoff;
 DR_HD uoff offx(int x) { return (uoff)(((x >> 3) << 9) | (x & 7)); }
@@ -779,9 +783,9 @@ template <typename VT> struct LinearAddr : RowFetch<LinearAddr<VT> > {
 #if defined(DR_BOUNDS_CHECK)
     long long n_elems;
 #endif
-    DR_HD void init(const DrDesc& d, const VT* p, const Layout&, const Centre& c)
+    DR_HD void init(const DrDesc& d, const VT* p, const Layout& L, const Centre& c)
     {
-        vp = p; sz = (uoff)d.X; sy = (uoff)(d.X * d.Z); i00 = (uoff)c.cidx;
+        vp = p; sz = (uoff)d.X; sy = (uoff)L.ycells; i00 = (uoff)c.cidx;
 #if defined(DR_BOUNDS_CHECK)
         n_elems = (long long)d.X * d.Y * d.Z;
 #endif
@@ -844,9 +848,9 @@ template <typename VT, bool DUAL> struct CellAddr {
 #if defined(DR_BOUNDS_CHECK)
     long long n_cells;
 #endif
-    DR_HD void init(const DrDesc& d, const VT* p, const Layout&, const Centre& c)
+    DR_HD void init(const DrDesc& d, const VT* p, const Layout& L, const Centre& c)
     {
-        vp = p; cell = (uoff)c.cidx; sz = (uoff)d.X; sy = (uoff)(d.X * d.Z);
+        vp = p; cell = (uoff)c.cidx; sz = (uoff)d.X; sy = (uoff)L.ycells;
 #if defined(DR_BOUNDS_CHECK)
         n_cells = (long long)d.X * d.Y * d.Z;
 #endif
@@ -871,7 +875,11 @@ template <typename VT, bool DUAL> struct CellAddr {
         DR_OOB_IF(bp != bc && (long long)(cell + st) >= n_cells);
         DR_OOB_IF(bm != bc && (long long)(cell - st) >= n_cells);
 #endif
-        rp = rec_add(vp, cell + st); rm = rec_add(vp, cell - st);
+        // centre record +- the axis' byte stride (a 64-bit uniform operand): two adds per neighbour instead of the index add, the
+        // widening multiply and the base add of rec_add(vp, cell +- st)  (8 issue slots per sample in the backward)
+        const char* rc = reinterpret_cast<const char*>(rec_add(vp, cell));
+        const long long off = (long long)st * (long long)(8 * sizeof(VT));
+        rp = reinterpret_cast<const VT*>(rc + off); rm = reinterpret_cast<const VT*>(rc - off);
     }
     DR_HD void plane_x(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
@@ -926,16 +934,22 @@ template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_CELL8, DUAL> { typede
 
 // cell-index bias of locate_centre; computed on the host and passed to the kernels as an argument (a constant-bank operand:
 // left to the device, the compiler re-derived it inside the march loop, 5 issue slots per sample)
-inline unsigned cell_bias(const DrDesc& d)
+inline LayoutConsts layout_consts(const DrDesc& d)
 {
-    return ((unsigned)kFloorBias * (unsigned)d.Z + (unsigned)kFloorBias) * (unsigned)d.X + (unsigned)kFloorBias;
+    LayoutConsts c;
+    c.cbias = ((unsigned)kFloorBias * (unsigned)d.Z + (unsigned)kFloorBias) * (unsigned)d.X + (unsigned)kFloorBias;
+    c.ycells = (unsigned)d.X * (unsigned)d.Z;
+    return c;
 }
-DR_HD Layout make_layout(const DrDesc& d, unsigned cbias)
+// `ycells_from_args` = false derives X*Z on the device as before: measured on B200 (profiles/r02_experiments.md) the argument helps
+// the backward (+1 %) and the forward kernels that carry the skip grid (+3..4 %: fewer spilled bytes at 80 registers) and costs the
+// every-sample-shaded forward 4.5 % (same instruction counts, another schedule), so each kernel picks its own
+DR_HD Layout make_layout(const DrDesc& d, LayoutConsts lc, bool ycells_from_args = true)
 {
     Layout L;
     L.sY = d.nbx * 512; L.sZ = d.nbx * d.nby * 512;
     L.mx = d.X - 1; L.my = d.Y - 1; L.mz = d.Z - 1;
-    L.cbias = cbias;
+    L.cbias = lc.cbias; L.ycells = ycells_from_args ? lc.ycells : (unsigned)(d.X * d.Z);
     return L;
 }
 
@@ -1065,13 +1079,13 @@ DR_HD F2 tap_rows(const VT* vp, uoff cell, float fx, float fy)      // x then y 
     return mix2(m0, m1, splat(DR_SUB(1.0f, fy)), splat(fy));
 }
 template <typename VT>
-DR_HD void eval_normals_direct(const DrDesc& d, const VT* vp, F3 pos, const Centre& c, Taps& t)
+DR_HD void eval_normals_direct(const DrDesc& d, const Layout& L, const VT* vp, F3 pos, const Centre& c, Taps& t)
 {
     t.cx = c.cx; t.cy = c.cy; t.cz = c.cz; t.cidx = c.cidx; t.I = c.I;
     locate_pair(pos.x, d.delta, d.scale[0], t.xp, t.xm);
     locate_pair(pos.y, d.delta, d.scale[1], t.yp, t.ym);
     locate_pair(pos.z, d.delta, d.scale[2], t.zp, t.zm);
-    const uoff cell = (uoff)c.cidx, sz = (uoff)d.X, sy = (uoff)(d.X * d.Z);
+    const uoff cell = (uoff)c.cidx, sz = (uoff)d.X, sy = (uoff)L.ycells;
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f, oz = DR_SUB(1.0f, fz);
     {   // x taps: cells cell + (b_tap - b_centre), x fraction of the tap
         const F2 p = tap_rows(vp, cell + (uoff)(t.xp.b - c.cx.b), t.xp.f, fy), m = tap_rows(vp, cell + (uoff)(t.xm.b - c.cx.b), t.xm.f, fy);
@@ -1136,7 +1150,7 @@ template <typename VT, int LAYOUT, int TAPS, bool DUAL>
 DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, const Centre& c, Taps& t)
 {
     if (TAPS == TAPS_GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
-    if (TAPS == TAPS_TWO && LAYOUT == LAYOUT_CELL8) { eval_normals_direct(d, vol.p, pos, c, t); return; }     // C5: fwd +6.6 %, bwd +3.3 %
+    if (TAPS == TAPS_TWO && LAYOUT == LAYOUT_CELL8) { eval_normals_direct(d, L, vol.p, pos, c, t); return; }     // C5: fwd +6.6 %, bwd +3.3 %
     typename AddrOf<VT, LAYOUT, DUAL>::type ad;
     ad.init(d, vol.p, L, c);
     eval_normals<TAPS>(d, ad, pos, c, t);
@@ -1322,7 +1336,7 @@ DR_HD void tap_weights(float adj, Loc ax, Loc ay, Loc az, float v[8])
 }
 
 template <typename Sink, bool GENERIC, bool TWO>
-DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const SampleAdj& a)
+DR_HD void scatter_volume_grad(const DrDesc& d, const Layout& L, Sink& sink, const Taps& t, const SampleAdj& a)
 {
     float v[8];
     const int cc = t.cidx;
@@ -1371,7 +1385,7 @@ DR_HD void scatter_volume_grad(const DrDesc& d, Sink& sink, const Taps& t, const
     // weights reuse the centre's pair products: only the weight pair of the shifted axis differs.  One block per AXIS (the
     // crossed tap is picked with selects; in a shaded warp some lane nearly always crossed on each axis, so a block per
     // tap would cost twice the issue slots); both taps of an axis cross only under TAPS_TWO (second pass of the loop).
-    const int sz = d.X, sy = d.X * d.Z;
+    const int sz = d.X, sy = (int)L.ycells;
 #pragma unroll
     for (int pass = 0; pass < (TWO ? 2 : 1); ++pass) {
         const bool fx = pass ? (xpc & xmc) : (xpc | xmc), fy = pass ? (ypc & ymc) : (ypc | ymc), fz = pass ? (zpc & zmc) : (zpc | zmc);
@@ -1662,7 +1676,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
                 a.dI = (h.x > 0.0f) ? dcw * h.d.w * d.tf_len : 0.0f;
                 if (a.dI != 0.0f) {
                     a.dg.x = a.dg.y = a.dg.z = 0.0f; a.has_dg = false;
-                    scatter_volume_grad<VolSink, TAPS == TAPS_GENERIC, TAPS == TAPS_TWO>(d, vsink, t, a);
+                    scatter_volume_grad<VolSink, TAPS == TAPS_GENERIC, TAPS == TAPS_TWO>(d, L, vsink, t, a);
                 }
             }
             continue;
@@ -1674,7 +1688,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         g.w -= Cg;
         if (WANT_TF) tsink.add(h.lo, h.f, a.dc);
         if (WANT_VOL && (a.has_dg || a.dI != 0.0f))          // exactly-zero contributions (transparent samples) are not scattered
-            scatter_volume_grad<VolSink, TAPS == TAPS_GENERIC, TAPS == TAPS_TWO>(d, vsink, t, a);
+            scatter_volume_grad<VolSink, TAPS == TAPS_GENERIC, TAPS == TAPS_TWO>(d, L, vsink, t, a);
     }
     if (WANT_TF) tsink.flush();
     if (WANT_VOL) vsink.flush();

@@ -58,7 +58,7 @@ void sim_macro_dims(const DrDesc* d, int* out4) { out4[0] = macro_ny(*d); out4[1
 // linear [Y][Z][X] -> bricked
 void sim_brick(const DrDesc* d, const float* lin, float* bricked)
 {
-    Layout L = make_layout(*d, cell_bias(*d));
+    Layout L = make_layout(*d, layout_consts(*d));
     memset(bricked, 0, sizeof(float) * sim_bricked_elems(d));
     for (int y = 0; y < d->Y; ++y) for (int z = 0; z < d->Z; ++z) for (int x = 0; x < d->X; ++x)
         bricked[offx(x) + offy(y, L.sY) + offz(z, L.sZ)] = lin[((size_t)y * d->Z + z) * d->X + x];
@@ -103,7 +103,7 @@ void sim_gather(const DrDesc* d, const float* gcell, float* lin)
 void sim_forward(const DrDesc* d, const float* vol_data, const float* tf, const float* cam3, const float* jitter,
                  float* out, int* out_K, float* out_Tprev, int* out_n, const unsigned char* skip_grid)
 {
-    Layout L = make_layout(*d, cell_bias(*d));
+    Layout L = make_layout(*d, layout_consts(*d));
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
     TfBin* tab = make_tf_table(*d, tf);
     const TfTable tf4 { tab };
@@ -143,7 +143,7 @@ void sim_backward(const DrDesc* d, const float* vol_data, const float* tf, const
                   const float* grad_out, const float* out, const int* Kin, const float* Tprev,
                   float* gvol_cells, float* gtf, const unsigned char* skip_grid)
 {
-    Layout L = make_layout(*d, cell_bias(*d));
+    Layout L = make_layout(*d, layout_consts(*d));
     VolView<float> vol { vol_data };          // bricked copy or the linear volume, per DR_F_LAYOUT_BRICK8
     TfBin* tab = make_tf_table(*d, tf);
     const TfTable tf4 { tab };
