@@ -23,6 +23,7 @@ installable here) on the host cores on a bounded sample of the same workload.
 """
 import argparse
 import ctypes
+import gc
 import hashlib
 import json
 import os
@@ -343,6 +344,8 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
         sampler.start()
         sampler.wait_ready()
         time.sleep(0.1)
+    gc.collect()
+    gc.disable()                 # a full collection over torch's module objects is a 30-50 ms host stall: not inside a timed step
     torch.cuda.synchronize()
     t_wall0 = time.time()
     if profiler_range:
@@ -356,6 +359,7 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
         launches += n_k
     t1.record()
     torch.cuda.synchronize()
+    gc.enable()
     if profiler_range:
         torch.cuda.profiler.stop()
     if world > 1:
@@ -661,6 +665,8 @@ def run_ours(args, cfg):
             e2e_step()
         if world > 1:
             dist.barrier()
+        gc.collect()
+        gc.disable()
         torch.cuda.synchronize()
         a, b = ev(), ev()
         a.record()
@@ -672,6 +678,7 @@ def run_ours(args, cfg):
         torch.cuda.current_stream().wait_stream(out_stream)                            # the last volume gradient has arrived on the host
         b.record()
         torch.cuda.synchronize()
+        gc.enable()
         losses.append(float(h_loss[(step_no[0] - 1) & 1][0]))                          # ... and so has the last loss
         for e in pending:
             for name, x, y in (("wait_for_inputs", 0, 1), ("forward", 1, 2), ("loss+backward", 2, 3), ("d2h", 3, 4)):

@@ -394,10 +394,17 @@ __global__ void __launch_bounds__(256) tf_reduce_kernel(DrDesc d, const float* _
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // r*4 + c
     const int lane = threadIdx.x & 31, tb = blockIdx.y;
     if (e >= d.R * 4) return;
-    const float* p = slots + (size_t)tb * kTfSlots * d.R * 4 + e;
+    // a copy has R + 1 bins: the march writes the pair (lo, lo + 1) without clamping, and what lands in the pad bin R belongs to
+    // bin R - 1 (the reference clamps the upper bin, :216-218)
+    const size_t copy = (size_t)(d.R + 1) * 4;
+    const float* p = slots + (size_t)tb * kTfSlots * copy + e;
+    const bool last = (e >> 2) == d.R - 1;
     float acc = 0.0f;
 #pragma unroll 8
-    for (int s = lane; s < kTfSlots; s += 32) acc += __ldg(p + (size_t)s * d.R * 4);
+    for (int s = lane; s < kTfSlots; s += 32) {
+        acc += __ldg(p + (size_t)s * copy);
+        if (last) acc += __ldg(p + (size_t)s * copy + 4);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane) return;
@@ -566,7 +573,7 @@ size_t dr_bricked_elems(const DrDesc* d) { return d ? (size_t)d->nbx * d->nby * 
 size_t dr_workspace_bytes(const DrDesc* d)
 {
     if (!d || !(d->flags & DR_F_NEEDS_TF_GRAD)) return 0;
-    return (size_t)d->Btf * kTfSlots * d->R * sizeof(float4);
+    return (size_t)d->Btf * kTfSlots * (d->R + 1) * sizeof(float4);          // R bins + one pad bin per privatised copy
 }
 
 int dr_brick_volume(const DrDesc* d, const void* vol_linear, void* vol_bricked, void* stream)

@@ -162,7 +162,7 @@ fwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     Ray r;
     setup_ray(d, cam, i, j, jit, r);
     const VolView<VT> vol { volp + (d.Bvol == 1 ? 0 : (size_t)b * vol_elems) };
-    const Layout L = make_layout(d, lc, SKIP);
+    const Layout L = make_layout(d, lc, SKIP && !NONDIFF);
     F4 A; int K; float Tp;
     // skip grid: a 16-byte header (the number of empty macro-cells: nothing to skip -> march as if there were no grid) + the bytes
     const unsigned char* grid = nullptr;
@@ -244,14 +244,14 @@ struct CellVolSink {
 // sample); the bin pair receives (S - S1, S1) when the bin changes.
 struct RedTfSink {
     float4* g;      // [R] of this CTA's slot
-    int cur, Rm1;
+    int cur;
     float4 s, s1;
     bool rgb;       // a shaded sample went into the current bin; otherwise the colour sums are exactly zero and stay home
     __device__ __forceinline__ void flush()
     {
         if (cur >= 0) {
             float4* p = g + cur;
-            float4* q = g + min(cur + 1, Rm1);           // the reference clamps the upper bin (:216-218)
+            float4* q = p + 1;                           // bin R is a pad bin that tf_reduce_kernel folds into bin R - 1 (the reference clamps the upper bin, :216-218)
             if (rgb) {
                 atomicAdd(p, make_float4(s.x - s1.x, s.y - s1.y, s.z - s1.z, s.w - s1.w));
                 atomicAdd(q, s1);
@@ -344,7 +344,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
     if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) DR_RAY_DONE;       // this ray's gradient is exactly zero
     const size_t voff = d.Bvol == 1 ? 0 : (size_t)b * vol_elems;
     const VolView<VT> vol { volp + voff };
-    const Layout L = make_layout(d, lc);
+    const Layout L = make_layout(d, lc, WANT_VOL);
     CellVolSink vs;
     vs.g = WANT_VOL ? gcell + (d.Bvol == 1 ? 0 : (size_t)b * d.X * d.Y * d.Z * 2) : nullptr;
     vs.cur = -1;
@@ -353,8 +353,7 @@ bwd_kernel(DrDesc d, const VT* __restrict__ volp, const float* __restrict__ tf, 
 #endif
     const int slot = (blockIdx.y * gridDim.x + blockIdx.x) & (kTfSlots - 1);      // (persistent launch: blockIdx.y == 0)
     RedTfSink ts;
-    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * d.R : nullptr;
-    ts.Rm1 = d.R - 1;
+    ts.g = WANT_TF ? tf_slots + ((size_t)tb * kTfSlots + slot) * (d.R + 1) : nullptr;
     ts.init();
     const unsigned char* grid = nullptr;
     if (SKIP && __ldg(reinterpret_cast<const unsigned*>(skip_grid)) != 0u) grid = skip_grid + kSkipHeader + (size_t)b * skip_stride;

@@ -835,7 +835,7 @@ template <typename VT> struct BrickAddr : RowFetch<BrickAddr<VT> > {
 // predicate) instead of one load from a selected address.  Twice the load instructions for fewer ALU instructions: it pays
 // in the ALU-bound backward while at most one tap of an axis crosses (C3: backward +7 %), and costs where loads matter
 // (forward -6 %) or crossings are frequent (C5, TAPS_TWO: backward -15 %), so only the TAPS_ONE backward uses it.
-template <typename VT, bool DUAL> struct CellAddr {
+template <typename VT, int DUAL> struct CellAddr {
     static constexpr bool kRecordTapsX = sizeof(VT) == 4;      // x taps read their own cell's record (cell_tap_x)
     const VT* vp; uoff cell, sy, sz;
     template <bool PLUS> DR_HD void tap_x(int bt, int bc, F2& a0, F2& b0, F2& a1, F2& b1) const
@@ -875,11 +875,16 @@ template <typename VT, bool DUAL> struct CellAddr {
         DR_OOB_IF(bp != bc && (long long)(cell + st) >= n_cells);
         DR_OOB_IF(bm != bc && (long long)(cell - st) >= n_cells);
 #endif
-        // centre record +- the axis' byte stride (a 64-bit uniform operand): two adds per neighbour instead of the index add, the
-        // widening multiply and the base add of rec_add(vp, cell +- st)  (8 issue slots per sample in the backward)
-        const char* rc = reinterpret_cast<const char*>(rec_add(vp, cell));
-        const long long off = (long long)st * (long long)(8 * sizeof(VT));
-        rp = reinterpret_cast<const VT*>(rc + off); rm = reinterpret_cast<const VT*>(rc - off);
+        if (DUAL == 2) {
+            // centre record +- the axis' byte stride (a 64-bit uniform operand): two adds per neighbour instead of the index add,
+            // the widening multiply and the base add of rec_add(vp, cell +- st)  (7 issue slots per sample in the backward with a
+            // volume gradient, +1 %; the TF-only backward lost 2.7 % with it and keeps the index form, DUAL == 1)
+            const char* rc = reinterpret_cast<const char*>(rec_add(vp, cell));
+            const long long off = (long long)st * (long long)(8 * sizeof(VT));
+            rp = reinterpret_cast<const VT*>(rc + off); rm = reinterpret_cast<const VT*>(rc - off);
+        } else {
+            rp = rec_add(vp, cell + st); rm = rec_add(vp, cell - st);
+        }
     }
     DR_HD void plane_x(int bp, int bm, int bc, F2& N0, F2& N1) const
     {
@@ -928,9 +933,9 @@ template <typename VT, bool DUAL> struct CellAddr {
         N0 = f2(n[0], n[1]); N1 = f2(n[2], n[3]);
     }
 };
-template <typename VT, int LAYOUT, bool DUAL> struct AddrOf { typedef LinearAddr<VT> type; };
-template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_BRICK8, DUAL> { typedef BrickAddr<VT> type; };
-template <typename VT, bool DUAL> struct AddrOf<VT, LAYOUT_CELL8, DUAL> { typedef CellAddr<VT, DUAL> type; };
+template <typename VT, int LAYOUT, int DUAL> struct AddrOf { typedef LinearAddr<VT> type; };
+template <typename VT, int DUAL> struct AddrOf<VT, LAYOUT_BRICK8, DUAL> { typedef BrickAddr<VT> type; };
+template <typename VT, int DUAL> struct AddrOf<VT, LAYOUT_CELL8, DUAL> { typedef CellAddr<VT, DUAL> type; };
 
 // cell-index bias of locate_centre; computed on the host and passed to the kernels as an argument (a constant-bank operand:
 // left to the device, the compiler re-derived it inside the march loop, 5 issue slots per sample)
@@ -1137,7 +1142,7 @@ DR_HD void eval_normals_generic(const DrDesc& d, const VT* vp, F3 pos, const Cen
 }
 
 // phase 1 / phase 2 dispatch on layout and tap path
-template <typename VT, int LAYOUT, int TAPS, bool DUAL = false>
+template <typename VT, int LAYOUT, int TAPS, int DUAL = 0>
 DR_HD void sample_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, Centre& c)
 {
     locate_centre(d, L, pos, c);
@@ -1146,7 +1151,7 @@ DR_HD void sample_centre(const DrDesc& d, const VolView<VT>& vol, const Layout& 
     ad.init(d, vol.p, L, c);
     eval_centre(ad, c);
 }
-template <typename VT, int LAYOUT, int TAPS, bool DUAL>
+template <typename VT, int LAYOUT, int TAPS, int DUAL>
 DR_HD void sample_normals(const DrDesc& d, const VolView<VT>& vol, const Layout& L, F3 pos, const Centre& c, Taps& t)
 {
     if (TAPS == TAPS_GENERIC) { eval_normals_generic(d, vol.p, pos, c, t); return; }
@@ -1591,7 +1596,7 @@ DR_HD void march_forward(const DrDesc& d, const VolView<VT>& vol, const Layout& 
         }
         tf_colour(h, false);
         Taps t;
-        sample_normals<VT, LAYOUT, TAPS, false>(d, vol, L, pos, c, t);
+        sample_normals<VT, LAYOUT, TAPS, 0>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, r.dir, ts, t.g, !NONDIFF, sh);
         const float ko = sh.k * o;
@@ -1659,7 +1664,7 @@ DR_HD void march_backward(const DrDesc& d, const VolView<VT>& vol, const Layout&
         // dc.rgb = k*o*dC = 0 and dI = tf_len * dc.w * h.d.w = 0, C = 0 (g.w unchanged) and T_{s-1} = T_s: nothing to do.
         if (!WANT_TF && o == 0.0f && h.d.w == 0.0f) continue;
         Taps t;
-        sample_normals<VT, LAYOUT, TAPS, TAPS == TAPS_ONE>(d, vol, L, pos, c, t);
+        sample_normals<VT, LAYOUT, TAPS, TAPS == TAPS_ONE ? (WANT_VOL ? 2 : 1) : 0>(d, vol, L, pos, c, t);
         Shade sh;
         shade(d, r.dir, ts, t.g, true, sh);
         if (o == 0.0f) {

@@ -43,7 +43,7 @@ def test_version_and_desc_init(lib):
     assert lib.dr_workspace_bytes(ctypes.byref(d)) == 0            # no TF gradient requested
     d2 = _lib.make_desc(37, 29, 45, 50, 34, 33, 512, 2, 1, 2, _lib.VOX_F16, _lib.F_NEEDS_TF_GRAD, 0.5, 30.0, 0.1)
     assert (d2.nbx, d2.nby, d2.nbz) == (5, 4, 6) and abs(d2.inv_sr - 2.0) < 1e-7
-    assert lib.dr_workspace_bytes(ctypes.byref(d2)) == 2 * 1024 * 33 * 16
+    assert lib.dr_workspace_bytes(ctypes.byref(d2)) == 2 * 1024 * (33 + 1) * 16        # R bins + one pad bin per privatised copy
     big = _lib.make_desc(2304, 64, 64, 64, 64, 16, 64, 1, 1, 1, _lib.VOX_F32, 0, 1.0, 30.0, 0.1)
     assert big.tap_generic == 1                                     # a normal tap can skip a whole cell: generic taps
 

@@ -104,6 +104,33 @@ def test_fp16_cell8_two_neighbour_taps_match_oracle(case, tf_name):
     assert torch.equal(out, out2) and torch.equal(K, K2) and torch.equal(Tp, Tp2)
 
 
+@pytest.mark.parametrize("tf_layout_4r", [False, True])
+def test_top_transfer_function_bin(tf_layout_4r):
+    """Intensities at and above 1: the centre bin clamps to R - 1 and BOTH halves of the gradient pair belong to bin
+    R - 1 (the reference clamps the upper index, :216-218).  The march writes the pair (lo, lo + 1) into copies padded by one bin and
+    tf_reduce_kernel folds the pad into bin R - 1: the last bins of the TF gradient must match the oracle entry by entry."""
+    from differender_b200._lib import F_TF_4R
+    vol, tf, cams, jit = case_inputs((32, 32, 32), (48, 40), 16, seed=21, views=2)
+    vol = (vol * 2.5).clamp(0.0, 1.3)                                          # a good share of the voxels at 1.0 .. 1.3
+    assert float((vol >= 1.0).float().mean()) > 0.05
+    ref, Kr, _ = oracle_forward_views(vol, tf, cams, (48, 40), jit, max_samples=2048)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    gv_ref, gt_ref = oracle_backward_views(vol, tf, cams, go.numpy(), (48, 40), jit, max_samples=2048)
+    vr, bricked, tf_r4, out, K, Tp = _cuda_forward(vol, tf, cams, (48, 40), jit)
+    same = K.cpu().numpy() == Kr
+    assert (~same).mean() <= 1e-4 and np.moveaxis(np.abs(out.cpu().numpy() - ref), 1, 0)[:, same].max() <= RGBA_TOL
+    c, j = cams.cuda().contiguous(), jit.cuda().contiguous()
+    if tf_layout_4r:
+        gv, gt = vr.march_backward(bricked, tf.cuda().contiguous()[None], c, 1.0, j, go.cuda().contiguous(), out, K, Tp, True, True, extra_flags=F_TF_4R)
+        gt = gt[0].cpu().numpy()
+    else:
+        gv, gt = vr.march_backward(bricked, tf_r4, c, 1.0, j, go.cuda().contiguous(), out, K, Tp, True, True)
+        gt = gt[0].cpu().numpy().T
+    assert np.abs(gt_ref[:, -1]).min() > 0                                    # the top bin really receives gradient
+    assert np.allclose(gt[:, -3:], gt_ref[:, -3:], rtol=1e-3, atol=1e-6 * np.abs(gt_ref).max())
+    assert rel_l2(gt, gt_ref) <= GRAD_TOL and rel_l2(gv[0].cpu().numpy(), gv_ref) <= GRAD_TOL
+
+
 def test_tf_only_and_volume_only_backward():
     vol, tf, cams, jit = case_inputs((48, 48, 48), (64, 48), 128, seed=3, tf_name="tf1", views=2)
     ref, _, _ = oracle_forward_views(vol, tf, cams, (64, 48), jit, max_samples=2048)
