@@ -40,7 +40,6 @@ import types
 
 import numpy as np
 
-np.seterr(all="ignore")
 f32 = np.float32
 f64 = np.float64
 _libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
@@ -511,7 +510,8 @@ class _BoundKernel:
         seg = Segment(TAPE)
         TAPE.seg = seg
         try:
-            self.k.fn(self.obj, *self._args(args))
+            with np.errstate(all="ignore"):          # 1/0, 0*inf, inf-inf are ordinary fp32 results here, not warnings
+                self.k.fn(self.obj, *self._args(args))
         finally:
             TAPE.seg = None
         seg.t1 = len(TAPE.out)
