@@ -141,6 +141,9 @@ class F:
     def __neg__(s):
         return F(-s.v) if s.i < 0 else TAPE.rec(-s.v, s.i, -1.0)
 
+    def __pow__(s, k):
+        return ti_pow(s, k)
+
     def __pos__(s):
         return s
 
@@ -204,6 +207,7 @@ class Vec:
     def __truediv__(s, o): return s._bin(o, operator.truediv)
     def __rtruediv__(s, o): return s._bin(o, operator.truediv, True)
     def __neg__(s): return Vec([-x for x in s.e])
+    def __pow__(s, k): return Vec([ti_pow(x, k) for x in s.e])
 
     # swizzles the reference uses
     x = property(lambda s: s.e[0], lambda s, v: s.e.__setitem__(0, v))
@@ -380,6 +384,27 @@ class GradField:
     def to_numpy64(self):
         return self.data.copy()
 
+    def to_numpy(self):
+        return self.data.astype(np.float32)
+
+    def from_numpy(self, a):
+        self.data[...] = a
+
+    def __getitem__(self, idx):                      # a kernel READING a gradient (the example's apply_grad): plain fp32 constants
+        idx = self.parent._idx(idx)
+        if self.parent.n:
+            return Vec([F(f32(self.data[idx + (c,)])) for c in range(self.parent.n)])
+        return F(f32(self.data[idx]))
+
+    def __setitem__(self, idx, val):
+        idx = self.parent._idx(idx)
+        if self.parent.n:
+            vals = val.e if type(val) is Vec else [val] * self.parent.n
+            for c, x in enumerate(vals):
+                self.data[idx + (c,)] = _builtin_float(_c(x).v)
+        else:
+            self.data[idx] = _builtin_float(_c(val).v)
+
 
 class Field:
     def __init__(self, dtype, n=0, needs_grad=False, shape=None):
@@ -410,6 +435,16 @@ class Field:
     def to_torch(self, device=None):
         import torch
         return torch.from_numpy(self.data.copy())
+
+    def from_numpy(self, a):
+        a = np.asarray(a)
+        if a.shape != self.data.shape:
+            raise ValueError(f"ti_shim: from_numpy shape {a.shape} != field shape {self.data.shape}")
+        self.data[...] = a
+        self.cur = {}
+
+    def to_numpy(self):
+        return self.data.copy()
 
     def fill(self, v):
         self.data[...] = v
@@ -598,11 +633,20 @@ def normalize(v):
 
 
 # --------------------------------------------------------------------------------------------------- the two modules
-_jitter = None
+_random_source = []
+
+
+def set_random_source(values):
+    """The numbers the next ti.random() calls return, in call order (the reference draws one per pixel in struct-for order, so a
+    jitter image in the raw (w, h) layout, flattened, reproduces a supplied jitter tensor without touching the source)."""
+    global _random_source
+    _random_source = [f32(v) for v in np.asarray(values, np.float32).reshape(-1)][::-1]
 
 
 def ti_random(dtype=None):
-    raise NotImplementedError("ti_shim: ti.random -- the probe replaces the reference's jitter by a field (taichi_probe.PATCH)")
+    if not _random_source:
+        raise RuntimeError("ti_shim: ti.random() called with no numbers left (set_random_source)")
+    return F(_random_source.pop())
 
 
 def make_modules():
@@ -627,15 +671,19 @@ def make_modules():
     tl.__shim__ = True
     tl.vec2, tl.vec3, tl.vec4 = _vecn(2), _vecn(3), _vecn(4)
     tl.mix, tl.clamp, tl.cross, tl.dot, tl.reflect, tl.normalize = mix, clamp, cross, dot, reflect, normalize
+    tl.summation = lambda v: v.sum()
     return ti, tl
 
 
-def load_reference(source, path="<reference>"):
+def load_reference(source, path="<reference>", extra_modules=None):
     """Executes the reference module's SOURCE TEXT (as read from the reference tree by the caller) against the stand-in modules, with
-    the kernel builtins re-interpreted; returns the module object."""
+    the kernel builtins re-interpreted; returns the module object.  `extra_modules`: {name: module} stubs for imports of the file that
+    are not on the path computed here (plotting, torchvtk)."""
     ti, tl = make_modules()
-    saved = {k: sys.modules.get(k) for k in ("taichi", "taichi_glsl")}
-    sys.modules["taichi"], sys.modules["taichi_glsl"] = ti, tl
+    mods = {"taichi": ti, "taichi_glsl": tl}
+    mods.update(extra_modules or {})
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
     try:
         mod = types.ModuleType("differender_reference_on_ti_shim")
         mod.__dict__.update(BUILTINS)

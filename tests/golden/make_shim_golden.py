@@ -115,7 +115,108 @@ def main_api():
         print(f"{path}: {os.path.getsize(path)} bytes, image {tuple(image.shape)}, grad_volume {tuple(volume.grad.shape)}, grad_tf {tuple(tft.grad.shape)}")
 
 
+EXAMPLE = os.path.join("examples", "taichi_volume_raycaster.py")
+
+
+def load_example():
+    """The reference's TF-optimisation demo (examples/taichi_volume_raycaster.py: its own copy of the kernels plus `backward()`,
+    :425-447, and the momentum step `apply_grad`, :375-381) on the interpreter.  Plotting and torchvtk imports are stubbed; jitter comes
+    from ti_shim.set_random_source (the file is executed unmodified)."""
+    import types
+    import warnings
+    from differender_b200.utils import tex_from_pts
+    root = os.path.dirname(os.path.dirname(tp.find_reference()))
+    path = os.path.join(root, EXAMPLE)
+    stubs = {n: types.ModuleType(n) for n in ("matplotlib", "matplotlib.pyplot", "torchvtk", "torchvtk.rendering", "torchvtk.utils")}
+    stubs["matplotlib"].pyplot = stubs["matplotlib.pyplot"]
+    stubs["torchvtk.rendering"].plot_tf = stubs["torchvtk.rendering"].plot_tfs = None
+    stubs["torchvtk.utils"].tex_from_pts, stubs["torchvtk.utils"].TFGenerator = tex_from_pts, None
+    stubs["torchvtk"].rendering, stubs["torchvtk"].utils = stubs["torchvtk.rendering"], stubs["torchvtk.utils"]
+    sys.path.insert(0, root)                                   # `from differender.utils import get_tf`
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return ti_shim.load_reference(open(path).read(), path, extra_modules=stubs)
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k == "differender" or k.startswith("differender.")]:
+            del sys.modules[k]
+
+
+# the eye sits inside the box: every ray has tens of samples, none has exactly one (whose position is 0/0 in the reference, SURVEY 7.3 H3)
+LOOP = dict(name="tf loop 12^3 black to tf1 R=32 16x16 sr 0.7", shape=(12, 12, 12), R=32, res=(16, 16), M=64, bw_sr=0.7, fw_sr=2.0,
+            cam_pos=(0.5, 0.3, -0.8), iters=3, lr=0.1, mom=0.9, clip=0.1, decay=0.99)
+
+
+def main_loop():
+    """C2 in miniature, every arithmetic step executed by reference code on the interpreter: the LIBRARY's kernels
+    (differender/volume_raycaster.py, the path under test) driven in the order of the demo's `backward()`
+    (examples/taichi_volume_raycaster.py:425-447: clear, compute_entry_exit with jitter, raycast, get_final_image,
+    torch.nn.functional.mse_loss against the reference image, get_final_image.grad, raycast.grad) and the DEMO's own momentum
+    step kernel `apply_grad` (:375-381) with its learning-rate decay (:596-602), from the `black` TF towards a target rendered with
+    `tf1` by the library's nondiff march.  (The demo file carries an older copy of the march kernels -- no min(1, .) on the Phong
+    factor, no min(1, rgba) on the nondiff image -- so its kernels are not the ones pinned here; only its optimiser step is.)"""
+    import torch
+    from differender_b200.synthetic import make_jitter, make_tf, make_volume
+    from oracle import cpu_oracle as co
+    c = LOOP
+    lib = tp._load_reference_module("shim")
+    demo = load_example()
+    ti_shim.reset()
+    vol = make_volume(c["shape"]).numpy()[0]
+    cam = np.asarray(c["cam_pos"], np.float32)
+    w, h = c["res"]
+    D, Hv, Wv = vol.shape
+    tf_target, tf0 = make_tf("tf1", c["R"]).numpy(), make_tf("black", c["R"]).numpy()
+    vr = lib.VolumeRaycaster((Wv, D, Hv), c["res"], max_samples=c["M"], tf_resolution=c["R"])
+    vr.set_cam_pos(torch.tensor(cam))
+    vr.set_volume(torch.tensor(vol).permute(2, 0, 1).contiguous())
+    vr.set_tf_tex(torch.tensor(tf_target).permute(1, 0).contiguous())
+    vr.clear_framebuffer()                                                     # Raycaster.raycast_nondiff (:514-520)
+    vr.compute_entry_exit(c["fw_sr"], 0)
+    vr.raycast_nondiff(c["fw_sr"])
+    vr.get_final_image_nondiff()
+    target_raw = vr.output_rgba.to_torch().clone()
+    opt = demo.VolumeRaycaster(volume_resolution=(4, 4, 4), render_resolution=(16, 16), max_samples=1, tf_resolution=c["R"])   # apply_grad only
+    tf = tf0.copy()
+    lr, tfs, grads, losses, jits = c["lr"], [], [], [], []
+    for k in range(c["iters"]):
+        jit = make_jitter(1, h, w, seed=900 + k)[0].numpy()
+        vr.set_tf_tex(torch.tensor(tf).permute(1, 0).contiguous())
+        vr.jitter_field.from_torch(torch.tensor(co._jitter_raw(jit)))
+        vr.clear_framebuffer(); vr.clear_grad()
+        vr.compute_entry_exit(c["bw_sr"], 1)
+        vr.raycast(c["bw_sr"])
+        vr.get_final_image()
+        out = vr.output_rgba.to_torch().requires_grad_(True)
+        loss = torch.nn.functional.mse_loss(out, target_raw)
+        loss.backward()
+        vr.output_rgba.grad.from_torch(out.grad)
+        vr.get_final_image.grad()
+        vr.raycast.grad(c["bw_sr"])
+        g = vr.tf_tex.grad.to_torch().numpy()                                   # (R, 4) fp32, as the demo's apply_grad reads it
+        assert np.isfinite(g).all() and int((vr.sample_step_nums.to_torch() == 1).sum()) == 0
+        opt.tf_tex.from_numpy(np.ascontiguousarray(tf.T)); opt.tf_tex.grad.from_numpy(g)
+        opt.apply_grad(lr, c["mom"], c["clip"])
+        lr *= c["decay"]
+        tf = np.ascontiguousarray(opt.tf_tex.to_numpy().T)
+        grads.append(g.T.copy()); losses.append(float(loss)); tfs.append(tf.copy()); jits.append(jit)
+        print(f"iteration {k}: loss {losses[-1]:.6f}, |grad| {np.abs(g).max():.3e}, tf alpha max {tf[3].max():.4f}")
+    out_dir = os.path.join(HERE, "shim_loop")
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, "l0_tf_loop.npz")
+    np.savez_compressed(path, name=c["name"], volume=vol, cam=cam, tf_init=tf0, target=co._raw_to_image(target_raw.numpy()), jitter=np.stack(jits),
+                        output_shape=np.array(c["res"]), max_samples=c["M"], bw_sampling_rate=c["bw_sr"], fw_sampling_rate=c["fw_sr"],
+                        tf_target=tf_target, lr=c["lr"], momentum=c["mom"], clip=c["clip"], lr_decay=c["decay"],
+                        tf_after=np.stack(tfs), grad_tf=np.stack(grads), loss=np.array(losses))
+    print(f"{path}: {os.path.getsize(path)} bytes")
+
+
 if __name__ == "__main__":
-    if "--api-only" not in sys.argv:
-        main()
-    main_api()
+    if "--loop-only" in sys.argv:
+        main_loop()
+    else:
+        if "--api-only" not in sys.argv:
+            main()
+        main_api()
+        main_loop()

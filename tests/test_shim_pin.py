@@ -316,3 +316,61 @@ def test_device_math_against_the_reference_source(path, layout):
     assert np.array_equal(K[live], z["K"][live])
     gv, gt = hs.backward(z["volume"], z["tf"], z["cam"], z["grad_image"], res, **kw)
     assert _rel(gv, z["grad_volume"], z["gvol_nan"]) <= GRAD_TOL and _rel(gt, z["grad_tf"], z["gtf_nan"]) <= GRAD_TOL
+
+
+# ------------------------------------------------- the reference's TF-optimisation DEMO loop (BASELINE config C2) on the interpreter
+LOOP_FIXTURE = os.path.join(os.path.dirname(__file__), "golden", "shim_loop", "l0_tf_loop.npz")
+
+
+def test_oracle_reproduces_the_reference_demo_loop():
+    """Reference code only, on the interpreter (make_shim_golden.py main_loop): the library's kernels driven in the order of the demo's
+    `backward()` (examples/taichi_volume_raycaster.py:425-447: jittered march at sr 0.7, F.mse_loss, TF gradient) and the demo's own
+    `apply_grad` kernel (:375-381) with its learning-rate decay, three iterations from `black` towards a `tf1` render.  The same loop with
+    the oracle (un-contracted build) and oracle/aux_ref.py."""
+    from oracle import aux_ref
+    z = np.load(LOOP_FIXTURE)
+    res = tuple(int(v) for v in z["output_shape"])
+    M, sr = int(z["max_samples"]), float(z["bw_sampling_rate"])
+    tgt = co.forward(z["volume"], z["tf_target"], z["cam"], res, sampling_rate=float(z["fw_sampling_rate"]), max_samples=M, nondiff=True,
+                     variant="source_order")
+    assert np.array_equal(_bits(tgt), _bits(z["target"]))                      # the target image (the library's nondiff march), bit for bit
+    tf, mom, lr = z["tf_init"].copy(), np.zeros_like(z["tf_init"]), float(z["lr"])
+    for k in range(z["tf_after"].shape[0]):
+        kw = dict(sampling_rate=sr, max_samples=M, jitter=z["jitter"][k], variant="source_order")
+        out, _, n = co.forward(z["volume"], tf, z["cam"], res, return_counts=True, **kw)
+        assert (n != 1).all()                                                 # no 0/0 rays in this case (H3)
+        d = out.astype(np.float32) - z["target"]
+        loss = float((d.astype(np.float64) ** 2).mean())
+        assert abs(loss - float(z["loss"][k])) <= 1e-6 * float(z["loss"][k])
+        go = (d * np.float32(2.0 / d.size)).astype(np.float32)                  # d mse_loss / d out
+        _, gt = co.backward(z["volume"], tf, z["cam"], go, res, want_vol=False, **kw)
+        assert _rel(gt, z["grad_tf"][k], np.zeros((), bool)) <= 2e-6
+        tf, mom = aux_ref.momentum_step(tf, gt.astype(np.float32), mom, lr, float(z["momentum"]), float(z["clip"]))
+        lr *= float(z["lr_decay"])
+        assert np.abs(tf - z["tf_after"][k]).max() <= 1e-7, k                   # the transfer function after each demo iteration
+    assert np.abs(z["tf_after"][-1] - z["tf_init"]).max() > 1e-2                # and the loop really moved it
+
+
+@pytest.mark.gpu
+def test_drop_in_loop_against_the_reference_demo_loop():
+    """The same three iterations through the product: Raycaster.mse_loss (render + MSE fused) + backward + MomentumSGD.step."""
+    from differender_b200 import MomentumSGD, Raycaster
+    z = np.load(LOOP_FIXTURE)
+    res = tuple(int(v) for v in z["output_shape"])
+    D, H, W = z["volume"].shape
+    rc = Raycaster((D, H, W), res, z["tf_init"].shape[1], sampling_rate=float(z["bw_sampling_rate"]), jitter=True, max_samples=int(z["max_samples"]))
+    vol = torch.tensor(z["volume"])[None].cuda()
+    cam = torch.tensor(z["cam"]).cuda()
+    nd = rc.raycast_nondiff(vol, torch.tensor(z["tf_target"]).cuda(), cam, sampling_rate=float(z["fw_sampling_rate"]))
+    assert np.abs(nd.cpu().numpy() - z["target"]).max() <= RGBA_TOL
+    target = torch.tensor(z["target"]).cuda()
+    tf = torch.tensor(z["tf_init"]).cuda().requires_grad_(True)
+    opt = MomentumSGD(tf, lr=float(z["lr"]), momentum=float(z["momentum"]), max_grad=float(z["clip"]), lr_decay=float(z["lr_decay"]))
+    for k in range(z["tf_after"].shape[0]):
+        tf.grad = None
+        loss, _ = rc.mse_loss(vol, tf, cam, target, jitter_tensor=torch.tensor(z["jitter"][k]).cuda())
+        loss.backward()
+        assert abs(float(loss) - float(z["loss"][k])) <= 1e-4 * float(z["loss"][k])
+        assert _rel(tf.grad.cpu().numpy(), z["grad_tf"][k], np.zeros((), bool)) <= GRAD_TOL
+        opt.step()
+        assert np.abs(tf.detach().cpu().numpy() - z["tf_after"][k]).max() <= 1e-5, k
