@@ -370,7 +370,7 @@ def test_drop_in_loop_against_the_reference_demo_loop():
         tf.grad = None
         loss, _ = rc.mse_loss(vol, tf, cam, target, jitter_tensor=torch.tensor(z["jitter"][k]).cuda())
         loss.backward()
-        assert abs(float(loss) - float(z["loss"][k])) <= 1e-4 * float(z["loss"][k])
+        assert abs(float(loss.detach()) - float(z["loss"][k])) <= 1e-4 * float(z["loss"][k])
         assert _rel(tf.grad.cpu().numpy(), z["grad_tf"][k], np.zeros((), bool)) <= GRAD_TOL
         opt.step()
         assert np.abs(tf.detach().cpu().numpy() - z["tf_after"][k]).max() <= 1e-5, k
