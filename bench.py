@@ -384,7 +384,14 @@ def time_workload(wl, steps, warmup, profiler_range=False, sample_clocks=False):
         all_samples = float(samples)
     del flush
     fwd_ms, bwd_ms = phase_ms["fwd"] / steps, (phase_ms["bwd"] / steps if wl.mode != "nondiff" else 0.0)
-    return dict(value=all_samples * steps / (total_ms * 1e-3) / 1e9, ms_per_step=total_ms / steps, samples=samples, all_samples=all_samples,
+
+    def med(xs):
+        xs = sorted(xs)
+        return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
+    # medians over the timed steps (this rank): a one-off host stall inside one step moves the mean of a 3-step measurement by 20 %
+    median = {"ms": med(each_ms), "fwd_ms": med([e[1].elapsed_time(e[2]) for e in evs]),
+              "bwd_ms": med([e[2].elapsed_time(e[3]) for e in evs]) if wl.mode != "nondiff" else 0.0}
+    return dict(value=all_samples * steps / (total_ms * 1e-3) / 1e9, ms_per_step=total_ms / steps, samples=samples, all_samples=all_samples, median=median,
                 samples_min_max_over_ranks=per_rank, shaded_fraction=shaded_fraction, launches=launches, clocks=clocks, each_ms=each_ms,
                 phase_ms={k: v / steps for k, v in phase_ms.items()}, fwd_ms=fwd_ms, bwd_ms=bwd_ms,
                 fwd=samples / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 and samples else None,
@@ -422,6 +429,12 @@ def small_line(name, cfg, r, extra=None):
     d = {"config": name, "workload": cfg["desc"], "metric": METRIC[cfg["mode"]], "value": r["value"], "unit": "Gsamples/s", "ms": r["ms_per_step"],
          "fwd": r["fwd"], "fwd_ms": r["fwd_ms"], "bwd": r["bwd"], "bwd_ms": r["bwd_ms"], "active_samples_per_step_per_gpu": r["samples"],
          "shaded_fraction": None if r["shaded_fraction"] is None else round(r["shaded_fraction"], 4)}
+    m = r.get("median")
+    if m and r["samples"]:
+        g = lambda ms: round(r["samples"] / (ms * 1e-3) / 1e9, 3) if ms and ms > 0 else None
+        d["median_of_steps"] = {"value": g(m["ms"]), "ms": round(m["ms"], 3), "fwd": g(m["fwd_ms"]), "bwd": g(m["bwd_ms"]),
+                                "ms_each_step": r["each_ms"][:20],
+                                "note": "value / ms / fwd / bwd above are means over the timed steps; these are per-step medians (robust to a one-off stall)"}
     if extra:
         d.update(extra)
     return d

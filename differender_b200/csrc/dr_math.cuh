@@ -1075,10 +1075,10 @@ DR_HD void eval_normals(const DrDesc& d, const A& ad, F3 pos, const Centre& c, T
 // two 16-byte (fp32) loads that mostly hit L1 -- with the same seven mixes in the same order on the same eight corners, so the
 // values are bit-identical to the other paths; there is no branch, no select and no second-plane case.
 template <typename VT>
-DR_HD F2 tap_rows(const VT* vp, uoff cell, float fx, float fy)      // x then y mixes of one cell record: the pair (value at z0, at z1)
+DR_HD F2 tap_rows(const VT* rec, float fx, float fy)      // x then y mixes of one cell record: the pair (value at z0, at z1)
 {
     float v[8];
-    load_vox8(rec_add(vp, cell), v);
+    load_vox8(rec, v);
     const F2 fx2 = splat(fx), ox2 = splat(DR_SUB(1.0f, fx));
     const F2 m0 = mix2(f2(v[0], v[1]), f2(v[2], v[3]), ox2, fx2), m1 = mix2(f2(v[4], v[5]), f2(v[6], v[7]), ox2, fx2);
     return mix2(m0, m1, splat(DR_SUB(1.0f, fy)), splat(fy));
@@ -1090,24 +1090,30 @@ DR_HD void eval_normals_direct(const DrDesc& d, const Layout& L, const VT* vp, F
     locate_pair(pos.x, d.delta, d.scale[0], t.xp, t.xm);
     locate_pair(pos.y, d.delta, d.scale[1], t.yp, t.ym);
     locate_pair(pos.z, d.delta, d.scale[2], t.zp, t.zm);
-    const uoff cell = (uoff)c.cidx, sz = (uoff)d.X, sy = (uoff)L.ycells;
+    // a tap's record = the centre record + (lo_tap - lo_centre) x the axis' byte stride: one widening multiply-add per tap on the centre
+    // POINTER (the strides fit 32 bits: X*Z*32 < 2^31 for axes <= 2000) instead of an index multiply-add, a widening multiply and the
+    // base add
+    const char* rc = reinterpret_cast<const char*>(rec_add(vp, (uoff)c.cidx));
+    const int rb = (int)(8 * sizeof(VT)), zb = d.X * rb, yb = (int)L.ycells * rb;
+#define DR_TAP_REC(db, stride) reinterpret_cast<const VT*>(rc + (long long)(db) * (long long)(stride))
     const float fx = c.cx.f, fy = c.cy.f, fz = c.cz.f, oz = DR_SUB(1.0f, fz);
     {   // x taps: cells cell + (b_tap - b_centre), x fraction of the tap
-        const F2 p = tap_rows(vp, cell + (uoff)(t.xp.b - c.cx.b), t.xp.f, fy), m = tap_rows(vp, cell + (uoff)(t.xm.b - c.cx.b), t.xm.f, fy);
+        const F2 p = tap_rows(DR_TAP_REC(t.xp.b - c.cx.b, rb), t.xp.f, fy), m = tap_rows(DR_TAP_REC(t.xm.b - c.cx.b, rb), t.xm.f, fy);
         const F2 v = mix2(f2(p.x, m.x), f2(p.y, m.y), splat(oz), splat(fz));
         t.g.x = DR_SUB(v.x, v.y);
     }
     {   // y taps
-        const F2 p = tap_rows(vp, cell + (uoff)(t.yp.b - c.cy.b) * sy, fx, t.yp.f), m = tap_rows(vp, cell + (uoff)(t.ym.b - c.cy.b) * sy, fx, t.ym.f);
+        const F2 p = tap_rows(DR_TAP_REC(t.yp.b - c.cy.b, yb), fx, t.yp.f), m = tap_rows(DR_TAP_REC(t.ym.b - c.cy.b, yb), fx, t.ym.f);
         const F2 v = mix2(f2(p.x, m.x), f2(p.y, m.y), splat(oz), splat(fz));
         t.g.y = DR_SUB(v.x, v.y);
     }
     {   // z taps: z fraction of the tap
-        const F2 p = tap_rows(vp, cell + (uoff)(t.zp.b - c.cz.b) * sz, fx, fy), m = tap_rows(vp, cell + (uoff)(t.zm.b - c.cz.b) * sz, fx, fy);
+        const F2 p = tap_rows(DR_TAP_REC(t.zp.b - c.cz.b, zb), fx, fy), m = tap_rows(DR_TAP_REC(t.zm.b - c.cz.b, zb), fx, fy);
         const F2 f = f2(t.zp.f, t.zm.f);
         const F2 v = mix2(f2(p.x, m.x), f2(p.y, m.y), sub2(splat(1.0f), f), f);
         t.g.z = DR_SUB(v.x, v.y);
     }
+#undef DR_TAP_REC
 }
 
 // Generic path (a normal tap can skip a whole cell: dims > ~2000; linear layout only): every tap is a full 8-load

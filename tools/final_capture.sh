@@ -1,8 +1,8 @@
 #!/bin/bash
 # The round-end evidence run on one B200 (gpurun): GPU tests, parity report, the bench line, then -- each only after its own command
 # exited 0 without ncu -- the launch list and the full captures of the two march kernels (C3, and C5 with 2 views).
-# Outputs under gpurun_out/final4/.
-O=gpurun_out/final4; mkdir -p $O
+# Outputs under gpurun_out/final5/.
+O=gpurun_out/final5; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log
 DIFFRENDER_LIB=differender_b200/libdiffrender_dbg.so timeout 900 python tools/bounds_suite.py > $O/bounds_suite.log 2>&1; tail -1 $O/bounds_suite.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit $?"
