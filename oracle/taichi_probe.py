@@ -9,7 +9,7 @@ oracle (oracle/cpu_ref.c) is unpinned against the real compiler's ROUNDING.  The
   * it loads the reference's own source, differender/volume_raycaster.py, from $DIFFERENDER_REFERENCE, /root/reference or
     baseline/_ref, UNMODIFIED except for a three-line patch (`PATCH` below) that replaces the `ti.random` jitter (:255) by a
     jitter FIELD so that the reference and the oracle march identical sample positions (north_star: "identical inputs and
-    jitter");
+    jitter") -- the `--shim` engine needs no patch at all: the interpreter's ti.random() returns the supplied jitter;
   * it bypasses `Raycaster.__init__` (which hard-codes `ti.init(arch=ti.cuda)`, :486) and drives the reference's
     `VolumeRaycaster` (:56-389) by hand after `ti.init(arch=ti.cpu, default_fp=ti.f32)` with exactly the call sequence of
     `RaycastFunction.forward / backward` for one item (:431-438, :467-476);
@@ -117,12 +117,26 @@ def _load_reference_module(engine="taichi"):
         from oracle import ti_shim
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", FutureWarning)       # torch.cuda.amp decorators of the reference's autograd wrapper
-            return ti_shim.load_reference(patched_source(path), path)
+            return ti_shim.load_reference(open(path).read(), path)     # UNMODIFIED: the interpreter serves ti.random from the supplied jitter
     import taichi as ti
     ti.init(arch=ti.cpu, default_fp=ti.f32)                      # the library hard-codes ti.cuda (:486); the probe runs ti.cpu
     mod = types.ModuleType("differender_reference_patched")
     exec(compile(patched_source(path), path + " [+taichi_probe.PATCH]", "exec"), mod.__dict__)
     return mod
+
+
+def set_jitter(vr, jit, copies=1):
+    """Makes the reference march the supplied jitter image ((H, W), image orientation).  Real Taichi: the jitter field of PATCH.  The
+    interpreter runs the UNMODIFIED source and serves its ti.random() calls -- one per pixel, in struct-for order = the raw (w, h)
+    layout -- from the same numbers (`copies` forwards' worth: the batched backward re-runs compute_entry_exit, :456)."""
+    import torch
+    from oracle.cpu_oracle import _jitter_raw
+    raw = _jitter_raw(jit)
+    if hasattr(vr, "jitter_field"):
+        vr.jitter_field.from_torch(torch.tensor(raw))
+    else:
+        from oracle import ti_shim
+        ti_shim.set_random_source(np.tile(raw.reshape(-1), copies))
 
 
 def run_reference(mod, vol, tf, cam, jit, grad_img, res, M, sr, nondiff=False, fov=30.0, near=0.1):
@@ -139,7 +153,7 @@ def run_reference(mod, vol, tf, cam, jit, grad_img, res, M, sr, nondiff=False, f
     vr.set_volume(torch.tensor(vol).permute(2, 0, 1).contiguous())                              # _determine_batch :571
     vr.set_tf_tex(torch.tensor(tf).permute(1, 0).contiguous())
     if jit is not None:
-        vr.jitter_field.from_torch(torch.tensor(_jitter_raw(jit)))
+        set_jitter(vr, jit)
     vr.clear_framebuffer()
     vr.compute_entry_exit(sr, 0 if (jit is None or nondiff) else 1)
     n = _raw_to_image(vr.sample_step_nums.to_torch().numpy()[..., None])[0]

@@ -5,7 +5,9 @@ differender/volume_raycaster.py uses, so that the reference's OWN SOURCE (read f
 can be executed in this container, where the real Taichi JIT is not installable (no network).
 
 What it is: two stand-in modules (`taichi`, `taichi_glsl`) plus replacements for the builtins that Taichi re-interprets inside
-kernels (`float`, `int`, `max`, `min`, `pow`).  With them the reference's `VolumeRaycaster` class (:56-389) runs as plain Python:
+kernels (`float`, `int`, `max`, `min`, `pow`).  With them the reference's source runs UNMODIFIED (its `ti.random()` jitter is served
+from a supplied tensor, set_random_source) -- the `VolumeRaycaster` class (:56-389), and the `Raycaster` / `RaycastFunction` wrappers on
+top of it -- as plain Python:
 every scalar is an fp32 value (`F`), every operator rounds once to fp32 in SOURCE ORDER (no contraction, no fast-math), struct-for
 loops iterate the field indices, fields are numpy arrays, and `kernel.grad()` is a reverse sweep over a tape of the scalar operations
 the forward call recorded (adjoints accumulated in float64; the select-style adjoints of max/min and the unconditional

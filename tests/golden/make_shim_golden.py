@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tests/golden/shim/*.npz: outputs of the REFERENCE'S OWN SOURCE (differender/volume_raycaster.py, read from /root/reference or
-$DIFFERENDER_REFERENCE, with the probe's 3-line jitter patch) executed on oracle/ti_shim.py, the strict-IEEE-fp32 interpreter of
+$DIFFERENDER_REFERENCE, UNMODIFIED: its ti.random() jitter is served from the supplied jitter tensor) executed on oracle/ti_shim.py, the strict-IEEE-fp32 interpreter of
 the Taichi subset it uses.  Run in the development container (the reference tree does not travel to the GPU box):
 
     python tests/golden/make_shim_golden.py
@@ -78,7 +78,7 @@ def main_api():
         ti_shim.reset()
         rc = mod.Raycaster((D, H, W), c["res"], tf.shape[1], sampling_rate=c["sr"], jitter=c["jitter"], max_samples=c["M"])
         if jit is not None:
-            rc.vr.jitter_field.from_torch(torch.tensor(co._jitter_raw(jit)))                   # the probe's jitter field (PATCH): every item marches it
+            tp.set_jitter(rc.vr, jit, copies=2 * bs + 2)                                       # every item marches it, forward and (batched, :456) backward re-run
         if c.get("batch_all"):                                                                 # every input batched, items differ
             volume = torch.tensor(np.stack([vol, np.clip(vol[::-1].copy() * 0.9 + 0.05, 0, 1)]))[:, None]
             tft = torch.tensor(np.stack([tf, tf[:, ::-1].copy()]))
@@ -183,7 +183,7 @@ def main_loop():
     for k in range(c["iters"]):
         jit = make_jitter(1, h, w, seed=900 + k)[0].numpy()
         vr.set_tf_tex(torch.tensor(tf).permute(1, 0).contiguous())
-        vr.jitter_field.from_torch(torch.tensor(co._jitter_raw(jit)))
+        tp.set_jitter(vr, jit)
         vr.clear_framebuffer(); vr.clear_grad()
         vr.compute_entry_exit(c["bw_sr"], 1)
         vr.raycast(c["bw_sr"])
