@@ -374,3 +374,30 @@ def test_drop_in_loop_against_the_reference_demo_loop():
         assert _rel(tf.grad.cpu().numpy(), z["grad_tf"][k], np.zeros((), bool)) <= GRAD_TOL
         opt.step()
         assert np.abs(tf.detach().cpu().numpy() - z["tf_after"][k]).max() <= 1e-5, k
+
+
+def test_determine_batch_matches_the_reference_rule():
+    """`Raycaster._determine_batch` (:551-571) of the reference source against the product's, for every combination of batched and
+    shared inputs: same batched flag, same batch size, same values (the product hands out views of shared inputs where the reference
+    expands and clones them)."""
+    if tp.find_reference() is None:
+        pytest.skip("reference source not mounted (GPU box)")
+    from differender_b200 import Raycaster
+    mod = tp._load_reference_module("shim")
+    ref_self, my_self = object.__new__(mod.Raycaster), object.__new__(Raycaster)
+    g = torch.Generator().manual_seed(3)
+    BS, D, H, W, R = 3, 4, 5, 6, 7
+    for bv in (False, True):
+        for bt in (False, True):
+            for bl in (False, True):
+                vol = torch.rand((BS, 1, D, H, W) if bv else (1, D, H, W), generator=g)
+                tf = torch.rand((BS, 4, R) if bt else (4, R), generator=g)
+                lf = torch.rand((BS, 3) if bl else (3,), generator=g)
+                rb, rbs, rv, rt, rl = mod.Raycaster._determine_batch(ref_self, vol, tf, lf)
+                mb, mbs, mv, mt, ml = Raycaster._determine_batch(my_self, vol, tf, lf)
+                assert bool(rb) == bool(mb) == (bv or bt or bl) and int(rbs) == int(mbs)
+                if rb:                                           # broadcast the product's shared views to the reference's cloned batch
+                    mv = mv if mv.ndim == 4 else mv.expand(BS, -1, -1, -1)
+                    mt = mt if mt.ndim == 3 else mt.expand(BS, -1, -1)
+                    ml = ml if ml.ndim == 2 else ml.expand(BS, -1)
+                assert torch.equal(rv, mv.contiguous()) and torch.equal(rt, mt.contiguous()) and torch.equal(rl, ml.contiguous()), (bv, bt, bl)
